@@ -301,11 +301,13 @@ uint64_t ref_planner_iterate(void* pp, int iters)
     uint64_t expansions = 0;
     for (int it = 0; it < iters; ++it)
     {
-        for (const tree_t& t : p->rrt->tree_layers_)
+        // body of expandTreeLayers_ (:331-334) with the early-return test of
+        // expandTree_ (:339) evaluated first so that expansions are counted exactly
+        for (tree_t& t : p->rrt->tree_layers_)
         {
             if (!(t.expandables.empty() || t.is_done)) ++expansions;
+            p->rrt->expandTree_(t);
         }
-        p->rrt->expandTreeLayers_();
     }
     return expansions;
 }
@@ -567,11 +569,11 @@ int ref_planner_run(void* pp, ref_log_row_t* rows, int cap, int64_t* iterations,
     std::cout.rdbuf(sink.rdbuf());   // logData_ prints unconditionally (:1014)
     while (!done_iter && !done_time && !done_exp)
     {
-        for (const tree_t& t : r.tree_layers_)
+        for (tree_t& t : r.tree_layers_)   // expandTreeLayers_ (:331-334), counted
         {
             if (!(t.expandables.empty() || t.is_done)) ++n_exp;
+            r.expandTree_(t);
         }
-        r.expandTreeLayers_();
         if (r.iteration_count_ % 100 == 0)
         {
             double before = r.shortest_path_cost_;
