@@ -1,0 +1,1257 @@
+// csrc/imomd_core.cuh -- device logic of the multi-tree expansion path.
+//
+// One CTA drives one query.  The reference's expansion is a strict sequence
+// ("sequential dependence"), so the CTA runs a small state
+// machine: thread 0 executes the inherently serial bookkeeping (JPS hops,
+// choose-parent, frontier hash maintenance, the rewire cascade, the tree-to-tree
+// connection check) and posts *service requests* that the whole CTA executes in
+// parallel:
+//
+//   REQ_NN      nearest frontier vertex to the sample          (steerNewNode_ :406-418)
+//   REQ_RESCAN  arg-min of the two-root heuristic over the frontier (updateExpandables :510-524)
+//   REQ_MHINS   heuristics of freshly inserted frontier vertices    (updateExpandables :541-556)
+//
+// Both searches are the same *pruned arg-min over the uniform-grid frontier hash*:
+// a conservative per-cell lower bound discards cells, the surviving 32-record
+// chunks are evaluated record-per-thread, and a shuffle/shared-memory reduction
+// returns (min, lowest id on exact ties, runner-up).  NN ranks by squared chord
+// between unit vectors (== 4 * haversine `a`, monotone in the reference's
+// distance); decisions closer than the rounding band are re-done with the full
+// double-precision haversine and counted (near_ties / unresolved_ties).
+//
+// Everything is written against a tiny `Cta` policy (thread id, barrier, block
+// reductions, shared counter) so that tests/hostsim can compile the very same
+// logic for the host with a one-thread policy and check it against the oracle
+// without a GPU.  That build is test infrastructure; the shipped library has no
+// CPU path.
+//
+// Reference lines cited below are under /root/reference.
+#ifndef IMOMD_CORE_CUH
+#define IMOMD_CORE_CUH
+
+#include <math.h>
+#include <stdint.h>
+
+#include "imomd_layout.h"
+
+#if defined(__CUDACC__)
+#define IMOMD_HD __host__ __device__
+#else
+#define IMOMD_HD
+#endif
+
+namespace imomd {
+
+constexpr double kDeg2Rad = 3.14159265358979323846 / 180;
+constexpr double kEarthRadius = 6371000.0;   // `int EARTH_RADIUS = 6371e3` upstream
+constexpr double kCellPadDeg = 1e-9;         // cell rectangles are grown by this much
+constexpr double kPruneSlack = 1e-9;         // relative slack of every pruning test
+constexpr double kTieRel = 1e-12;            // "cannot be decided in device arithmetic"
+
+enum ReqType { REQ_EXIT = 0, REQ_NN = 1, REQ_RESCAN = 2, REQ_MHINS = 3 };
+enum Phase { PH_NEXT_TREE = 0, PH_AFTER_NN = 1, PH_JPS = 2, PH_INSERT = 3, PH_FINISH = 4 };
+
+// include/osm_converter/compute_haversine.hpp:41-58, same expression order.
+IMOMD_HD inline double haversine(double lat1, double lon1, double lat2, double lon2)
+{
+    double lat1_rad = lat1 * kDeg2Rad;
+    double lat2_rad = lat2 * kDeg2Rad;
+    double diff_lat_rad = (lat2 - lat1) * kDeg2Rad;
+    double diff_long_rad = (lon2 - lon1) * kDeg2Rad;
+    double s1 = sin(diff_lat_rad / 2);
+    double s2 = sin(diff_long_rad / 2);
+    double a = s1 * s1 + cos(lat1_rad) * cos(lat2_rad) * (s2 * s2);
+    double c = 2 * atan2(sqrt(a), sqrt(1 - a));
+    return kEarthRadius * c;
+}
+
+// distance for a haversine `a` value (used for the cell lower bounds)
+IMOMD_HD inline double dist_of_a(double a)
+{
+    if (a > 1.0) a = 1.0;
+    return kEarthRadius * (2 * atan2(sqrt(a), sqrt(1 - a)));
+}
+
+// Lower bound of haversine `a` between (qlat, qlon) and any point of hash cell c.
+// a = sin^2(dphi/2) + cos(phi_q) cos(phi_v) sin^2(dlam/2) is increasing in |dphi| and
+// |dlam| (both below pi here) and cos(phi_v) >= cosrow[row].
+IMOMD_HD inline double cell_lower_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
+                                    double cos_qlat)
+{
+    if (!g.prune) return 0.0;
+    int row = (int)(c / (uint32_t)g.G), colm = (int)(c % (uint32_t)g.G);
+    double lo = g.lat0 + row * g.hlat - kCellPadDeg;
+    double hi = g.lat0 + (row + 1) * g.hlat + kCellPadDeg;
+    double dphi = 0.0;
+    if (qlat < lo) dphi = lo - qlat;
+    else if (qlat > hi) dphi = qlat - hi;
+    double lo2 = g.lon0 + colm * g.hlon - kCellPadDeg;
+    double hi2 = g.lon0 + (colm + 1) * g.hlon + kCellPadDeg;
+    double dlam = 0.0;
+    if (qlon < lo2) dlam = lo2 - qlon;
+    else if (qlon > hi2) dlam = qlon - hi2;
+    double s1 = sin(dphi * kDeg2Rad / 2);
+    double s2 = sin(dlam * kDeg2Rad / 2);
+    double a = s1 * s1 + cos_qlat * g.cosrow[row] * (s2 * s2);
+    return a * (1.0 - kPruneSlack);
+}
+
+// unit vector + hash cell of one vertex (graph upload)
+IMOMD_HD inline VRec make_vrec(uint32_t v, double lat, double lon, int G, double lat0, double lon0,
+                               double hlat, double hlon)
+{
+    double la = lat * kDeg2Rad, lo = lon * kDeg2Rad;
+    double cl = cos(la), sl = sin(la), co = cos(lo), so = sin(lo);
+    VRec r;
+    r.x = cl * co;
+    r.y = cl * so;
+    r.z = sl;
+    r.id = v;
+    int row = (int)((lat - lat0) / hlat);
+    int colm = (int)((lon - lon0) / hlon);
+    row = row < 0 ? 0 : (row >= G ? G - 1 : row);
+    colm = colm < 0 ? 0 : (colm >= G ? G - 1 : colm);
+    r.cell = (uint32_t)(row * G + colm);
+    return r;
+}
+
+// lbd[q][t][c]: lower bound (metres) of haversine(root of tree t, any point of cell c)
+IMOMD_HD inline double lbd_entry(const PlannerDev& P, size_t i)
+{
+    uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
+    uint32_t c = (uint32_t)(i % cells);
+    int t = (int)((i / cells) % P.K);
+    int q = (int)(i / ((size_t)cells * P.K));
+    uint32_t root = P.query[q].dest[t];
+    double rlat = P.g.lat[root], rlon = P.g.lon[root];
+    double a = cell_lower_a(P.g, c, rlat, rlon, cos(rlat * kDeg2Rad));
+    return dist_of_a(a) * (1.0 - kPruneSlack);
+}
+
+// --------------------------------------------------------- per-tree views ---
+
+struct TreeRef
+{
+    uint32_t* parent;
+    double* cost;
+    uint32_t* fslot;
+    uint32_t* chl;
+    uint8_t* nchl;
+    uint32_t* cell_head;
+    uint32_t* cell_cnt;
+    VRec* rec;
+    uint32_t* chunk_next;
+    uint32_t* free_stack;
+};
+
+IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
+{
+    size_t qt = (size_t)q * P.K + k;
+    size_t cells = (size_t)P.g.G * P.g.G;
+    TreeRef t;
+    t.parent = P.parent + qt * P.g.n;
+    t.cost = P.cost + qt * P.g.n;
+    t.fslot = P.fslot + qt * P.g.n;
+    t.chl = P.chl + qt * P.g.arcs;
+    t.nchl = P.nchl + qt * P.g.n;
+    t.cell_head = P.cell_head + qt * cells;
+    t.cell_cnt = P.cell_cnt + qt * cells;
+    t.rec = P.rec + qt * (size_t)P.chunks * IMOMD_CHUNK;
+    t.chunk_next = P.chunk_next + qt * P.chunks;
+    t.free_stack = P.free_stack + qt * P.chunks;
+    return t;
+}
+
+struct Best
+{
+    double v1;       // minimum
+    uint32_t id1;    // its vertex (lowest id among exact ties)
+    double v2;       // runner-up value (== v1 when the minimum is attained twice)
+};
+
+IMOMD_HD inline Best best_empty()
+{
+    Best b;
+    b.v1 = INFINITY;
+    b.id1 = IMOMD_NONE;
+    b.v2 = INFINITY;
+    return b;
+}
+
+IMOMD_HD inline void best_add(Best& b, double v, uint32_t id)
+{
+    if (v < b.v1 || (v == b.v1 && id < b.id1))
+    {
+        b.v2 = b.v1;
+        b.v1 = v;
+        b.id1 = id;
+    }
+    else if (v < b.v2)
+    {
+        b.v2 = v;
+    }
+}
+
+IMOMD_HD inline Best best_merge(const Best& a, const Best& b)
+{
+    Best r;
+    if (b.v1 < a.v1 || (b.v1 == a.v1 && b.id1 < a.id1))
+    {
+        r.v1 = b.v1;
+        r.id1 = b.id1;
+        r.v2 = a.v1 < b.v2 ? a.v1 : b.v2;
+    }
+    else
+    {
+        r.v1 = a.v1;
+        r.id1 = a.id1;
+        r.v2 = a.v2 < b.v1 ? a.v2 : b.v1;
+    }
+    return r;
+}
+
+// State shared by the threads of the CTA (shared memory on the device).
+struct Shared
+{
+    // request posted by the sequential thread
+    int32_t req;
+    int32_t phase;
+    int32_t it;            // iterations completed in this launch
+    int32_t k;             // tree being expanded
+    // sample (selectRandomVertex_)
+    uint64_t rand_id;
+    double qlat, qlon;
+    // search results
+    Best result;
+    int32_t ambiguous;
+    uint32_t x_new;
+    // rescan / heuristic-insert requests
+    int32_t n_rescan;
+    int32_t rescan_o[IMOMD_KMAX];
+    int32_t n_ys;
+    uint32_t ys[IMOMD_MAXDEG];
+    double h[IMOMD_MAXDEG * IMOMD_KMAX];
+    // work list of the pruned search
+    uint32_t n_list;
+    uint32_t star_cell;
+    // block reduction scratch
+    Best red[32];
+};
+
+// --------------------------------------------------- frontier hash (serial) ---
+
+IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& T, int k,
+                               uint32_t v)
+{
+    if (T.fslot[v] != IMOMD_NONE) return true;
+    VRec r = P.g.vrec[v];
+    uint32_t c = r.cell;
+    uint32_t cnt = T.cell_cnt[c];
+    uint32_t off = cnt % IMOMD_CHUNK;
+    uint32_t head;
+    if (off == 0)
+    {
+        if (Q->free_top[k] == 0)
+        {
+            Q->status = 2;   // IMOMD_RUN_FRONTIER_FULL
+            return false;
+        }
+        head = T.free_stack[--Q->free_top[k]];
+        T.chunk_next[head] = cnt ? T.cell_head[c] : IMOMD_NONE;
+        T.cell_head[c] = head;
+    }
+    else
+    {
+        head = T.cell_head[c];
+    }
+    uint32_t slot = head * IMOMD_CHUNK + off;
+    T.rec[slot] = r;
+    T.fslot[v] = slot;
+    T.cell_cnt[c] = cnt + 1;
+    Q->frontier_count[k] += 1;
+    return true;
+}
+
+IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T, int k,
+                              uint32_t v)
+{
+    uint32_t s = T.fslot[v];
+    if (s == IMOMD_NONE) return;
+    uint32_t c = P.g.vrec[v].cell;
+    uint32_t cnt = T.cell_cnt[c];
+    uint32_t head = T.cell_head[c];
+    uint32_t off = (cnt - 1) % IMOMD_CHUNK;
+    uint32_t last = head * IMOMD_CHUNK + off;
+    if (last != s)
+    {
+        VRec m = T.rec[last];
+        T.rec[s] = m;
+        T.fslot[m.id] = s;
+    }
+    T.fslot[v] = IMOMD_NONE;
+    T.cell_cnt[c] = cnt - 1;
+    Q->frontier_count[k] -= 1;
+    if (off == 0)
+    {
+        T.cell_head[c] = T.chunk_next[head];
+        T.free_stack[Q->free_top[k]++] = head;
+    }
+}
+
+// ---------------------------------------- children lists (container order) ---
+// unordered_set<size_t> with <= 13 elements: a new key goes to the head of its
+// bucket's run (bucket = key % 13) or, for an empty bucket, to the list head
+// (SURVEY.md 8a-7).  Rows are CSR-aligned: children of p are neighbours of p.
+
+IMOMD_HD inline void chl_insert(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
+{
+    uint32_t* row = T.chl + g.row_ptr[p];
+    uint32_t n = T.nchl[p];
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (row[i] == x) return;
+    }
+    uint32_t at = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (row[i] % 13 == x % 13)
+        {
+            at = i;
+            break;
+        }
+    }
+    for (uint32_t i = n; i > at; --i) row[i] = row[i - 1];
+    row[at] = x;
+    T.nchl[p] = (uint8_t)(n + 1);
+}
+
+IMOMD_HD inline void chl_erase(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
+{
+    uint32_t* row = T.chl + g.row_ptr[p];
+    uint32_t n = T.nchl[p];
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (row[i] == x)
+        {
+            for (uint32_t j = i; j + 1 < n; ++j) row[j] = row[j + 1];
+            T.nchl[p] = (uint8_t)(n - 1);
+            return;
+        }
+    }
+}
+
+IMOMD_HD inline void chl_assign_single(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
+{
+    T.chl[g.row_ptr[p]] = x;
+    T.nchl[p] = 1;
+}
+
+// (*connection_ptr_)[a][b]; the graph was validated symmetric at upload
+IMOMD_HD inline double edge_weight(const GraphDev& g, uint32_t a, uint32_t b)
+{
+    uint32_t e0 = g.row_ptr[a], e1 = g.row_ptr[a + 1];
+    for (uint32_t e = e0; e < e1; ++e)
+    {
+        if (g.col[e] == b) return g.w[e];
+    }
+    return 0.0;
+}
+
+// ------------------------------------------------- random sample stream ----
+// libstdc++ on top of raw mt19937 words.
+
+struct WordStream
+{
+    const uint32_t* words;
+    uint64_t cursor;
+    IMOMD_HD uint32_t next() { return words[cursor++]; }
+};
+
+// std::generate_canonical<double,53>: (w0 + w1 * 2^32) / 2^64, clamped below 1
+IMOMD_HD inline double ws_canonical(WordStream& ws)
+{
+    double sum = 0.0;
+    double tmp = 1.0;
+    sum += (double)ws.next() * tmp;
+    tmp *= 4294967296.0;
+    sum += (double)ws.next() * tmp;
+    tmp *= 4294967296.0;
+    double ret = sum / tmp;
+    if (ret >= 1.0) ret = 0.99999999999999988897769753748;   // nextafter(1.0, 0.0)
+    return ret;
+}
+
+IMOMD_HD inline double ws_uniform_real(WordStream& ws, double a, double b)
+{
+    return ws_canonical(ws) * (b - a) + a;
+}
+
+// std::uniform_int_distribution over [0, urange], urange < 2^32 - 1 (Lemire)
+IMOMD_HD inline uint32_t ws_uniform_u32(WordStream& ws, uint32_t urange)
+{
+    if (urange == 0xFFFFFFFFu) return ws.next();
+    uint32_t range = urange + 1u;
+    uint64_t product = (uint64_t)ws.next() * (uint64_t)range;
+    uint32_t low = (uint32_t)product;
+    if (low < range)
+    {
+        uint32_t threshold = (0u - range) % range;
+        while (low < threshold)
+        {
+            product = (uint64_t)ws.next() * (uint64_t)range;
+            low = (uint32_t)product;
+        }
+    }
+    return (uint32_t)(product >> 32);
+}
+
+// ===================================================== sequential stages =====
+
+struct Seq
+{
+    const PlannerDev& P;
+    QueryDev* Q;
+    int q;
+    Shared& S;
+    uint32_t* arena;
+
+    IMOMD_HD Seq(const PlannerDev& P_, int q_, Shared& S_)
+        : P(P_), Q(P_.query + q_), q(q_), S(S_), arena(P_.arena + (size_t)q_ * P_.arena_entries)
+    {
+    }
+
+    IMOMD_HD uint32_t deg(uint32_t v) const { return P.g.row_ptr[v + 1] - P.g.row_ptr[v]; }
+
+    // selectRandomVertex_, src/imomd_rrt_star.cpp:358-400
+    IMOMD_HD void sample(int k, const TreeRef& T)
+    {
+        const GraphDev& g = P.g;
+        int K = Q->K;
+        WordStream ws;
+        ws.words = P.words;
+        ws.cursor = Q->word_cursor;
+        if (ws_uniform_real(ws, 0, 1) < P.goal_bias)
+        {
+            double rnd = ws_uniform_real(ws, 0, 1);
+            int i = 0;
+            while (rnd >= 0)
+            {
+                if (i >= K)
+                {
+                    Q->status = 4;   // IMOMD_RUN_CDF_OVERRUN
+                    break;
+                }
+                rnd -= Q->P[k * K + i++];
+            }
+            uint32_t random_dest = Q->view_root[i - 1];
+            double rlat = g.lat[random_dest];
+            double rlon = g.lon[random_dest];
+            if (T.parent[random_dest] != IMOMD_NONE)
+            {
+                double ratio = ws_uniform_real(ws, 0.0, 0.5);
+                uint32_t root = Q->view_root[k];
+                rlat *= ratio;
+                rlon *= ratio;
+                rlat += (1.0 - ratio) * g.lat[root];
+                rlon += (1.0 - ratio) * g.lon[root];
+            }
+            S.rand_id = random_dest;
+            S.qlat = rlat;
+            S.qlon = rlon;
+        }
+        else
+        {
+            uint32_t v = ws_uniform_u32(ws, g.n - 1);
+            S.rand_id = v;
+            S.qlat = g.lat[v];
+            S.qlon = g.lon[v];
+        }
+        Q->word_cursor = ws.cursor;
+    }
+
+    // which (k, o) min-heuristic holders equal x  (updateExpandables :503-512)
+    IMOMD_HD void collect_rescans(int k, uint32_t x)
+    {
+        int K = Q->K;
+        S.n_rescan = 0;
+        for (int o = 0; o < K; ++o)
+        {
+            if (o == k) continue;
+            if (Q->MHi[k * K + o] == x) S.rescan_o[S.n_rescan++] = o;
+        }
+    }
+
+    // updateConnectionTree_, src/imomd_rrt_star.cpp:645-706
+    IMOMD_HD void update_connection(int k, const TreeRef& T, uint32_t x)
+    {
+        int K = Q->K;
+        double cx = T.cost[x];
+        for (int o = 0; o < K; ++o)
+        {
+            if (o == k) continue;
+            TreeRef O = tree_ref(P, q, o);
+            if (O.parent[x] == IMOMD_NONE) continue;
+            int set_idx = (o > k) ? o * (o - 1) / 2 + k : k * (k - 1) / 2 + o;
+            if (!Q->contact[set_idx])
+            {
+                Q->contact[set_idx] = 1;
+                if (P.pseudo) log_connection((uint32_t)set_idx, x);
+                connect_two_trees(k, o);
+            }
+            double distance = cx + O.cost[x];
+            if (distance < Q->D[k * K + o] - 0.1)
+            {
+                Q->D[k * K + o] = distance;
+                Q->D[o * K + k] = distance;
+                Q->CN[k * K + o] = x;
+                Q->CN[o * K + k] = x;
+                Q->dm_updated = 1;
+            }
+            if (P.pseudo)
+            {
+                uint32_t x_parent = T.parent[x];
+                if (O.parent[x_parent] == IMOMD_NONE ||
+                    (O.parent[x_parent] != x && O.parent[x] != x_parent))
+                {
+                    log_connection((uint32_t)set_idx, x);
+                }
+            }
+        }
+    }
+
+    IMOMD_HD void log_connection(uint32_t set_idx, uint32_t x)
+    {
+        uint32_t* lg = P.log + (size_t)q * 2 * P.log_entries;
+        uint32_t i = Q->log_count;
+        if (i < P.log_entries)
+        {
+            lg[2 * i] = set_idx;
+            lg[2 * i + 1] = x;
+        }
+        Q->log_count = i + 1;   // an overflow is visible to the host as count > capacity
+    }
+
+    // connectTwoTree_, src/imomd_rrt_star.cpp:708-742 (flat relabel: same labels)
+    IMOMD_HD void connect_two_trees(int a, int b)
+    {
+        if (Q->connected) return;
+        int K = Q->K;
+        int lo = Q->ds_parent[a], hi = Q->ds_parent[b];
+        if (lo == hi) return;
+        if (hi < lo)
+        {
+            int t = lo;
+            lo = hi;
+            hi = t;
+        }
+        for (int i = 0; i < K; ++i)
+        {
+            if (Q->ds_parent[i] == hi) Q->ds_parent[i] = lo;
+        }
+        int all = 1;
+        for (int i = 1; i < K; ++i)
+        {
+            if (Q->ds_parent[i] != Q->ds_parent[0]) all = 0;
+        }
+        Q->connected = all;
+    }
+
+    // the four statements of :443-446 / :453-456
+    IMOMD_HD void attach_chain(int k, const TreeRef& T, uint32_t x, uint32_t via)
+    {
+        if (T.parent[x] == IMOMD_NONE) Q->tree_size[k] += 1;
+        T.parent[x] = via;
+        chl_assign_single(P.g, T, via, x);
+        T.cost[x] = T.cost[via] + edge_weight(P.g, via, x);
+        update_connection(k, T, x);
+    }
+
+    // jump-point search of steerNewNode_, src/imomd_rrt_star.cpp:427-459
+    IMOMD_HD uint32_t jps(int k, const TreeRef& T, uint32_t x_new)
+    {
+        const GraphDev& g = P.g;
+        bool done = false;
+        while (deg(x_new) == 2 && !done)
+        {
+            uint32_t e = g.row_ptr[x_new];
+            uint32_t x_1 = g.col[e];
+            uint32_t x_2 = g.col[e + 1];
+            if (T.parent[x_1] != IMOMD_NONE)
+            {
+                if (T.parent[x_2] != IMOMD_NONE)
+                {
+                    done = true;
+                }
+                else
+                {
+                    attach_chain(k, T, x_new, x_1);
+                    x_new = x_2;
+                }
+            }
+            else
+            {
+                attach_chain(k, T, x_new, x_2);
+                x_new = x_1;
+            }
+        }
+        return x_new;
+    }
+
+    // connectNewNode_, src/imomd_rrt_star.cpp:465-496
+    IMOMD_HD void connect_new_node(int k, const TreeRef& T, uint32_t x_new)
+    {
+        const GraphDev& g = P.g;
+        uint32_t x_parent = IMOMD_NONE;
+        double min_cost = INFINITY;
+        uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
+        for (uint32_t e = e0; e < e1; ++e)
+        {
+            uint32_t y = g.col[e];
+            if (T.parent[y] != IMOMD_NONE)
+            {
+                double c = T.cost[y] + g.w[e];
+                if (c < min_cost)
+                {
+                    x_parent = y;
+                    min_cost = c;
+                }
+            }
+        }
+        if (x_parent != IMOMD_NONE)
+        {
+            if (T.parent[x_new] == IMOMD_NONE) Q->tree_size[k] += 1;
+            T.parent[x_new] = x_parent;
+            chl_insert(g, T, x_parent, x_new);
+            T.cost[x_new] = min_cost;
+        }
+    }
+
+    // neighbour part of updateExpandables, src/imomd_rrt_star.cpp:533-558 (the
+    // heuristic updates of the listed vertices run as the REQ_MHINS service)
+    IMOMD_HD void insert_neighbours(int k, const TreeRef& T, uint32_t x_new)
+    {
+        const GraphDev& g = P.g;
+        S.n_ys = 0;
+        uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
+        for (uint32_t e = e0; e < e1; ++e)
+        {
+            uint32_t y = g.col[e];
+            if (T.parent[y] == IMOMD_NONE)
+            {
+                if (!fr_insert(P, Q, T, k, y)) return;
+                S.ys[S.n_ys++] = y;
+            }
+        }
+    }
+
+    // tree_t::updateCost, include/imomd_rrt_star/imomd_rrt_star.h:102-123.  The list of
+    // updated vertices is appended to the arena at `lo`; returns its end (or NONE).
+    IMOMD_HD uint32_t update_cost(const TreeRef& T, uint32_t rewired, double new_cost, uint32_t lo)
+    {
+        const GraphDev& g = P.g;
+        uint32_t cap = P.arena_entries;
+        if (lo >= cap) return IMOMD_NONE;
+        uint32_t hi = lo;
+        arena[hi++] = rewired;
+        uint32_t head = lo;
+        double old = T.cost[rewired];
+        while (head < hi)
+        {
+            uint32_t par = arena[head++];
+            const uint32_t* row = T.chl + g.row_ptr[par];
+            uint32_t n = T.nchl[par];
+            if (hi + n > cap) return IMOMD_NONE;
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                uint32_t child = row[i];
+                T.cost[child] = new_cost + T.cost[child] - old;
+                arena[hi++] = child;
+            }
+        }
+        T.cost[rewired] = new_cost;
+        return hi;
+    }
+
+    // rewireTree_, src/imomd_rrt_star.cpp:561-600.  The recursion is unrolled onto an
+    // explicit LIFO in the arena: frames {prev, x, e, end, skip, lo, cur} and, above
+    // the frame that owns it, the `updated_nodes` list of the active re-parenting.
+    IMOMD_HD void rewire(int k, const TreeRef& T, uint32_t x_start)
+    {
+        const GraphDev& g = P.g;
+        const uint32_t cap = P.arena_entries;
+        const uint32_t FR = 7;
+        uint32_t top = 0;
+        uint32_t fp = IMOMD_NONE;
+        // push first frame
+        {
+            uint32_t* f = arena + top;
+            f[0] = fp;
+            f[1] = x_start;
+            f[2] = g.row_ptr[x_start];
+            f[3] = g.row_ptr[x_start + 1];
+            f[4] = IMOMD_NONE;
+            f[5] = IMOMD_NONE;
+            f[6] = 0;
+            fp = top;
+            top += FR;
+        }
+        while (fp != IMOMD_NONE)
+        {
+            uint32_t* f = arena + fp;
+            if (f[5] != IMOMD_NONE)
+            {
+                // walking updated_nodes in reverse (:589-596)
+                if (f[6] <= f[5])
+                {
+                    top = f[5];         // list exhausted: release it
+                    f[5] = IMOMD_NONE;
+                    continue;
+                }
+                uint32_t u = arena[--f[6]];
+                if (u == f[4]) continue;
+                if (top + FR > cap)
+                {
+                    Q->status = 3;   // IMOMD_RUN_ARENA_FULL
+                    return;
+                }
+                uint32_t* nf = arena + top;
+                nf[0] = fp;
+                nf[1] = u;
+                nf[2] = g.row_ptr[u];
+                nf[3] = g.row_ptr[u + 1];
+                nf[4] = IMOMD_NONE;
+                nf[5] = IMOMD_NONE;
+                nf[6] = 0;
+                fp = top;
+                top += FR;
+                continue;
+            }
+            if (f[2] >= f[3])
+            {
+                top = fp;
+                fp = f[0];
+                continue;
+            }
+            uint32_t e = f[2]++;
+            uint32_t x = f[1];
+            uint32_t y = g.col[e];
+            uint32_t py = T.parent[y];
+            if (py != IMOMD_NONE && y != T.parent[x])
+            {
+                double nc = T.cost[x] + g.w[e];
+                if (T.cost[y] > nc)
+                {
+                    chl_erase(g, T, py, y);
+                    T.parent[y] = x;
+                    chl_insert(g, T, x, y);
+                    uint32_t hi = update_cost(T, y, nc, top);
+                    if (hi == IMOMD_NONE)
+                    {
+                        Q->status = 3;
+                        return;
+                    }
+                    update_connection(k, T, y);
+                    f[4] = y;
+                    f[5] = top;
+                    f[6] = hi;
+                    top = hi;
+                }
+            }
+        }
+    }
+
+    // updateSelectionProbability, src/imomd_rrt_star.cpp:602-643
+    IMOMD_HD void update_selection_probability(int k)
+    {
+        int K = Q->K;
+        int other = K;
+        for (int i = 0; i < K; ++i)
+        {
+            if ((uint64_t)Q->dest[i] == S.rand_id)
+            {
+                other = i;
+                break;
+            }
+        }
+        if (other == K) return;
+        if (Q->MHv[k * K + other] > Q->D[k * K + other])
+        {
+            double* Pm = Q->P;
+            Pm[k * K + other] = 0.0;
+            Pm[other * K + k] = 0.0;
+            int dk = 1, dother = 1;
+            for (int i = 0; i < K; ++i)
+            {
+                if (!(Pm[k * K + i] == 0)) dk = 0;
+            }
+            Q->is_done[k] = dk;
+            for (int i = 0; i < K; ++i)
+            {
+                if (!(Pm[other * K + i] == 0)) dother = 0;
+            }
+            Q->is_done[other] = dother;
+            double sum_t = 0.0, sum_o = 0.0;
+            for (int i = 0; i < K; ++i) sum_t += Pm[k * K + i];
+            for (int i = 0; i < K; ++i) sum_o += Pm[other * K + i];
+            for (int i = 0; i < K; ++i)
+            {
+                Pm[k * K + i] /= sum_t;
+                Pm[other * K + i] /= sum_o;
+            }
+        }
+    }
+
+    // Runs the serial part of expandTree_ (:337-356) until it needs the CTA or the
+    // launch is over; S.req tells the CTA what to do next.
+    IMOMD_HD void step(int iters)
+    {
+        int K = Q->K;
+        for (;;)
+        {
+            if (Q->status != 0)
+            {
+                S.req = REQ_EXIT;
+                return;
+            }
+            int k = S.k;
+            TreeRef T = tree_ref(P, q, k < K ? k : 0);
+            switch (S.phase)
+            {
+                case PH_NEXT_TREE:
+                {
+                    if (k >= K)
+                    {
+                        S.it += 1;
+                        S.k = 0;
+                        Q->iterations += 1;
+                        continue;
+                    }
+                    if (S.it >= iters)
+                    {
+                        S.req = REQ_EXIT;
+                        return;
+                    }
+                    if (k == 0)
+                    {
+                        int active = 0;
+                        for (int j = 0; j < K; ++j)
+                        {
+                            if (Q->frontier_count[j] != 0 && !Q->is_done[j]) ++active;
+                        }
+                        if (active == 0)
+                        {
+                            // nothing can expand any more: the remaining passes are no-ops
+                            Q->iterations += iters - S.it;
+                            S.it = iters;
+                            S.req = REQ_EXIT;
+                            return;
+                        }
+                    }
+                    if (Q->frontier_count[k] == 0 || Q->is_done[k])
+                    {
+                        S.k = k + 1;
+                        continue;
+                    }
+                    if (Q->word_cursor + IMOMD_WORD_MARGIN > P.words_avail)
+                    {
+                        Q->status = 1;   // IMOMD_RUN_NEED_WORDS (resumable)
+                        continue;
+                    }
+                    sample(k, T);
+                    if (Q->status != 0) continue;
+                    S.req = REQ_NN;
+                    S.phase = PH_AFTER_NN;
+                    return;
+                }
+                case PH_AFTER_NN:
+                {
+                    uint32_t x = S.result.id1;
+                    S.x_new = x;
+                    S.phase = PH_JPS;
+                    if (deg(x) == 2)
+                    {
+                        // updateExpandables(tree, x_new, false), :422-425
+                        fr_erase(P, Q, T, k, x);
+                        collect_rescans(k, x);
+                        if (S.n_rescan > 0)
+                        {
+                            S.req = REQ_RESCAN;
+                            return;
+                        }
+                    }
+                    continue;
+                }
+                case PH_JPS:
+                {
+                    uint32_t x_new = jps(k, T, S.x_new);
+                    S.x_new = x_new;
+                    connect_new_node(k, T, x_new);
+                    // updateExpandables(tree, x_new, true), first half
+                    fr_erase(P, Q, T, k, x_new);
+                    collect_rescans(k, x_new);
+                    S.phase = PH_INSERT;
+                    if (S.n_rescan > 0)
+                    {
+                        S.req = REQ_RESCAN;
+                        return;
+                    }
+                    continue;
+                }
+                case PH_INSERT:
+                {
+                    insert_neighbours(k, T, S.x_new);
+                    S.phase = PH_FINISH;
+                    if (Q->status == 0 && S.n_ys > 0)
+                    {
+                        S.req = REQ_MHINS;
+                        return;
+                    }
+                    continue;
+                }
+                case PH_FINISH:
+                {
+                    rewire(k, T, S.x_new);
+                    if (Q->status != 0) continue;
+                    update_selection_probability(k);
+                    update_connection(k, T, S.x_new);
+                    Q->expansions += 1;
+                    S.k = k + 1;
+                    S.phase = PH_NEXT_TREE;
+                    continue;
+                }
+            }
+        }
+    }
+};
+
+// ====================================================== CTA-wide services ====
+
+// All threads: evaluate the records of the chunk work list with `eval(rec)`.
+template <class Cta, class Eval>
+IMOMD_HD inline Best scan_list(Cta& cta, const TreeRef& T, const uint32_t* clist, uint32_t first,
+                               uint32_t n_list, Eval eval)
+{
+    Best b = best_empty();
+    uint32_t total = (n_list - first) * IMOMD_CHUNK;
+    for (uint32_t i = cta.tid(); i < total; i += cta.nt())
+    {
+        uint32_t li = first + i / IMOMD_CHUNK;
+        uint32_t lane = i % IMOMD_CHUNK;
+        uint32_t chunk = clist[2 * li];
+        uint32_t cnt = clist[2 * li + 1];
+        if (lane < cnt)
+        {
+            const VRec& r = T.rec[(size_t)chunk * IMOMD_CHUNK + lane];
+            best_add(b, eval(r), r.id);
+        }
+    }
+    return b;
+}
+
+// one thread: append the chunk chain of cell c to the work list
+template <class Cta>
+IMOMD_HD inline void list_cell(Cta& cta, const TreeRef& T, uint32_t* clist, uint32_t* n_list,
+                               uint32_t c, uint32_t cnt)
+{
+    uint32_t chunk = T.cell_head[c];
+    uint32_t in_head = (cnt - 1) % IMOMD_CHUNK + 1;
+    uint32_t n = in_head;
+    while (chunk != IMOMD_NONE && cnt > 0)
+    {
+        uint32_t at = cta.counter_add(n_list, 1u);
+        clist[2 * at] = chunk;
+        clist[2 * at + 1] = n;
+        cnt -= n;
+        n = IMOMD_CHUNK;
+        chunk = T.chunk_next[chunk];
+    }
+}
+
+// Pruned arg-min over the frontier hash of one tree.
+//   lower(c)  conservative lower bound of the objective over cell c
+//   eval(r)   objective of a frontier record
+//   bound(m)  largest lower bound a cell may have and still matter once the best
+//             value so far is m
+// Returns the same Best on every thread.  `lb` holds G*G doubles.
+template <class Cta, class Lower, class Eval, class Bound>
+IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef& T, Shared& S,
+                                   double* lb, uint32_t* clist, Lower lower, Eval eval,
+                                   Bound bound)
+{
+    uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
+    // 1. lower bounds of the occupied cells; the most promising cell
+    Best star = best_empty();
+    for (uint32_t c = cta.tid(); c < cells; c += cta.nt())
+    {
+        double v = INFINITY;
+        if (T.cell_cnt[c] != 0)
+        {
+            v = lower(c);
+            best_add(star, v, c);
+        }
+        lb[c] = v;
+    }
+    star = cta.reduce(star, S.red);
+    if (star.id1 == IMOMD_NONE) return best_empty();   // empty frontier
+    // 2. its records give the first upper bound
+    if (cta.tid() == 0)
+    {
+        S.n_list = 0;
+        list_cell(cta, T, clist, &S.n_list, star.id1, T.cell_cnt[star.id1]);
+    }
+    cta.sync();
+    uint32_t n0 = S.n_list;
+    Best b0 = scan_list(cta, T, clist, 0u, n0, eval);
+    b0 = cta.reduce(b0, S.red);
+    double limit = bound(b0.v1);
+    // 3. every other occupied cell whose bound does not exceed it
+    for (uint32_t c = cta.tid(); c < cells; c += cta.nt())
+    {
+        if (c != star.id1 && lb[c] <= limit) list_cell(cta, T, clist, &S.n_list, c, T.cell_cnt[c]);
+    }
+    cta.sync();
+    uint32_t n1 = S.n_list;
+    Best b1 = scan_list(cta, T, clist, n0, n1, eval);
+    if (cta.tid() == 0) b1 = best_merge(b1, b0);
+    b1 = cta.reduce(b1, S.red);
+    return b1;
+}
+
+// steerNewNode_ arg-min (src/imomd_rrt_star.cpp:406-418) for the sample in S.
+template <class Cta>
+IMOMD_HD inline void svc_nearest(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
+                                 double* lb, uint32_t* clist, int64_t* near_ties,
+                                 int64_t* unresolved_ties)
+{
+    const GraphDev& g = P.g;
+    TreeRef T = tree_ref(P, q, k);
+    double qlat = S.qlat, qlon = S.qlon;
+    double cl = cos(qlat * kDeg2Rad), sl = sin(qlat * kDeg2Rad);
+    double co = cos(qlon * kDeg2Rad), so = sin(qlon * kDeg2Rad);
+    double qx = cl * co, qy = cl * so, qz = sl;
+    auto lower = [&](uint32_t c) { return 4.0 * cell_lower_a(g, c, qlat, qlon, cl); };
+    auto eval = [&](const VRec& r) {
+        double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+        return dx * dx + dy * dy + dz * dz;
+    };
+    // rounding band of a squared chord m: unit-vector components carry ~1e-16 each
+    auto band = [](double m) { return 2e-12 * m + 4e-15 * sqrt(m); };
+    auto bound = [&](double m) { return m * (1.0 + kPruneSlack) + 4.0 * band(m); };
+    Best b = pruned_argmin(cta, P, T, S, lb, clist, lower, eval, bound);
+    int ambiguous = (b.id1 != IMOMD_NONE) && (b.v2 - b.v1 <= band(b.v1));
+    if (ambiguous)
+    {
+        // slow exact pass: full haversine for everything inside the band
+        double cut = b.v1 + 2.0 * band(b.v1);
+        auto eval2 = [&](const VRec& r) {
+            double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+            double c2 = dx * dx + dy * dy + dz * dz;
+            if (c2 > cut) return (double)INFINITY;
+            return haversine(g.lat[r.id], g.lon[r.id], qlat, qlon);
+        };
+        Best e = scan_list(cta, T, clist, 0u, S.n_list, eval2);
+        e = cta.reduce(e, S.red);
+        b = e;
+        if (cta.tid() == 0)
+        {
+            *near_ties += 1;
+            if (e.v2 - e.v1 <= kTieRel * e.v1) *unresolved_ties += 1;
+        }
+    }
+    if (cta.tid() == 0)
+    {
+        S.result = b;
+        S.ambiguous = ambiguous;
+    }
+}
+
+// frontier rescans of updateExpandables (src/imomd_rrt_star.cpp:510-524) for the
+// pairs (k, o) listed in S.rescan_o
+template <class Cta>
+IMOMD_HD inline void svc_rescan(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, double* lb)
+{
+    const GraphDev& g = P.g;
+    QueryDev* Q = P.query + q;
+    TreeRef T = tree_ref(P, q, k);
+    int K = Q->K;
+    uint32_t cells = (uint32_t)g.G * (uint32_t)g.G;
+    uint32_t* clist = P.clist + (size_t)q * 2 * P.chunks;
+    const double* lbd = P.lbd + (size_t)q * K * cells;
+    uint32_t rk = Q->view_root[k];
+    double klat = g.lat[rk], klon = g.lon[rk];
+    int n = S.n_rescan;
+    for (int i = 0; i < n; ++i)
+    {
+        int o = S.rescan_o[i];
+        uint32_t ro = Q->view_root[o];
+        double olat = g.lat[ro], olon = g.lon[ro];
+        const double* lk = lbd + (size_t)k * cells;
+        const double* lo = lbd + (size_t)o * cells;
+        auto lower = [&](uint32_t c) { return lk[c] + lo[c]; };
+        auto eval = [&](const VRec& r) {
+            double vlat = g.lat[r.id], vlon = g.lon[r.id];
+            return haversine(vlat, vlon, klat, klon) + haversine(vlat, vlon, olat, olon);
+        };
+        auto bound = [&](double m) { return m * (1.0 + kPruneSlack); };
+        Best b = pruned_argmin(cta, P, T, S, lb, clist, lower, eval, bound);
+        if (cta.tid() == 0)
+        {
+            Q->MHi[k * K + o] = b.id1;
+            Q->MHv[k * K + o] = b.v1;
+            if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1) Q->unresolved_ties += 1;
+        }
+        cta.sync();
+    }
+}
+
+// heuristic updates for the vertices just inserted into the frontier
+// (src/imomd_rrt_star.cpp:541-556): h(y, o) = hav(y, root_k) + hav(y, root_o)
+template <class Cta>
+IMOMD_HD inline void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
+{
+    const GraphDev& g = P.g;
+    QueryDev* Q = P.query + q;
+    int K = Q->K;
+    int m = S.n_ys;
+    for (int i = cta.tid(); i < m * K; i += cta.nt())
+    {
+        int yi = i / K, o = i % K;
+        uint32_t y = S.ys[yi];
+        uint32_t r = Q->view_root[o];
+        S.h[yi * IMOMD_KMAX + o] = haversine(g.lat[y], g.lon[y], g.lat[r], g.lon[r]);
+    }
+    cta.sync();
+    for (int o = cta.tid(); o < K; o += cta.nt())
+    {
+        if (o == k) continue;
+        double best = Q->MHv[k * K + o];
+        uint32_t arg = Q->MHi[k * K + o];
+        for (int yi = 0; yi < m; ++yi)
+        {
+            double h = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
+            if (h < best)
+            {
+                best = h;
+                arg = S.ys[yi];
+            }
+        }
+        Q->MHv[k * K + o] = best;
+        Q->MHi[k * K + o] = arg;
+    }
+}
+
+// Tree construction of the planner constructor (src/imomd_rrt_star.cpp:73-78):
+// tree i gets its root and updateExpandables(root, true) while trees j > i still
+// read as id 0 / root 0.  Serial; runs once per query.
+IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
+{
+    const GraphDev& g = P.g;
+    QueryDev* Q = P.query + q;
+    int K = Q->K;
+    for (int i = 0; i < K; ++i)
+    {
+        Q->view_id[i] = 0;
+        Q->view_root[i] = 0;
+    }
+    for (int i = 0; i < K; ++i)
+    {
+        TreeRef T = tree_ref(P, q, i);
+        uint32_t root = Q->dest[i];
+        Q->view_id[i] = i;
+        Q->view_root[i] = root;
+        T.parent[root] = root;
+        T.cost[root] = 0.0;
+        Q->tree_size[i] = 1;
+        Q->ds_parent[i] = i;
+        // erase(root) is a no-op and no holder equals the root yet; neighbours:
+        uint32_t e0 = g.row_ptr[root], e1 = g.row_ptr[root + 1];
+        for (uint32_t e = e0; e < e1; ++e)
+        {
+            uint32_t y = g.col[e];
+            if (T.parent[y] != IMOMD_NONE) continue;
+            if (!fr_insert(P, Q, T, i, y)) return;
+            for (int o = 0; o < K; ++o)
+            {
+                if (Q->view_id[o] == i) continue;
+                int oid = Q->view_id[o];
+                uint32_t oroot = Q->view_root[o];
+                double h = haversine(g.lat[y], g.lon[y], g.lat[root], g.lon[root]) +
+                           haversine(g.lat[y], g.lon[y], g.lat[oroot], g.lon[oroot]);
+                if (h < Q->MHv[i * K + oid])
+                {
+                    Q->MHv[i * K + oid] = h;
+                    Q->MHi[i * K + oid] = y;
+                }
+            }
+        }
+    }
+}
+
+// The per-query driver: the loop every CTA runs (device) / the host simulation runs.
+template <class Cta>
+IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
+                               double* lb)
+{
+    QueryDev* Q = P.query + q;
+    if (cta.tid() == 0)
+    {
+        S.phase = PH_NEXT_TREE;
+        S.it = 0;
+        S.k = Q->resume_k;         // resume point inside an interrupted pass
+        S.req = REQ_EXIT;
+        if (Q->status == 1) Q->status = 0;   // NEED_WORDS is resumable
+        Q->last_iterations = Q->iterations;
+        Q->last_expansions = Q->expansions;
+    }
+    cta.sync();
+    for (;;)
+    {
+        if (cta.tid() == 0)
+        {
+            Seq seq(P, q, S);
+            seq.step(iters);
+        }
+        cta.sync();
+        int req = S.req;
+        int k = S.k;
+        if (req == REQ_EXIT) break;
+        if (req == REQ_NN)
+        {
+            svc_nearest(cta, P, q, k, S, lb, P.clist + (size_t)q * 2 * P.chunks, &Q->near_ties,
+                        &Q->unresolved_ties);
+        }
+        else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
+        else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);
+        cta.sync();
+    }
+    if (cta.tid() == 0)
+    {
+        Q->resume_k = S.k < Q->K ? S.k : 0;
+        Q->last_iterations = Q->iterations - Q->last_iterations;
+        Q->last_expansions = Q->expansions - Q->last_expansions;
+        int active = 0;
+        int64_t tv = 0;
+        for (int j = 0; j < Q->K; ++j)
+        {
+            if (Q->frontier_count[j] != 0 && !Q->is_done[j]) ++active;
+            tv += (int64_t)Q->tree_size[j];
+        }
+        Q->active_trees = active;
+        ReportDev* R = P.reports + q;
+        R->status = Q->status;
+        R->active_trees = active;
+        R->iterations = Q->last_iterations;
+        R->expansions = Q->last_expansions;
+        R->tree_vertices = tv;
+        R->words_consumed = (int64_t)Q->word_cursor;
+        R->connected = Q->connected;
+        R->dm_updated = Q->dm_updated;
+        R->near_ties = Q->near_ties;
+        R->unresolved_ties = Q->unresolved_ties;
+        R->log_entries = (int64_t)Q->log_count;
+    }
+}
+
+}  // namespace imomd
+
+#endif  // IMOMD_CORE_CUH

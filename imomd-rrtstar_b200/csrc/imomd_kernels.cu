@@ -1,0 +1,873 @@
+// csrc/imomd_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/imomd_b200.h.
+//
+// Kernels
+//   k_build_vrec     unit vectors + hash cell of every vertex (graph upload)
+//   k_lower_bounds   per (query, tree root, cell) haversine lower bounds
+//   k_init_trees     free-chunk stacks + tree construction (ImomdRRT ctor :73-78)
+//   k_expand         persistent expansion kernel: one CTA per query, `iters` passes
+//                    of expandTreeLayers_ (:329-356) without returning to the host
+//   k_nearest        parity hook: batched nearest-frontier-vertex lookups
+//   k_walk           parent-pointer walk for updatePath_ (:936-954)
+//   k_ga_eval        one warp per tour, sequential path cost (eci :442-450)
+//
+// There is no CPU fallback in this library: every entry point that computes needs a
+// CUDA device and fails with IMOMD_ERR_CUDA otherwise.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/imomd_b200.h"
+#include "imomd_core.cuh"
+#include "imomd_setup.h"
+
+using namespace imomd;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do                                                                                   \
+    {                                                                                    \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(IMOMD_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+    } while (0)
+
+constexpr int kThreads = 256;   // CTA size of the expansion kernel (8 warps)
+
+// ------------------------------------------------------------ Cta policy ---
+
+struct CtaDev
+{
+    __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+    __device__ __forceinline__ int nt() const { return (int)blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ uint32_t counter_add(uint32_t* p, uint32_t v) const
+    {
+        return atomicAdd(p, v);
+    }
+    // block-wide merge; every thread gets the result.  Warp shuffles, then one slot
+    // per warp in shared memory.
+    __device__ __forceinline__ Best reduce(Best b, Best* red) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            Best o;
+            o.v1 = __shfl_down_sync(full, b.v1, off);
+            o.id1 = __shfl_down_sync(full, b.id1, off);
+            o.v2 = __shfl_down_sync(full, b.v2, off);
+            b = best_merge(b, o);
+        }
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if (lane == 0) red[warp] = b;
+        __syncthreads();
+        if (warp == 0)
+        {
+            b = lane < nw ? red[lane] : best_empty();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+            {
+                Best o;
+                o.v1 = __shfl_down_sync(full, b.v1, off);
+                o.id1 = __shfl_down_sync(full, b.id1, off);
+                o.v2 = __shfl_down_sync(full, b.v2, off);
+                b = best_merge(b, o);
+            }
+            if (lane == 0) red[0] = b;
+        }
+        __syncthreads();
+        b = red[0];
+        __syncthreads();
+        return b;
+    }
+};
+
+// ---------------------------------------------------------------- kernels ---
+
+__global__ void k_build_vrec(uint32_t n, const double* __restrict__ lat,
+                             const double* __restrict__ lon, VRec* __restrict__ vrec, int G,
+                             double lat0, double lon0, double hlat, double hlon)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    vrec[v] = make_vrec(v, lat[v], lon[v], G, lat0, lon0, hlat, hlon);
+}
+
+// lbd[q][t][c] = lower bound (metres) of haversine(root of tree t, any point of cell c)
+__global__ void k_lower_bounds(PlannerDev P)
+{
+    size_t total = (size_t)P.Q * P.K * P.g.G * P.g.G;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    P.lbd[i] = lbd_entry(P, i);
+}
+
+__global__ void k_init_trees(PlannerDev P)
+{
+    int q = blockIdx.x;
+    int K = P.K;
+    // free-chunk stacks: pop order 0, 1, 2, ...
+    for (int k = 0; k < K; ++k)
+    {
+        uint32_t* fs = P.free_stack + ((size_t)q * K + k) * P.chunks;
+        for (int i = threadIdx.x; i < P.chunks; i += blockDim.x) fs[i] = (uint32_t)(P.chunks - 1 - i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        QueryDev* Q = P.query + q;
+        for (int k = 0; k < K; ++k) Q->free_top[k] = (uint32_t)P.chunks;
+        construct_trees(P, q);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_expand(PlannerDev P, int iters)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+    double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
+    CtaDev cta;
+    for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
+    {
+        run_query(cta, P, q, iters, S, lb);
+        __syncthreads();
+    }
+}
+
+// One CTA per lookup slot (grid-stride over the lookups); scratch chunk lists are per CTA.
+__global__ void __launch_bounds__(kThreads)
+k_nearest(PlannerDev P, int n, const imomd_nn_query* __restrict__ qs, uint32_t* __restrict__ idx,
+          double* __restrict__ dist, uint32_t* scratch, int64_t* stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+    double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
+    CtaDev cta;
+    uint32_t* clist = scratch + (size_t)blockIdx.x * 2 * P.chunks;
+    __shared__ int64_t near_ties, unresolved;
+    if (threadIdx.x == 0)
+    {
+        near_ties = 0;
+        unresolved = 0;
+    }
+    for (int i = blockIdx.x; i < n; i += gridDim.x)
+    {
+        imomd_nn_query nq = qs[i];
+        if (threadIdx.x == 0)
+        {
+            S.qlat = nq.lat;
+            S.qlon = nq.lon;
+        }
+        __syncthreads();
+        svc_nearest(cta, P, nq.query, nq.tree, S, lb, clist, &near_ties, &unresolved);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            uint32_t v = S.result.id1;
+            idx[i] = v;
+            dist[i] = v == IMOMD_NONE
+                          ? INFINITY
+                          : haversine(P.g.lat[v], P.g.lon[v], nq.lat, nq.lon);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && stats)
+    {
+        atomicAdd((unsigned long long*)&stats[0], (unsigned long long)near_ties);
+        atomicAdd((unsigned long long*)&stats[1], (unsigned long long)unresolved);
+    }
+}
+
+__global__ void k_walk(const uint32_t* __restrict__ parent, uint32_t vertex, uint32_t root,
+                       uint32_t* out, uint32_t cap, uint32_t* len)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t n = 0;
+    uint32_t v = vertex;
+    if (n < cap) out[n] = v;
+    ++n;
+    while (v != root && v != IMOMD_NONE)
+    {
+        v = parent[v];
+        if (n < cap) out[n] = v;
+        ++n;
+        if (n > 0x7FFFFFF0u) break;
+    }
+    *len = n;
+}
+
+// one warp per tour; lanes gather the leg lengths, the sum is formed left to right
+constexpr int kGaMaxLen = 128;
+__global__ void __launch_bounds__(256)
+k_ga_eval(int K, const double* __restrict__ D, int n_tours, int stride,
+          const int32_t* __restrict__ tours, const int32_t* __restrict__ lens,
+          double* __restrict__ cost)
+{
+    extern __shared__ double sD[];
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) sD[i] = D[i];
+    __syncthreads();
+    const unsigned full = 0xFFFFFFFFu;
+    int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = warp; t < n_tours; t += nwarps)
+    {
+        const int32_t* s = tours + (size_t)t * stride;
+        int legs = lens[t] - 1;
+        double vals[kGaMaxLen / 32];
+#pragma unroll
+        for (int j = 0; j < kGaMaxLen / 32; ++j)
+        {
+            int i = j * 32 + lane;
+            vals[j] = i < legs ? sD[s[i] * K + s[i + 1]] : 0.0;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < kGaMaxLen / 32; ++j)
+        {
+            for (int l = 0; l < 32; ++l)
+            {
+                double v = __shfl_sync(full, vals[j], l);
+                if (j * 32 + l < legs) acc += v;
+            }
+        }
+        if (lane == 0) cost[t] = acc;
+    }
+}
+
+}  // namespace
+
+// ================================================================= C ABI =====
+
+struct imomd_graph
+{
+    int device;
+    GraphDev d;
+    uint32_t* row_ptr;
+    uint32_t* col;
+    double* w;
+    double* lat;
+    double* lon;
+    VRec* vrec;
+    double* cosrow;
+    uint32_t max_degree;
+};
+
+struct imomd_planner
+{
+    imomd_graph* g;
+    PlannerDev d;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    std::vector<QueryDev> init;     // headers of the freshly constructed state
+    uint32_t* words;
+    size_t words_cap, words_fed;
+    size_t smem_bytes;
+    float last_ms;
+    bool pending;
+    // lookup scratch (imomd_nearest)
+    uint32_t* nn_scratch;
+    int nn_ctas;
+    int64_t* nn_stats;
+    uint32_t* walk_buf;
+    uint32_t walk_cap;
+};
+
+struct imomd_ctx
+{
+    int device;
+    cudaStream_t stream;
+    double* D;
+    int32_t* tours;
+    int32_t* lens;
+    double* cost;
+    size_t cap_tours, cap_n;
+};
+
+namespace {
+
+template <class T>
+cudaError_t dmalloc(T** p, size_t count)
+{
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+int planner_fill_initial(imomd_planner* p)
+{
+    PlannerDev& d = p->d;
+    const size_t qk = (size_t)d.Q * d.K;
+    const size_t n = d.g.n;
+    const size_t cells = (size_t)d.g.G * d.g.G;
+    CU(cudaMemsetAsync(d.parent, 0xFF, qk * n * sizeof(uint32_t), p->stream));
+    CU(cudaMemsetAsync(d.cost, 0, qk * n * sizeof(double), p->stream));
+    CU(cudaMemsetAsync(d.fslot, 0xFF, qk * n * sizeof(uint32_t), p->stream));
+    CU(cudaMemsetAsync(d.nchl, 0, qk * n, p->stream));
+    CU(cudaMemsetAsync(d.cell_cnt, 0, qk * cells * sizeof(uint32_t), p->stream));
+    CU(cudaMemsetAsync(d.cell_head, 0xFF, qk * cells * sizeof(uint32_t), p->stream));
+    CU(cudaMemcpyAsync(d.query, p->init.data(), (size_t)d.Q * sizeof(QueryDev),
+                       cudaMemcpyHostToDevice, p->stream));
+    k_init_trees<<<d.Q, 128, 0, p->stream>>>(d);
+    CU(cudaGetLastError());
+    return IMOMD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* imomd_last_error(void) { return g_err; }
+
+const char* imomd_version(void) { return "imomd_b200 0.1 (sm_100a)"; }
+
+int imomd_graph_create(int device, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
+                       const double* w, const double* lat, const double* lon, imomd_graph** out)
+{
+    return imomd_graph_create_ex(device, n, row_ptr, col, w, lat, lon, 0, out);
+}
+
+int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
+                          const double* w, const double* lat, const double* lon, int grid_dim,
+                          imomd_graph** out)
+{
+    if (!out || !row_ptr || !col || !w || !lat || !lon || n == 0)
+        return fail(IMOMD_ERR_ARG, "imomd_graph_create: null argument or empty graph");
+    *out = nullptr;
+    const uint32_t arcs = row_ptr[n];
+    uint32_t max_deg = 0;
+    std::string verr;
+    if (!validate_graph(n, row_ptr, col, &max_deg, &verr)) return fail(IMOMD_ERR_GRAPH, "%s", verr.c_str());
+    CU(cudaSetDevice(device));
+    imomd_graph* g = new (std::nothrow) imomd_graph();
+    if (!g) return fail(IMOMD_ERR_NOMEM, "out of host memory");
+    g->device = device;
+    g->max_degree = max_deg;
+    GraphDev& d = g->d;
+    d.n = n;
+    d.arcs = arcs;
+    std::vector<double> cosrow;
+    setup_grid(d, n, lat, lon, grid_dim, &cosrow);
+    const int G = d.G;
+    CU(dmalloc(&g->row_ptr, (size_t)n + 1));
+    CU(dmalloc(&g->col, arcs));
+    CU(dmalloc(&g->w, arcs));
+    CU(dmalloc(&g->lat, n));
+    CU(dmalloc(&g->lon, n));
+    CU(dmalloc(&g->vrec, n));
+    CU(dmalloc(&g->cosrow, G));
+    CU(cudaMemcpy(g->row_ptr, row_ptr, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->col, col, (size_t)arcs * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->w, w, (size_t)arcs * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->lat, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->lon, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->cosrow, cosrow.data(), G * sizeof(double), cudaMemcpyHostToDevice));
+    d.row_ptr = g->row_ptr;
+    d.col = g->col;
+    d.w = g->w;
+    d.lat = g->lat;
+    d.lon = g->lon;
+    d.vrec = g->vrec;
+    d.cosrow = g->cosrow;
+    k_build_vrec<<<(n + 255) / 256, 256>>>(n, g->lat, g->lon, g->vrec, G, d.lat0, d.lon0, d.hlat,
+                                           d.hlon);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    *out = g;
+    return IMOMD_OK;
+}
+
+int imomd_graph_destroy(imomd_graph* g)
+{
+    if (!g) return IMOMD_OK;
+    cudaSetDevice(g->device);
+    cudaFree(g->row_ptr);
+    cudaFree(g->col);
+    cudaFree(g->w);
+    cudaFree(g->lat);
+    cudaFree(g->lon);
+    cudaFree(g->vrec);
+    cudaFree(g->cosrow);
+    delete g;
+    return IMOMD_OK;
+}
+
+int imomd_graph_info(const imomd_graph* g, uint32_t* n, uint32_t* arcs, int32_t* grid_dim,
+                     int32_t* device)
+{
+    if (!g) return fail(IMOMD_ERR_ARG, "null graph");
+    if (n) *n = g->d.n;
+    if (arcs) *arcs = g->d.arcs;
+    if (grid_dim) *grid_dim = g->d.G;
+    if (device) *device = g->device;
+    return IMOMD_OK;
+}
+
+int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* dest,
+                         const double* prob, const imomd_params* params, imomd_planner** out)
+{
+    if (!g || !dest || !prob || !params || !out)
+        return fail(IMOMD_ERR_ARG, "imomd_planner_create: null argument");
+    if (n_queries < 1) return fail(IMOMD_ERR_ARG, "n_queries must be positive");
+    if (K < 2 || K > (int)IMOMD_KMAX) return fail(IMOMD_ERR_ARG, "K must be in [2, %u]", IMOMD_KMAX);
+    for (size_t i = 0; i < (size_t)n_queries * K; ++i)
+    {
+        if (dest[i] >= g->d.n) return fail(IMOMD_ERR_ARG, "destination %u out of range", dest[i]);
+    }
+    *out = nullptr;
+    CU(cudaSetDevice(g->device));
+    imomd_planner* p = new (std::nothrow) imomd_planner();
+    if (!p) return fail(IMOMD_ERR_NOMEM, "out of host memory");
+    p->g = g;
+    p->words = nullptr;
+    p->words_cap = p->words_fed = 0;
+    p->pending = false;
+    p->last_ms = 0.f;
+    p->nn_scratch = nullptr;
+    p->nn_ctas = 0;
+    p->nn_stats = nullptr;
+    p->walk_buf = nullptr;
+    p->walk_cap = 0;
+    PlannerDev& d = p->d;
+    d.g = g->d;
+    d.Q = n_queries;
+    d.K = K;
+    d.goal_bias = params->goal_bias;
+    d.pseudo = params->pseudo_mode ? 1 : 0;
+    const size_t n = g->d.n;
+    const size_t cells = (size_t)g->d.G * g->d.G;
+    default_sizes(d, params->frontier_chunks, params->arena_entries, params->log_entries);
+    const size_t chunks = (size_t)d.chunks;
+    const size_t qk = (size_t)n_queries * K;
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&p->ev0));
+    CU(cudaEventCreate(&p->ev1));
+    CU(dmalloc(&d.query, (size_t)n_queries));
+    CU(dmalloc(&d.parent, qk * n));
+    CU(dmalloc(&d.cost, qk * n));
+    CU(dmalloc(&d.fslot, qk * n));
+    CU(dmalloc(&d.chl, qk * g->d.arcs));
+    CU(dmalloc(&d.nchl, qk * n));
+    CU(dmalloc(&d.cell_head, qk * cells));
+    CU(dmalloc(&d.cell_cnt, qk * cells));
+    CU(dmalloc(&d.rec, qk * chunks * IMOMD_CHUNK));
+    CU(dmalloc(&d.chunk_next, qk * chunks));
+    CU(dmalloc(&d.free_stack, qk * chunks));
+    CU(dmalloc(&d.lbd, qk * cells));
+    CU(dmalloc(&d.arena, (size_t)n_queries * d.arena_entries));
+    CU(dmalloc(&d.clist, (size_t)n_queries * 2 * chunks));
+    CU(dmalloc(&d.log, (size_t)n_queries * 2 * d.log_entries));
+    CU(dmalloc(&d.reports, (size_t)n_queries));
+    d.words = nullptr;
+    d.words_avail = 0;
+    // initial headers
+    p->init.assign(n_queries, QueryDev());
+    for (int q = 0; q < n_queries; ++q)
+    {
+        fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
+    }
+    p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double);
+    CU(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)p->smem_bytes));
+    CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)p->smem_bytes));
+    int rc = planner_fill_initial(p);
+    if (rc != IMOMD_OK) return rc;
+    size_t total = qk * cells;
+    k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(d);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(p->stream));
+    *out = p;
+    return IMOMD_OK;
+}
+
+int imomd_planner_destroy(imomd_planner* p)
+{
+    if (!p) return IMOMD_OK;
+    cudaSetDevice(p->g->device);
+    cudaStreamSynchronize(p->stream);
+    PlannerDev& d = p->d;
+    cudaFree(d.query);
+    cudaFree(d.parent);
+    cudaFree(d.cost);
+    cudaFree(d.fslot);
+    cudaFree(d.chl);
+    cudaFree(d.nchl);
+    cudaFree(d.cell_head);
+    cudaFree(d.cell_cnt);
+    cudaFree(d.rec);
+    cudaFree(d.chunk_next);
+    cudaFree(d.free_stack);
+    cudaFree(d.lbd);
+    cudaFree(d.arena);
+    cudaFree(d.clist);
+    cudaFree(d.log);
+    cudaFree(d.reports);
+    cudaFree(p->words);
+    cudaFree(p->nn_scratch);
+    cudaFree(p->nn_stats);
+    cudaFree(p->walk_buf);
+    cudaEventDestroy(p->ev0);
+    cudaEventDestroy(p->ev1);
+    cudaStreamDestroy(p->stream);
+    delete p;
+    return IMOMD_OK;
+}
+
+int imomd_planner_reset(imomd_planner* p)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null planner");
+    CU(cudaSetDevice(p->g->device));
+    int rc = planner_fill_initial(p);
+    if (rc != IMOMD_OK) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    return IMOMD_OK;
+}
+
+int imomd_planner_feed_words(imomd_planner* p, const uint32_t* words, size_t n)
+{
+    if (!p || (!words && n)) return fail(IMOMD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(p->g->device));
+    if (p->words_fed + n > p->words_cap)
+    {
+        size_t cap = std::max<size_t>(p->words_cap * 2, p->words_fed + n);
+        cap = std::max<size_t>(cap, 1 << 16);
+        uint32_t* nw = nullptr;
+        CU(dmalloc(&nw, cap));
+        CU(cudaStreamSynchronize(p->stream));
+        if (p->words_fed)
+            CU(cudaMemcpy(nw, p->words, p->words_fed * 4, cudaMemcpyDeviceToDevice));
+        cudaFree(p->words);
+        p->words = nw;
+        p->words_cap = cap;
+    }
+    CU(cudaMemcpyAsync(p->words + p->words_fed, words, n * 4, cudaMemcpyHostToDevice, p->stream));
+    p->words_fed += n;
+    p->d.words = p->words;
+    p->d.words_avail = p->words_fed;
+    return IMOMD_OK;
+}
+
+int imomd_planner_words_available(const imomd_planner* p, uint64_t* total_fed)
+{
+    if (!p || !total_fed) return fail(IMOMD_ERR_ARG, "null argument");
+    *total_fed = p->words_fed;
+    return IMOMD_OK;
+}
+
+int imomd_expand_async(imomd_planner* p, int iters)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null planner");
+    if (iters < 0) return fail(IMOMD_ERR_ARG, "negative iteration count");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaEventRecord(p->ev0, p->stream));
+    k_expand<<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev1, p->stream));
+    p->pending = true;
+    return IMOMD_OK;
+}
+
+int imomd_sync(imomd_planner* p, imomd_query_report* reports)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null planner");
+    CU(cudaSetDevice(p->g->device));
+    static_assert(sizeof(imomd_query_report) == sizeof(ReportDev), "report layouts must agree");
+    if (reports)
+        CU(cudaMemcpyAsync(reports, p->d.reports, (size_t)p->d.Q * sizeof(ReportDev),
+                           cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    if (p->pending)
+    {
+        CU(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+        p->pending = false;
+    }
+    return IMOMD_OK;
+}
+
+int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports)
+{
+    int rc = imomd_expand_async(p, iters);
+    if (rc != IMOMD_OK) return rc;
+    return imomd_sync(p, reports);
+}
+
+int imomd_last_kernel_ms(imomd_planner* p, float* ms)
+{
+    if (!p || !ms) return fail(IMOMD_ERR_ARG, "null argument");
+    *ms = p->last_ms;
+    return IMOMD_OK;
+}
+
+int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node, double* prob,
+                    uint32_t* mh_id, double* mh_val, int32_t* is_done, int32_t* ds_parent)
+{
+    if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    QueryDev h;
+    CU(cudaMemcpy(&h, p->d.query + query, sizeof(h), cudaMemcpyDeviceToHost));
+    int K = p->d.K;
+    for (int i = 0; i < K * K; ++i)
+    {
+        if (D) D[i] = h.D[i];
+        if (conn_node) conn_node[i] = h.CN[i];
+        if (prob) prob[i] = h.P[i];
+        if (mh_id) mh_id[i] = h.MHi[i];
+        if (mh_val) mh_val[i] = h.MHv[i];
+    }
+    for (int k = 0; k < K; ++k)
+    {
+        if (is_done) is_done[k] = h.is_done[k];
+        if (ds_parent) ds_parent[k] = h.ds_parent[k];
+    }
+    return IMOMD_OK;
+}
+
+int imomd_clear_dm_updated(imomd_planner* p, int query)
+{
+    if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
+    CU(cudaSetDevice(p->g->device));
+    int32_t zero = 0;
+    QueryDev* qd = p->d.query + query;
+    CU(cudaMemcpyAsync(&qd->dm_updated, &zero, sizeof(zero), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return IMOMD_OK;
+}
+
+int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, double* cost)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !parent)
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    size_t n = p->d.g.n;
+    size_t qt = (size_t)query * p->d.K + tree;
+    CU(cudaMemcpy(parent, p->d.parent + qt * n, n * 4, cudaMemcpyDeviceToHost));
+    if (cost)
+    {
+        CU(cudaMemcpy(cost, p->d.cost + qt * n, n * 8, cudaMemcpyDeviceToHost));
+        for (size_t v = 0; v < n; ++v)
+        {
+            if (parent[v] == IMOMD_NONE) cost[v] = INFINITY;
+        }
+    }
+    return IMOMD_OK;
+}
+
+int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
+                       uint32_t* count)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !count)
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    size_t n = p->d.g.n;
+    size_t qt = (size_t)query * p->d.K + tree;
+    std::vector<uint32_t> slot(n);
+    CU(cudaMemcpy(slot.data(), p->d.fslot + qt * n, n * 4, cudaMemcpyDeviceToHost));
+    uint32_t c = 0;
+    for (size_t v = 0; v < n; ++v)
+    {
+        if (slot[v] != IMOMD_NONE)
+        {
+            if (out && c < cap) out[c] = (uint32_t)v;
+            ++c;
+        }
+    }
+    *count = c;
+    return IMOMD_OK;
+}
+
+int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* out,
+                       uint32_t cap, uint32_t* len)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !out || !len)
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    if (vertex >= p->d.g.n) return fail(IMOMD_ERR_ARG, "vertex out of range");
+    CU(cudaSetDevice(p->g->device));
+    if (p->walk_cap < cap + 1)
+    {
+        cudaFree(p->walk_buf);
+        p->walk_buf = nullptr;
+        CU(dmalloc(&p->walk_buf, (size_t)cap + 1));
+        p->walk_cap = cap + 1;
+    }
+    size_t n = p->d.g.n;
+    size_t qt = (size_t)query * p->d.K + tree;
+    uint32_t root = p->init[query].dest[tree];
+    k_walk<<<1, 32, 0, p->stream>>>(p->d.parent + qt * n, vertex, root, p->walk_buf + 1, cap,
+                                    p->walk_buf);
+    CU(cudaGetLastError());
+    uint32_t l = 0;
+    CU(cudaMemcpyAsync(&l, p->walk_buf, 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    *len = l;
+    uint32_t take = std::min(l, cap);
+    if (take) CU(cudaMemcpy(out, p->walk_buf + 1, (size_t)take * 4, cudaMemcpyDeviceToHost));
+    return IMOMD_OK;
+}
+
+int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uint32_t* vertex,
+                             uint32_t cap, uint32_t* count)
+{
+    if (!p || query < 0 || query >= p->d.Q || !count) return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    QueryDev h;
+    CU(cudaMemcpy(&h, p->d.query + query, sizeof(h), cudaMemcpyDeviceToHost));
+    *count = h.log_count;
+    uint32_t take = std::min(std::min(h.log_count, p->d.log_entries), cap);
+    if (take && set_idx && vertex)
+    {
+        std::vector<uint32_t> buf((size_t)take * 2);
+        CU(cudaMemcpy(buf.data(), p->d.log + (size_t)query * 2 * p->d.log_entries,
+                      (size_t)take * 8, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < take; ++i)
+        {
+            set_idx[i] = buf[2 * i];
+            vertex[i] = buf[2 * i + 1];
+        }
+    }
+    return IMOMD_OK;
+}
+
+int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* idx, double* dist)
+{
+    if (!p || !q || !idx || !dist || n < 0) return fail(IMOMD_ERR_ARG, "bad argument");
+    if (n == 0) return IMOMD_OK;
+    for (int i = 0; i < n; ++i)
+    {
+        if (q[i].query < 0 || q[i].query >= p->d.Q || q[i].tree < 0 || q[i].tree >= p->d.K)
+            return fail(IMOMD_ERR_ARG, "lookup %d: query/tree out of range", i);
+    }
+    CU(cudaSetDevice(p->g->device));
+    int ctas = std::min(n, 148 * 4);
+    if (p->nn_ctas < ctas)
+    {
+        cudaFree(p->nn_scratch);
+        p->nn_scratch = nullptr;
+        CU(dmalloc(&p->nn_scratch, (size_t)ctas * 2 * p->d.chunks));
+        p->nn_ctas = ctas;
+    }
+    if (!p->nn_stats) CU(dmalloc(&p->nn_stats, 2));
+    imomd_nn_query* dq = nullptr;
+    uint32_t* didx = nullptr;
+    double* ddist = nullptr;
+    CU(dmalloc(&dq, (size_t)n));
+    CU(dmalloc(&didx, (size_t)n));
+    CU(dmalloc(&ddist, (size_t)n));
+    CU(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(imomd_nn_query), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemsetAsync(p->nn_stats, 0, 16, p->stream));
+    k_nearest<<<ctas, kThreads, p->smem_bytes, p->stream>>>(p->d, n, dq, didx, ddist, p->nn_scratch,
+                                                            p->nn_stats);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(idx, didx, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    cudaFree(dq);
+    cudaFree(didx);
+    cudaFree(ddist);
+    return IMOMD_OK;
+}
+
+int imomd_ctx_create(int device, imomd_ctx** out)
+{
+    if (!out) return fail(IMOMD_ERR_ARG, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(device));
+    imomd_ctx* c = new (std::nothrow) imomd_ctx();
+    if (!c) return fail(IMOMD_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->D = nullptr;
+    c->tours = nullptr;
+    c->lens = nullptr;
+    c->cost = nullptr;
+    c->cap_tours = c->cap_n = 0;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(dmalloc(&c->D, (size_t)IMOMD_KMAX * IMOMD_KMAX));
+    *out = c;
+    return IMOMD_OK;
+}
+
+int imomd_ctx_destroy(imomd_ctx* c)
+{
+    if (!c) return IMOMD_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->D);
+    cudaFree(c->tours);
+    cudaFree(c->lens);
+    cudaFree(c->cost);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return IMOMD_OK;
+}
+
+int imomd_ga_eval(imomd_ctx* c, int K, const double* D, int n_tours, int stride,
+                  const int32_t* tours, const int32_t* lens, double* cost_out)
+{
+    if (!c || !D || !tours || !lens || !cost_out) return fail(IMOMD_ERR_ARG, "null argument");
+    if (K < 1 || K > (int)IMOMD_KMAX) return fail(IMOMD_ERR_ARG, "K out of range");
+    if (stride < 1 || stride > kGaMaxLen) return fail(IMOMD_ERR_ARG, "stride must be in [1, %d]", kGaMaxLen);
+    if (n_tours <= 0) return n_tours == 0 ? IMOMD_OK : fail(IMOMD_ERR_ARG, "negative tour count");
+    for (int t = 0; t < n_tours; ++t)
+    {
+        if (lens[t] < 1 || lens[t] > stride) return fail(IMOMD_ERR_ARG, "tour %d: bad length", t);
+        for (int i = 0; i < lens[t]; ++i)
+        {
+            int32_t v = tours[(size_t)t * stride + i];
+            if (v < 0 || v >= K) return fail(IMOMD_ERR_ARG, "tour %d: id out of range", t);
+        }
+    }
+    CU(cudaSetDevice(c->device));
+    size_t need = (size_t)n_tours * stride;
+    if (need > c->cap_tours)
+    {
+        cudaFree(c->tours);
+        c->tours = nullptr;
+        CU(dmalloc(&c->tours, need));
+        c->cap_tours = need;
+    }
+    if ((size_t)n_tours > c->cap_n)
+    {
+        cudaFree(c->lens);
+        cudaFree(c->cost);
+        c->lens = nullptr;
+        c->cost = nullptr;
+        CU(dmalloc(&c->lens, (size_t)n_tours));
+        CU(dmalloc(&c->cost, (size_t)n_tours));
+        c->cap_n = n_tours;
+    }
+    CU(cudaMemcpyAsync(c->D, D, (size_t)K * K * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->tours, tours, need * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->lens, lens, (size_t)n_tours * 4, cudaMemcpyHostToDevice, c->stream));
+    int warps_per_block = 8;
+    int blocks = std::min((n_tours + warps_per_block - 1) / warps_per_block, 148 * 8);
+    k_ga_eval<<<blocks, 256, (size_t)K * K * 8, c->stream>>>(K, c->D, n_tours, stride, c->tours,
+                                                             c->lens, c->cost);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cost_out, c->cost, (size_t)n_tours * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return IMOMD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// csrc/imomd_layout.h -- how the expansion path's state is laid out in HBM.
+//
+// Plain structs shared by the CUDA kernels (imomd_kernels.cu), the sequential /
+// CTA-parallel device logic (imomd_core.cuh) and the host-side C ABI glue.
+//
+// Road graph (uploaded once, read-only, shared by every query of every planner):
+//   row_ptr u32[N+1], col u32[2E], w f64[2E]   CSR, native container order
+//   lat f64[N], lon f64[N]                     SoA coordinates (degrees)
+//   vrec VRec[N]                               32-byte vertex records: unit vector
+//                                              (x,y,z), id, frontier-hash cell
+// Per query (one CTA drives one query):
+//   QueryDev header                            K x K matrices, flags, counters
+//   lbd f64[K][G*G]                            haversine lower bound root -> cell
+//   arena u32[arena_entries]                   rewire scratch (updateCost lists, frames)
+//   clist u32x2[chunks_per_tree]               chunk work list of the pruned searches
+// Per (query, tree):
+//   parent u32[N] (NONE = not visited), cost f64[N], fslot u32[N] (frontier slot)
+//   chl u32[2E] + nchl u8[N]                   CSR-aligned child lists, container order
+//   cell_head u32[G*G], cell_cnt u32[G*G]      frontier hash: per-cell chunk chain
+//   rec VRec[chunks*32], chunk_next u32[chunks], free_stack u32[chunks]
+#ifndef IMOMD_LAYOUT_H
+#define IMOMD_LAYOUT_H
+
+#include <stdint.h>
+
+#ifndef IMOMD_KMAX
+#define IMOMD_KMAX 32u
+#endif
+#ifndef IMOMD_NONE
+#define IMOMD_NONE 0xFFFFFFFFu
+#endif
+#define IMOMD_CHUNK 32               // frontier records per chunk (one warp-wide load)
+#define IMOMD_MAXDEG 13
+#define IMOMD_WORD_MARGIN 64         // words that must be available to start an expansion
+
+// 32-byte record: two 128-bit loads.  Doubles as the frontier entry.
+struct __attribute__((aligned(16))) VRec
+{
+    double x, y, z;      // unit vector of (lat, lon)
+    uint32_t id;         // vertex
+    uint32_t cell;       // frontier-hash cell (row * G + col)
+};
+
+struct GraphDev
+{
+    uint32_t n;
+    uint32_t arcs;
+    const uint32_t* row_ptr;
+    const uint32_t* col;
+    const double* w;
+    const double* lat;
+    const double* lon;
+    const VRec* vrec;
+    int32_t G;            // cells per axis
+    int32_t prune;        // 0 = map too large for the cell bound: scan every cell
+    double lat0, lon0;    // south-west corner of the hash (degrees)
+    double hlat, hlon;    // cell size (degrees)
+    const double* cosrow; // [G] min cos(lat) over the padded latitude span of a cell row
+};
+
+// K x K matrices are stored with stride K.
+struct QueryDev
+{
+    int32_t K;
+    int32_t status;
+    int32_t connected;
+    int32_t dm_updated;
+    uint32_t dest[IMOMD_KMAX];            // destinations_
+    int32_t view_id[IMOMD_KMAX];          // tree_layers_[i].id   (0 until constructed)
+    uint32_t view_root[IMOMD_KMAX];       // tree_layers_[i].root (0 until constructed)
+    int32_t is_done[IMOMD_KMAX];
+    int32_t ds_parent[IMOMD_KMAX];
+    uint32_t frontier_count[IMOMD_KMAX];
+    uint32_t free_top[IMOMD_KMAX];        // free chunks left on the tree's stack
+    uint64_t tree_size[IMOMD_KMAX];       // parent.size()
+    double P[IMOMD_KMAX * IMOMD_KMAX];    // probability_matrix_
+    double D[IMOMD_KMAX * IMOMD_KMAX];    // distance_matrix_
+    double MHv[IMOMD_KMAX * IMOMD_KMAX];  // expandables_min_heuristic_matrix_ .second
+    uint32_t MHi[IMOMD_KMAX * IMOMD_KMAX];// ... .first
+    uint32_t CN[IMOMD_KMAX * IMOMD_KMAX]; // connection_node_matrix_
+    uint8_t contact[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2 + 8];   // connection_nodes_set_[i] non-empty
+    uint64_t word_cursor;                 // next word of the injected stream
+    int64_t iterations;                   // cumulative
+    int64_t expansions;                   // cumulative
+    int64_t near_ties;
+    int64_t unresolved_ties;
+    uint32_t log_count;                   // pseudo-mode connection log entries
+    int32_t resume_k;                     // tree to resume at inside an interrupted pass
+    // what the last launch did
+    int64_t last_iterations;
+    int64_t last_expansions;
+    int32_t active_trees;
+    int32_t pad0;
+};
+
+// mirrors imomd_query_report (include/imomd_b200.h)
+struct ReportDev
+{
+    int32_t status;
+    int32_t active_trees;
+    int64_t iterations;
+    int64_t expansions;
+    int64_t tree_vertices;
+    int64_t words_consumed;
+    int32_t connected;
+    int32_t dm_updated;
+    int64_t near_ties;
+    int64_t unresolved_ties;
+    int64_t log_entries;
+};
+
+struct PlannerDev
+{
+    GraphDev g;
+    int32_t Q;                 // queries
+    int32_t K;
+    double goal_bias;
+    int32_t pseudo;
+    int32_t chunks;            // chunks per tree
+    uint32_t arena_entries;
+    uint32_t log_entries;
+    QueryDev* query;           // [Q]
+    // per (query, tree), index qt = q*K + k
+    uint32_t* parent;          // [Q*K][n]
+    double* cost;              // [Q*K][n]
+    uint32_t* fslot;           // [Q*K][n]
+    uint32_t* chl;             // [Q*K][arcs]
+    uint8_t* nchl;             // [Q*K][n]
+    uint32_t* cell_head;       // [Q*K][G*G]
+    uint32_t* cell_cnt;        // [Q*K][G*G]
+    VRec* rec;                 // [Q*K][chunks*32]
+    uint32_t* chunk_next;      // [Q*K][chunks]
+    uint32_t* free_stack;      // [Q*K][chunks]
+    // per query
+    double* lbd;               // [Q][K][G*G]
+    uint32_t* arena;           // [Q][arena_entries]
+    uint32_t* clist;           // [Q][2*chunks]   (chunk id, valid count)
+    uint32_t* log;             // [Q][2*log_entries] (set idx, vertex)
+    struct ReportDev* reports; // [Q] compact per-launch report (copied back to the host)
+    // injected random words
+    const uint32_t* words;
+    uint64_t words_avail;
+};
+
+#endif  // IMOMD_LAYOUT_H

@@ -1,0 +1,255 @@
+"""ctypes binding of the C ABI (include/imomd_b200.h) and of the host library.
+
+This is plumbing: numpy arrays in, numpy arrays out, every call goes through
+libimomd_b200.so (CUDA).  Loading fails loudly when the library is missing and every
+compute call fails loudly (ImomdError) without a CUDA device -- there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_CUDA = os.path.join(PKG, "lib", "libimomd_b200.so")
+LIB_HOST = os.path.join(PKG, "lib", "libimomd_host.so")
+
+NONE = 0xFFFFFFFF
+KMAX = 32
+
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+
+
+class ImomdError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("goal_bias", C.c_double), ("pseudo_mode", C.c_int32), ("reserved0", C.c_int32),
+                ("frontier_chunks", C.c_uint32), ("arena_entries", C.c_uint32),
+                ("log_entries", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Report(C.Structure):
+    _fields_ = [("status", C.c_int32), ("active_trees", C.c_int32), ("iterations", C.c_int64),
+                ("expansions", C.c_int64), ("tree_vertices", C.c_int64),
+                ("words_consumed", C.c_int64), ("connected", C.c_int32), ("dm_updated", C.c_int32),
+                ("near_ties", C.c_int64), ("unresolved_ties", C.c_int64), ("log_entries", C.c_int64)]
+
+
+class NNQuery(C.Structure):
+    _fields_ = [("query", C.c_int32), ("tree", C.c_int32), ("lat", C.c_double), ("lon", C.c_double)]
+
+
+NN_DTYPE = np.dtype([("query", np.int32), ("tree", np.int32), ("lat", np.float64), ("lon", np.float64)])
+
+_cuda = None
+_host = None
+
+
+def cuda_lib():
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(LIB_CUDA):
+            raise ImomdError(f"{LIB_CUDA} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                             " (there is no CPU fallback)")
+        L = C.CDLL(LIB_CUDA)
+        vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+        L.imomd_last_error.restype = C.c_char_p
+        L.imomd_version.restype = C.c_char_p
+        L.imomd_graph_create.argtypes = [C.c_int, C.c_uint32, u32p, u32p, f64p, f64p, f64p, vpp]
+        L.imomd_graph_create_ex.argtypes = [C.c_int, C.c_uint32, u32p, u32p, f64p, f64p, f64p, C.c_int, vpp]
+        L.imomd_graph_destroy.argtypes = [vp]
+        L.imomd_graph_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.imomd_planner_create.argtypes = [vp, C.c_int, C.c_int, u32p, f64p, C.POINTER(Params), vpp]
+        L.imomd_planner_destroy.argtypes = [vp]
+        L.imomd_planner_reset.argtypes = [vp]
+        L.imomd_planner_feed_words.argtypes = [vp, u32p, C.c_size_t]
+        L.imomd_planner_words_available.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.imomd_expand.argtypes = [vp, C.c_int, C.POINTER(Report)]
+        L.imomd_expand_async.argtypes = [vp, C.c_int]
+        L.imomd_sync.argtypes = [vp, C.POINTER(Report)]
+        L.imomd_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.imomd_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p]
+        L.imomd_clear_dm_updated.argtypes = [vp, C.c_int]
+        L.imomd_get_tree.argtypes = [vp, C.c_int, C.c_int, u32p, f64p]
+        L.imomd_get_frontier.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.imomd_walk_to_root.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, u32p, C.c_uint32,
+                                         C.POINTER(C.c_uint32)]
+        L.imomd_get_connection_log.argtypes = [vp, C.c_int, u32p, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.imomd_nearest.argtypes = [vp, C.c_int, C.c_void_p, u32p, f64p]
+        L.imomd_ctx_create.argtypes = [C.c_int, vpp]
+        L.imomd_ctx_destroy.argtypes = [vp]
+        L.imomd_ga_eval.argtypes = [vp, C.c_int, f64p, C.c_int, C.c_int, i32p, i32p, f64p]
+        _cuda = L
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        if not os.path.exists(LIB_HOST):
+            raise ImomdError(f"{LIB_HOST} is missing: run __graft_entry__.build()")
+        L = C.CDLL(LIB_HOST)
+        L.imomd_host_selection_probabilities.argtypes = [C.c_int, f64p, f64p, f64p]
+        L.imomd_host_great_circle_m.restype = C.c_double
+        L.imomd_host_great_circle_m.argtypes = [C.c_double] * 4
+        _host = L
+    return _host
+
+
+def _check(rc):
+    if rc != 0:
+        raise ImomdError(f"status {rc}: {cuda_lib().imomd_last_error().decode()}")
+
+
+def selection_probabilities(g, dest):
+    """K x K matrix of the planner constructor (host facade, glibc math)."""
+    d = np.asarray(dest, np.int64)
+    lat = np.ascontiguousarray(g.lat[d]); lon = np.ascontiguousarray(g.lon[d])
+    P = np.empty(len(d) * len(d))
+    host_lib().imomd_host_selection_probabilities(len(d), lat, lon, P)
+    return P.reshape(len(d), len(d))
+
+
+def mt19937_words(seed: int, n: int) -> np.ndarray:
+    """Raw std::mt19937 words (numpy's MT19937 is the same generator; init_genrand seeding)."""
+    bg = np.random.MT19937()
+    st = bg.state
+    key = np.empty(624, np.uint32)
+    key[0] = seed & 0xFFFFFFFF
+    for i in range(1, 624):
+        key[i] = (1812433253 * (int(key[i - 1]) ^ (int(key[i - 1]) >> 30)) + i) & 0xFFFFFFFF
+    st["state"]["key"] = key
+    st["state"]["pos"] = 624
+    bg.state = st
+    return bg.random_raw(n).astype(np.uint32)
+
+
+class DeviceGraph:
+    def __init__(self, g, device=0, grid_dim=0):
+        L = cuda_lib()
+        self.g = g
+        self.h = C.c_void_p()
+        _check(L.imomd_graph_create_ex(device, g.n, g.row_ptr, g.col, g.w, g.lat, g.lon, grid_dim,
+                                       C.byref(self.h)))
+
+    def info(self):
+        n, a, G, d = C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_int32()
+        _check(cuda_lib().imomd_graph_info(self.h, C.byref(n), C.byref(a), C.byref(G), C.byref(d)))
+        return dict(n=n.value, arcs=a.value, grid_dim=G.value, device=d.value)
+
+    def close(self):
+        if self.h:
+            cuda_lib().imomd_graph_destroy(self.h)
+            self.h = None
+
+
+class DevicePlanner:
+    """Q independent queries (K trees each) on one device graph."""
+
+    def __init__(self, dg: DeviceGraph, dests, probs=None, goal_bias=1.0, pseudo=False,
+                 frontier_chunks=0, arena_entries=0, log_entries=0):
+        L = cuda_lib()
+        self.dg, self.g = dg, dg.g
+        self.Q, self.K = len(dests), len(dests[0])
+        if probs is None:
+            probs = [selection_probabilities(self.g, d) for d in dests]
+        d = np.ascontiguousarray(np.asarray(dests, np.uint32).ravel())
+        pr = np.ascontiguousarray(np.asarray(probs, np.float64).ravel())
+        par = Params(goal_bias, int(pseudo), 0, frontier_chunks, arena_entries, log_entries, 0)
+        self.h = C.c_void_p()
+        _check(L.imomd_planner_create(dg.h, self.Q, self.K, d, pr, C.byref(par), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            cuda_lib().imomd_planner_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        _check(cuda_lib().imomd_planner_reset(self.h))
+
+    def feed(self, words):
+        w = np.ascontiguousarray(words, np.uint32)
+        _check(cuda_lib().imomd_planner_feed_words(self.h, w, w.size))
+
+    def expand(self, iters):
+        rep = (Report * self.Q)()
+        _check(cuda_lib().imomd_expand(self.h, iters, rep))
+        return list(rep)
+
+    def expand_async(self, iters):
+        _check(cuda_lib().imomd_expand_async(self.h, iters))
+
+    def sync(self):
+        rep = (Report * self.Q)()
+        _check(cuda_lib().imomd_sync(self.h, rep))
+        return list(rep)
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(cuda_lib().imomd_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def tree(self, k, q=0):
+        par = np.empty(self.g.n, np.uint32); cost = np.empty(self.g.n)
+        _check(cuda_lib().imomd_get_tree(self.h, q, k, par, cost))
+        return par, cost
+
+    def state(self, q=0):
+        K = self.K
+        D = np.empty(K * K); cn = np.empty(K * K, np.uint32); P = np.empty(K * K)
+        mi = np.empty(K * K, np.uint32); mv = np.empty(K * K)
+        done = np.empty(K, np.int32); ds = np.empty(K, np.int32)
+        _check(cuda_lib().imomd_get_state(self.h, q, D, cn, P, mi, mv, done, ds))
+        return dict(D=D.reshape(K, K), conn=cn.reshape(K, K), P=P.reshape(K, K),
+                    mh_id=mi.reshape(K, K), mh_val=mv.reshape(K, K), is_done=done, ds_parent=ds)
+
+    def frontier(self, k, q=0):
+        out = np.empty(self.g.n, np.uint32); c = C.c_uint32()
+        _check(cuda_lib().imomd_get_frontier(self.h, q, k, out, self.g.n, C.byref(c)))
+        return np.sort(out[:c.value]).astype(np.uint64)
+
+    def walk_to_root(self, k, vertex, q=0, cap=1 << 20):
+        out = np.empty(cap, np.uint32); ln = C.c_uint32()
+        _check(cuda_lib().imomd_walk_to_root(self.h, q, k, vertex, out, cap, C.byref(ln)))
+        return out[:min(ln.value, cap)].copy()
+
+    def connection_log(self, q=0, cap=1 << 20):
+        si = np.empty(cap, np.uint32); vx = np.empty(cap, np.uint32); c = C.c_uint32()
+        _check(cuda_lib().imomd_get_connection_log(self.h, q, si, vx, cap, C.byref(c)))
+        n = min(c.value, cap)
+        return si[:n].copy(), vx[:n].copy()
+
+    def nearest(self, lookups):
+        """lookups: structured array NN_DTYPE -> (idx u32[n], dist f64[n])."""
+        lk = np.ascontiguousarray(lookups, NN_DTYPE)
+        n = lk.shape[0]
+        idx = np.empty(n, np.uint32); dist = np.empty(n)
+        _check(cuda_lib().imomd_nearest(self.h, n, lk.ctypes.data_as(C.c_void_p), idx, dist))
+        return idx, dist
+
+
+class GaContext:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(cuda_lib().imomd_ctx_create(device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            cuda_lib().imomd_ctx_destroy(self.h)
+            self.h = None
+
+    def eval(self, D, tours, lens):
+        D = np.ascontiguousarray(D, np.float64)
+        K = D.shape[0]
+        tours = np.ascontiguousarray(tours, np.int32)
+        lens = np.ascontiguousarray(lens, np.int32)
+        out = np.empty(tours.shape[0])
+        _check(cuda_lib().imomd_ga_eval(self.h, K, D.ravel(), tours.shape[0], tours.shape[1],
+                                        tours.ravel(), lens, out))
+        return out

@@ -1,0 +1,177 @@
+/* include/imomd_b200.h -- the C ABI of the B200-native IMOMD-RRT* expansion path.
+ *
+ * This is the only boundary between the C++ host (the reference's library API,
+ * imomd-rrtstar_b200/host/) and CUDA (imomd-rrtstar_b200/csrc/ -> libimomd_b200.so).
+ * The reference has no FFI of its own: its API is the C++
+ * class ImomdRRT.  Each entry point below therefore cites the reference member
+ * whose work it takes over (paths under the reference checkout).
+ *
+ * Conventions: every function returns an int status (IMOMD_OK == 0), nothing
+ * throws, no C++ or torch types cross the line, the caller owns every host buffer
+ * and the library owns all device memory.  One handle lives on one device and one
+ * stream; a handle is not thread-safe, distinct handles may be used from distinct
+ * host threads.  imomd_last_error() returns a thread-local message for the last
+ * non-zero status.  There is NO CPU fallback: without a CUDA device every call
+ * that needs one fails with IMOMD_ERR_CUDA.
+ */
+#ifndef IMOMD_B200_H
+#define IMOMD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMOMD_KMAX 32u              /* trees per query: source + target + <= 30 objectives */
+#define IMOMD_NONE 0xFFFFFFFFu      /* "no vertex" / "not visited" */
+#define IMOMD_MAX_DEGREE 13u        /* children order is defined for <= 13 */
+
+enum imomd_status
+{
+    IMOMD_OK = 0,
+    IMOMD_ERR_ARG = 1,          /* bad argument */
+    IMOMD_ERR_CUDA = 2,         /* CUDA runtime error or no device */
+    IMOMD_ERR_GRAPH = 3,        /* asymmetric adjacency, self loop, degree > 13, ... */
+    IMOMD_ERR_NOMEM = 4
+};
+
+/* per-query run status written by the device (imomd_query_report.status) */
+enum imomd_run_status
+{
+    IMOMD_RUN_OK = 0,
+    IMOMD_RUN_NEED_WORDS = 1,   /* RNG word stream exhausted: feed more, call again */
+    IMOMD_RUN_FRONTIER_FULL = 2,/* frontier chunk pool exhausted (raise frontier_chunks) */
+    IMOMD_RUN_ARENA_FULL = 3,   /* rewire scratch exhausted (raise arena_entries) */
+    IMOMD_RUN_CDF_OVERRUN = 4,  /* goal-bias CDF walk ran past the row (UB upstream) */
+    IMOMD_RUN_BAD_STATE = 5
+};
+
+typedef struct imomd_graph imomd_graph;       /* road graph resident in HBM */
+typedef struct imomd_planner imomd_planner;   /* Q independent queries (K trees each) on one graph */
+typedef struct imomd_ctx imomd_ctx;           /* device context for the GA evaluation */
+
+/* Mirrors imomd_setting_t (include/setting/imomd_setting_t.h:39-48) for the fields
+ * the expansion path reads, plus sizing knobs of the device data structures. */
+typedef struct imomd_params
+{
+    double goal_bias;           /* setting.goal_bias */
+    int32_t pseudo_mode;        /* setting.pseudo_mode */
+    int32_t reserved0;
+    uint32_t frontier_chunks;   /* 32-record chunks per tree, 0 = auto */
+    uint32_t arena_entries;     /* rewire scratch (uint32 entries) per query, 0 = auto */
+    uint32_t log_entries;       /* pseudo-mode connection log entries per query, 0 = auto */
+    uint32_t reserved;
+} imomd_params;
+
+/* what one imomd_expand call did for one query */
+typedef struct imomd_query_report
+{
+    int32_t status;             /* imomd_run_status */
+    int32_t active_trees;       /* trees that can still expand */
+    int64_t iterations;         /* expandTreeLayers_ passes executed by this call */
+    int64_t expansions;         /* non-early-returning expandTree_ calls, this call */
+    int64_t tree_vertices;      /* sum over trees of visited vertices (logData_ tree_size) */
+    int64_t words_consumed;     /* absolute cursor into the injected word stream */
+    int32_t connected;          /* is_connected_graph_ */
+    int32_t dm_updated;         /* is_distance_matrix_updated_ */
+    int64_t near_ties;          /* arg-min decisions certified on the slow exact path */
+    int64_t unresolved_ties;    /* decisions closer than 1e-12 relative (lowest id taken) */
+    int64_t log_entries;        /* pseudo-mode connection log length */
+} imomd_query_report;
+
+typedef struct imomd_nn_query
+{
+    int32_t query;              /* which query of the planner */
+    int32_t tree;               /* which tree of that query */
+    double lat;
+    double lon;
+} imomd_nn_query;
+
+/* ------------------------------------------------------------------ graph ---
+ * Replaces the two shared_ptr containers the reference planner is constructed
+ * with (include/imomd_rrt_star/imomd_rrt_star.h:130-133, :147-149): uploaded once
+ * as CSR in the containers' native iteration order + SoA coordinates.  Validates
+ * symmetry, absence of self loops and max degree <= 13. */
+int imomd_graph_create(int device, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
+                       const double* w, const double* lat, const double* lon,
+                       imomd_graph** out);
+/* same, with the number of hash cells per axis forced (0 = automatic) */
+int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
+                          const double* w, const double* lat, const double* lon, int grid_dim,
+                          imomd_graph** out);
+int imomd_graph_destroy(imomd_graph* g);
+int imomd_graph_info(const imomd_graph* g, uint32_t* n, uint32_t* arcs, int32_t* grid_dim,
+                     int32_t* device);
+
+/* ---------------------------------------------------------------- planner ---
+ * ImomdRRT::ImomdRRT (src/imomd_rrt_star.cpp:39-223): `dest` holds, per query,
+ * {source, objectives..., target}; `prob` the K x K selection-probability matrix
+ * the host facade computes with the reference's formula (:84-185, glibc math),
+ * row-major.  Tree construction incl. the initial frontier / min-heuristic rows
+ * (:73-78) runs on the device. */
+int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* dest,
+                         const double* prob, const imomd_params* params, imomd_planner** out);
+int imomd_planner_destroy(imomd_planner* p);
+/* back to the freshly constructed state (same dest / prob), word cursors to 0 */
+int imomd_planner_reset(imomd_planner* p);
+
+/* RNG sample stream injected from the host: raw std::mt19937 words, appended to the
+ * planner's stream (all queries read the same stream, each at its own cursor --
+ * the reference seeds every planner with mt19937{0}, :198-201).  The device turns
+ * words into samples with libstdc++'s formulas (selectRandomVertex_, :358-400). */
+int imomd_planner_feed_words(imomd_planner* p, const uint32_t* words, size_t n);
+int imomd_planner_words_available(const imomd_planner* p, uint64_t* total_fed);
+
+/* `iters` passes of expandTreeLayers_ (:329-356) for every query of the planner, in
+ * one persistent kernel.  reports[n_queries] may be NULL.  Asynchronous variant:
+ * imomd_expand_async enqueues on the planner's stream, imomd_sync waits and fills
+ * the reports. */
+int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports);
+int imomd_expand_async(imomd_planner* p, int iters);
+int imomd_sync(imomd_planner* p, imomd_query_report* reports);
+/* device time of the last imomd_expand kernel in milliseconds (CUDA events) */
+int imomd_last_kernel_ms(imomd_planner* p, float* ms);
+
+/* K x K state of one query (any pointer may be NULL):
+ * distance_matrix_, connection_node_matrix_, probability_matrix_,
+ * expandables_min_heuristic_matrix_ (ids, values), tree is_done flags,
+ * disjoint_set_parent_ (include/imomd_rrt_star/imomd_rrt_star.h:159-178) */
+int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node, double* prob,
+                    uint32_t* mh_id, double* mh_val, int32_t* is_done, int32_t* ds_parent);
+/* the facade clears is_distance_matrix_updated_ after updatePath_ (:960) */
+int imomd_clear_dm_updated(imomd_planner* p, int query);
+
+/* dense tree arrays: parent[N] (IMOMD_NONE = not visited) and cost[N] (+inf there) */
+int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, double* cost);
+/* frontier ("expandables") of one tree, unordered; *count receives its size */
+int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
+                       uint32_t* count);
+/* parent-pointer walk vertex -> root of `tree` (updatePath_, :936-954); out[0] = vertex */
+int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* out,
+                       uint32_t cap, uint32_t* len);
+/* pseudo mode: ordered (set index, vertex) insertions into connection_nodes_set_ (:692-703) */
+int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uint32_t* vertex,
+                             uint32_t cap, uint32_t* count);
+
+/* Parity hook for the nearest-frontier-vertex search (steerNewNode_ arg-min,
+ * :406-418): n independent (query, tree, lat, lon) lookups against the current
+ * frontiers; idx = IMOMD_NONE when the frontier is empty; dist = haversine metres. */
+int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* idx, double* dist);
+
+/* ---------------------------------------------------------------- ECI-Gen ---
+ * EciGenSolver::calculatePathCost_ (src/eci_gen_tsp_solver.cpp:442-450) for a batch
+ * of tours: one warp per tour, sequential left-to-right sum (bit-exact). */
+int imomd_ctx_create(int device, imomd_ctx** out);
+int imomd_ctx_destroy(imomd_ctx* c);
+int imomd_ga_eval(imomd_ctx* c, int K, const double* D, int n_tours, int stride,
+                  const int32_t* tours, const int32_t* lens, double* cost_out);
+
+const char* imomd_last_error(void);
+const char* imomd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMOMD_B200_H */

@@ -1,0 +1,271 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Compiles the device logic of imomd-rrtstar_b200/csrc/imomd_core.cuh for the host
+// with a one-thread `Cta` policy, so that the state machine, the frontier hash, the
+// pruned searches and the rewire stack can be checked against the oracle on the CPU
+// box (no GPU there).  It is NOT a fallback: the shipped library
+// (libimomd_b200.so) contains no host execution path and fails without a device.
+// Only tests/ builds and loads this file.
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../imomd-rrtstar_b200/csrc/imomd_core.cuh"
+#include "../../imomd-rrtstar_b200/csrc/imomd_setup.h"
+
+using namespace imomd;
+
+namespace {
+
+struct CtaHost
+{
+    int tid() const { return 0; }
+    int nt() const { return 1; }
+    void sync() const {}
+    uint32_t counter_add(uint32_t* p, uint32_t v) const
+    {
+        uint32_t old = *p;
+        *p += v;
+        return old;
+    }
+    Best reduce(Best b, Best*) const { return b; }
+};
+
+struct HsPlanner
+{
+    PlannerDev d;
+    std::vector<uint32_t> row_ptr, col;
+    std::vector<double> w, lat, lon, cosrow;
+    std::vector<VRec> vrec;
+    std::vector<QueryDev> query;
+    std::vector<uint32_t> parent, fslot, chl, cell_head, cell_cnt, chunk_next, free_stack, arena,
+        clist, log, words;
+    std::vector<double> cost, lbd;
+    std::vector<uint8_t> nchl;
+    std::vector<VRec> rec;
+    std::vector<ReportDev> reports;
+    std::vector<double> lb;
+    Shared S;
+};
+
+}  // namespace
+
+extern "C" {
+
+void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const double* w,
+                const double* lat, const double* lon, int Q, int K, const uint32_t* dest,
+                const double* prob, double goal_bias, int pseudo, int grid_dim, char* err,
+                int errlen)
+{
+    uint32_t md = 0;
+    std::string verr;
+    if (!validate_graph(n, row_ptr, col, &md, &verr))
+    {
+        std::strncpy(err, verr.c_str(), errlen - 1);
+        return nullptr;
+    }
+    HsPlanner* p = new HsPlanner;
+    uint32_t arcs = row_ptr[n];
+    p->row_ptr.assign(row_ptr, row_ptr + n + 1);
+    p->col.assign(col, col + arcs);
+    p->w.assign(w, w + arcs);
+    p->lat.assign(lat, lat + n);
+    p->lon.assign(lon, lon + n);
+    PlannerDev& d = p->d;
+    std::memset(&d, 0, sizeof(d));
+    d.g.n = n;
+    d.g.arcs = arcs;
+    setup_grid(d.g, n, lat, lon, grid_dim, &p->cosrow);
+    p->vrec.resize(n);
+    for (uint32_t v = 0; v < n; ++v)
+        p->vrec[v] = make_vrec(v, lat[v], lon[v], d.g.G, d.g.lat0, d.g.lon0, d.g.hlat, d.g.hlon);
+    d.g.row_ptr = p->row_ptr.data();
+    d.g.col = p->col.data();
+    d.g.w = p->w.data();
+    d.g.lat = p->lat.data();
+    d.g.lon = p->lon.data();
+    d.g.vrec = p->vrec.data();
+    d.g.cosrow = p->cosrow.data();
+    d.Q = Q;
+    d.K = K;
+    d.goal_bias = goal_bias;
+    d.pseudo = pseudo;
+    default_sizes(d, 0, 0, 0);
+    size_t qk = (size_t)Q * K, cells = (size_t)d.g.G * d.g.G, chunks = d.chunks;
+    p->query.resize(Q);
+    for (int q = 0; q < Q; ++q)
+        fill_initial_header(p->query[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
+    p->parent.assign(qk * n, IMOMD_NONE);
+    p->cost.assign(qk * n, 0.0);
+    p->fslot.assign(qk * n, IMOMD_NONE);
+    p->chl.assign(qk * arcs, IMOMD_NONE);
+    p->nchl.assign(qk * n, 0);
+    p->cell_head.assign(qk * cells, IMOMD_NONE);
+    p->cell_cnt.assign(qk * cells, 0);
+    p->rec.resize(qk * chunks * IMOMD_CHUNK);
+    p->chunk_next.assign(qk * chunks, IMOMD_NONE);
+    p->free_stack.resize(qk * chunks);
+    p->lbd.resize(qk * cells);
+    p->arena.resize((size_t)Q * d.arena_entries);
+    p->clist.resize((size_t)Q * 2 * chunks);
+    p->log.resize((size_t)Q * 2 * d.log_entries);
+    p->reports.resize(Q);
+    p->lb.resize(cells);
+    d.query = p->query.data();
+    d.parent = p->parent.data();
+    d.cost = p->cost.data();
+    d.fslot = p->fslot.data();
+    d.chl = p->chl.data();
+    d.nchl = p->nchl.data();
+    d.cell_head = p->cell_head.data();
+    d.cell_cnt = p->cell_cnt.data();
+    d.rec = p->rec.data();
+    d.chunk_next = p->chunk_next.data();
+    d.free_stack = p->free_stack.data();
+    d.lbd = p->lbd.data();
+    d.arena = p->arena.data();
+    d.clist = p->clist.data();
+    d.log = p->log.data();
+    d.reports = p->reports.data();
+    for (size_t i = 0; i < qk; ++i)
+        for (size_t c = 0; c < chunks; ++c) p->free_stack[i * chunks + c] = (uint32_t)(chunks - 1 - c);
+    for (int q = 0; q < Q; ++q)
+    {
+        for (int k = 0; k < K; ++k) p->query[q].free_top[k] = (uint32_t)chunks;
+        construct_trees(d, q);
+    }
+    for (size_t i = 0; i < qk * cells; ++i) p->lbd[i] = lbd_entry(d, i);
+    return p;
+}
+
+void hs_destroy(void* hp) { delete (HsPlanner*)hp; }
+
+int hs_grid_dim(void* hp) { return ((HsPlanner*)hp)->d.g.G; }
+
+void hs_feed_words(void* hp, const uint32_t* words, size_t n)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    p->words.insert(p->words.end(), words, words + n);
+    p->d.words = p->words.data();
+    p->d.words_avail = p->words.size();
+}
+
+void hs_expand(void* hp, int iters, ReportDev* reports)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    CtaHost cta;
+    for (int q = 0; q < p->d.Q; ++q) run_query(cta, p->d, q, iters, p->S, p->lb.data());
+    if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
+}
+
+void hs_get_tree(void* hp, int q, int k, uint32_t* parent, double* cost)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    size_t n = p->d.g.n, qt = (size_t)q * p->d.K + k;
+    for (size_t v = 0; v < n; ++v)
+    {
+        parent[v] = p->parent[qt * n + v];
+        cost[v] = parent[v] == IMOMD_NONE ? INFINITY : p->cost[qt * n + v];
+    }
+}
+
+void hs_get_state(void* hp, int q, double* D, uint32_t* cn, double* prob, uint32_t* mhi,
+                  double* mhv, int32_t* is_done, int32_t* ds_parent, int32_t* flags)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    const QueryDev& h = p->query[q];
+    int K = p->d.K;
+    for (int i = 0; i < K * K; ++i)
+    {
+        D[i] = h.D[i];
+        cn[i] = h.CN[i];
+        prob[i] = h.P[i];
+        mhi[i] = h.MHi[i];
+        mhv[i] = h.MHv[i];
+    }
+    for (int k = 0; k < K; ++k)
+    {
+        is_done[k] = h.is_done[k];
+        ds_parent[k] = h.ds_parent[k];
+    }
+    flags[0] = h.connected;
+    flags[1] = h.dm_updated;
+}
+
+uint32_t hs_get_frontier(void* hp, int q, int k, uint32_t* out)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    size_t n = p->d.g.n, qt = (size_t)q * p->d.K + k;
+    uint32_t c = 0;
+    for (size_t v = 0; v < n; ++v)
+        if (p->fslot[qt * n + v] != IMOMD_NONE) out[c++] = (uint32_t)v;
+    return c;
+}
+
+// consistency of the frontier hash: every listed record sits in the right cell, slots
+// agree with fslot, counts agree; returns 0 when consistent
+int hs_check_hash(void* hp, int q, int k)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    TreeRef T = tree_ref(p->d, q, k);
+    size_t cells = (size_t)p->d.g.G * p->d.g.G;
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < cells; ++c)
+    {
+        uint32_t cnt = T.cell_cnt[c];
+        if (!cnt) continue;
+        uint32_t chunk = T.cell_head[c];
+        uint32_t nrec = (cnt - 1) % IMOMD_CHUNK + 1, left = cnt;
+        while (left)
+        {
+            if (chunk == IMOMD_NONE) return 1;
+            for (uint32_t i = 0; i < nrec; ++i)
+            {
+                const VRec& r = T.rec[(size_t)chunk * IMOMD_CHUNK + i];
+                if (r.cell != c) return 2;
+                if (T.fslot[r.id] != chunk * IMOMD_CHUNK + i) return 3;
+                if (T.parent[r.id] != IMOMD_NONE) return 4;
+            }
+            left -= nrec;
+            total += nrec;
+            nrec = IMOMD_CHUNK;
+            chunk = T.chunk_next[chunk];
+        }
+    }
+    if (total != p->query[q].frontier_count[k]) return 5;
+    return 0;
+}
+
+void hs_nearest(void* hp, int q, int k, double lat, double lon, uint32_t* idx, double* dist,
+                int64_t* stats)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    CtaHost cta;
+    p->S.qlat = lat;
+    p->S.qlon = lon;
+    svc_nearest(cta, p->d, q, k, p->S, p->lb.data(), p->clist.data() + (size_t)q * 2 * p->d.chunks,
+                &stats[0], &stats[1]);
+    uint32_t v = p->S.result.id1;
+    *idx = v;
+    *dist = v == IMOMD_NONE ? INFINITY : haversine(p->lat[v], p->lon[v], lat, lon);
+    stats[2] = p->S.n_list;   // chunks examined by the pruned search
+}
+
+uint32_t hs_connection_log(void* hp, int q, uint32_t* set_idx, uint32_t* vertex, uint32_t cap)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    uint32_t c = p->query[q].log_count;
+    const uint32_t* lg = p->log.data() + (size_t)q * 2 * p->d.log_entries;
+    for (uint32_t i = 0; i < c && i < cap && i < p->d.log_entries; ++i)
+    {
+        set_idx[i] = lg[2 * i];
+        vertex[i] = lg[2 * i + 1];
+    }
+    return c;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""Parity of the CUDA path (through the C ABI, libimomd_b200.so) against the oracle
+restatement on the same seeded inputs.  Bars (BASELINE.json north_star): nearest-vertex
+indices bit-exact, batch-size-1 parent arrays exact, costs within 1e-9 relative -- here
+costs are compared BIT FOR BIT (they are sums of host-supplied edge weights); only the
+min-heuristic *values*, which go through CUDA's libm, get a 1e-12 relative tolerance."""
+import numpy as np
+import pytest
+
+import oraclelib as ol
+from imomd_b200 import capi, graphs
+from parity import compare_with_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(g, dest, goal_bias=1.0, pseudo=False, grid_dim=0):
+    op = ol.OraclePlanner(g, dest, goal_bias, pseudo)
+    dg = capi.DeviceGraph(g, 0, grid_dim)
+    dp = capi.DevicePlanner(dg, [dest], None, goal_bias, pseudo)
+    return op, dg, dp
+
+
+@pytest.mark.parametrize("width,K,grid_dim,gb", [(60, 6, 0, 1.0), (60, 6, 16, 1.0), (90, 12, 8, 1.0),
+                                                 (50, 4, 4, 0.5), (70, 2, 0, 1.0), (40, 5, 32, 0.0),
+                                                 (150, 12, 0, 1.0)])
+def test_grid_expansion_matches_oracle(width, K, grid_dim, gb):
+    g = graphs.jittered_grid(width, seed=width)
+    dest = graphs.pick_destinations(g, K, seed=K)
+    op, dg, dp = _pair(g, dest, gb, grid_dim=grid_dim)
+    compare_with_oracle(dp, op, K, False)
+    dp.feed(capi.mt19937_words(0, 600000))
+    for chunk in (1, 7, 92, 400, 1000):
+        rep = dp.expand(chunk)[0]
+        e = op.iterate(chunk)
+        assert rep.status == 0 and rep.iterations == chunk and rep.expansions == e
+        compare_with_oracle(dp, op, K, False)
+    assert rep.unresolved_ties == 0
+    dp.close(); dg.close(); op.close()
+
+
+def test_roadlike_jps_and_pseudo_mode():
+    g = graphs.road_like(6000, seed=2)
+    dest = graphs.pick_destinations(g, 6, seed=1)
+    for pseudo in (False, True):
+        op, dg, dp = _pair(g, dest, 1.0, pseudo)
+        dp.feed(capi.mt19937_words(0, 300000))
+        for chunk in (50, 450, 1000):
+            rep = dp.expand(chunk)[0]
+            assert rep.status == 0 and rep.expansions == op.iterate(chunk)
+            compare_with_oracle(dp, op, 6, False)
+        if pseudo:
+            a, b = dp.connection_log(), op.connection_log()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].astype(np.uint64), b[1])
+        dp.close(); dg.close(); op.close()
+
+
+def test_nearest_indices_bit_exact():
+    """10^4 random (tree state, sample) lookups: indices identical, distances to 1e-12."""
+    g = graphs.jittered_grid(200, seed=11)
+    dest = graphs.pick_destinations(g, 6, seed=4)
+    op, dg, dp = _pair(g, dest)
+    dp.feed(capi.mt19937_words(0, 400000))
+    rng = np.random.default_rng(0)
+    total = 0
+    for chunk in (200, 800, 2000):
+        dp.expand(chunk); op.iterate(chunk)
+        n = 3500
+        lk = np.empty(n, capi.NN_DTYPE)
+        lk["query"] = 0
+        lk["tree"] = rng.integers(0, 6, n)
+        lk["lat"] = rng.uniform(g.lat.min() - 1e-3, g.lat.max() + 1e-3, n)
+        lk["lon"] = rng.uniform(g.lon.min() - 1e-3, g.lon.max() + 1e-3, n)
+        # a third of the samples sit exactly on destination roots (the goal-biased case)
+        roots = rng.integers(0, 6, n // 3)
+        lk["lat"][: n // 3] = g.lat[np.asarray(dest)[roots]]
+        lk["lon"][: n // 3] = g.lon[np.asarray(dest)[roots]]
+        idx, dist = dp.nearest(lk)
+        for i in range(n):
+            ok, want, d, ties, second = op.nearest(int(lk["tree"][i]), float(lk["lat"][i]), float(lk["lon"][i]))
+            assert ok and ties == 1
+            assert int(idx[i]) == want, (i, idx[i], want, dist[i], d, second)
+            assert abs(dist[i] - d) <= 1e-12 * max(d, 1.0)
+        total += n
+    assert total >= 10000
+    dp.close(); dg.close(); op.close()
+
+
+def test_multi_query_batch():
+    """config 5 shape: many independent queries with K = 2 on one road graph."""
+    g = graphs.road_like(3000, seed=7)
+    rng = np.random.default_rng(3)
+    Q = 40
+    dests = [graphs.pick_destinations(g, 2, seed=int(s)) for s in rng.integers(0, 100000, Q)]
+    dg = capi.DeviceGraph(g)
+    dp = capi.DevicePlanner(dg, dests)
+    dp.feed(capi.mt19937_words(0, 100000))
+    reps = dp.expand(400)
+    for q in range(Q):
+        o = ol.OraclePlanner(g, dests[q])
+        assert reps[q].status == 0 and reps[q].expansions == o.iterate(400)
+        compare_with_oracle(dp, o, 2, False, q=q)
+        o.close()
+    dp.close(); dg.close()
+
+
+def test_reset_reproduces():
+    g = graphs.jittered_grid(60, seed=3)
+    dest = graphs.pick_destinations(g, 5, seed=9)
+    op, dg, dp = _pair(g, dest)
+    dp.feed(capi.mt19937_words(0, 100000))
+    dp.expand(500)
+    a = [dp.tree(k) for k in range(5)]
+    dp.reset()
+    dp.expand(200); dp.expand(300)
+    for k in range(5):
+        p2, c2 = dp.tree(k)
+        assert np.array_equal(a[k][0], p2) and np.array_equal(a[k][1].view(np.uint64), c2.view(np.uint64))
+    op.iterate(500)
+    compare_with_oracle(dp, op, 5, False)
+    dp.close(); dg.close(); op.close()
+
+
+def test_walk_to_root_and_word_starvation():
+    g = graphs.jittered_grid(50, seed=5)
+    dest = graphs.pick_destinations(g, 5, seed=2)
+    op, dg, dp = _pair(g, dest)
+    words = capi.mt19937_words(0, 200000)
+    fed = done = 0
+    starved = 0
+    while done < 300:
+        dp.feed(words[fed:fed + 900]); fed += 900
+        rep = dp.expand(300 - done)[0]
+        done += rep.iterations
+        starved += rep.status == 1
+        assert rep.status in (0, 1)
+    assert starved > 2
+    op.iterate(300)
+    compare_with_oracle(dp, op, 5, False)
+    par, _ = dp.tree(0)
+    vs = np.nonzero(par != capi.NONE)[0]
+    v = int(vs[len(vs) // 2])
+    path = dp.walk_to_root(0, v)
+    assert path[0] == v and path[-1] == dest[0]
+    for a, b in zip(path[:-1], path[1:]):
+        assert par[a] == b
+    dp.close(); dg.close(); op.close()
+
+
+def test_ga_eval_bit_exact():
+    ctx = capi.GaContext(0)
+    rng = np.random.default_rng(4)
+    for K in (4, 12, 22, 32):
+        D = rng.uniform(100.0, 5000.0, (K, K)); D = (D + D.T) / 2
+        D[rng.random((K, K)) < 0.2] = np.inf
+        np.fill_diagonal(D, 0.0)
+        n, stride = 15000, 64
+        lens = rng.integers(1, min(stride, 2 * K + 2), n).astype(np.int32)
+        tours = rng.integers(0, K, (n, stride)).astype(np.int32)
+        got = ctx.eval(D, tours, lens)
+        want = np.empty(n)
+        ol.oracle().orc_path_costs(K, np.ascontiguousarray(D).ravel(), n, stride, tours.ravel(), lens, want)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), K
+    ctx.close()
+
+
+def test_full_size_grid_1m_matches_oracle_prefix():
+    """BASELINE config 3 (1000 x 1000 grid, K = 12): the first 600 passes against the
+    oracle (hash of every parent and cost bit), then structural invariants at depth."""
+    g = graphs.jittered_grid(1000, seed=123)
+    dest = graphs.pick_destinations(g, 12, seed=7)
+    op, dg, dp = _pair(g, dest)
+    dp.feed(capi.mt19937_words(0, 2_000_000))
+    rep = dp.expand(600)[0]
+    assert rep.status == 0 and rep.expansions == op.iterate(600)
+    compare_with_oracle(dp, op, 12, False, check_frontier=False)
+    rep = dp.expand(2400)[0]
+    assert rep.status == 0
+    deg = g.degree()
+    for k in (0, 5, 11):
+        par, cost = dp.tree(k)
+        vis = par != capi.NONE
+        v = np.nonzero(vis)[0]
+        v = v[v != dest[k]]
+        # every parent is a graph neighbour and is itself visited
+        rows = [g.col[g.row_ptr[x]:g.row_ptr[x + 1]] for x in v[:2000]]
+        assert all(par[x] in r for x, r in zip(v[:2000], rows))
+        assert vis[par[v]].all()
+        # frontier = unvisited neighbours of visited vertices
+        fr = dp.frontier(k)
+        assert not vis[fr.astype(np.int64)].any()
+        nb = np.unique(np.concatenate([g.col[g.row_ptr[x]:g.row_ptr[x + 1]] for x in np.nonzero(vis)[0]]))
+        assert np.array_equal(np.sort(nb[~vis[nb]]).astype(np.uint64), fr)
+    dp.close(); dg.close(); op.close()

@@ -1,0 +1,47 @@
+"""Ad-hoc device timing of the expansion kernel (development aid, not the bench)."""
+import sys, os, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "imomd-rrtstar_b200"))
+import numpy as np
+from imomd_b200 import capi, graphs
+
+def run(name, g, dests, iters_list, **kw):
+    dg = capi.DeviceGraph(g)
+    t0 = time.time()
+    dp = capi.DevicePlanner(dg, dests, **kw)
+    t_create = time.time() - t0
+    dp.feed(capi.mt19937_words(0, 3_000_000))
+    out = []
+    for it in iters_list:
+        t0 = time.time()
+        reps = dp.expand(it)
+        wall = time.time() - t0
+        ms = dp.last_kernel_ms()
+        ex = sum(r.expansions for r in reps)
+        out.append(dict(iters=it, expansions=ex, kernel_ms=round(ms, 3), wall_ms=round(wall * 1e3, 3),
+                        exp_per_s=round(ex / (ms / 1e3), 1), status=[r.status for r in reps][:4],
+                        tree_vertices=sum(r.tree_vertices for r in reps),
+                        near=sum(r.near_ties for r in reps), unres=sum(r.unresolved_ties for r in reps)))
+    print(json.dumps(dict(name=name, n=g.n, Q=len(dests), K=len(dests[0]), G=dg.info()["grid_dim"],
+                          create_s=round(t_create, 3), runs=out)), flush=True)
+    dp.close(); dg.close()
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["grid300", "grid1000", "roadlike"]
+    if "grid300" in which:
+        g = graphs.jittered_grid(300, seed=123)
+        run("grid300_K12", g, [graphs.pick_destinations(g, 12, seed=7)], [100, 900, 2000])
+    if "grid1000" in which:
+        g = graphs.jittered_grid(1000, seed=123)
+        run("grid1000_K12", g, [graphs.pick_destinations(g, 12, seed=7)], [100, 900, 2000, 2000])
+    if "roadlike" in which:
+        g = graphs.road_like(7000, seed=11)
+        rng = np.random.default_rng(1)
+        dests = [graphs.pick_destinations(g, 2, seed=int(s)) for s in rng.integers(0, 1 << 30, 1024)]
+        run("roadlike7k_Q1024_K2", g, dests, [100, 900, 2000])
+    if "multi" in which:
+        g = graphs.jittered_grid(1000, seed=123)
+        rng = np.random.default_rng(2)
+        for Q in (8, 64):
+            dests = [graphs.pick_destinations(g, 12, seed=int(s)) for s in rng.integers(0, 1 << 30, Q)]
+            run(f"grid1000_K12_Q{Q}", g, dests, [100, 900, 2000])
