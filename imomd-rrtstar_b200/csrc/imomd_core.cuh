@@ -48,8 +48,27 @@ constexpr double kCellPadDeg = 1e-9;         // cell rectangles are grown by thi
 constexpr double kPruneSlack = 1e-9;         // relative slack of every pruning test
 constexpr double kTieRel = 1e-12;            // "cannot be decided in device arithmetic"
 
-enum ReqType { REQ_EXIT = 0, REQ_NN = 1, REQ_RESCAN = 2, REQ_MHINS = 3 };
-enum Phase { PH_NEXT_TREE = 0, PH_AFTER_NN = 1, PH_JPS = 2, PH_INSERT = 3, PH_FINISH = 4 };
+enum ReqType
+{
+    REQ_EXIT = 0,
+    REQ_NN = 1,
+    REQ_RESCAN = 2,
+    REQ_MHINS = 3,
+    REQ_CONN = 4,
+    REQ_BFS = 5,
+    REQ_CHECK = 6
+};
+enum Phase
+{
+    PH_NEXT_TREE = 0,
+    PH_AFTER_NN = 1,
+    PH_JPS = 2,
+    PH_INSERT = 3,
+    PH_FINISH = 4,
+    PH_REWIRE = 5,
+    PH_LAST_CONN = 6
+};
+constexpr uint32_t kCheckBatch = 64;   // rewire calls examined per speculative check
 
 // include/osm_converter/compute_haversine.hpp:41-58, same expression order.
 IMOMD_HD inline double haversine(double lat1, double lon1, double lat2, double lon2)
@@ -233,9 +252,26 @@ struct Shared
     double h[IMOMD_MAXDEG * IMOMD_KMAX];
     // work list of the pruned search
     uint32_t n_list;
-    uint32_t star_cell;
-    // block reduction scratch
+    // connection gather: the other trees' (parent, cost) at conn_x (REQ_CONN / REQ_BFS)
+    uint32_t conn_x;
+    int32_t conn_pending;
+    uint32_t conn_par[IMOMD_KMAX];
+    double conn_cost[IMOMD_KMAX];
+    // jump-point search in flight
+    uint32_t jps_next;
+    // rewire machine: explicit LIFO in the arena
+    uint32_t rw_fp, rw_top;
+    // cost propagation request / result (tree_t::updateCost)
+    uint32_t bfs_node, bfs_lo, bfs_hi;
+    int32_t bfs_valid;
+    double bfs_cost;
+    // speculative no-op check of the next rewire calls
+    uint32_t chk_hi, chk_lo, chk_skip;
+    uint32_t chk_noop, chk_slot;
+    int32_t chk_valid;
+    // block reduction / scan scratch
     Best red[32];
+    uint32_t scan[40];
 };
 
 // --------------------------------------------------- frontier hash (serial) ---
@@ -481,16 +517,17 @@ struct Seq
         }
     }
 
-    // updateConnectionTree_, src/imomd_rrt_star.cpp:645-706
-    IMOMD_HD void update_connection(int k, const TreeRef& T, uint32_t x)
+    // updateConnectionTree_, src/imomd_rrt_star.cpp:645-706.  The other trees' parent
+    // and cost at x were gathered into S.conn_par / S.conn_cost by the CTA
+    // (svc_conn_gather); they cannot change while tree k is being expanded.
+    IMOMD_HD void apply_connection(int k, const TreeRef& T, uint32_t x)
     {
         int K = Q->K;
         double cx = T.cost[x];
         for (int o = 0; o < K; ++o)
         {
             if (o == k) continue;
-            TreeRef O = tree_ref(P, q, o);
-            if (O.parent[x] == IMOMD_NONE) continue;
+            if (S.conn_par[o] == IMOMD_NONE) continue;
             int set_idx = (o > k) ? o * (o - 1) / 2 + k : k * (k - 1) / 2 + o;
             if (!Q->contact[set_idx])
             {
@@ -498,7 +535,7 @@ struct Seq
                 if (P.pseudo) log_connection((uint32_t)set_idx, x);
                 connect_two_trees(k, o);
             }
-            double distance = cx + O.cost[x];
+            double distance = cx + S.conn_cost[o];
             if (distance < Q->D[k * K + o] - 0.1)
             {
                 Q->D[k * K + o] = distance;
@@ -509,9 +546,10 @@ struct Seq
             }
             if (P.pseudo)
             {
+                TreeRef O = tree_ref(P, q, o);
                 uint32_t x_parent = T.parent[x];
-                if (O.parent[x_parent] == IMOMD_NONE ||
-                    (O.parent[x_parent] != x && O.parent[x] != x_parent))
+                uint32_t opp = O.parent[x_parent];
+                if (opp == IMOMD_NONE || (opp != x && S.conn_par[o] != x_parent))
                 {
                     log_connection((uint32_t)set_idx, x);
                 }
@@ -556,45 +594,37 @@ struct Seq
         Q->connected = all;
     }
 
-    // the four statements of :443-446 / :453-456
-    IMOMD_HD void attach_chain(int k, const TreeRef& T, uint32_t x, uint32_t via)
-    {
-        if (T.parent[x] == IMOMD_NONE) Q->tree_size[k] += 1;
-        T.parent[x] = via;
-        chl_assign_single(P.g, T, via, x);
-        T.cost[x] = T.cost[via] + edge_weight(P.g, via, x);
-        update_connection(k, T, x);
-    }
-
-    // jump-point search of steerNewNode_, src/imomd_rrt_star.cpp:427-459
-    IMOMD_HD uint32_t jps(int k, const TreeRef& T, uint32_t x_new)
+    // One hop of the jump-point search of steerNewNode_ (src/imomd_rrt_star.cpp:427-459).
+    // Returns true when a chain vertex was attached (:443-445 / :453-455): its
+    // connection check (:446 / :456) is then pending and S.jps_next holds the vertex the
+    // search continues from.  Returns false when the search is over at S.x_new.
+    IMOMD_HD bool jps_hop(int k, const TreeRef& T)
     {
         const GraphDev& g = P.g;
-        bool done = false;
-        while (deg(x_new) == 2 && !done)
+        uint32_t x_new = S.x_new;
+        if (deg(x_new) != 2) return false;
+        uint32_t e = g.row_ptr[x_new];
+        uint32_t x_1 = g.col[e];
+        uint32_t x_2 = g.col[e + 1];
+        uint32_t via, next;
+        if (T.parent[x_1] != IMOMD_NONE)
         {
-            uint32_t e = g.row_ptr[x_new];
-            uint32_t x_1 = g.col[e];
-            uint32_t x_2 = g.col[e + 1];
-            if (T.parent[x_1] != IMOMD_NONE)
-            {
-                if (T.parent[x_2] != IMOMD_NONE)
-                {
-                    done = true;
-                }
-                else
-                {
-                    attach_chain(k, T, x_new, x_1);
-                    x_new = x_2;
-                }
-            }
-            else
-            {
-                attach_chain(k, T, x_new, x_2);
-                x_new = x_1;
-            }
+            if (T.parent[x_2] != IMOMD_NONE) return false;   // both sides visited: done
+            via = x_1;
+            next = x_2;
         }
-        return x_new;
+        else
+        {
+            via = x_2;
+            next = x_1;
+        }
+        if (T.parent[x_new] == IMOMD_NONE) Q->tree_size[k] += 1;
+        T.parent[x_new] = via;
+        chl_assign_single(g, T, via, x_new);
+        T.cost[x_new] = T.cost[via] + edge_weight(g, via, x_new);
+        S.conn_x = x_new;
+        S.jps_next = next;
+        return true;
     }
 
     // connectNewNode_, src/imomd_rrt_star.cpp:465-496
@@ -644,92 +674,90 @@ struct Seq
         }
     }
 
-    // tree_t::updateCost, include/imomd_rrt_star/imomd_rrt_star.h:102-123.  The list of
-    // updated vertices is appended to the arena at `lo`; returns its end (or NONE).
-    IMOMD_HD uint32_t update_cost(const TreeRef& T, uint32_t rewired, double new_cost, uint32_t lo)
+    // ---- rewireTree_, src/imomd_rrt_star.cpp:561-600 ------------------------------
+    // The recursion is unrolled onto an explicit LIFO in the arena.  A frame is
+    // {prev, x, e, end, skip, lo, cur}; above the frame that owns it sits the
+    // `updated_nodes` list [lo, cur) of the active re-parenting, consumed from the back
+    // (:589-596).  Two steps are handed to the whole CTA: the cost propagation
+    // (tree_t::updateCost, REQ_BFS) and the speculative examination of the next calls of
+    // the list, almost all of which change nothing (REQ_CHECK).
+    static constexpr uint32_t FR = 7;
+
+    IMOMD_HD bool push_frame(uint32_t x, uint32_t e)
     {
-        const GraphDev& g = P.g;
-        uint32_t cap = P.arena_entries;
-        if (lo >= cap) return IMOMD_NONE;
-        uint32_t hi = lo;
-        arena[hi++] = rewired;
-        uint32_t head = lo;
-        double old = T.cost[rewired];
-        while (head < hi)
+        uint32_t top = S.rw_top;
+        if (top + FR > P.arena_entries)
         {
-            uint32_t par = arena[head++];
-            const uint32_t* row = T.chl + g.row_ptr[par];
-            uint32_t n = T.nchl[par];
-            if (hi + n > cap) return IMOMD_NONE;
-            for (uint32_t i = 0; i < n; ++i)
-            {
-                uint32_t child = row[i];
-                T.cost[child] = new_cost + T.cost[child] - old;
-                arena[hi++] = child;
-            }
+            Q->status = 3;   // IMOMD_RUN_ARENA_FULL
+            return false;
         }
-        T.cost[rewired] = new_cost;
-        return hi;
+        uint32_t* f = arena + top;
+        f[0] = S.rw_fp;
+        f[1] = x;
+        f[2] = e;
+        f[3] = P.g.row_ptr[x + 1];
+        f[4] = IMOMD_NONE;
+        f[5] = IMOMD_NONE;
+        f[6] = 0;
+        S.rw_fp = top;
+        S.rw_top = top + FR;
+        return true;
     }
 
-    // rewireTree_, src/imomd_rrt_star.cpp:561-600.  The recursion is unrolled onto an
-    // explicit LIFO in the arena: frames {prev, x, e, end, skip, lo, cur} and, above
-    // the frame that owns it, the `updated_nodes` list of the active re-parenting.
-    IMOMD_HD void rewire(int k, const TreeRef& T, uint32_t x_start)
+    // returns true when the cascade is finished, false when a service was requested
+    IMOMD_HD bool rewire_run(int k, const TreeRef& T)
     {
         const GraphDev& g = P.g;
-        const uint32_t cap = P.arena_entries;
-        const uint32_t FR = 7;
-        uint32_t top = 0;
-        uint32_t fp = IMOMD_NONE;
-        // push first frame
+        while (S.rw_fp != IMOMD_NONE)
         {
-            uint32_t* f = arena + top;
-            f[0] = fp;
-            f[1] = x_start;
-            f[2] = g.row_ptr[x_start];
-            f[3] = g.row_ptr[x_start + 1];
-            f[4] = IMOMD_NONE;
-            f[5] = IMOMD_NONE;
-            f[6] = 0;
-            fp = top;
-            top += FR;
-        }
-        while (fp != IMOMD_NONE)
-        {
-            uint32_t* f = arena + fp;
+            if (Q->status != 0) return true;
+            uint32_t* f = arena + S.rw_fp;
             if (f[5] != IMOMD_NONE)
             {
-                // walking updated_nodes in reverse (:589-596)
+                // walking updated_nodes in reverse
+                if (S.chk_valid)
+                {
+                    S.chk_valid = 0;
+                    f[6] -= S.chk_noop;          // calls that would have changed nothing
+                    if (S.chk_slot != IMOMD_NONE)
+                    {
+                        uint32_t u = arena[--f[6]];
+                        if (!push_frame(u, g.row_ptr[u] + S.chk_slot)) return true;
+                    }
+                    continue;
+                }
                 if (f[6] <= f[5])
                 {
-                    top = f[5];         // list exhausted: release it
+                    S.rw_top = f[5];             // list exhausted: release it
                     f[5] = IMOMD_NONE;
                     continue;
                 }
-                uint32_t u = arena[--f[6]];
-                if (u == f[4]) continue;
-                if (top + FR > cap)
+                S.chk_hi = f[6];
+                S.chk_lo = f[5];
+                S.chk_skip = f[4];
+                S.req = REQ_CHECK;
+                return false;
+            }
+            if (S.bfs_valid)
+            {
+                // the re-parenting started below has its updated_nodes list now
+                S.bfs_valid = 0;
+                if (S.bfs_hi == IMOMD_NONE)
                 {
-                    Q->status = 3;   // IMOMD_RUN_ARENA_FULL
-                    return;
+                    Q->status = 3;
+                    return true;
                 }
-                uint32_t* nf = arena + top;
-                nf[0] = fp;
-                nf[1] = u;
-                nf[2] = g.row_ptr[u];
-                nf[3] = g.row_ptr[u + 1];
-                nf[4] = IMOMD_NONE;
-                nf[5] = IMOMD_NONE;
-                nf[6] = 0;
-                fp = top;
-                top += FR;
+                apply_connection(k, T, S.bfs_node);      // :586
+                f[4] = S.bfs_node;
+                f[5] = S.rw_top;
+                f[6] = S.bfs_hi;
+                S.rw_top = S.bfs_hi;
                 continue;
             }
             if (f[2] >= f[3])
             {
-                top = fp;
-                fp = f[0];
+                S.rw_top = S.rw_fp;
+                S.rw_fp = f[0];
                 continue;
             }
             uint32_t e = f[2]++;
@@ -744,20 +772,15 @@ struct Seq
                     chl_erase(g, T, py, y);
                     T.parent[y] = x;
                     chl_insert(g, T, x, y);
-                    uint32_t hi = update_cost(T, y, nc, top);
-                    if (hi == IMOMD_NONE)
-                    {
-                        Q->status = 3;
-                        return;
-                    }
-                    update_connection(k, T, y);
-                    f[4] = y;
-                    f[5] = top;
-                    f[6] = hi;
-                    top = hi;
+                    S.bfs_node = y;
+                    S.bfs_cost = nc;
+                    S.bfs_lo = S.rw_top;
+                    S.req = REQ_BFS;
+                    return false;
                 }
             }
         }
+        return true;
     }
 
     // updateSelectionProbability, src/imomd_rrt_star.cpp:602-643
@@ -867,6 +890,7 @@ struct Seq
                 {
                     uint32_t x = S.result.id1;
                     S.x_new = x;
+                    S.conn_pending = 0;
                     S.phase = PH_JPS;
                     if (deg(x) == 2)
                     {
@@ -883,8 +907,20 @@ struct Seq
                 }
                 case PH_JPS:
                 {
-                    uint32_t x_new = jps(k, T, S.x_new);
-                    S.x_new = x_new;
+                    if (S.conn_pending)
+                    {
+                        // the hop's updateConnectionTree_ (:446 / :456), then move on
+                        apply_connection(k, T, S.conn_x);
+                        S.conn_pending = 0;
+                        S.x_new = S.jps_next;
+                    }
+                    if (jps_hop(k, T))
+                    {
+                        S.conn_pending = 1;
+                        S.req = REQ_CONN;
+                        return;
+                    }
+                    uint32_t x_new = S.x_new;
                     connect_new_node(k, T, x_new);
                     // updateExpandables(tree, x_new, true), first half
                     fr_erase(P, Q, T, k, x_new);
@@ -910,10 +946,27 @@ struct Seq
                 }
                 case PH_FINISH:
                 {
-                    rewire(k, T, S.x_new);
+                    S.rw_fp = IMOMD_NONE;
+                    S.rw_top = 0;
+                    S.bfs_valid = 0;
+                    S.chk_valid = 0;
+                    push_frame(S.x_new, P.g.row_ptr[S.x_new]);
+                    S.phase = PH_REWIRE;
+                    continue;
+                }
+                case PH_REWIRE:
+                {
+                    if (!rewire_run(k, T)) return;   // REQ_BFS or REQ_CHECK posted
                     if (Q->status != 0) continue;
                     update_selection_probability(k);
-                    update_connection(k, T, S.x_new);
+                    S.conn_x = S.x_new;
+                    S.req = REQ_CONN;
+                    S.phase = PH_LAST_CONN;
+                    return;
+                }
+                case PH_LAST_CONN:
+                {
+                    apply_connection(k, T, S.x_new);         // :355
                     Q->expansions += 1;
                     S.k = k + 1;
                     S.phase = PH_NEXT_TREE;
@@ -1140,6 +1193,115 @@ IMOMD_HD inline void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shar
     }
 }
 
+// the other trees' parent / cost at vertex x, one tree per thread
+template <class Cta>
+IMOMD_HD inline void svc_conn_gather(Cta& cta, const PlannerDev& P, int q, uint32_t x, Shared& S)
+{
+    int K = P.K;
+    const size_t n = P.g.n;
+    for (int o = cta.tid(); o < K; o += cta.nt())
+    {
+        size_t qt = (size_t)q * K + o;
+        S.conn_par[o] = P.parent[qt * n + x];
+        S.conn_cost[o] = P.cost[qt * n + x];
+    }
+}
+
+// tree_t::updateCost (include/imomd_rrt_star/imomd_rrt_star.h:102-123) as a level-wise
+// parallel BFS.  The queue is the output list: entry i of a round is expanded by thread i,
+// an exclusive scan of the child counts keeps the FIFO order of the sequential loop, so
+// `updated_nodes` comes out identical.  Every vertex sits in at most one child list, so the
+// cost updates of a round never collide.
+template <class Cta>
+IMOMD_HD inline void svc_bfs(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
+{
+    const GraphDev& g = P.g;
+    TreeRef T = tree_ref(P, q, k);
+    uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
+    const uint32_t cap = P.arena_entries;
+    const uint32_t rewired = S.bfs_node;
+    const double new_cost = S.bfs_cost;
+    const uint32_t lo = S.bfs_lo;
+    const double old = T.cost[rewired];
+    uint32_t head = lo, tail = lo + 1;
+    bool overflow = lo >= cap;
+    if (!overflow && cta.tid() == 0) arena[lo] = rewired;
+    cta.sync();
+    while (!overflow && head < tail)
+    {
+        uint32_t m = tail - head;
+        if (m > (uint32_t)cta.nt()) m = (uint32_t)cta.nt();
+        uint32_t cnt = 0;
+        const uint32_t* row = nullptr;
+        if ((uint32_t)cta.tid() < m)
+        {
+            uint32_t par = arena[head + cta.tid()];
+            cnt = T.nchl[par];
+            row = T.chl + g.row_ptr[par];
+        }
+        uint32_t total = 0;
+        uint32_t off = cta.scan_exclusive(cnt, &total, S.scan);
+        if (tail + total > cap)
+        {
+            overflow = true;
+            break;
+        }
+        for (uint32_t i = 0; i < cnt; ++i)
+        {
+            uint32_t child = row[i];
+            T.cost[child] = new_cost + T.cost[child] - old;
+            arena[tail + off + i] = child;
+        }
+        head += m;
+        tail += total;
+        cta.sync();
+    }
+    svc_conn_gather(cta, P, q, rewired, S);
+    if (cta.tid() == 0)
+    {
+        if (!overflow) T.cost[rewired] = new_cost;
+        S.bfs_hi = overflow ? IMOMD_NONE : tail;
+        S.bfs_valid = 1;
+    }
+}
+
+// Speculative examination of the next calls `rewireTree_(u)` of an updated_nodes list
+// (src/imomd_rrt_star.cpp:589-596): a call changes nothing unless some visited neighbour
+// y != parent[u] has cost[y] > cost[u] + w (:569-572).  All (call, adjacency slot) pairs of
+// a batch are tested at once against the current tree; the first pair that would re-parent
+// (in call order, then slot order) is reported, everything before it is skipped exactly.
+template <class Cta>
+IMOMD_HD inline void svc_check(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
+{
+    const GraphDev& g = P.g;
+    TreeRef T = tree_ref(P, q, k);
+    const uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
+    const uint32_t W = (uint32_t)g.width;
+    uint32_t n = S.chk_hi - S.chk_lo;
+    if (n > kCheckBatch) n = kCheckBatch;
+    const uint32_t hi = S.chk_hi, skip = S.chk_skip;
+    uint32_t key = IMOMD_NONE;
+    for (uint32_t idx = cta.tid(); idx < n * W; idx += cta.nt())
+    {
+        uint32_t i = idx / W, j = idx % W;
+        uint32_t u = arena[hi - 1 - i];
+        if (u == skip) continue;
+        uint32_t e = g.row_ptr[u] + j;
+        if (e >= g.row_ptr[u + 1]) continue;
+        uint32_t y = g.col[e];
+        if (T.parent[y] == IMOMD_NONE || y == T.parent[u]) continue;
+        double nc = T.cost[u] + g.w[e];
+        if (T.cost[y] > nc && idx < key) key = idx;
+    }
+    key = cta.reduce_min_u32(key, S.scan);
+    if (cta.tid() == 0)
+    {
+        S.chk_noop = key == IMOMD_NONE ? n : key / W;
+        S.chk_slot = key == IMOMD_NONE ? IMOMD_NONE : key % W;
+        S.chk_valid = 1;
+    }
+}
+
 // Tree construction of the planner constructor (src/imomd_rrt_star.cpp:73-78):
 // tree i gets its root and updateExpandables(root, true) while trees j > i still
 // read as id 0 / root 0.  Serial; runs once per query.
@@ -1222,6 +1384,9 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         }
         else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
         else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);
+        else if (req == REQ_CONN) svc_conn_gather(cta, P, q, S.conn_x, S);
+        else if (req == REQ_BFS) svc_bfs(cta, P, q, k, S);
+        else if (req == REQ_CHECK) svc_check(cta, P, q, k, S);
         cta.sync();
     }
     if (cta.tid() == 0)

@@ -65,6 +65,57 @@ struct CtaDev
     {
         return atomicAdd(p, v);
     }
+    // block-wide exclusive prefix sum (returns this thread's offset, *total to everyone)
+    __device__ __forceinline__ uint32_t scan_exclusive(uint32_t v, uint32_t* total, uint32_t* scr) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        uint32_t inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(full, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) scr[warp] = inc;
+        __syncthreads();
+        if (warp == 0)
+        {
+            uint32_t w = lane < nw ? scr[lane] : 0u;
+            uint32_t winc = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                uint32_t t = __shfl_up_sync(full, winc, off);
+                if (lane >= off) winc += t;
+            }
+            if (lane < nw) scr[lane] = winc - w;     // exclusive warp offsets
+            if (lane == nw - 1) scr[32] = winc;      // grand total
+        }
+        __syncthreads();
+        uint32_t res = scr[warp] + inc - v;
+        *total = scr[32];
+        __syncthreads();
+        return res;
+    }
+    __device__ __forceinline__ uint32_t reduce_min_u32(uint32_t v, uint32_t* scr) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        v = __reduce_min_sync(full, v);
+        if (lane == 0) scr[warp] = v;
+        __syncthreads();
+        if (warp == 0)
+        {
+            uint32_t w = lane < nw ? scr[lane] : 0xFFFFFFFFu;
+            w = __reduce_min_sync(full, w);
+            if (lane == 0) scr[32] = w;
+        }
+        __syncthreads();
+        v = scr[32];
+        __syncthreads();
+        return v;
+    }
     // block-wide merge; every thread gets the result.  Warp shuffles, then one slot
     // per warp in shared memory.
     __device__ __forceinline__ Best reduce(Best b, Best* red) const
@@ -366,7 +417,7 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     d.n = n;
     d.arcs = arcs;
     std::vector<double> cosrow;
-    setup_grid(d, n, lat, lon, grid_dim, &cosrow);
+    setup_grid(d, n, lat, lon, grid_dim, max_deg, &cosrow);
     const int G = d.G;
     CU(dmalloc(&g->row_ptr, (size_t)n + 1));
     CU(dmalloc(&g->col, arcs));
@@ -640,6 +691,19 @@ int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node,
         if (is_done) is_done[k] = h.is_done[k];
         if (ds_parent) ds_parent[k] = h.ds_parent[k];
     }
+    return IMOMD_OK;
+}
+
+int imomd_get_flags(imomd_planner* p, int query, int32_t* connected, int32_t* dm_updated)
+{
+    if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    int32_t v[2];
+    QueryDev* qd = p->d.query + query;
+    CU(cudaMemcpy(v, &qd->connected, sizeof(v), cudaMemcpyDeviceToHost));   // connected, dm_updated
+    if (connected) *connected = v[0];
+    if (dm_updated) *dm_updated = v[1];
     return IMOMD_OK;
 }
 

@@ -53,6 +53,8 @@ struct GraphDev
     const VRec* vrec;
     int32_t G;            // cells per axis
     int32_t prune;        // 0 = map too large for the cell bound: scan every cell
+    int32_t width;        // adjacency slots per vertex in the batched checks: pow2 >= max degree
+    int32_t pad_;
     double lat0, lon0;    // south-west corner of the hash (degrees)
     double hlat, hlon;    // cell size (degrees)
     const double* cosrow; // [G] min cos(lat) over the padded latitude span of a cell row

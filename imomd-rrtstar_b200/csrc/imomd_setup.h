@@ -83,8 +83,10 @@ inline bool validate_graph(uint32_t n, const uint32_t* row_ptr, const uint32_t* 
 // Geometry of the frontier hash: G x G cells over the bounding box, about 256
 // vertices per cell, G a power of two in [4, 64] unless forced.
 inline void setup_grid(GraphDev& d, uint32_t n, const double* lat, const double* lon, int forced_G,
-                       std::vector<double>* cosrow)
+                       uint32_t max_degree, std::vector<double>* cosrow)
 {
+    d.width = 4;
+    while ((uint32_t)d.width < max_degree) d.width *= 2;
     double lat_min = lat[0], lat_max = lat[0], lon_min = lon[0], lon_max = lon[0];
     for (uint32_t v = 1; v < n; ++v)
     {

@@ -76,6 +76,7 @@ def cuda_lib():
         L.imomd_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.imomd_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p]
         L.imomd_clear_dm_updated.argtypes = [vp, C.c_int]
+        L.imomd_get_flags.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.imomd_get_tree.argtypes = [vp, C.c_int, C.c_int, u32p, f64p]
         L.imomd_get_frontier.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.imomd_walk_to_root.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, u32p, C.c_uint32,
@@ -206,8 +207,11 @@ class DevicePlanner:
         mi = np.empty(K * K, np.uint32); mv = np.empty(K * K)
         done = np.empty(K, np.int32); ds = np.empty(K, np.int32)
         _check(cuda_lib().imomd_get_state(self.h, q, D, cn, P, mi, mv, done, ds))
+        c, u = C.c_int32(), C.c_int32()
+        _check(cuda_lib().imomd_get_flags(self.h, q, C.byref(c), C.byref(u)))
         return dict(D=D.reshape(K, K), conn=cn.reshape(K, K), P=P.reshape(K, K),
-                    mh_id=mi.reshape(K, K), mh_val=mv.reshape(K, K), is_done=done, ds_parent=ds)
+                    mh_id=mi.reshape(K, K), mh_val=mv.reshape(K, K), is_done=done, ds_parent=ds,
+                    connected=c.value, dm_updated=u.value)
 
     def frontier(self, k, q=0):
         out = np.empty(self.g.n, np.uint32); c = C.c_uint32()

@@ -140,6 +140,8 @@ int imomd_last_kernel_ms(imomd_planner* p, float* ms);
  * disjoint_set_parent_ (include/imomd_rrt_star/imomd_rrt_star.h:159-178) */
 int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node, double* prob,
                     uint32_t* mh_id, double* mh_val, int32_t* is_done, int32_t* ds_parent);
+/* is_connected_graph_ / is_distance_matrix_updated_ (imomd_rrt_star.h:178, :190) */
+int imomd_get_flags(imomd_planner* p, int query, int32_t* connected, int32_t* dm_updated);
 /* the facade clears is_distance_matrix_updated_ after updatePath_ (:960) */
 int imomd_clear_dm_updated(imomd_planner* p, int query);
 

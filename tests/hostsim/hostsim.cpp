@@ -33,6 +33,12 @@ struct CtaHost
         return old;
     }
     Best reduce(Best b, Best*) const { return b; }
+    uint32_t scan_exclusive(uint32_t v, uint32_t* total, uint32_t*) const
+    {
+        *total = v;
+        return 0;
+    }
+    uint32_t reduce_min_u32(uint32_t v, uint32_t*) const { return v; }
 };
 
 struct HsPlanner
@@ -79,7 +85,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     std::memset(&d, 0, sizeof(d));
     d.g.n = n;
     d.g.arcs = arcs;
-    setup_grid(d.g, n, lat, lon, grid_dim, &p->cosrow);
+    setup_grid(d.g, n, lat, lon, grid_dim, md, &p->cosrow);
     p->vrec.resize(n);
     for (uint32_t v = 0; v < n; ++v)
         p->vrec[v] = make_vrec(v, lat[v], lon[v], d.g.G, d.g.lat0, d.g.lon0, d.g.hlat, d.g.hlon);
