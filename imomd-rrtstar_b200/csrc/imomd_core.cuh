@@ -155,7 +155,6 @@ struct TreeRef
     double* cost;
     uint32_t* fslot;
     uint32_t* chl;
-    uint8_t* nchl;
     uint32_t* cell_head;
     uint32_t* cell_cnt;
     VRec* rec;
@@ -171,8 +170,7 @@ IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
     t.parent = P.parent + qt * P.g.n;
     t.cost = P.cost + qt * P.g.n;
     t.fslot = P.fslot + qt * P.g.n;
-    t.chl = P.chl + qt * P.g.arcs;
-    t.nchl = P.nchl + qt * P.g.n;
+    t.chl = P.chl + qt * (size_t)P.g.n * P.g.width;
     t.cell_head = P.cell_head + qt * cells;
     t.cell_cnt = P.cell_cnt + qt * cells;
     t.rec = P.rec + qt * (size_t)P.chunks * IMOMD_CHUNK;
@@ -265,6 +263,8 @@ struct Shared
     uint32_t bfs_node, bfs_lo, bfs_hi;
     int32_t bfs_valid;
     double bfs_cost;
+    uint32_t lv_cur, lv_start, lv_n, lv_tail;
+    int32_t lv_overflow;
     // speculative no-op check of the next rewire calls
     uint32_t chk_hi, chk_lo, chk_skip;
     uint32_t chk_noop, chk_slot;
@@ -337,49 +337,133 @@ IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T
 // ---------------------------------------- children lists (container order) ---
 // unordered_set<size_t> with <= 13 elements: a new key goes to the head of its
 // bucket's run (bucket = key % 13) or, for an empty bucket, to the list head
-// (SURVEY.md 8a-7).  Rows are CSR-aligned: children of p are neighbours of p.
+// (SURVEY.md 8a-7).  Each vertex owns a fixed row of `width` slots (width = power of
+// two >= max degree, children of p are neighbours of p), NONE-terminated, so a row is
+// read or written with one or a few 128-bit accesses and needs no row_ptr lookup.
+
+struct __attribute__((aligned(16))) U4
+{
+    uint32_t x, y, z, w;
+};
+
+template <int W>
+struct ChlRow
+{
+    uint32_t v[W];
+};
+
+template <int W>
+IMOMD_HD inline ChlRow<W> chl_load(const uint32_t* chl, uint32_t p)
+{
+    ChlRow<W> r;
+    const U4* src = reinterpret_cast<const U4*>(chl + (size_t)p * W);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i)
+    {
+        U4 t = src[i];
+        r.v[4 * i] = t.x;
+        r.v[4 * i + 1] = t.y;
+        r.v[4 * i + 2] = t.z;
+        r.v[4 * i + 3] = t.w;
+    }
+    return r;
+}
+
+template <int W>
+IMOMD_HD inline void chl_store(uint32_t* chl, uint32_t p, const ChlRow<W>& r)
+{
+    U4* dst = reinterpret_cast<U4*>(chl + (size_t)p * W);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i)
+    {
+        U4 t;
+        t.x = r.v[4 * i];
+        t.y = r.v[4 * i + 1];
+        t.z = r.v[4 * i + 2];
+        t.w = r.v[4 * i + 3];
+        dst[i] = t;
+    }
+}
+
+template <int W>
+IMOMD_HD inline void chl_insert_w(uint32_t* chl, uint32_t p, uint32_t x)
+{
+    ChlRow<W> r = chl_load<W>(chl, p);
+    int n = 0, at = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (r.v[i] != IMOMD_NONE)
+        {
+            if (r.v[i] == x) return;
+            if (at < 0 && r.v[i] % 13 == x % 13) at = i;
+            n = i + 1;
+        }
+    }
+    if (at < 0) at = 0;
+    if (n >= W) return;   // cannot happen: children are distinct neighbours, W >= degree
+#pragma unroll
+    for (int i = W - 1; i > 0; --i)
+    {
+        if (i > at) r.v[i] = r.v[i - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (i == at) r.v[i] = x;
+    }
+    chl_store<W>(chl, p, r);
+}
+
+template <int W>
+IMOMD_HD inline void chl_erase_w(uint32_t* chl, uint32_t p, uint32_t x)
+{
+    ChlRow<W> r = chl_load<W>(chl, p);
+    int at = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (r.v[i] == x) at = i;
+    }
+    if (at < 0) return;
+#pragma unroll
+    for (int i = 0; i < W - 1; ++i)
+    {
+        if (i >= at) r.v[i] = r.v[i + 1];
+    }
+    r.v[W - 1] = IMOMD_NONE;
+    chl_store<W>(chl, p, r);
+}
+
+template <int W>
+IMOMD_HD inline void chl_assign_single_w(uint32_t* chl, uint32_t p, uint32_t x)
+{
+    ChlRow<W> r;
+#pragma unroll
+    for (int i = 0; i < W; ++i) r.v[i] = IMOMD_NONE;
+    r.v[0] = x;
+    chl_store<W>(chl, p, r);
+}
 
 IMOMD_HD inline void chl_insert(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
 {
-    uint32_t* row = T.chl + g.row_ptr[p];
-    uint32_t n = T.nchl[p];
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        if (row[i] == x) return;
-    }
-    uint32_t at = 0;
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        if (row[i] % 13 == x % 13)
-        {
-            at = i;
-            break;
-        }
-    }
-    for (uint32_t i = n; i > at; --i) row[i] = row[i - 1];
-    row[at] = x;
-    T.nchl[p] = (uint8_t)(n + 1);
+    if (g.width == 4) chl_insert_w<4>(T.chl, p, x);
+    else if (g.width == 8) chl_insert_w<8>(T.chl, p, x);
+    else chl_insert_w<16>(T.chl, p, x);
 }
 
 IMOMD_HD inline void chl_erase(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
 {
-    uint32_t* row = T.chl + g.row_ptr[p];
-    uint32_t n = T.nchl[p];
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        if (row[i] == x)
-        {
-            for (uint32_t j = i; j + 1 < n; ++j) row[j] = row[j + 1];
-            T.nchl[p] = (uint8_t)(n - 1);
-            return;
-        }
-    }
+    if (g.width == 4) chl_erase_w<4>(T.chl, p, x);
+    else if (g.width == 8) chl_erase_w<8>(T.chl, p, x);
+    else chl_erase_w<16>(T.chl, p, x);
 }
 
 IMOMD_HD inline void chl_assign_single(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
 {
-    T.chl[g.row_ptr[p]] = x;
-    T.nchl[p] = 1;
+    if (g.width == 4) chl_assign_single_w<4>(T.chl, p, x);
+    else if (g.width == 8) chl_assign_single_w<8>(T.chl, p, x);
+    else chl_assign_single_w<16>(T.chl, p, x);
 }
 
 // (*connection_ptr_)[a][b]; the graph was validated symmetric at upload
@@ -1208,14 +1292,66 @@ IMOMD_HD inline void svc_conn_gather(Cta& cta, const PlannerDev& P, int q, uint3
 }
 
 // tree_t::updateCost (include/imomd_rrt_star/imomd_rrt_star.h:102-123) as a level-wise
-// parallel BFS.  The queue is the output list: entry i of a round is expanded by thread i,
-// an exclusive scan of the child counts keeps the FIFO order of the sequential loop, so
-// `updated_nodes` comes out identical.  Every vertex sits in at most one child list, so the
-// cost updates of a round never collide.
-template <class Cta>
-IMOMD_HD inline void svc_bfs(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
+// parallel BFS.  The FIFO queue of the sequential loop IS the output list
+// (`updated_nodes`): the vertices of one level are expanded one per thread, an exclusive
+// scan of the child counts places their children behind everything queued before, so the
+// list comes out in exactly the sequential order.  Every vertex sits in at most one child
+// list, so the cost updates never collide.
+//
+// Latency is what matters here (deep, narrow subtrees): the current level lives in shared
+// memory, a child row is one 128-bit load, the read-modify-write of the children's costs
+// is deferred by one round so that only the child-row load is on the critical path, and
+// levels of at most 32 vertices are walked by warp 0 alone with shuffles (no block barrier).
+constexpr uint32_t kLevelCap = 512;
+
+template <int W>
+struct BfsPending
 {
-    const GraphDev& g = P.g;
+    uint32_t v[W];
+    int n;
+};
+
+template <int W>
+IMOMD_HD inline void bfs_flush(const TreeRef& T, BfsPending<W>& pd, double new_cost, double old)
+{
+    double c[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (i < pd.n) c[i] = T.cost[pd.v[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (i < pd.n) T.cost[pd.v[i]] = new_cost + c[i] - old;
+    }
+    pd.n = 0;
+}
+
+// one vertex of the current level: returns its child row and count; the previous
+// round's cost updates are issued while the row load is in flight
+template <int W>
+IMOMD_HD inline int bfs_expand(const TreeRef& T, uint32_t node, bool active, BfsPending<W>& pd,
+                               double new_cost, double old, ChlRow<W>& row)
+{
+    int cnt = 0;
+    if (active) row = chl_load<W>(T.chl, node);
+    bfs_flush<W>(T, pd, new_cost, old);
+    if (active)
+    {
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (row.v[i] != IMOMD_NONE) cnt = i + 1;
+        }
+    }
+    return cnt;
+}
+
+template <int W, class Cta>
+IMOMD_HD inline void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
+                               uint32_t* lvl)
+{
     TreeRef T = tree_ref(P, q, k);
     uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
     const uint32_t cap = P.arena_entries;
@@ -1223,46 +1359,144 @@ IMOMD_HD inline void svc_bfs(Cta& cta, const PlannerDev& P, int q, int k, Shared
     const double new_cost = S.bfs_cost;
     const uint32_t lo = S.bfs_lo;
     const double old = T.cost[rewired];
-    uint32_t head = lo, tail = lo + 1;
-    bool overflow = lo >= cap;
-    if (!overflow && cta.tid() == 0) arena[lo] = rewired;
-    cta.sync();
-    while (!overflow && head < tail)
+    BfsPending<W> pd;
+    pd.n = 0;
+    if (cta.tid() == 0)
     {
-        uint32_t m = tail - head;
-        if (m > (uint32_t)cta.nt()) m = (uint32_t)cta.nt();
-        uint32_t cnt = 0;
-        const uint32_t* row = nullptr;
-        if ((uint32_t)cta.tid() < m)
+        S.lv_overflow = lo >= cap ? 1 : 0;
+        if (!S.lv_overflow)
         {
-            uint32_t par = arena[head + cta.tid()];
-            cnt = T.nchl[par];
-            row = T.chl + g.row_ptr[par];
+            arena[lo] = rewired;
+            lvl[0] = rewired;
         }
-        uint32_t total = 0;
-        uint32_t off = cta.scan_exclusive(cnt, &total, S.scan);
-        if (tail + total > cap)
-        {
-            overflow = true;
-            break;
-        }
-        for (uint32_t i = 0; i < cnt; ++i)
-        {
-            uint32_t child = row[i];
-            T.cost[child] = new_cost + T.cost[child] - old;
-            arena[tail + off + i] = child;
-        }
-        head += m;
-        tail += total;
-        cta.sync();
+        S.lv_cur = 0;
+        S.lv_start = lo;
+        S.lv_n = 1;
+        S.lv_tail = lo + 1;
     }
+    cta.sync();
+    for (;;)
+    {
+        uint32_t n = S.lv_n;
+        if (n == 0 || S.lv_overflow) break;
+        if (n <= (uint32_t)cta.warp_width())
+        {
+            // ---- narrow levels: warp 0 only, shuffles, no block barrier ----
+            if (cta.warp() == 0)
+            {
+                uint32_t cur = S.lv_cur, start = S.lv_start, tail = S.lv_tail;
+                bool ovf = false;
+                while (n != 0 && n <= (uint32_t)cta.warp_width())
+                {
+                    uint32_t* cl = lvl + cur * kLevelCap;
+                    uint32_t* nl = lvl + (cur ^ 1u) * kLevelCap;
+                    bool active = (uint32_t)cta.lane() < n;
+                    uint32_t node = active ? cl[cta.lane()] : 0u;
+                    ChlRow<W> row;
+                    int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row);
+                    uint32_t total = 0;
+                    uint32_t off = cta.warp_scan_exclusive((uint32_t)cnt, &total);
+                    if (tail + total > cap)
+                    {
+                        ovf = true;
+                        break;
+                    }
+#pragma unroll
+                    for (int i = 0; i < W; ++i)
+                    {
+                        if (i < cnt)
+                        {
+                            uint32_t child = row.v[i];
+                            arena[tail + off + i] = child;
+                            if (off + i < kLevelCap) nl[off + i] = child;
+                            pd.v[i] = child;
+                        }
+                    }
+                    pd.n = cnt;
+                    start = tail;
+                    tail += total;
+                    n = total;
+                    cur ^= 1u;
+                    cta.warp_sync();
+                }
+                if (cta.lane() == 0)
+                {
+                    S.lv_cur = cur;
+                    S.lv_start = start;
+                    S.lv_tail = tail;
+                    S.lv_n = n;
+                    if (ovf) S.lv_overflow = 1;
+                }
+            }
+            cta.sync();
+            continue;
+        }
+        // ---- wide level: the whole CTA, chunks of nt vertices ----
+        {
+            uint32_t cur = S.lv_cur, start = S.lv_start, tail = S.lv_tail;
+            uint32_t* cl = lvl + cur * kLevelCap;
+            uint32_t* nl = lvl + (cur ^ 1u) * kLevelCap;
+            uint32_t produced = 0;
+            bool ovf = false;
+            for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)cta.nt())
+            {
+                uint32_t idx = c0 + (uint32_t)cta.tid();
+                bool active = idx < n;
+                uint32_t node = 0u;
+                if (active) node = idx < kLevelCap ? cl[idx] : arena[start + idx];
+                ChlRow<W> row;
+                int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row);
+                uint32_t total = 0;
+                uint32_t off = cta.scan_exclusive((uint32_t)cnt, &total, S.scan);
+                if (tail + produced + total > cap)
+                {
+                    ovf = true;
+                    break;
+                }
+#pragma unroll
+                for (int i = 0; i < W; ++i)
+                {
+                    if (i < cnt)
+                    {
+                        uint32_t child = row.v[i];
+                        uint32_t at = produced + off + i;
+                        arena[tail + at] = child;
+                        if (at < kLevelCap) nl[at] = child;
+                        pd.v[i] = child;
+                    }
+                }
+                pd.n = cnt;
+                produced += total;
+            }
+            cta.sync();
+            if (cta.tid() == 0)
+            {
+                S.lv_cur = cur ^ 1u;
+                S.lv_start = tail;
+                S.lv_tail = tail + produced;
+                S.lv_n = produced;
+                if (ovf) S.lv_overflow = 1;
+            }
+            cta.sync();
+        }
+    }
+    bfs_flush<W>(T, pd, new_cost, old);
     svc_conn_gather(cta, P, q, rewired, S);
     if (cta.tid() == 0)
     {
+        bool overflow = S.lv_overflow != 0;
         if (!overflow) T.cost[rewired] = new_cost;
-        S.bfs_hi = overflow ? IMOMD_NONE : tail;
+        S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;
         S.bfs_valid = 1;
     }
+}
+
+template <class Cta>
+IMOMD_HD inline void svc_bfs(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, uint32_t* lvl)
+{
+    if (P.g.width == 4) svc_bfs_w<4>(cta, P, q, k, S, lvl);
+    else if (P.g.width == 8) svc_bfs_w<8>(cta, P, q, k, S, lvl);
+    else svc_bfs_w<16>(cta, P, q, k, S, lvl);
 }
 
 // Speculative examination of the next calls `rewireTree_(u)` of an updated_nodes list
@@ -1352,7 +1586,7 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
 // The per-query driver: the loop every CTA runs (device) / the host simulation runs.
 template <class Cta>
 IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
-                               double* lb)
+                               double* lb, uint32_t* lvl)
 {
     QueryDev* Q = P.query + q;
     if (cta.tid() == 0)
@@ -1368,6 +1602,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     cta.sync();
     for (;;)
     {
+        long long t0 = cta.clock();
         if (cta.tid() == 0)
         {
             Seq seq(P, q, S);
@@ -1376,6 +1611,12 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         cta.sync();
         int req = S.req;
         int k = S.k;
+        long long t1 = cta.clock();
+        if (cta.tid() == 0)
+        {
+            Q->prof_cycles[7] += (uint64_t)(t1 - t0);
+            Q->prof_count[7] += 1;
+        }
         if (req == REQ_EXIT) break;
         if (req == REQ_NN)
         {
@@ -1385,9 +1626,14 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
         else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);
         else if (req == REQ_CONN) svc_conn_gather(cta, P, q, S.conn_x, S);
-        else if (req == REQ_BFS) svc_bfs(cta, P, q, k, S);
+        else if (req == REQ_BFS) svc_bfs(cta, P, q, k, S, lvl);
         else if (req == REQ_CHECK) svc_check(cta, P, q, k, S);
         cta.sync();
+        if (cta.tid() == 0)
+        {
+            Q->prof_cycles[req & 7] += (uint64_t)(cta.clock() - t1);
+            Q->prof_count[req & 7] += 1;
+        }
     }
     if (cta.tid() == 0)
     {

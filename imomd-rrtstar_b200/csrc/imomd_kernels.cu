@@ -61,6 +61,25 @@ struct CtaDev
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int nt() const { return (int)blockDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ long long clock() const { return clock64(); }
+    __device__ __forceinline__ int warp() const { return (int)(threadIdx.x >> 5); }
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ int warp_width() const { return 32; }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t warp_scan_exclusive(uint32_t v, uint32_t* total) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        int ln = threadIdx.x & 31;
+        uint32_t inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(full, inc, off);
+            if (ln >= off) inc += t;
+        }
+        *total = __shfl_sync(full, inc, 31);
+        return inc - v;
+    }
     __device__ __forceinline__ uint32_t counter_add(uint32_t* p, uint32_t v) const
     {
         return atomicAdd(p, v);
@@ -198,10 +217,11 @@ __global__ void __launch_bounds__(kThreads) k_expand(PlannerDev P, int iters)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
+    uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + (size_t)P.g.G * P.g.G);
     CtaDev cta;
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
-        run_query(cta, P, q, iters, S, lb);
+        run_query(cta, P, q, iters, S, lb, lvl);
         __syncthreads();
     }
 }
@@ -373,7 +393,7 @@ int planner_fill_initial(imomd_planner* p)
     CU(cudaMemsetAsync(d.parent, 0xFF, qk * n * sizeof(uint32_t), p->stream));
     CU(cudaMemsetAsync(d.cost, 0, qk * n * sizeof(double), p->stream));
     CU(cudaMemsetAsync(d.fslot, 0xFF, qk * n * sizeof(uint32_t), p->stream));
-    CU(cudaMemsetAsync(d.nchl, 0, qk * n, p->stream));
+    CU(cudaMemsetAsync(d.chl, 0xFF, qk * n * d.g.width * sizeof(uint32_t), p->stream));
     CU(cudaMemsetAsync(d.cell_cnt, 0, qk * cells * sizeof(uint32_t), p->stream));
     CU(cudaMemsetAsync(d.cell_head, 0xFF, qk * cells * sizeof(uint32_t), p->stream));
     CU(cudaMemcpyAsync(d.query, p->init.data(), (size_t)d.Q * sizeof(QueryDev),
@@ -516,8 +536,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     CU(dmalloc(&d.parent, qk * n));
     CU(dmalloc(&d.cost, qk * n));
     CU(dmalloc(&d.fslot, qk * n));
-    CU(dmalloc(&d.chl, qk * g->d.arcs));
-    CU(dmalloc(&d.nchl, qk * n));
+    CU(dmalloc(&d.chl, qk * n * g->d.width));
     CU(dmalloc(&d.cell_head, qk * cells));
     CU(dmalloc(&d.cell_cnt, qk * cells));
     CU(dmalloc(&d.rec, qk * chunks * IMOMD_CHUNK));
@@ -536,7 +555,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     {
         fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
     }
-    p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double);
+    p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
+                    2 * kLevelCap * sizeof(uint32_t);
     CU(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
     CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -562,7 +582,6 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(d.cost);
     cudaFree(d.fslot);
     cudaFree(d.chl);
-    cudaFree(d.nchl);
     cudaFree(d.cell_head);
     cudaFree(d.cell_cnt);
     cudaFree(d.rec);
@@ -704,6 +723,18 @@ int imomd_get_flags(imomd_planner* p, int query, int32_t* connected, int32_t* dm
     CU(cudaMemcpy(v, &qd->connected, sizeof(v), cudaMemcpyDeviceToHost));   // connected, dm_updated
     if (connected) *connected = v[0];
     if (dm_updated) *dm_updated = v[1];
+    return IMOMD_OK;
+}
+
+int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts)
+{
+    if (!p || query < 0 || query >= p->d.Q || !cycles || !counts)
+        return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    QueryDev* qd = p->d.query + query;
+    CU(cudaMemcpy(cycles, qd->prof_cycles, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(counts, qd->prof_count, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return IMOMD_OK;
 }
 

@@ -15,7 +15,7 @@
 //   clist u32x2[chunks_per_tree]               chunk work list of the pruned searches
 // Per (query, tree):
 //   parent u32[N] (NONE = not visited), cost f64[N], fslot u32[N] (frontier slot)
-//   chl u32[2E] + nchl u8[N]                   CSR-aligned child lists, container order
+//   chl u32[N][width]                          child rows (NONE-terminated), container order
 //   cell_head u32[G*G], cell_cnt u32[G*G]      frontier hash: per-cell chunk chain
 //   rec VRec[chunks*32], chunk_next u32[chunks], free_stack u32[chunks]
 #ifndef IMOMD_LAYOUT_H
@@ -93,6 +93,9 @@ struct QueryDev
     int64_t last_expansions;
     int32_t active_trees;
     int32_t pad0;
+    // SM-clock cycles and call counts per request type (index = ReqType, 7 = serial steps)
+    uint64_t prof_cycles[8];
+    uint64_t prof_count[8];
 };
 
 // mirrors imomd_query_report (include/imomd_b200.h)
@@ -126,8 +129,7 @@ struct PlannerDev
     uint32_t* parent;          // [Q*K][n]
     double* cost;              // [Q*K][n]
     uint32_t* fslot;           // [Q*K][n]
-    uint32_t* chl;             // [Q*K][arcs]
-    uint8_t* nchl;             // [Q*K][n]
+    uint32_t* chl;             // [Q*K][n*width]
     uint32_t* cell_head;       // [Q*K][G*G]
     uint32_t* cell_cnt;        // [Q*K][G*G]
     VRec* rec;                 // [Q*K][chunks*32]

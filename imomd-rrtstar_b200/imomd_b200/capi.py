@@ -76,6 +76,8 @@ def cuda_lib():
         L.imomd_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.imomd_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p]
         L.imomd_clear_dm_updated.argtypes = [vp, C.c_int]
+        L.imomd_get_profile.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
+                                        np.ctypeslib.ndpointer(np.uint64, flags="C")]
         L.imomd_get_flags.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.imomd_get_tree.argtypes = [vp, C.c_int, C.c_int, u32p, f64p]
         L.imomd_get_frontier.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -195,6 +197,12 @@ class DevicePlanner:
         ms = C.c_float()
         _check(cuda_lib().imomd_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def profile(self, q=0):
+        cyc = np.zeros(8, np.uint64); cnt = np.zeros(8, np.uint64)
+        _check(cuda_lib().imomd_get_profile(self.h, q, cyc, cnt))
+        names = ["-", "nn", "rescan", "mhins", "conn", "bfs", "check", "serial"]
+        return {names[i]: (int(cyc[i]), int(cnt[i])) for i in range(1, 8)}
 
     def tree(self, k, q=0):
         par = np.empty(self.g.n, np.uint32); cost = np.empty(self.g.n)

@@ -131,6 +131,10 @@ int imomd_planner_words_available(const imomd_planner* p, uint64_t* total_fed);
 int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports);
 int imomd_expand_async(imomd_planner* p, int iters);
 int imomd_sync(imomd_planner* p, imomd_query_report* reports);
+/* cumulative SM-clock cycles and call counts per kind of work of one query: index 1..6 =
+ * nearest search, heuristic rescan, heuristic insert, connection gather, cost propagation,
+ * rewire batch check; index 7 = the serial steps in between (development / profiling aid) */
+int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts);
 /* device time of the last imomd_expand kernel in milliseconds (CUDA events) */
 int imomd_last_kernel_ms(imomd_planner* p, float* ms);
 

@@ -26,6 +26,16 @@ struct CtaHost
     int tid() const { return 0; }
     int nt() const { return 1; }
     void sync() const {}
+    long long clock() const { return 0; }
+    int warp() const { return 0; }
+    int lane() const { return 0; }
+    int warp_width() const { return 1; }
+    void warp_sync() const {}
+    uint32_t warp_scan_exclusive(uint32_t v, uint32_t* total) const
+    {
+        *total = v;
+        return 0;
+    }
     uint32_t counter_add(uint32_t* p, uint32_t v) const
     {
         uint32_t old = *p;
@@ -51,10 +61,10 @@ struct HsPlanner
     std::vector<uint32_t> parent, fslot, chl, cell_head, cell_cnt, chunk_next, free_stack, arena,
         clist, log, words;
     std::vector<double> cost, lbd;
-    std::vector<uint8_t> nchl;
     std::vector<VRec> rec;
     std::vector<ReportDev> reports;
     std::vector<double> lb;
+    std::vector<uint32_t> lvl;
     Shared S;
 };
 
@@ -108,8 +118,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->parent.assign(qk * n, IMOMD_NONE);
     p->cost.assign(qk * n, 0.0);
     p->fslot.assign(qk * n, IMOMD_NONE);
-    p->chl.assign(qk * arcs, IMOMD_NONE);
-    p->nchl.assign(qk * n, 0);
+    p->chl.assign(qk * (size_t)n * d.g.width, IMOMD_NONE);
     p->cell_head.assign(qk * cells, IMOMD_NONE);
     p->cell_cnt.assign(qk * cells, 0);
     p->rec.resize(qk * chunks * IMOMD_CHUNK);
@@ -121,12 +130,12 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->log.resize((size_t)Q * 2 * d.log_entries);
     p->reports.resize(Q);
     p->lb.resize(cells);
+    p->lvl.resize(2 * kLevelCap);
     d.query = p->query.data();
     d.parent = p->parent.data();
     d.cost = p->cost.data();
     d.fslot = p->fslot.data();
     d.chl = p->chl.data();
-    d.nchl = p->nchl.data();
     d.cell_head = p->cell_head.data();
     d.cell_cnt = p->cell_cnt.data();
     d.rec = p->rec.data();
@@ -164,7 +173,7 @@ void hs_expand(void* hp, int iters, ReportDev* reports)
 {
     HsPlanner* p = (HsPlanner*)hp;
     CtaHost cta;
-    for (int q = 0; q < p->d.Q; ++q) run_query(cta, p->d, q, iters, p->S, p->lb.data());
+    for (int q = 0; q < p->d.Q; ++q) run_query(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data());
     if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
 }
 
