@@ -36,8 +36,10 @@
 
 #if defined(__CUDACC__)
 #define IMOMD_HD __host__ __device__
+#define IMOMD_NOINLINE __noinline__
 #else
 #define IMOMD_HD
+#define IMOMD_NOINLINE
 #endif
 
 namespace imomd {
@@ -910,7 +912,7 @@ struct Seq
 
     // Runs the serial part of expandTree_ (:337-356) until it needs the CTA or the
     // launch is over; S.req tells the CTA what to do next.
-    IMOMD_HD void step(int iters)
+    IMOMD_HD IMOMD_NOINLINE void step(int iters)
     {
         int K = Q->K;
         for (;;)
@@ -1156,7 +1158,7 @@ IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef&
 
 // steerNewNode_ arg-min (src/imomd_rrt_star.cpp:406-418) for the sample in S.
 template <class Cta>
-IMOMD_HD inline void svc_nearest(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
+IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
                                  double* lb, uint32_t* clist, int64_t* near_ties,
                                  int64_t* unresolved_ties)
 {
@@ -1205,7 +1207,7 @@ IMOMD_HD inline void svc_nearest(Cta& cta, const PlannerDev& P, int q, int k, Sh
 // frontier rescans of updateExpandables (src/imomd_rrt_star.cpp:510-524) for the
 // pairs (k, o) listed in S.rescan_o
 template <class Cta>
-IMOMD_HD inline void svc_rescan(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, double* lb)
+IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, double* lb)
 {
     const GraphDev& g = P.g;
     QueryDev* Q = P.query + q;
@@ -1244,7 +1246,7 @@ IMOMD_HD inline void svc_rescan(Cta& cta, const PlannerDev& P, int q, int k, Sha
 // heuristic updates for the vertices just inserted into the frontier
 // (src/imomd_rrt_star.cpp:541-556): h(y, o) = hav(y, root_k) + hav(y, root_o)
 template <class Cta>
-IMOMD_HD inline void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
+IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
 {
     const GraphDev& g = P.g;
     QueryDev* Q = P.query + q;
@@ -1279,7 +1281,7 @@ IMOMD_HD inline void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shar
 
 // the other trees' parent / cost at vertex x, one tree per thread
 template <class Cta>
-IMOMD_HD inline void svc_conn_gather(Cta& cta, const PlannerDev& P, int q, uint32_t x, Shared& S)
+IMOMD_HD IMOMD_NOINLINE void svc_conn_gather(Cta& cta, const PlannerDev& P, int q, uint32_t x, Shared& S)
 {
     int K = P.K;
     const size_t n = P.g.n;
@@ -1349,7 +1351,7 @@ IMOMD_HD inline int bfs_expand(const TreeRef& T, uint32_t node, bool active, Bfs
 }
 
 template <int W, class Cta>
-IMOMD_HD inline void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
+IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
                                uint32_t* lvl)
 {
     TreeRef T = tree_ref(P, q, k);
@@ -1386,6 +1388,7 @@ IMOMD_HD inline void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shar
             {
                 uint32_t cur = S.lv_cur, start = S.lv_start, tail = S.lv_tail;
                 bool ovf = false;
+                uint32_t levels = 0;
                 while (n != 0 && n <= (uint32_t)cta.warp_width())
                 {
                     uint32_t* cl = lvl + cur * kLevelCap;
@@ -1417,10 +1420,12 @@ IMOMD_HD inline void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shar
                     tail += total;
                     n = total;
                     cur ^= 1u;
+                    ++levels;
                     cta.warp_sync();
                 }
                 if (cta.lane() == 0)
                 {
+                    P.query[q].prof_count[0] += levels;
                     S.lv_cur = cur;
                     S.lv_start = start;
                     S.lv_tail = tail;
@@ -1471,6 +1476,7 @@ IMOMD_HD inline void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shar
             cta.sync();
             if (cta.tid() == 0)
             {
+                P.query[q].prof_count[0] += 1;
                 S.lv_cur = cur ^ 1u;
                 S.lv_start = tail;
                 S.lv_tail = tail + produced;
@@ -1484,6 +1490,8 @@ IMOMD_HD inline void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shar
     svc_conn_gather(cta, P, q, rewired, S);
     if (cta.tid() == 0)
     {
+        // statistics: [0] = subtree vertices (cycles slot) and levels... see imomd_get_profile
+        P.query[q].prof_cycles[0] += (uint64_t)(S.lv_tail - lo);
         bool overflow = S.lv_overflow != 0;
         if (!overflow) T.cost[rewired] = new_cost;
         S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;
@@ -1505,7 +1513,7 @@ IMOMD_HD inline void svc_bfs(Cta& cta, const PlannerDev& P, int q, int k, Shared
 // a batch are tested at once against the current tree; the first pair that would re-parent
 // (in call order, then slot order) is reported, everything before it is skipped exactly.
 template <class Cta>
-IMOMD_HD inline void svc_check(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
+IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
 {
     const GraphDev& g = P.g;
     TreeRef T = tree_ref(P, q, k);

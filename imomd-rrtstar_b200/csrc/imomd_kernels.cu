@@ -212,7 +212,12 @@ __global__ void k_init_trees(PlannerDev P)
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_expand(PlannerDev P, int iters)
+// The expansion kernel in two register budgets: a latency build (one query per SM, all
+// 255 registers, no spills) for planners with few queries, and a throughput build (four
+// CTAs per SM) whose point is to hide each query's dependent-load latency behind the
+// other resident queries.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_expand(PlannerDev P, int iters)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
@@ -557,7 +562,9 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     }
     p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
                     2 * kLevelCap * sizeof(uint32_t);
-    CU(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(k_expand<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)p->smem_bytes));
+    CU(cudaFuncSetAttribute(k_expand<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
     CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
@@ -650,7 +657,10 @@ int imomd_expand_async(imomd_planner* p, int iters)
     if (iters < 0) return fail(IMOMD_ERR_ARG, "negative iteration count");
     CU(cudaSetDevice(p->g->device));
     CU(cudaEventRecord(p->ev0, p->stream));
-    k_expand<<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+    if (p->d.Q <= 2 * 148)
+        k_expand<1><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+    else
+        k_expand<4><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     p->pending = true;

@@ -202,7 +202,9 @@ class DevicePlanner:
         cyc = np.zeros(8, np.uint64); cnt = np.zeros(8, np.uint64)
         _check(cuda_lib().imomd_get_profile(self.h, q, cyc, cnt))
         names = ["-", "nn", "rescan", "mhins", "conn", "bfs", "check", "serial"]
-        return {names[i]: (int(cyc[i]), int(cnt[i])) for i in range(1, 8)}
+        d = {names[i]: (int(cyc[i]), int(cnt[i])) for i in range(1, 8)}
+        d["bfs_vertices_levels"] = (int(cyc[0]), int(cnt[0]))
+        return d
 
     def tree(self, k, q=0):
         par = np.empty(self.g.n, np.uint32); cost = np.empty(self.g.n)

@@ -23,6 +23,7 @@ def run(name, g, dests, iters_list, **kw):
                         tree_vertices=sum(r.tree_vertices for r in reps),
                         near=sum(r.near_ties for r in reps), unres=sum(r.unresolved_ties for r in reps)))
     prof = dp.profile(0)
+    print("  bfs vertices, levels:", prof.pop("bfs_vertices_levels"))
     tot = sum(c for c, _ in prof.values()) or 1
     print("  profile q0:", {k: f"{100*c/tot:.1f}% n={n} {c/max(n,1):.0f}cyc" for k, (c, n) in prof.items()})
     print(json.dumps(dict(name=name, n=g.n, Q=len(dests), K=len(dests[0]), G=dg.info()["grid_dim"],
