@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- RRT* expansions/s of the IMOMD-RRT* multi-tree expansion hot path.
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path
+
+Workload (BASELINE.json configs[2], the configuration the north-star target is quoted on):
+jittered 1000 x 1000 grid road graph (1 M vertices), K = 12 trees per query (source, target,
+10 destinations), default goal_bias 1.0, seed-0 mt19937 sample stream.  One *step* is one pass
+of the hot path over one batch of synthetic input: `--queries` independent queries, each
+expanded from scratch for `--iters` passes of expandTreeLayers_ (default 3000, the window
+BASELINE.md quotes the CPU numbers on).  Metric: expansions/s = non-early-returning
+expandTree_ calls per second, whole job (all queries, all GPUs).
+
+  value   device-resident: query state already in HBM, timed region = the persistent
+          expansion kernel (CUDA events on the planner's stream)
+  e2e     through the C ABI with HOST buffers every step: destinations + selection
+          probabilities + the mt19937 word stream go host->device (pinned memory), the
+          state is rebuilt, the kernel runs, per-query reports and the K x K distance /
+          connection-node matrices come back device->host
+  roofline       algorithmic bytes of the expansion kernel (work counters x the per-unit
+                 figures of SURVEY.md 8d, DESIGN.md "Roofline") / its device time, against
+                 the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline   the unmodified reference (oracle/_ref/ref_probe) on the box's host cores,
+                 one process per core, a bounded sample of the same workload
+
+With N > 1 (torchrun) every rank drives its own GPU with its own `--queries` queries
+(independent queries shard with no data-path collective): weak scaling, value = all ranks'
+expansions / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "imomd-rrtstar_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "rrt_star_expansions_per_s"
+UNIT = "expansions/s"
+K_TREES = 12
+REF_PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=64, help="independent queries per GPU")
+    ap.add_argument("--iters", type=int, default=3000, help="expandTreeLayers_ passes per query")
+    ap.add_argument("--grid", type=int, default=1000, help="grid width (1000 = 1 M vertices)")
+    ap.add_argument("--cpu-sample-iters", type=int, default=0,
+                    help="iterations of the CPU sample (0 = same as --iters)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_workload(args, rank):
+    from imomd_b200 import graphs
+
+    g = graphs.jittered_grid(args.grid, seed=123)
+    # query q of rank r: destinations drawn with seed 1000 + r*queries + q (query 0 of rank 0
+    # is the survey's `mt19937{7}`-style pick, seed 7)
+    dests = []
+    lab = None
+    for q in range(args.queries):
+        seed = 7 if (rank == 0 and q == 0) else 1000 + rank * args.queries + q
+        rng = np.random.default_rng(seed)
+        dests.append([int(v) for v in rng.choice(g.n, size=K_TREES, replace=False)])
+    return g, dests
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4)
+                          if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------- CPU reference ---
+
+def run_reference_sample(g, dests, iters, cores, graph_file=None):
+    """`cores` concurrent ref_probe processes, one query each; returns (expansions/s, info)."""
+    if not os.path.exists(REF_PROBE):
+        return None, "oracle/_ref/ref_probe not built"
+    own = graph_file is None
+    if own:
+        fd, graph_file = tempfile.mkstemp(suffix=".bin", prefix="imomd_graph_")
+        os.close(fd)
+        g.write_probe_file(graph_file)
+    try:
+        procs = []
+        t0 = time.time()
+        for d in dests[:cores]:
+            procs.append(subprocess.Popen(
+                [REF_PROBE, "--graph", graph_file, "--dest", ",".join(map(str, d)), "--iters", str(iters),
+                 "--goal-bias", "1.0"], stdout=subprocess.PIPE, text=True))
+        outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+        wall = time.time() - t0
+    finally:
+        if own:
+            os.unlink(graph_file)
+    exp = sum(o["expansions"] for o in outs)
+    secs = max(o["seconds"] for o in outs)          # loop time only (graph load excluded)
+    return exp / secs, {"expansions": exp, "loop_seconds": secs, "wall_seconds": wall,
+                        "per_process_exp_per_s": [round(o["expansions_per_s"], 1) for o in outs],
+                        "toolchain": outs[0]["toolchain"]}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    g, dests = make_workload(args, 0)
+    while len(dests) < cores:      # more cores than queries: more queries of the same family
+        rng = np.random.default_rng(5000 + len(dests))
+        dests.append([int(v) for v in rng.choice(g.n, size=K_TREES, replace=False)])
+    iters = args.cpu_sample_iters or args.iters
+    fd, gf = tempfile.mkstemp(suffix=".bin", prefix="imomd_graph_")
+    os.close(fd)
+    g.write_probe_file(gf)
+    try:
+        for _ in range(args.warmup):
+            run_reference_sample(g, dests, min(iters, 200), cores, gf)
+        rates, t_total, exp_total = [], 0.0, 0
+        for s in range(args.steps):
+            rate, info = run_reference_sample(g, dests, iters, cores, gf)
+            if rate is None:
+                print(json.dumps({"impl": "reference", "unavailable": info}))
+                return 0
+            rates.append(rate)
+            t_total += info["loop_seconds"]
+            exp_total += info["expansions"]
+    finally:
+        os.unlink(gf)
+    value = exp_total / t_total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"grid{args.grid}x{args.grid}_K{K_TREES}_iters{iters}",
+                   "graph": "jittered 4-neighbour grid, seed 123", "trees_per_query": K_TREES,
+                   "iters_per_query": iters, "goal_bias": 1.0,
+                   "queries_per_step": cores, "note": "one reference process per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{cores} queries x {iters} passes per step, unmodified reference "
+                                   f"(oracle/_ref/ref_probe), {cpu_model()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------- CUDA arm ----
+
+def algorithmic_bytes(counters, avg_degree, K):
+    """SURVEY.md 8(d) per-unit figures x work counters (see DESIGN.md 'Roofline')."""
+    c = counters.sum(axis=0).astype(np.float64)
+    cells, recs_nn, calls, slots, reparent, desc, conn, recs_rescan = c
+    nn = 8.0 * cells + 32.0 * (recs_nn + recs_rescan)          # cell headers + 32 B records
+    rewire = calls * (8.0 + 24.0 * avg_degree) + 24.0 * reparent + 16.0 * desc
+    connect = 12.0 * (K - 1) * conn
+    return nn + rewire + connect, {"nn_bytes": nn, "rewire_bytes": rewire, "connect_bytes": connect}
+
+
+def b200_arm(args):
+    import torch
+    from imomd_b200 import capi
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = local
+    torch.cuda.set_device(device)
+    g, dests = make_workload(args, rank)
+    Q, K = args.queries, K_TREES
+    dg = capi.DeviceGraph(g, device=device)
+    probs = np.stack([capi.selection_probabilities(g, d) for d in dests])
+    dp = capi.DevicePlanner(dg, dests, probs)
+    n_words = args.iters * K * 8 + 4096
+    words_np = capi.mt19937_words(0, n_words)
+
+    # pinned host staging buffers for the end-to-end path
+    pin_words = torch.empty(n_words, dtype=torch.int32).pin_memory()
+    pin_dest = torch.empty(Q * K, dtype=torch.int32).pin_memory()
+    pin_prob = torch.empty(Q * K * K, dtype=torch.float64).pin_memory()
+    w_view = pin_words.numpy().view(np.uint32); w_view[:] = words_np
+    d_view = pin_dest.numpy().view(np.uint32); d_view[:] = np.asarray(dests, np.uint32).ravel()
+    p_view = pin_prob.numpy(); p_view[:] = probs.ravel()
+    h2d = w_view.nbytes + d_view.nbytes + p_view.nbytes
+    d2h = Q * (88 + capi.sizeof_query_state())
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(collect):
+        """reset -> kernel.  Returns (device ms of the kernel, expansions, e2e seconds)."""
+        t0 = time.perf_counter()
+        dp.clear_words()
+        dp.set_queries(d_view, p_view)           # H2D destinations + probabilities, rebuild state
+        dp.feed(w_view)                          # H2D sample stream
+        reps = dp.expand(args.iters)             # kernel + D2H reports
+        if collect:
+            for q in range(Q):
+                dp.state(q)                      # D2H K x K matrices
+        e2e_s = time.perf_counter() - t0
+        bad = [r.status for r in reps if r.status != 0]
+        if bad:
+            raise SystemExit(f"bench.py: device run status {bad[:4]}")
+        return dp.last_kernel_ms(), sum(r.expansions for r in reps), e2e_s, reps
+
+    for _ in range(max(args.warmup, 0)):
+        one_step(True)
+    barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
+    ker_ms, exps, e2e_secs = [], [], []
+    reps = None
+    for _ in range(args.steps):
+        ms, ex, es, reps = one_step(True)
+        ker_ms.append(ms); exps.append(ex); e2e_secs.append(es)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    counters = dp.counters()
+    t_dev = sum(ker_ms) / 1e3
+    t_e2e = sum(e2e_secs)
+    exp_total = sum(exps)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e = torch.tensor([float(exp_total)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(e, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+        exp_total = float(e[0])
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return 0
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    avg_deg = g.arcs / g.n
+    # counters are cumulative over the last set_queries (= one step); per launch:
+    bytes_step, parts = algorithmic_bytes(counters, avg_deg, K)
+    launch_s = ker_ms[-1] / 1e3
+    achieved = bytes_step / launch_s / 1e9
+    line = {
+        "metric": METRIC, "value": exp_total / t_dev, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"grid{args.grid}x{args.grid}_K{K}_iters{args.iters}",
+                   "graph": "jittered 4-neighbour grid, seed 123", "vertices": g.n,
+                   "trees_per_query": K, "iters_per_query": args.iters, "goal_bias": 1.0,
+                   "queries_per_gpu": Q, "l2": "inputs_larger_than_l2 (state rebuilt every step)",
+                   "hash_cells_per_axis": dg.info()["grid_dim"]},
+        "e2e": {"value": exp_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(args.steps * (2 + 1)),   # k_init_trees + k_lower_bounds + k_expand per step
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "kernel": "k_expand",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_step,
+                     "launch_ms": ker_ms[-1],
+                     "note": "latency-bound: one CTA per query walks dependent parent/child chains; "
+                             "see DESIGN.md 'Roofline'", **{k: float(v) for k, v in parts.items()}},
+        "clocks": sampler.summary(),
+        "tree_vertices_per_step": int(sum(r.tree_vertices for r in reps)),
+        "unresolved_ties": int(sum(r.unresolved_ties for r in reps)),
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cd = list(dests)
+        while len(cd) < cores:
+            rng = np.random.default_rng(5000 + len(cd))
+            cd.append([int(v) for v in rng.choice(g.n, size=K, replace=False)])
+        iters = args.cpu_sample_iters or args.iters
+        rate, info = run_reference_sample(g, cd, iters, cores)
+        if rate is None:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": info}
+        else:
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{cores} queries x {iters} passes, one unmodified-reference process per core "
+                          f"({cpu_model()}); single-core mean "
+                          f"{np.mean(info['per_process_exp_per_s']):.0f} expansions/s"}
+    print(json.dumps(line))
+    dp.close(); dg.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -252,6 +252,7 @@ struct Shared
     double h[IMOMD_MAXDEG * IMOMD_KMAX];
     // work list of the pruned search
     uint32_t n_list;
+    uint32_t n_cells, n_recs;   // statistics of the current search
     // connection gather: the other trees' (parent, cost) at conn_x (REQ_CONN / REQ_BFS)
     uint32_t conn_x;
     int32_t conn_pending;
@@ -610,6 +611,7 @@ struct Seq
     {
         int K = Q->K;
         double cx = T.cost[x];
+        Q->stat[6] += 1;
         for (int o = 0; o < K; ++o)
         {
             if (o == k) continue;
@@ -777,6 +779,7 @@ struct Seq
             Q->status = 3;   // IMOMD_RUN_ARENA_FULL
             return false;
         }
+        Q->stat[2] += 1;
         uint32_t* f = arena + top;
         f[0] = S.rw_fp;
         f[1] = x;
@@ -804,6 +807,7 @@ struct Seq
                 if (S.chk_valid)
                 {
                     S.chk_valid = 0;
+                    Q->stat[2] += S.chk_noop;
                     f[6] -= S.chk_noop;          // calls that would have changed nothing
                     if (S.chk_slot != IMOMD_NONE)
                     {
@@ -850,11 +854,13 @@ struct Seq
             uint32_t x = f[1];
             uint32_t y = g.col[e];
             uint32_t py = T.parent[y];
+            Q->stat[3] += 1;
             if (py != IMOMD_NONE && y != T.parent[x])
             {
                 double nc = T.cost[x] + g.w[e];
                 if (T.cost[y] > nc)
                 {
+                    Q->stat[4] += 1;
                     chl_erase(g, T, py, y);
                     T.parent[y] = x;
                     chl_insert(g, T, x, y);
@@ -1100,6 +1106,7 @@ IMOMD_HD inline void list_cell(Cta& cta, const TreeRef& T, uint32_t* clist, uint
         uint32_t at = cta.counter_add(n_list, 1u);
         clist[2 * at] = chunk;
         clist[2 * at + 1] = n;
+        cta.counter_add(n_list + 2, n);   // Shared::n_recs sits two words after n_list
         cnt -= n;
         n = IMOMD_CHUNK;
         chunk = T.chunk_next[chunk];
@@ -1120,6 +1127,7 @@ IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef&
     uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
     // 1. lower bounds of the occupied cells; the most promising cell
     Best star = best_empty();
+    uint32_t occupied = 0;
     for (uint32_t c = cta.tid(); c < cells; c += cta.nt())
     {
         double v = INFINITY;
@@ -1127,9 +1135,11 @@ IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef&
         {
             v = lower(c);
             best_add(star, v, c);
+            ++occupied;
         }
         lb[c] = v;
     }
+    if (occupied) cta.counter_add(&S.n_cells, occupied);
     star = cta.reduce(star, S.red);
     if (star.id1 == IMOMD_NONE) return best_empty();   // empty frontier
     // 2. its records give the first upper bound
@@ -1176,6 +1186,12 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     // rounding band of a squared chord m: unit-vector components carry ~1e-16 each
     auto band = [](double m) { return 2e-12 * m + 4e-15 * sqrt(m); };
     auto bound = [&](double m) { return m * (1.0 + kPruneSlack) + 4.0 * band(m); };
+    if (cta.tid() == 0)
+    {
+        S.n_cells = 0;
+        S.n_recs = 0;
+    }
+    cta.sync();
     Best b = pruned_argmin(cta, P, T, S, lb, clist, lower, eval, bound);
     int ambiguous = (b.id1 != IMOMD_NONE) && (b.v2 - b.v1 <= band(b.v1));
     if (ambiguous)
@@ -1201,6 +1217,9 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     {
         S.result = b;
         S.ambiguous = ambiguous;
+        QueryDev* Qs = P.query + q;
+        Qs->stat[0] += S.n_cells;
+        Qs->stat[1] += S.n_recs;
     }
 }
 
@@ -1232,9 +1251,17 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
             return haversine(vlat, vlon, klat, klon) + haversine(vlat, vlon, olat, olon);
         };
         auto bound = [&](double m) { return m * (1.0 + kPruneSlack); };
+        if (cta.tid() == 0)
+        {
+            S.n_cells = 0;
+            S.n_recs = 0;
+        }
+        cta.sync();
         Best b = pruned_argmin(cta, P, T, S, lb, clist, lower, eval, bound);
         if (cta.tid() == 0)
         {
+            Q->stat[0] += S.n_cells;
+            Q->stat[7] += S.n_recs;
             Q->MHi[k * K + o] = b.id1;
             Q->MHv[k * K + o] = b.v1;
             if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1) Q->unresolved_ties += 1;
@@ -1492,6 +1519,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     {
         // statistics: [0] = subtree vertices (cycles slot) and levels... see imomd_get_profile
         P.query[q].prof_cycles[0] += (uint64_t)(S.lv_tail - lo);
+        P.query[q].stat[5] += (uint64_t)(S.lv_tail - lo - 1);
         bool overflow = S.lv_overflow != 0;
         if (!overflow) T.cost[rewired] = new_cost;
         S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;

@@ -416,6 +416,8 @@ const char* imomd_last_error(void) { return g_err; }
 
 const char* imomd_version(void) { return "imomd_b200 0.1 (sm_100a)"; }
 
+size_t imomd_sizeof_query_state(void) { return sizeof(QueryDev); }
+
 int imomd_graph_create(int device, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
                        const double* w, const double* lat, const double* lon, imomd_graph** out)
 {
@@ -607,6 +609,46 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->stream);
     delete p;
+    return IMOMD_OK;
+}
+
+int imomd_planner_set_queries(imomd_planner* p, const uint32_t* dest, const double* prob)
+{
+    if (!p || !dest || !prob) return fail(IMOMD_ERR_ARG, "null argument");
+    const int Q = p->d.Q, K = p->d.K;
+    for (size_t i = 0; i < (size_t)Q * K; ++i)
+    {
+        if (dest[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "destination %u out of range", dest[i]);
+    }
+    CU(cudaSetDevice(p->g->device));
+    for (int q = 0; q < Q; ++q)
+        fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
+    int rc = planner_fill_initial(p);
+    if (rc != IMOMD_OK) return rc;
+    size_t total = (size_t)Q * K * p->d.g.G * p->d.g.G;
+    k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(p->d);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(p->stream));
+    return IMOMD_OK;
+}
+
+int imomd_get_counters(imomd_planner* p, uint64_t* out)
+{
+    if (!p || !out) return fail(IMOMD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaMemcpy2D(out, 8 * sizeof(uint64_t), p->d.query[0].stat, sizeof(QueryDev),
+                    8 * sizeof(uint64_t), (size_t)p->d.Q, cudaMemcpyDeviceToHost));
+    return IMOMD_OK;
+}
+
+int imomd_planner_clear_words(imomd_planner* p)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null planner");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    p->words_fed = 0;
+    p->d.words_avail = 0;
     return IMOMD_OK;
 }
 

@@ -96,6 +96,11 @@ struct QueryDev
     // SM-clock cycles and call counts per request type (index = ReqType, 7 = serial steps)
     uint64_t prof_cycles[8];
     uint64_t prof_count[8];
+    // work counters behind the algorithmic-bytes figure ("roofline"):
+    // 0 hash cells bounded, 1 frontier records ranked (nearest), 2 rewireTree_ calls,
+    // 3 adjacency slots read by serial scans, 4 re-parentings, 5 cost-propagated
+    // descendants, 6 connection-checked vertices, 7 frontier records ranked (rescans)
+    uint64_t stat[8];
 };
 
 // mirrors imomd_query_report (include/imomd_b200.h)

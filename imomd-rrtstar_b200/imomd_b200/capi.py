@@ -60,6 +60,7 @@ def cuda_lib():
         vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
         L.imomd_last_error.restype = C.c_char_p
         L.imomd_version.restype = C.c_char_p
+        L.imomd_sizeof_query_state.restype = C.c_size_t
         L.imomd_graph_create.argtypes = [C.c_int, C.c_uint32, u32p, u32p, f64p, f64p, f64p, vpp]
         L.imomd_graph_create_ex.argtypes = [C.c_int, C.c_uint32, u32p, u32p, f64p, f64p, f64p, C.c_int, vpp]
         L.imomd_graph_destroy.argtypes = [vp]
@@ -68,6 +69,9 @@ def cuda_lib():
         L.imomd_planner_create.argtypes = [vp, C.c_int, C.c_int, u32p, f64p, C.POINTER(Params), vpp]
         L.imomd_planner_destroy.argtypes = [vp]
         L.imomd_planner_reset.argtypes = [vp]
+        L.imomd_planner_set_queries.argtypes = [vp, u32p, f64p]
+        L.imomd_planner_clear_words.argtypes = [vp]
+        L.imomd_get_counters.argtypes = [vp, np.ctypeslib.ndpointer(np.uint64, flags="C")]
         L.imomd_planner_feed_words.argtypes = [vp, u32p, C.c_size_t]
         L.imomd_planner_words_available.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.imomd_expand.argtypes = [vp, C.c_int, C.POINTER(Report)]
@@ -103,6 +107,10 @@ def host_lib():
         L.imomd_host_great_circle_m.argtypes = [C.c_double] * 4
         _host = L
     return _host
+
+
+def sizeof_query_state() -> int:
+    return int(cuda_lib().imomd_sizeof_query_state())
 
 
 def _check(rc):
@@ -175,6 +183,18 @@ class DevicePlanner:
 
     def reset(self):
         _check(cuda_lib().imomd_planner_reset(self.h))
+
+    def set_queries(self, dests_u32, probs_f64):
+        """dests_u32: contiguous u32[Q*K]; probs_f64: contiguous f64[Q*K*K] (host buffers)."""
+        _check(cuda_lib().imomd_planner_set_queries(self.h, dests_u32, probs_f64))
+
+    def counters(self):
+        out = np.zeros((self.Q, 8), np.uint64)
+        _check(cuda_lib().imomd_get_counters(self.h, out))
+        return out
+
+    def clear_words(self):
+        _check(cuda_lib().imomd_planner_clear_words(self.h))
 
     def feed(self, words):
         w = np.ascontiguousarray(words, np.uint32)

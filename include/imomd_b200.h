@@ -114,6 +114,9 @@ int imomd_graph_info(const imomd_graph* g, uint32_t* n, uint32_t* arcs, int32_t*
 int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* dest,
                          const double* prob, const imomd_params* params, imomd_planner** out);
 int imomd_planner_destroy(imomd_planner* p);
+/* new destinations / probability matrices for every query (same Q and K, host buffers
+ * laid out as for imomd_planner_create), followed by a reset */
+int imomd_planner_set_queries(imomd_planner* p, const uint32_t* dest, const double* prob);
 /* back to the freshly constructed state (same dest / prob), word cursors to 0 */
 int imomd_planner_reset(imomd_planner* p);
 
@@ -123,6 +126,8 @@ int imomd_planner_reset(imomd_planner* p);
  * words into samples with libstdc++'s formulas (selectRandomVertex_, :358-400). */
 int imomd_planner_feed_words(imomd_planner* p, const uint32_t* words, size_t n);
 int imomd_planner_words_available(const imomd_planner* p, uint64_t* total_fed);
+/* forget the injected stream (the next feed starts again at word 0) */
+int imomd_planner_clear_words(imomd_planner* p);
 
 /* `iters` passes of expandTreeLayers_ (:329-356) for every query of the planner, in
  * one persistent kernel.  reports[n_queries] may be NULL.  Asynchronous variant:
@@ -135,6 +140,11 @@ int imomd_sync(imomd_planner* p, imomd_query_report* reports);
  * nearest search, heuristic rescan, heuristic insert, connection gather, cost propagation,
  * rewire batch check; index 7 = the serial steps in between (development / profiling aid) */
 int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts);
+/* cumulative work counters of every query, out[Q][8]: hash cells bounded, frontier records
+ * ranked by nearest searches, rewireTree_ calls, adjacency slots read by serial scans,
+ * re-parentings, cost-propagated descendants, connection-checked vertices, frontier
+ * records ranked by heuristic rescans (the inputs of the algorithmic-bytes figure) */
+int imomd_get_counters(imomd_planner* p, uint64_t* out);
 /* device time of the last imomd_expand kernel in milliseconds (CUDA events) */
 int imomd_last_kernel_ms(imomd_planner* p, float* ms);
 
@@ -176,6 +186,8 @@ int imomd_ga_eval(imomd_ctx* c, int K, const double* D, int n_tours, int stride,
 
 const char* imomd_last_error(void);
 const char* imomd_version(void);
+/* bytes imomd_get_state moves device->host per query */
+size_t imomd_sizeof_query_state(void);
 
 #ifdef __cplusplus
 }
