@@ -1414,21 +1414,74 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
             if (cta.warp() == 0)
             {
                 uint32_t cur = S.lv_cur, start = S.lv_start, tail = S.lv_tail;
-                bool ovf = false;
+                uint32_t ovf = 0;
                 uint32_t levels = 0;
-                while (n != 0 && n <= (uint32_t)cta.warp_width())
+                while (n != 0 && n <= (uint32_t)cta.warp_width() && !ovf)
                 {
                     uint32_t* cl = lvl + cur * kLevelCap;
                     uint32_t* nl = lvl + (cur ^ 1u) * kLevelCap;
+                    if (n == 1)
+                    {
+                        // chain walk: most levels of a rewired subtree hold a single vertex
+                        // (1.4 on average on a grid), so lane 0 follows child pointers with
+                        // nothing but the child-row load on the critical path
+                        if (cta.lane() == 0)
+                        {
+                            uint32_t node = cl[0];
+                            for (;;)
+                            {
+                                ChlRow<W> row;
+                                int cnt = bfs_expand<W>(T, node, true, pd, new_cost, old, row);
+                                if (tail + (uint32_t)cnt > cap)
+                                {
+                                    ovf = 1;
+                                    break;
+                                }
+#pragma unroll
+                                for (int i = 0; i < W; ++i)
+                                {
+                                    if (i < cnt)
+                                    {
+                                        arena[tail + i] = row.v[i];
+                                        pd.v[i] = row.v[i];
+                                    }
+                                }
+                                pd.n = cnt;
+                                start = tail;
+                                tail += (uint32_t)cnt;
+                                ++levels;
+                                if (cnt != 1)
+                                {
+#pragma unroll
+                                    for (int i = 0; i < W; ++i)
+                                    {
+                                        if (i < cnt) nl[i] = row.v[i];
+                                    }
+                                    n = (uint32_t)cnt;
+                                    cur ^= 1u;
+                                    break;
+                                }
+                                node = row.v[0];
+                            }
+                        }
+                        n = cta.warp_bcast(n);
+                        cur = cta.warp_bcast(cur);
+                        start = cta.warp_bcast(start);
+                        tail = cta.warp_bcast(tail);
+                        ovf = cta.warp_bcast(ovf);
+                        levels = cta.warp_bcast(levels);
+                        cta.warp_sync();
+                        continue;
+                    }
                     bool active = (uint32_t)cta.lane() < n;
                     uint32_t node = active ? cl[cta.lane()] : 0u;
                     ChlRow<W> row;
                     int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row);
                     uint32_t total = 0;
-                    uint32_t off = cta.warp_scan_exclusive((uint32_t)cnt, &total);
+                    uint32_t off = cta.warp_scan_small((uint32_t)cnt, W, &total);
                     if (tail + total > cap)
                     {
-                        ovf = true;
+                        ovf = 1;
                         break;
                     }
 #pragma unroll

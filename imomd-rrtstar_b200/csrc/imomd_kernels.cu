@@ -66,6 +66,22 @@ struct CtaDev
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
     __device__ __forceinline__ int warp_width() const { return 32; }
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t warp_bcast(uint32_t v) const { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+    // exclusive scan of per-lane counts in [0, maxv]: one ballot per possible count
+    __device__ __forceinline__ uint32_t warp_scan_small(uint32_t v, int maxv, uint32_t* total) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+        uint32_t off = 0, tot = 0;
+        for (int j = 1; j <= maxv; ++j)
+        {
+            unsigned b = __ballot_sync(full, v >= (uint32_t)j);
+            off += __popc(b & lt);
+            tot += __popc(b);
+        }
+        *total = tot;
+        return off;
+    }
     __device__ __forceinline__ uint32_t warp_scan_exclusive(uint32_t v, uint32_t* total) const
     {
         const unsigned full = 0xFFFFFFFFu;
@@ -566,6 +582,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
                     2 * kLevelCap * sizeof(uint32_t);
     CU(cudaFuncSetAttribute(k_expand<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
+    CU(cudaFuncSetAttribute(k_expand<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)p->smem_bytes));
     CU(cudaFuncSetAttribute(k_expand<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
     CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -699,8 +717,10 @@ int imomd_expand_async(imomd_planner* p, int iters)
     if (iters < 0) return fail(IMOMD_ERR_ARG, "negative iteration count");
     CU(cudaSetDevice(p->g->device));
     CU(cudaEventRecord(p->ev0, p->stream));
-    if (p->d.Q <= 2 * 148)
+    if (p->d.Q <= 148)
         k_expand<1><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+    else if (p->d.Q <= 2 * 148)
+        k_expand<2><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
     else
         k_expand<4><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
     CU(cudaGetLastError());

@@ -122,11 +122,14 @@ inline void default_sizes(PlannerDev& d, uint32_t frontier_chunks, uint32_t aren
 {
     const size_t n = d.g.n;
     const size_t cells = (size_t)d.g.G * d.g.G;
-    size_t chunks = frontier_chunks ? frontier_chunks : cells + n / 64 + 64;
+    // a tree's frontier needs at most (occupied cells + entries / 32) chunks; the default
+    // covers frontiers of up to ~N/8 vertices (the run stops with FRONTIER_FULL beyond it)
+    size_t chunks = frontier_chunks ? frontier_chunks : cells + n / 256 + 64;
     d.chunks = (int32_t)chunks;
+    // rewire scratch: update lists are bounded by the tree size, frames by the depth
     d.arena_entries = arena_entries
                           ? arena_entries
-                          : (uint32_t)std::min<size_t>(std::max<size_t>(1u << 16, 4 * n), 1u << 28);
+                          : (uint32_t)std::min<size_t>(std::max<size_t>(1u << 16, n), 1u << 28);
     d.log_entries = log_entries ? log_entries : (d.pseudo ? (uint32_t)std::max<size_t>(4 * n, 1024) : 16u);
 }
 

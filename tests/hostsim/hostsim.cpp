@@ -31,6 +31,12 @@ struct CtaHost
     int lane() const { return 0; }
     int warp_width() const { return 1; }
     void warp_sync() const {}
+    uint32_t warp_bcast(uint32_t v) const { return v; }
+    uint32_t warp_scan_small(uint32_t v, int, uint32_t* total) const
+    {
+        *total = v;
+        return 0;
+    }
     uint32_t warp_scan_exclusive(uint32_t v, uint32_t* total) const
     {
         *total = v;
