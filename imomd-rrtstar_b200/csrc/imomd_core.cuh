@@ -31,6 +31,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "imomd_layout.h"
 
@@ -151,17 +152,54 @@ IMOMD_HD inline double lbd_entry(const PlannerDev& P, size_t i)
 
 // --------------------------------------------------------- per-tree views ---
 
+// One record per (tree, vertex): {parent, frontier slot, cost} in the first 16 bytes (one
+// 128-bit load answers "visited? at what cost? in the frontier?"), then the child row.
+struct __attribute__((aligned(16))) U4
+{
+    uint32_t x, y, z, w;
+};
+
+struct THead
+{
+    uint32_t parent;   // NONE = not visited
+    uint32_t fslot;    // frontier slot, NONE = not in the frontier
+    double cost;
+};
+
 struct TreeRef
 {
-    uint32_t* parent;
-    double* cost;
-    uint32_t* fslot;
-    uint32_t* chl;
+    unsigned char* base;
+    uint32_t stride;          // bytes per vertex record: 16 + 4 * width
     uint32_t* cell_head;
     uint32_t* cell_cnt;
     VRec* rec;
     uint32_t* chunk_next;
     uint32_t* free_stack;
+
+    IMOMD_HD THead* hp(uint32_t v) const
+    {
+        return reinterpret_cast<THead*>(base + (size_t)v * stride);
+    }
+    IMOMD_HD THead head(uint32_t v) const   // one 128-bit load
+    {
+        U4 t = *reinterpret_cast<const U4*>(base + (size_t)v * stride);
+        THead h;
+        h.parent = t.x;
+        h.fslot = t.y;
+        unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
+        memcpy(&h.cost, &bits, 8);
+        return h;
+    }
+    IMOMD_HD uint32_t parent(uint32_t v) const { return hp(v)->parent; }
+    IMOMD_HD uint32_t fslot(uint32_t v) const { return hp(v)->fslot; }
+    IMOMD_HD double cost(uint32_t v) const { return hp(v)->cost; }
+    IMOMD_HD void set_parent(uint32_t v, uint32_t p) const { hp(v)->parent = p; }
+    IMOMD_HD void set_fslot(uint32_t v, uint32_t f) const { hp(v)->fslot = f; }
+    IMOMD_HD void set_cost(uint32_t v, double c) const { hp(v)->cost = c; }
+    IMOMD_HD uint32_t* chl(uint32_t v) const
+    {
+        return reinterpret_cast<uint32_t*>(base + (size_t)v * stride + 16);
+    }
 };
 
 IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
@@ -169,10 +207,8 @@ IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
     size_t qt = (size_t)q * P.K + k;
     size_t cells = (size_t)P.g.G * P.g.G;
     TreeRef t;
-    t.parent = P.parent + qt * P.g.n;
-    t.cost = P.cost + qt * P.g.n;
-    t.fslot = P.fslot + qt * P.g.n;
-    t.chl = P.chl + qt * (size_t)P.g.n * P.g.width;
+    t.stride = P.trec_stride;
+    t.base = P.trec + qt * (size_t)P.g.n * P.trec_stride;
     t.cell_head = P.cell_head + qt * cells;
     t.cell_cnt = P.cell_cnt + qt * cells;
     t.rec = P.rec + qt * (size_t)P.chunks * IMOMD_CHUNK;
@@ -272,6 +308,12 @@ struct Shared
     uint32_t chk_hi, chk_lo, chk_skip;
     uint32_t chk_noop, chk_slot;
     int32_t chk_valid;
+    // the query's K x K matrices, staged in shared memory for the duration of a launch
+    double* mP;
+    double* mD;
+    double* mMHv;
+    uint32_t* mMHi;
+    uint32_t* mCN;
     // block reduction / scan scratch
     Best red[32];
     uint32_t scan[40];
@@ -282,7 +324,7 @@ struct Shared
 IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& T, int k,
                                uint32_t v)
 {
-    if (T.fslot[v] != IMOMD_NONE) return true;
+    if (T.fslot(v) != IMOMD_NONE) return true;
     VRec r = P.g.vrec[v];
     uint32_t c = r.cell;
     uint32_t cnt = T.cell_cnt[c];
@@ -305,7 +347,7 @@ IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& 
     }
     uint32_t slot = head * IMOMD_CHUNK + off;
     T.rec[slot] = r;
-    T.fslot[v] = slot;
+    T.set_fslot(v, slot);
     T.cell_cnt[c] = cnt + 1;
     Q->frontier_count[k] += 1;
     return true;
@@ -314,7 +356,7 @@ IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& 
 IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T, int k,
                               uint32_t v)
 {
-    uint32_t s = T.fslot[v];
+    uint32_t s = T.fslot(v);
     if (s == IMOMD_NONE) return;
     uint32_t c = P.g.vrec[v].cell;
     uint32_t cnt = T.cell_cnt[c];
@@ -325,9 +367,9 @@ IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T
     {
         VRec m = T.rec[last];
         T.rec[s] = m;
-        T.fslot[m.id] = s;
+        T.set_fslot(m.id, s);
     }
-    T.fslot[v] = IMOMD_NONE;
+    T.set_fslot(v, IMOMD_NONE);
     T.cell_cnt[c] = cnt - 1;
     Q->frontier_count[k] -= 1;
     if (off == 0)
@@ -344,11 +386,6 @@ IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T
 // two >= max degree, children of p are neighbours of p), NONE-terminated, so a row is
 // read or written with one or a few 128-bit accesses and needs no row_ptr lookup.
 
-struct __attribute__((aligned(16))) U4
-{
-    uint32_t x, y, z, w;
-};
-
 template <int W>
 struct ChlRow
 {
@@ -356,10 +393,10 @@ struct ChlRow
 };
 
 template <int W>
-IMOMD_HD inline ChlRow<W> chl_load(const uint32_t* chl, uint32_t p)
+IMOMD_HD inline ChlRow<W> chl_load(const uint32_t* rowp)
 {
     ChlRow<W> r;
-    const U4* src = reinterpret_cast<const U4*>(chl + (size_t)p * W);
+    const U4* src = reinterpret_cast<const U4*>(rowp);
 #pragma unroll
     for (int i = 0; i < W / 4; ++i)
     {
@@ -373,9 +410,9 @@ IMOMD_HD inline ChlRow<W> chl_load(const uint32_t* chl, uint32_t p)
 }
 
 template <int W>
-IMOMD_HD inline void chl_store(uint32_t* chl, uint32_t p, const ChlRow<W>& r)
+IMOMD_HD inline void chl_store(uint32_t* rowp, const ChlRow<W>& r)
 {
-    U4* dst = reinterpret_cast<U4*>(chl + (size_t)p * W);
+    U4* dst = reinterpret_cast<U4*>(rowp);
 #pragma unroll
     for (int i = 0; i < W / 4; ++i)
     {
@@ -389,9 +426,9 @@ IMOMD_HD inline void chl_store(uint32_t* chl, uint32_t p, const ChlRow<W>& r)
 }
 
 template <int W>
-IMOMD_HD inline void chl_insert_w(uint32_t* chl, uint32_t p, uint32_t x)
+IMOMD_HD inline void chl_insert_w(uint32_t* rowp, uint32_t x)
 {
-    ChlRow<W> r = chl_load<W>(chl, p);
+    ChlRow<W> r = chl_load<W>(rowp);
     int n = 0, at = -1;
 #pragma unroll
     for (int i = 0; i < W; ++i)
@@ -415,13 +452,13 @@ IMOMD_HD inline void chl_insert_w(uint32_t* chl, uint32_t p, uint32_t x)
     {
         if (i == at) r.v[i] = x;
     }
-    chl_store<W>(chl, p, r);
+    chl_store<W>(rowp, r);
 }
 
 template <int W>
-IMOMD_HD inline void chl_erase_w(uint32_t* chl, uint32_t p, uint32_t x)
+IMOMD_HD inline void chl_erase_w(uint32_t* rowp, uint32_t x)
 {
-    ChlRow<W> r = chl_load<W>(chl, p);
+    ChlRow<W> r = chl_load<W>(rowp);
     int at = -1;
 #pragma unroll
     for (int i = 0; i < W; ++i)
@@ -435,38 +472,38 @@ IMOMD_HD inline void chl_erase_w(uint32_t* chl, uint32_t p, uint32_t x)
         if (i >= at) r.v[i] = r.v[i + 1];
     }
     r.v[W - 1] = IMOMD_NONE;
-    chl_store<W>(chl, p, r);
+    chl_store<W>(rowp, r);
 }
 
 template <int W>
-IMOMD_HD inline void chl_assign_single_w(uint32_t* chl, uint32_t p, uint32_t x)
+IMOMD_HD inline void chl_assign_single_w(uint32_t* rowp, uint32_t x)
 {
     ChlRow<W> r;
 #pragma unroll
     for (int i = 0; i < W; ++i) r.v[i] = IMOMD_NONE;
     r.v[0] = x;
-    chl_store<W>(chl, p, r);
+    chl_store<W>(rowp, r);
 }
 
 IMOMD_HD inline void chl_insert(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
 {
-    if (g.width == 4) chl_insert_w<4>(T.chl, p, x);
-    else if (g.width == 8) chl_insert_w<8>(T.chl, p, x);
-    else chl_insert_w<16>(T.chl, p, x);
+    if (g.width == 4) chl_insert_w<4>(T.chl(p), x);
+    else if (g.width == 8) chl_insert_w<8>(T.chl(p), x);
+    else chl_insert_w<16>(T.chl(p), x);
 }
 
 IMOMD_HD inline void chl_erase(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
 {
-    if (g.width == 4) chl_erase_w<4>(T.chl, p, x);
-    else if (g.width == 8) chl_erase_w<8>(T.chl, p, x);
-    else chl_erase_w<16>(T.chl, p, x);
+    if (g.width == 4) chl_erase_w<4>(T.chl(p), x);
+    else if (g.width == 8) chl_erase_w<8>(T.chl(p), x);
+    else chl_erase_w<16>(T.chl(p), x);
 }
 
 IMOMD_HD inline void chl_assign_single(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
 {
-    if (g.width == 4) chl_assign_single_w<4>(T.chl, p, x);
-    else if (g.width == 8) chl_assign_single_w<8>(T.chl, p, x);
-    else chl_assign_single_w<16>(T.chl, p, x);
+    if (g.width == 4) chl_assign_single_w<4>(T.chl(p), x);
+    else if (g.width == 8) chl_assign_single_w<8>(T.chl(p), x);
+    else chl_assign_single_w<16>(T.chl(p), x);
 }
 
 // (*connection_ptr_)[a][b]; the graph was validated symmetric at upload
@@ -564,12 +601,12 @@ struct Seq
                     Q->status = 4;   // IMOMD_RUN_CDF_OVERRUN
                     break;
                 }
-                rnd -= Q->P[k * K + i++];
+                rnd -= S.mP[k * K + i++];
             }
             uint32_t random_dest = Q->view_root[i - 1];
             double rlat = g.lat[random_dest];
             double rlon = g.lon[random_dest];
-            if (T.parent[random_dest] != IMOMD_NONE)
+            if (T.parent(random_dest) != IMOMD_NONE)
             {
                 double ratio = ws_uniform_real(ws, 0.0, 0.5);
                 uint32_t root = Q->view_root[k];
@@ -600,7 +637,7 @@ struct Seq
         for (int o = 0; o < K; ++o)
         {
             if (o == k) continue;
-            if (Q->MHi[k * K + o] == x) S.rescan_o[S.n_rescan++] = o;
+            if (S.mMHi[k * K + o] == x) S.rescan_o[S.n_rescan++] = o;
         }
     }
 
@@ -610,7 +647,7 @@ struct Seq
     IMOMD_HD void apply_connection(int k, const TreeRef& T, uint32_t x)
     {
         int K = Q->K;
-        double cx = T.cost[x];
+        double cx = T.cost(x);
         Q->stat[6] += 1;
         for (int o = 0; o < K; ++o)
         {
@@ -624,19 +661,19 @@ struct Seq
                 connect_two_trees(k, o);
             }
             double distance = cx + S.conn_cost[o];
-            if (distance < Q->D[k * K + o] - 0.1)
+            if (distance < S.mD[k * K + o] - 0.1)
             {
-                Q->D[k * K + o] = distance;
-                Q->D[o * K + k] = distance;
-                Q->CN[k * K + o] = x;
-                Q->CN[o * K + k] = x;
+                S.mD[k * K + o] = distance;
+                S.mD[o * K + k] = distance;
+                S.mCN[k * K + o] = x;
+                S.mCN[o * K + k] = x;
                 Q->dm_updated = 1;
             }
             if (P.pseudo)
             {
                 TreeRef O = tree_ref(P, q, o);
-                uint32_t x_parent = T.parent[x];
-                uint32_t opp = O.parent[x_parent];
+                uint32_t x_parent = T.parent(x);
+                uint32_t opp = O.parent(x_parent);
                 if (opp == IMOMD_NONE || (opp != x && S.conn_par[o] != x_parent))
                 {
                     log_connection((uint32_t)set_idx, x);
@@ -695,9 +732,9 @@ struct Seq
         uint32_t x_1 = g.col[e];
         uint32_t x_2 = g.col[e + 1];
         uint32_t via, next;
-        if (T.parent[x_1] != IMOMD_NONE)
+        if (T.parent(x_1) != IMOMD_NONE)
         {
-            if (T.parent[x_2] != IMOMD_NONE) return false;   // both sides visited: done
+            if (T.parent(x_2) != IMOMD_NONE) return false;   // both sides visited: done
             via = x_1;
             next = x_2;
         }
@@ -706,60 +743,107 @@ struct Seq
             via = x_2;
             next = x_1;
         }
-        if (T.parent[x_new] == IMOMD_NONE) Q->tree_size[k] += 1;
-        T.parent[x_new] = via;
+        if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
+        T.set_parent(x_new, via);
         chl_assign_single(g, T, via, x_new);
-        T.cost[x_new] = T.cost[via] + edge_weight(g, via, x_new);
+        T.set_cost(x_new, T.cost(via) + edge_weight(g, via, x_new));
         S.conn_x = x_new;
         S.jps_next = next;
         return true;
     }
 
-    // connectNewNode_, src/imomd_rrt_star.cpp:465-496
-    IMOMD_HD void connect_new_node(int k, const TreeRef& T, uint32_t x_new)
+    // connectNewNode_, src/imomd_rrt_star.cpp:465-496.  All neighbour records are
+    // requested before the first one is looked at (one round trip instead of one per
+    // neighbour); the decision loop then runs in adjacency order with strict `<`.
+    template <int W>
+    IMOMD_HD void connect_new_node_w(int k, const TreeRef& T, uint32_t x_new)
     {
         const GraphDev& g = P.g;
+        uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
+        uint32_t ys[W];
+        double ws[W];
+        THead hs[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (e0 + i < e1)
+            {
+                ys[i] = g.col[e0 + i];
+                ws[i] = g.w[e0 + i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (e0 + i < e1) hs[i] = T.head(ys[i]);
+        }
         uint32_t x_parent = IMOMD_NONE;
         double min_cost = INFINITY;
-        uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
-        for (uint32_t e = e0; e < e1; ++e)
+#pragma unroll
+        for (int i = 0; i < W; ++i)
         {
-            uint32_t y = g.col[e];
-            if (T.parent[y] != IMOMD_NONE)
+            if (e0 + i < e1 && hs[i].parent != IMOMD_NONE)
             {
-                double c = T.cost[y] + g.w[e];
+                double c = hs[i].cost + ws[i];
                 if (c < min_cost)
                 {
-                    x_parent = y;
+                    x_parent = ys[i];
                     min_cost = c;
                 }
             }
         }
         if (x_parent != IMOMD_NONE)
         {
-            if (T.parent[x_new] == IMOMD_NONE) Q->tree_size[k] += 1;
-            T.parent[x_new] = x_parent;
+            if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
+            T.set_parent(x_new, x_parent);
             chl_insert(g, T, x_parent, x_new);
-            T.cost[x_new] = min_cost;
+            T.set_cost(x_new, min_cost);
         }
+    }
+
+    IMOMD_HD void connect_new_node(int k, const TreeRef& T, uint32_t x_new)
+    {
+        if (P.g.width == 4) connect_new_node_w<4>(k, T, x_new);
+        else if (P.g.width == 8) connect_new_node_w<8>(k, T, x_new);
+        else connect_new_node_w<16>(k, T, x_new);
     }
 
     // neighbour part of updateExpandables, src/imomd_rrt_star.cpp:533-558 (the
     // heuristic updates of the listed vertices run as the REQ_MHINS service)
-    IMOMD_HD void insert_neighbours(int k, const TreeRef& T, uint32_t x_new)
+    template <int W>
+    IMOMD_HD void insert_neighbours_w(int k, const TreeRef& T, uint32_t x_new)
     {
         const GraphDev& g = P.g;
         S.n_ys = 0;
         uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
-        for (uint32_t e = e0; e < e1; ++e)
+        uint32_t ys[W];
+        uint32_t par[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i)
         {
-            uint32_t y = g.col[e];
-            if (T.parent[y] == IMOMD_NONE)
+            if (e0 + i < e1) ys[i] = g.col[e0 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (e0 + i < e1) par[i] = T.parent(ys[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (e0 + i < e1 && par[i] == IMOMD_NONE)
             {
-                if (!fr_insert(P, Q, T, k, y)) return;
-                S.ys[S.n_ys++] = y;
+                if (!fr_insert(P, Q, T, k, ys[i])) return;
+                S.ys[S.n_ys++] = ys[i];
             }
         }
+    }
+
+    IMOMD_HD void insert_neighbours(int k, const TreeRef& T, uint32_t x_new)
+    {
+        if (P.g.width == 4) insert_neighbours_w<4>(k, T, x_new);
+        else if (P.g.width == 8) insert_neighbours_w<8>(k, T, x_new);
+        else insert_neighbours_w<16>(k, T, x_new);
     }
 
     // ---- rewireTree_, src/imomd_rrt_star.cpp:561-600 ------------------------------
@@ -791,6 +875,48 @@ struct Seq
         S.rw_fp = top;
         S.rw_top = top + FR;
         return true;
+    }
+
+    template <int W>
+    IMOMD_HD void scan_frame(const TreeRef& T, const uint32_t* f, uint32_t& hit_e, uint32_t& hit_y,
+                             uint32_t& hit_py, double& hit_nc)
+    {
+        const GraphDev& g = P.g;
+        const uint32_t x = f[1], e0 = f[2], e1 = f[3];
+        uint32_t ys[W];
+        double ws[W];
+        THead hs[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (e0 + i < e1)
+            {
+                ys[i] = g.col[e0 + i];
+                ws[i] = g.w[e0 + i];
+            }
+        }
+        THead hx = T.head(x);
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (e0 + i < e1) hs[i] = T.head(ys[i]);
+        }
+        Q->stat[3] += e1 - e0;
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+        {
+            if (hit_e == IMOMD_NONE && e0 + i < e1 && hs[i].parent != IMOMD_NONE && ys[i] != hx.parent)
+            {
+                double nc = hx.cost + ws[i];
+                if (hs[i].cost > nc)
+                {
+                    hit_e = e0 + i;
+                    hit_y = ys[i];
+                    hit_py = hs[i].parent;
+                    hit_nc = nc;
+                }
+            }
+        }
     }
 
     // returns true when the cascade is finished, false when a service was requested
@@ -850,27 +976,28 @@ struct Seq
                 S.rw_fp = f[0];
                 continue;
             }
-            uint32_t e = f[2]++;
-            uint32_t x = f[1];
-            uint32_t y = g.col[e];
-            uint32_t py = T.parent[y];
-            Q->stat[3] += 1;
-            if (py != IMOMD_NONE && y != T.parent[x])
+            // serial scan of x's adjacency (:565-572): the remaining slots are fetched
+            // together, the first one that re-parents is acted on
+            uint32_t hit_e = IMOMD_NONE, hit_y = IMOMD_NONE, hit_py = IMOMD_NONE;
+            double hit_nc = 0.0;
+            if (g.width == 4) scan_frame<4>(T, f, hit_e, hit_y, hit_py, hit_nc);
+            else if (g.width == 8) scan_frame<8>(T, f, hit_e, hit_y, hit_py, hit_nc);
+            else scan_frame<16>(T, f, hit_e, hit_y, hit_py, hit_nc);
+            if (hit_e == IMOMD_NONE)
             {
-                double nc = T.cost[x] + g.w[e];
-                if (T.cost[y] > nc)
-                {
-                    Q->stat[4] += 1;
-                    chl_erase(g, T, py, y);
-                    T.parent[y] = x;
-                    chl_insert(g, T, x, y);
-                    S.bfs_node = y;
-                    S.bfs_cost = nc;
-                    S.bfs_lo = S.rw_top;
-                    S.req = REQ_BFS;
-                    return false;
-                }
+                f[2] = f[3];
+                continue;
             }
+            f[2] = hit_e + 1;
+            Q->stat[4] += 1;
+            chl_erase(g, T, hit_py, hit_y);
+            T.set_parent(hit_y, f[1]);
+            chl_insert(g, T, f[1], hit_y);
+            S.bfs_node = hit_y;
+            S.bfs_cost = hit_nc;
+            S.bfs_lo = S.rw_top;
+            S.req = REQ_BFS;
+            return false;
         }
         return true;
     }
@@ -889,9 +1016,9 @@ struct Seq
             }
         }
         if (other == K) return;
-        if (Q->MHv[k * K + other] > Q->D[k * K + other])
+        if (S.mMHv[k * K + other] > S.mD[k * K + other])
         {
-            double* Pm = Q->P;
+            double* Pm = S.mP;
             Pm[k * K + other] = 0.0;
             Pm[other * K + k] = 0.0;
             int dk = 1, dother = 1;
@@ -1262,8 +1389,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
         {
             Q->stat[0] += S.n_cells;
             Q->stat[7] += S.n_recs;
-            Q->MHi[k * K + o] = b.id1;
-            Q->MHv[k * K + o] = b.v1;
+            S.mMHi[k * K + o] = b.id1;
+            S.mMHv[k * K + o] = b.v1;
             if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1) Q->unresolved_ties += 1;
         }
         cta.sync();
@@ -1290,8 +1417,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
     for (int o = cta.tid(); o < K; o += cta.nt())
     {
         if (o == k) continue;
-        double best = Q->MHv[k * K + o];
-        uint32_t arg = Q->MHi[k * K + o];
+        double best = S.mMHv[k * K + o];
+        uint32_t arg = S.mMHi[k * K + o];
         for (int yi = 0; yi < m; ++yi)
         {
             double h = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
@@ -1301,8 +1428,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
                 arg = S.ys[yi];
             }
         }
-        Q->MHv[k * K + o] = best;
-        Q->MHi[k * K + o] = arg;
+        S.mMHv[k * K + o] = best;
+        S.mMHi[k * K + o] = arg;
     }
 }
 
@@ -1315,8 +1442,12 @@ IMOMD_HD IMOMD_NOINLINE void svc_conn_gather(Cta& cta, const PlannerDev& P, int 
     for (int o = cta.tid(); o < K; o += cta.nt())
     {
         size_t qt = (size_t)q * K + o;
-        S.conn_par[o] = P.parent[qt * n + x];
-        S.conn_cost[o] = P.cost[qt * n + x];
+        const U4 t = *reinterpret_cast<const U4*>(P.trec + (qt * n + x) * (size_t)P.trec_stride);
+        unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
+        double c;
+        memcpy(&c, &bits, 8);
+        S.conn_par[o] = t.x;
+        S.conn_cost[o] = c;
     }
 }
 
@@ -1336,38 +1467,26 @@ constexpr uint32_t kLevelCap = 512;
 template <int W>
 struct BfsPending
 {
-    uint32_t v[W];
-    int n;
+    int n;   // (kept for the interface; cost updates ride on the record load now)
 };
 
 template <int W>
-IMOMD_HD inline void bfs_flush(const TreeRef& T, BfsPending<W>& pd, double new_cost, double old)
+IMOMD_HD inline void bfs_flush(const TreeRef&, BfsPending<W>&, double, double)
 {
-    double c[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i)
-    {
-        if (i < pd.n) c[i] = T.cost[pd.v[i]];
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i)
-    {
-        if (i < pd.n) T.cost[pd.v[i]] = new_cost + c[i] - old;
-    }
-    pd.n = 0;
 }
 
-// one vertex of the current level: returns its child row and count; the previous
-// round's cost updates are issued while the row load is in flight
+// one vertex of the current level: a single record load returns its cost (updated in
+// place, include/imomd_rrt_star/imomd_rrt_star.h:116) and its child row
 template <int W>
-IMOMD_HD inline int bfs_expand(const TreeRef& T, uint32_t node, bool active, BfsPending<W>& pd,
-                               double new_cost, double old, ChlRow<W>& row)
+IMOMD_HD inline int bfs_expand(const TreeRef& T, uint32_t node, bool active, BfsPending<W>&,
+                               double new_cost, double old, ChlRow<W>& row, uint32_t rewired)
 {
     int cnt = 0;
-    if (active) row = chl_load<W>(T.chl, node);
-    bfs_flush<W>(T, pd, new_cost, old);
     if (active)
     {
+        THead h = T.head(node);
+        row = chl_load<W>(T.chl(node));
+        if (node != rewired) T.set_cost(node, new_cost + h.cost - old);
 #pragma unroll
         for (int i = 0; i < W; ++i)
         {
@@ -1387,7 +1506,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     const uint32_t rewired = S.bfs_node;
     const double new_cost = S.bfs_cost;
     const uint32_t lo = S.bfs_lo;
-    const double old = T.cost[rewired];
+    const double old = T.cost(rewired);
     BfsPending<W> pd;
     pd.n = 0;
     if (cta.tid() == 0)
@@ -1431,7 +1550,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                             for (;;)
                             {
                                 ChlRow<W> row;
-                                int cnt = bfs_expand<W>(T, node, true, pd, new_cost, old, row);
+                                int cnt = bfs_expand<W>(T, node, true, pd, new_cost, old, row, rewired);
                                 if (tail + (uint32_t)cnt > cap)
                                 {
                                     ovf = 1;
@@ -1443,7 +1562,6 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                                     if (i < cnt)
                                     {
                                         arena[tail + i] = row.v[i];
-                                        pd.v[i] = row.v[i];
                                     }
                                 }
                                 pd.n = cnt;
@@ -1476,7 +1594,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                     bool active = (uint32_t)cta.lane() < n;
                     uint32_t node = active ? cl[cta.lane()] : 0u;
                     ChlRow<W> row;
-                    int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row);
+                    int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row, rewired);
                     uint32_t total = 0;
                     uint32_t off = cta.warp_scan_small((uint32_t)cnt, W, &total);
                     if (tail + total > cap)
@@ -1492,7 +1610,6 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                             uint32_t child = row.v[i];
                             arena[tail + off + i] = child;
                             if (off + i < kLevelCap) nl[off + i] = child;
-                            pd.v[i] = child;
                         }
                     }
                     pd.n = cnt;
@@ -1530,7 +1647,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                 uint32_t node = 0u;
                 if (active) node = idx < kLevelCap ? cl[idx] : arena[start + idx];
                 ChlRow<W> row;
-                int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row);
+                int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row, rewired);
                 uint32_t total = 0;
                 uint32_t off = cta.scan_exclusive((uint32_t)cnt, &total, S.scan);
                 if (tail + produced + total > cap)
@@ -1547,7 +1664,6 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                         uint32_t at = produced + off + i;
                         arena[tail + at] = child;
                         if (at < kLevelCap) nl[at] = child;
-                        pd.v[i] = child;
                     }
                 }
                 pd.n = cnt;
@@ -1574,7 +1690,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
         P.query[q].prof_cycles[0] += (uint64_t)(S.lv_tail - lo);
         P.query[q].stat[5] += (uint64_t)(S.lv_tail - lo - 1);
         bool overflow = S.lv_overflow != 0;
-        if (!overflow) T.cost[rewired] = new_cost;
+        if (!overflow) T.set_cost(rewired, new_cost);
         S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;
         S.bfs_valid = 1;
     }
@@ -1612,9 +1728,12 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
         uint32_t e = g.row_ptr[u] + j;
         if (e >= g.row_ptr[u + 1]) continue;
         uint32_t y = g.col[e];
-        if (T.parent[y] == IMOMD_NONE || y == T.parent[u]) continue;
-        double nc = T.cost[u] + g.w[e];
-        if (T.cost[y] > nc && idx < key) key = idx;
+        double w = g.w[e];
+        THead hu = T.head(u);
+        THead hy = T.head(y);
+        if (hy.parent == IMOMD_NONE || y == hu.parent) continue;
+        double nc = hu.cost + w;
+        if (hy.cost > nc && idx < key) key = idx;
     }
     key = cta.reduce_min_u32(key, S.scan);
     if (cta.tid() == 0)
@@ -1644,8 +1763,8 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
         uint32_t root = Q->dest[i];
         Q->view_id[i] = i;
         Q->view_root[i] = root;
-        T.parent[root] = root;
-        T.cost[root] = 0.0;
+        T.set_parent(root, root);
+        T.set_cost(root, 0.0);
         Q->tree_size[i] = 1;
         Q->ds_parent[i] = i;
         // erase(root) is a no-op and no holder equals the root yet; neighbours:
@@ -1653,7 +1772,7 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
         for (uint32_t e = e0; e < e1; ++e)
         {
             uint32_t y = g.col[e];
-            if (T.parent[y] != IMOMD_NONE) continue;
+            if (T.parent(y) != IMOMD_NONE) continue;
             if (!fr_insert(P, Q, T, i, y)) return;
             for (int o = 0; o < K; ++o)
             {
@@ -1675,9 +1794,27 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
 // The per-query driver: the loop every CTA runs (device) / the host simulation runs.
 template <class Cta>
 IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
-                               double* lb, uint32_t* lvl)
+                               double* lb, uint32_t* lvl, double* mat)
 {
     QueryDev* Q = P.query + q;
+    const int KK = P.K * P.K;
+    if (cta.tid() == 0)
+    {
+        S.mP = mat;
+        S.mD = mat + KK;
+        S.mMHv = mat + 2 * KK;
+        S.mMHi = reinterpret_cast<uint32_t*>(mat + 3 * KK);
+        S.mCN = S.mMHi + KK;
+    }
+    cta.sync();
+    for (int i = cta.tid(); i < KK; i += cta.nt())
+    {
+        S.mP[i] = Q->P[i];
+        S.mD[i] = Q->D[i];
+        S.mMHv[i] = Q->MHv[i];
+        S.mMHi[i] = Q->MHi[i];
+        S.mCN[i] = Q->CN[i];
+    }
     if (cta.tid() == 0)
     {
         S.phase = PH_NEXT_TREE;
@@ -1723,6 +1860,14 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
             Q->prof_cycles[req & 7] += (uint64_t)(cta.clock() - t1);
             Q->prof_count[req & 7] += 1;
         }
+    }
+    for (int i = cta.tid(); i < KK; i += cta.nt())
+    {
+        Q->P[i] = S.mP[i];
+        Q->D[i] = S.mD[i];
+        Q->MHv[i] = S.mMHv[i];
+        Q->MHi[i] = S.mMHi[i];
+        Q->CN[i] = S.mCN[i];
     }
     if (cta.tid() == 0)
     {

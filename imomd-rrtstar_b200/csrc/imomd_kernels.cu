@@ -239,10 +239,11 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_expand(PlannerDev P, i
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
     uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + (size_t)P.g.G * P.g.G);
+    double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
     CtaDev cta;
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
-        run_query(cta, P, q, iters, S, lb, lvl);
+        run_query(cta, P, q, iters, S, lb, lvl, mat);
         __syncthreads();
     }
 }
@@ -291,8 +292,8 @@ k_nearest(PlannerDev P, int n, const imomd_nn_query* __restrict__ qs, uint32_t* 
     }
 }
 
-__global__ void k_walk(const uint32_t* __restrict__ parent, uint32_t vertex, uint32_t root,
-                       uint32_t* out, uint32_t cap, uint32_t* len)
+__global__ void k_walk(const unsigned char* __restrict__ trec, uint32_t stride, uint32_t vertex,
+                       uint32_t root, uint32_t* out, uint32_t cap, uint32_t* len)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t n = 0;
@@ -301,7 +302,7 @@ __global__ void k_walk(const uint32_t* __restrict__ parent, uint32_t vertex, uin
     ++n;
     while (v != root && v != IMOMD_NONE)
     {
-        v = parent[v];
+        v = *reinterpret_cast<const uint32_t*>(trec + (size_t)v * stride);
         if (n < cap) out[n] = v;
         ++n;
         if (n > 0x7FFFFFF0u) break;
@@ -411,10 +412,9 @@ int planner_fill_initial(imomd_planner* p)
     const size_t qk = (size_t)d.Q * d.K;
     const size_t n = d.g.n;
     const size_t cells = (size_t)d.g.G * d.g.G;
-    CU(cudaMemsetAsync(d.parent, 0xFF, qk * n * sizeof(uint32_t), p->stream));
-    CU(cudaMemsetAsync(d.cost, 0, qk * n * sizeof(double), p->stream));
-    CU(cudaMemsetAsync(d.fslot, 0xFF, qk * n * sizeof(uint32_t), p->stream));
-    CU(cudaMemsetAsync(d.chl, 0xFF, qk * n * d.g.width * sizeof(uint32_t), p->stream));
+    // all-ones = not visited / not in the frontier / no children (the cost field is written
+    // before it is ever read)
+    CU(cudaMemsetAsync(d.trec, 0xFF, qk * n * d.trec_stride, p->stream));
     CU(cudaMemsetAsync(d.cell_cnt, 0, qk * cells * sizeof(uint32_t), p->stream));
     CU(cudaMemsetAsync(d.cell_head, 0xFF, qk * cells * sizeof(uint32_t), p->stream));
     CU(cudaMemcpyAsync(d.query, p->init.data(), (size_t)d.Q * sizeof(QueryDev),
@@ -556,10 +556,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     CU(cudaEventCreate(&p->ev0));
     CU(cudaEventCreate(&p->ev1));
     CU(dmalloc(&d.query, (size_t)n_queries));
-    CU(dmalloc(&d.parent, qk * n));
-    CU(dmalloc(&d.cost, qk * n));
-    CU(dmalloc(&d.fslot, qk * n));
-    CU(dmalloc(&d.chl, qk * n * g->d.width));
+    d.trec_stride = 16u + 4u * (uint32_t)g->d.width;
+    CU(dmalloc(&d.trec, qk * n * d.trec_stride));
     CU(dmalloc(&d.cell_head, qk * cells));
     CU(dmalloc(&d.cell_cnt, qk * cells));
     CU(dmalloc(&d.rec, qk * chunks * IMOMD_CHUNK));
@@ -579,7 +577,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
         fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
     }
     p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
-                    2 * kLevelCap * sizeof(uint32_t);
+                    2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32;
     CU(cudaFuncSetAttribute(k_expand<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
     CU(cudaFuncSetAttribute(k_expand<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -605,10 +603,7 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaStreamSynchronize(p->stream);
     PlannerDev& d = p->d;
     cudaFree(d.query);
-    cudaFree(d.parent);
-    cudaFree(d.cost);
-    cudaFree(d.fslot);
-    cudaFree(d.chl);
+    cudaFree(d.trec);
     cudaFree(d.cell_head);
     cudaFree(d.cell_cnt);
     cudaFree(d.rec);
@@ -829,10 +824,11 @@ int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, doub
     CU(cudaStreamSynchronize(p->stream));
     size_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
-    CU(cudaMemcpy(parent, p->d.parent + qt * n, n * 4, cudaMemcpyDeviceToHost));
+    const unsigned char* base = p->d.trec + qt * n * p->d.trec_stride;
+    CU(cudaMemcpy2D(parent, 4, base, p->d.trec_stride, 4, n, cudaMemcpyDeviceToHost));
     if (cost)
     {
-        CU(cudaMemcpy(cost, p->d.cost + qt * n, n * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy2D(cost, 8, base + 8, p->d.trec_stride, 8, n, cudaMemcpyDeviceToHost));
         for (size_t v = 0; v < n; ++v)
         {
             if (parent[v] == IMOMD_NONE) cost[v] = INFINITY;
@@ -851,7 +847,8 @@ int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uin
     size_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
     std::vector<uint32_t> slot(n);
-    CU(cudaMemcpy(slot.data(), p->d.fslot + qt * n, n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy2D(slot.data(), 4, p->d.trec + qt * n * p->d.trec_stride + 4, p->d.trec_stride, 4, n,
+                    cudaMemcpyDeviceToHost));
     uint32_t c = 0;
     for (size_t v = 0; v < n; ++v)
     {
@@ -882,8 +879,8 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
     size_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
     uint32_t root = p->init[query].dest[tree];
-    k_walk<<<1, 32, 0, p->stream>>>(p->d.parent + qt * n, vertex, root, p->walk_buf + 1, cap,
-                                    p->walk_buf);
+    k_walk<<<1, 32, 0, p->stream>>>(p->d.trec + qt * n * p->d.trec_stride, p->d.trec_stride, vertex,
+                                    root, p->walk_buf + 1, cap, p->walk_buf);
     CU(cudaGetLastError());
     uint32_t l = 0;
     CU(cudaMemcpyAsync(&l, p->walk_buf, 4, cudaMemcpyDeviceToHost, p->stream));

@@ -14,8 +14,8 @@
 //   arena u32[arena_entries]                   rewire scratch (updateCost lists, frames)
 //   clist u32x2[chunks_per_tree]               chunk work list of the pruned searches
 // Per (query, tree):
-//   parent u32[N] (NONE = not visited), cost f64[N], fslot u32[N] (frontier slot)
-//   chl u32[N][width]                          child rows (NONE-terminated), container order
+//   trec[N]: {parent u32 (NONE = not visited), frontier slot u32, cost f64,
+//             child[width] u32 (NONE-terminated, container order)}  -- 32 B when width = 4
 //   cell_head u32[G*G], cell_cnt u32[G*G]      frontier hash: per-cell chunk chain
 //   rec VRec[chunks*32], chunk_next u32[chunks], free_stack u32[chunks]
 #ifndef IMOMD_LAYOUT_H
@@ -131,10 +131,10 @@ struct PlannerDev
     uint32_t log_entries;
     QueryDev* query;           // [Q]
     // per (query, tree), index qt = q*K + k
-    uint32_t* parent;          // [Q*K][n]
-    double* cost;              // [Q*K][n]
-    uint32_t* fslot;           // [Q*K][n]
-    uint32_t* chl;             // [Q*K][n*width]
+    unsigned char* trec;       // [Q*K][n] vertex records of trec_stride bytes:
+                               //   {u32 parent, u32 frontier slot, f64 cost, u32 child[width]}
+    uint32_t trec_stride;      // 16 + 4 * width
+    uint32_t pad1_;
     uint32_t* cell_head;       // [Q*K][G*G]
     uint32_t* cell_cnt;        // [Q*K][G*G]
     VRec* rec;                 // [Q*K][chunks*32]

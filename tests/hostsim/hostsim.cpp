@@ -64,13 +64,15 @@ struct HsPlanner
     std::vector<double> w, lat, lon, cosrow;
     std::vector<VRec> vrec;
     std::vector<QueryDev> query;
-    std::vector<uint32_t> parent, fslot, chl, cell_head, cell_cnt, chunk_next, free_stack, arena,
+    std::vector<unsigned char> trec;
+    std::vector<uint32_t> cell_head, cell_cnt, chunk_next, free_stack, arena,
         clist, log, words;
-    std::vector<double> cost, lbd;
+    std::vector<double> lbd;
     std::vector<VRec> rec;
     std::vector<ReportDev> reports;
     std::vector<double> lb;
     std::vector<uint32_t> lvl;
+    std::vector<double> mat;
     Shared S;
 };
 
@@ -121,10 +123,8 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->query.resize(Q);
     for (int q = 0; q < Q; ++q)
         fill_initial_header(p->query[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
-    p->parent.assign(qk * n, IMOMD_NONE);
-    p->cost.assign(qk * n, 0.0);
-    p->fslot.assign(qk * n, IMOMD_NONE);
-    p->chl.assign(qk * (size_t)n * d.g.width, IMOMD_NONE);
+    d.trec_stride = 16u + 4u * (uint32_t)d.g.width;
+    p->trec.assign(qk * (size_t)n * d.trec_stride + 16, 0xFF);
     p->cell_head.assign(qk * cells, IMOMD_NONE);
     p->cell_cnt.assign(qk * cells, 0);
     p->rec.resize(qk * chunks * IMOMD_CHUNK);
@@ -137,11 +137,9 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->reports.resize(Q);
     p->lb.resize(cells);
     p->lvl.resize(2 * kLevelCap);
+    p->mat.resize((size_t)K * K * 4);
     d.query = p->query.data();
-    d.parent = p->parent.data();
-    d.cost = p->cost.data();
-    d.fslot = p->fslot.data();
-    d.chl = p->chl.data();
+    d.trec = reinterpret_cast<unsigned char*>(((uintptr_t)p->trec.data() + 15) & ~(uintptr_t)15);
     d.cell_head = p->cell_head.data();
     d.cell_cnt = p->cell_cnt.data();
     d.rec = p->rec.data();
@@ -179,18 +177,19 @@ void hs_expand(void* hp, int iters, ReportDev* reports)
 {
     HsPlanner* p = (HsPlanner*)hp;
     CtaHost cta;
-    for (int q = 0; q < p->d.Q; ++q) run_query(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data());
+    for (int q = 0; q < p->d.Q; ++q) run_query(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data());
     if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
 }
 
 void hs_get_tree(void* hp, int q, int k, uint32_t* parent, double* cost)
 {
     HsPlanner* p = (HsPlanner*)hp;
-    size_t n = p->d.g.n, qt = (size_t)q * p->d.K + k;
+    size_t n = p->d.g.n;
+    TreeRef T = tree_ref(p->d, q, k);
     for (size_t v = 0; v < n; ++v)
     {
-        parent[v] = p->parent[qt * n + v];
-        cost[v] = parent[v] == IMOMD_NONE ? INFINITY : p->cost[qt * n + v];
+        parent[v] = T.parent((uint32_t)v);
+        cost[v] = parent[v] == IMOMD_NONE ? INFINITY : T.cost((uint32_t)v);
     }
 }
 
@@ -220,10 +219,11 @@ void hs_get_state(void* hp, int q, double* D, uint32_t* cn, double* prob, uint32
 uint32_t hs_get_frontier(void* hp, int q, int k, uint32_t* out)
 {
     HsPlanner* p = (HsPlanner*)hp;
-    size_t n = p->d.g.n, qt = (size_t)q * p->d.K + k;
+    size_t n = p->d.g.n;
+    TreeRef T = tree_ref(p->d, q, k);
     uint32_t c = 0;
     for (size_t v = 0; v < n; ++v)
-        if (p->fslot[qt * n + v] != IMOMD_NONE) out[c++] = (uint32_t)v;
+        if (T.fslot((uint32_t)v) != IMOMD_NONE) out[c++] = (uint32_t)v;
     return c;
 }
 
@@ -248,8 +248,8 @@ int hs_check_hash(void* hp, int q, int k)
             {
                 const VRec& r = T.rec[(size_t)chunk * IMOMD_CHUNK + i];
                 if (r.cell != c) return 2;
-                if (T.fslot[r.id] != chunk * IMOMD_CHUNK + i) return 3;
-                if (T.parent[r.id] != IMOMD_NONE) return 4;
+                if (T.fslot(r.id) != chunk * IMOMD_CHUNK + i) return 3;
+                if (T.parent(r.id) != IMOMD_NONE) return 4;
             }
             left -= nrec;
             total += nrec;
