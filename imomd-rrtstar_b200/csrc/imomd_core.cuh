@@ -118,6 +118,28 @@ IMOMD_HD inline double cell_lower_a(const GraphDev& g, uint32_t c, double qlat, 
     return a * (1.0 - kPruneSlack);
 }
 
+// Upper bound of haversine `a` between (qlat, qlon) and any point of hash cell c (the far
+// corner of the padded cell rectangle with the largest cos(lat) of the row).
+IMOMD_HD inline double cell_upper_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
+                                    double cos_qlat)
+{
+    if (!g.prune) return 1.0;
+    int row = (int)(c / (uint32_t)g.G), colm = (int)(c % (uint32_t)g.G);
+    double lo = g.lat0 + row * g.hlat - kCellPadDeg;
+    double hi = g.lat0 + (row + 1) * g.hlat + kCellPadDeg;
+    double d1 = fabs(qlat - lo), d2 = fabs(qlat - hi);
+    double dphi = d1 > d2 ? d1 : d2;
+    double lo2 = g.lon0 + colm * g.hlon - kCellPadDeg;
+    double hi2 = g.lon0 + (colm + 1) * g.hlon + kCellPadDeg;
+    double e1 = fabs(qlon - lo2), e2 = fabs(qlon - hi2);
+    double dlam = e1 > e2 ? e1 : e2;
+    double s1 = sin(dphi * kDeg2Rad / 2);
+    double s2 = sin(dlam * kDeg2Rad / 2);
+    double a = s1 * s1 + cos_qlat * g.cosrow[g.G + row] * (s2 * s2);
+    a *= (1.0 + kPruneSlack);
+    return a > 1.0 ? 1.0 : a;
+}
+
 // unit vector + hash cell of one vertex (graph upload)
 IMOMD_HD inline VRec make_vrec(uint32_t v, double lat, double lon, int G, double lat0, double lon0,
                                double hlat, double hlon)
@@ -150,6 +172,18 @@ IMOMD_HD inline double lbd_entry(const PlannerDev& P, size_t i)
     return dist_of_a(a) * (1.0 - kPruneSlack);
 }
 
+IMOMD_HD inline double ubd_entry(const PlannerDev& P, size_t i)
+{
+    uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
+    uint32_t c = (uint32_t)(i % cells);
+    int t = (int)((i / cells) % P.K);
+    int q = (int)(i / ((size_t)cells * P.K));
+    uint32_t root = P.query[q].dest[t];
+    double rlat = P.g.lat[root], rlon = P.g.lon[root];
+    double a = cell_upper_a(P.g, c, rlat, rlon, cos(rlat * kDeg2Rad));
+    return dist_of_a(a) * (1.0 + kPruneSlack);
+}
+
 // --------------------------------------------------------- per-tree views ---
 
 // One record per (tree, vertex): {parent, frontier slot, cost} in the first 16 bytes (one
@@ -172,6 +206,7 @@ struct TreeRef
     uint32_t stride;          // bytes per vertex record: 16 + 4 * width
     uint32_t* cell_head;
     uint32_t* cell_cnt;
+    uint32_t* occ;        // [cells] occupied cells, then [cells] cell -> position
     VRec* rec;
     uint32_t* chunk_next;
     uint32_t* free_stack;
@@ -211,6 +246,7 @@ IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
     t.base = P.trec + qt * (size_t)P.g.n * P.trec_stride;
     t.cell_head = P.cell_head + qt * cells;
     t.cell_cnt = P.cell_cnt + qt * cells;
+    t.occ = P.occ + qt * 2 * cells;
     t.rec = P.rec + qt * (size_t)P.chunks * IMOMD_CHUNK;
     t.chunk_next = P.chunk_next + qt * P.chunks;
     t.free_stack = P.free_stack + qt * P.chunks;
@@ -340,6 +376,12 @@ IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& 
         head = T.free_stack[--Q->free_top[k]];
         T.chunk_next[head] = cnt ? T.cell_head[c] : IMOMD_NONE;
         T.cell_head[c] = head;
+        if (cnt == 0)
+        {
+            uint32_t pos = Q->n_occ[k]++;
+            T.occ[pos] = c;
+            T.occ[(size_t)P.g.G * P.g.G + c] = pos;
+        }
     }
     else
     {
@@ -376,6 +418,14 @@ IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T
     {
         T.cell_head[c] = T.chunk_next[head];
         T.free_stack[Q->free_top[k]++] = head;
+        if (cnt == 1)
+        {
+            size_t cells = (size_t)P.g.G * P.g.G;
+            uint32_t pos = T.occ[cells + c];
+            uint32_t last = T.occ[--Q->n_occ[k]];
+            T.occ[pos] = last;
+            T.occ[cells + last] = pos;
+        }
     }
 }
 
@@ -1241,63 +1291,93 @@ IMOMD_HD inline void list_cell(Cta& cta, const TreeRef& T, uint32_t* clist, uint
 }
 
 // Pruned arg-min over the frontier hash of one tree.
-//   lower(c)  conservative lower bound of the objective over cell c
-//   eval(r)   objective of a frontier record
-//   bound(m)  largest lower bound a cell may have and still matter once the best
-//             value so far is m
-// Returns the same Best on every thread.  `lb` holds G*G doubles.
-template <class Cta, class Lower, class Eval, class Bound>
+//   lower(c) / upper(c)  conservative bounds of the objective over cell c
+//   eval(r)              objective of a frontier record
+//   bound(m)             largest lower bound a cell may have and still matter when the
+//                        minimum is known to be at most m
+// The smallest upper bound over the occupied cells caps the minimum, every occupied cell
+// whose lower bound does not exceed that cap is listed, its 32-record chunks are ranked one
+// record per thread.  Returns the same Best on every thread.  `lb` holds G*G doubles.
+template <class Cta, class Lower, class Upper, class Eval, class Bound>
 IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef& T, Shared& S,
-                                   double* lb, uint32_t* clist, Lower lower, Eval eval,
-                                   Bound bound)
+                                   uint32_t n_occ, double* lb, uint32_t* clist, Lower lower,
+                                   Upper upper, Eval eval, Bound bound)
 {
-    uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
-    // 1. lower bounds of the occupied cells; the most promising cell
-    Best star = best_empty();
-    uint32_t occupied = 0;
-    for (uint32_t c = cta.tid(); c < cells; c += cta.nt())
+    if (n_occ == 0) return best_empty();
+    double mub = INFINITY;
+    for (uint32_t i = cta.tid(); i < n_occ; i += cta.nt())
     {
-        double v = INFINITY;
-        if (T.cell_cnt[c] != 0)
-        {
-            v = lower(c);
-            best_add(star, v, c);
-            ++occupied;
-        }
-        lb[c] = v;
+        uint32_t c = T.occ[i];
+        lb[i] = lower(c);
+        double u = upper(c);
+        if (u < mub) mub = u;
     }
-    if (occupied) cta.counter_add(&S.n_cells, occupied);
-    star = cta.reduce(star, S.red);
-    if (star.id1 == IMOMD_NONE) return best_empty();   // empty frontier
-    // 2. its records give the first upper bound
     if (cta.tid() == 0)
     {
         S.n_list = 0;
-        list_cell(cta, T, clist, &S.n_list, star.id1, T.cell_cnt[star.id1]);
+        S.n_cells += n_occ;
     }
-    cta.sync();
-    uint32_t n0 = S.n_list;
-    Best b0 = scan_list(cta, T, clist, 0u, n0, eval);
-    b0 = cta.reduce(b0, S.red);
-    double limit = bound(b0.v1);
-    // 3. every other occupied cell whose bound does not exceed it
-    for (uint32_t c = cta.tid(); c < cells; c += cta.nt())
+    mub = cta.reduce_min_f64(mub, S.red);   // (barriers inside order the writes above)
+    const double limit = bound(mub);
+    for (uint32_t i = cta.tid(); i < n_occ; i += cta.nt())
     {
-        if (c != star.id1 && lb[c] <= limit) list_cell(cta, T, clist, &S.n_list, c, T.cell_cnt[c]);
+        if (lb[i] <= limit)
+        {
+            uint32_t c = T.occ[i];
+            list_cell(cta, T, clist, &S.n_list, c, T.cell_cnt[c]);
+        }
     }
     cta.sync();
-    uint32_t n1 = S.n_list;
-    Best b1 = scan_list(cta, T, clist, n0, n1, eval);
-    if (cta.tid() == 0) b1 = best_merge(b1, b0);
-    b1 = cta.reduce(b1, S.red);
-    return b1;
+    Best b = scan_list(cta, T, clist, 0u, S.n_list, eval);
+    return cta.reduce(b, S.red);
+}
+
+// Helper-thread prefetch.  The serial bookkeeping that follows a nearest search touches
+// lines nobody has looked at yet (records of unvisited neighbours, their hash cells, the
+// chunk that gives up its last record): one dependent DRAM round trip each when thread 0
+// meets them alone.  Here the idle threads of the CTA fetch those lines in parallel --
+// one thread per neighbour -- so the serial code finds them in L1/L2.  Purely a latency
+// optimisation: nothing is written, results are discarded.
+template <class Cta>
+IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef& T, int q, int k,
+                                    uint32_t x, Shared& S)
+{
+    const GraphDev& g = P.g;
+    if (x == IMOMD_NONE || cta.nt() < 64) return;
+    const uint32_t e0 = g.row_ptr[x], e1 = g.row_ptr[x + 1];
+    uint32_t acc = 0;
+    const uint32_t t = (uint32_t)cta.tid();
+    if (t < e1 - e0)
+    {
+        uint32_t y = g.col[e0 + t];
+        double w = g.w[e0 + t];
+        THead h = T.head(y);
+        acc += T.chl(y)[0] + h.parent + (w > 0.0 ? 1u : 0u);
+        VRec v = g.vrec[y];
+        acc += T.cell_cnt[v.cell] + T.cell_head[v.cell];
+        acc += g.row_ptr[y] + g.row_ptr[y + 1];
+    }
+    else if (t == 32)
+    {
+        THead h = T.head(x);
+        uint32_t c = g.vrec[x].cell;
+        uint32_t cnt = T.cell_cnt[c], hd = T.cell_head[c];
+        if (cnt != 0 && hd != IMOMD_NONE) acc += T.rec[(size_t)hd * IMOMD_CHUNK + (cnt - 1) % IMOMD_CHUNK].id;
+        acc += h.fslot + T.chl(x)[0];
+    }
+    else if (t == 33)
+    {
+        uint32_t ft = P.query[q].free_top[k];
+        if (ft >= 2) acc += T.free_stack[ft - 1] + T.free_stack[ft - 2];
+    }
+    if (acc == 0x9E3779B9u) S.scan[39] = acc;   // keeps the loads alive, practically never taken
 }
 
 // steerNewNode_ arg-min (src/imomd_rrt_star.cpp:406-418) for the sample in S.
 template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
                                  double* lb, uint32_t* clist, int64_t* near_ties,
-                                 int64_t* unresolved_ties)
+                                 int64_t* unresolved_ties, bool warm)
 {
     const GraphDev& g = P.g;
     TreeRef T = tree_ref(P, q, k);
@@ -1306,6 +1386,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     double co = cos(qlon * kDeg2Rad), so = sin(qlon * kDeg2Rad);
     double qx = cl * co, qy = cl * so, qz = sl;
     auto lower = [&](uint32_t c) { return 4.0 * cell_lower_a(g, c, qlat, qlon, cl); };
+    auto upper = [&](uint32_t c) { return 4.0 * cell_upper_a(g, c, qlat, qlon, cl); };
     auto eval = [&](const VRec& r) {
         double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
         return dx * dx + dy * dy + dz * dz;
@@ -1319,7 +1400,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         S.n_recs = 0;
     }
     cta.sync();
-    Best b = pruned_argmin(cta, P, T, S, lb, clist, lower, eval, bound);
+    Best b = pruned_argmin(cta, P, T, S, P.query[q].n_occ[k], lb, clist, lower, upper, eval, bound);
     int ambiguous = (b.id1 != IMOMD_NONE) && (b.v2 - b.v1 <= band(b.v1));
     if (ambiguous)
     {
@@ -1340,6 +1421,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
             if (e.v2 - e.v1 <= kTieRel * e.v1) *unresolved_ties += 1;
         }
     }
+    if (warm) warm_expansion(cta, P, T, q, k, b.id1, S);
     if (cta.tid() == 0)
     {
         S.result = b;
@@ -1362,6 +1444,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
     uint32_t cells = (uint32_t)g.G * (uint32_t)g.G;
     uint32_t* clist = P.clist + (size_t)q * 2 * P.chunks;
     const double* lbd = P.lbd + (size_t)q * K * cells;
+    const double* ubd = P.ubd + (size_t)q * K * cells;
     uint32_t rk = Q->view_root[k];
     double klat = g.lat[rk], klon = g.lon[rk];
     int n = S.n_rescan;
@@ -1372,7 +1455,10 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
         double olat = g.lat[ro], olon = g.lon[ro];
         const double* lk = lbd + (size_t)k * cells;
         const double* lo = lbd + (size_t)o * cells;
+        const double* uk = ubd + (size_t)k * cells;
+        const double* uo = ubd + (size_t)o * cells;
         auto lower = [&](uint32_t c) { return lk[c] + lo[c]; };
+        auto upper = [&](uint32_t c) { return uk[c] + uo[c]; };
         auto eval = [&](const VRec& r) {
             double vlat = g.lat[r.id], vlon = g.lon[r.id];
             return haversine(vlat, vlon, klat, klon) + haversine(vlat, vlon, olat, olon);
@@ -1384,7 +1470,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
             S.n_recs = 0;
         }
         cta.sync();
-        Best b = pruned_argmin(cta, P, T, S, lb, clist, lower, eval, bound);
+        Best b = pruned_argmin(cta, P, T, S, Q->n_occ[k], lb, clist, lower, upper, eval, bound);
         if (cta.tid() == 0)
         {
             Q->stat[0] += S.n_cells;
@@ -1847,7 +1933,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         if (req == REQ_NN)
         {
             svc_nearest(cta, P, q, k, S, lb, P.clist + (size_t)q * 2 * P.chunks, &Q->near_ties,
-                        &Q->unresolved_ties);
+                        &Q->unresolved_ties, true);
         }
         else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
         else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);

@@ -151,6 +151,26 @@ struct CtaDev
         __syncthreads();
         return v;
     }
+    __device__ __forceinline__ double reduce_min_f64(double v, Best* red) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_down_sync(full, v, off));
+        if (lane == 0) red[warp].v1 = v;
+        __syncthreads();
+        if (warp == 0)
+        {
+            v = lane < nw ? red[lane].v1 : INFINITY;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_down_sync(full, v, off));
+            if (lane == 0) red[0].v2 = v;
+        }
+        __syncthreads();
+        v = red[0].v2;
+        __syncthreads();
+        return v;
+    }
     // block-wide merge; every thread gets the result.  Warp shuffles, then one slot
     // per warp in shared memory.
     __device__ __forceinline__ Best reduce(Best b, Best* red) const
@@ -207,6 +227,7 @@ __global__ void k_lower_bounds(PlannerDev P)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     P.lbd[i] = lbd_entry(P, i);
+    P.ubd[i] = ubd_entry(P, i);
 }
 
 __global__ void k_init_trees(PlannerDev P)
@@ -273,7 +294,7 @@ k_nearest(PlannerDev P, int n, const imomd_nn_query* __restrict__ qs, uint32_t* 
             S.qlon = nq.lon;
         }
         __syncthreads();
-        svc_nearest(cta, P, nq.query, nq.tree, S, lb, clist, &near_ties, &unresolved);
+        svc_nearest(cta, P, nq.query, nq.tree, S, lb, clist, &near_ties, &unresolved, false);
         __syncthreads();
         if (threadIdx.x == 0)
         {
@@ -468,13 +489,13 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     CU(dmalloc(&g->lat, n));
     CU(dmalloc(&g->lon, n));
     CU(dmalloc(&g->vrec, n));
-    CU(dmalloc(&g->cosrow, G));
+    CU(dmalloc(&g->cosrow, 2 * (size_t)G));
     CU(cudaMemcpy(g->row_ptr, row_ptr, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->col, col, (size_t)arcs * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->w, w, (size_t)arcs * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->lat, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->lon, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->cosrow, cosrow.data(), G * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->cosrow, cosrow.data(), 2 * (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
     d.row_ptr = g->row_ptr;
     d.col = g->col;
     d.w = g->w;
@@ -564,6 +585,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     CU(dmalloc(&d.chunk_next, qk * chunks));
     CU(dmalloc(&d.free_stack, qk * chunks));
     CU(dmalloc(&d.lbd, qk * cells));
+    CU(dmalloc(&d.ubd, qk * cells));
+    CU(dmalloc(&d.occ, qk * 2 * cells));
     CU(dmalloc(&d.arena, (size_t)n_queries * d.arena_entries));
     CU(dmalloc(&d.clist, (size_t)n_queries * 2 * chunks));
     CU(dmalloc(&d.log, (size_t)n_queries * 2 * d.log_entries));
@@ -610,6 +633,8 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(d.chunk_next);
     cudaFree(d.free_stack);
     cudaFree(d.lbd);
+    cudaFree(d.ubd);
+    cudaFree(d.occ);
     cudaFree(d.arena);
     cudaFree(d.clist);
     cudaFree(d.log);

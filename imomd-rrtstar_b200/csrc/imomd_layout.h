@@ -17,6 +17,7 @@
 //   trec[N]: {parent u32 (NONE = not visited), frontier slot u32, cost f64,
 //             child[width] u32 (NONE-terminated, container order)}  -- 32 B when width = 4
 //   cell_head u32[G*G], cell_cnt u32[G*G]      frontier hash: per-cell chunk chain
+//   occ u32[2*G*G]                             occupied cells (list + inverse)
 //   rec VRec[chunks*32], chunk_next u32[chunks], free_stack u32[chunks]
 #ifndef IMOMD_LAYOUT_H
 #define IMOMD_LAYOUT_H
@@ -57,7 +58,8 @@ struct GraphDev
     int32_t pad_;
     double lat0, lon0;    // south-west corner of the hash (degrees)
     double hlat, hlon;    // cell size (degrees)
-    const double* cosrow; // [G] min cos(lat) over the padded latitude span of a cell row
+    const double* cosrow; // [2G]: min cos(lat) over the padded latitude span of each cell row,
+                          //       then the max over the same span
 };
 
 // K x K matrices are stored with stride K.
@@ -74,6 +76,7 @@ struct QueryDev
     int32_t ds_parent[IMOMD_KMAX];
     uint32_t frontier_count[IMOMD_KMAX];
     uint32_t free_top[IMOMD_KMAX];        // free chunks left on the tree's stack
+    uint32_t n_occ[IMOMD_KMAX];           // occupied cells of the tree's frontier hash
     uint64_t tree_size[IMOMD_KMAX];       // parent.size()
     double P[IMOMD_KMAX * IMOMD_KMAX];    // probability_matrix_
     double D[IMOMD_KMAX * IMOMD_KMAX];    // distance_matrix_
@@ -137,11 +140,13 @@ struct PlannerDev
     uint32_t pad1_;
     uint32_t* cell_head;       // [Q*K][G*G]
     uint32_t* cell_cnt;        // [Q*K][G*G]
+    uint32_t* occ;             // [Q*K][2*G*G] list of occupied cells, then cell -> list position
     VRec* rec;                 // [Q*K][chunks*32]
     uint32_t* chunk_next;      // [Q*K][chunks]
     uint32_t* free_stack;      // [Q*K][chunks]
     // per query
-    double* lbd;               // [Q][K][G*G]
+    double* lbd;               // [Q][K][G*G] lower bound root -> cell (metres)
+    double* ubd;               // [Q][K][G*G] upper bound root -> cell (metres)
     uint32_t* arena;           // [Q][arena_entries]
     uint32_t* clist;           // [Q][2*chunks]   (chunk id, valid count)
     uint32_t* log;             // [Q][2*log_entries] (set idx, vertex)

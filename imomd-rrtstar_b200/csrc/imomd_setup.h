@@ -108,12 +108,14 @@ inline void setup_grid(GraphDev& d, uint32_t n, const double* lat, const double*
     // the cell bound needs |lat| < 90 and longitude differences below 180 degrees
     d.prune = (lat_min > -89.0 && lat_max < 89.0 && span_lon < 170.0) ? 1 : 0;
     const double d2r = 3.14159265358979323846 / 180;
-    cosrow->resize(G);
+    cosrow->resize(2 * (size_t)G);
     for (int r = 0; r < G; ++r)
     {
         double lo = (d.lat0 + r * d.hlat - 1e-9) * d2r;
         double hi = (d.lat0 + (r + 1) * d.hlat + 1e-9) * d2r;
         (*cosrow)[r] = std::max(0.0, std::min(std::cos(lo), std::cos(hi)) * (1.0 - 1e-12));
+        double mx = (lo <= 0.0 && hi >= 0.0) ? 1.0 : std::max(std::cos(lo), std::cos(hi));
+        (*cosrow)[G + r] = std::min(1.0, mx * (1.0 + 1e-12));
     }
 }
 

@@ -49,6 +49,7 @@ struct CtaHost
         return old;
     }
     Best reduce(Best b, Best*) const { return b; }
+    double reduce_min_f64(double v, Best*) const { return v; }
     uint32_t scan_exclusive(uint32_t v, uint32_t* total, uint32_t*) const
     {
         *total = v;
@@ -67,7 +68,8 @@ struct HsPlanner
     std::vector<unsigned char> trec;
     std::vector<uint32_t> cell_head, cell_cnt, chunk_next, free_stack, arena,
         clist, log, words;
-    std::vector<double> lbd;
+    std::vector<double> lbd, ubd;
+    std::vector<uint32_t> occ;
     std::vector<VRec> rec;
     std::vector<ReportDev> reports;
     std::vector<double> lb;
@@ -131,6 +133,8 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->chunk_next.assign(qk * chunks, IMOMD_NONE);
     p->free_stack.resize(qk * chunks);
     p->lbd.resize(qk * cells);
+    p->ubd.resize(qk * cells);
+    p->occ.assign(qk * 2 * cells, 0);
     p->arena.resize((size_t)Q * d.arena_entries);
     p->clist.resize((size_t)Q * 2 * chunks);
     p->log.resize((size_t)Q * 2 * d.log_entries);
@@ -146,6 +150,8 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     d.chunk_next = p->chunk_next.data();
     d.free_stack = p->free_stack.data();
     d.lbd = p->lbd.data();
+    d.ubd = p->ubd.data();
+    d.occ = p->occ.data();
     d.arena = p->arena.data();
     d.clist = p->clist.data();
     d.log = p->log.data();
@@ -157,7 +163,11 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
         for (int k = 0; k < K; ++k) p->query[q].free_top[k] = (uint32_t)chunks;
         construct_trees(d, q);
     }
-    for (size_t i = 0; i < qk * cells; ++i) p->lbd[i] = lbd_entry(d, i);
+    for (size_t i = 0; i < qk * cells; ++i)
+    {
+        p->lbd[i] = lbd_entry(d, i);
+        p->ubd[i] = ubd_entry(d, i);
+    }
     return p;
 }
 
@@ -269,7 +279,7 @@ void hs_nearest(void* hp, int q, int k, double lat, double lon, uint32_t* idx, d
     p->S.qlat = lat;
     p->S.qlon = lon;
     svc_nearest(cta, p->d, q, k, p->S, p->lb.data(), p->clist.data() + (size_t)q * 2 * p->d.chunks,
-                &stats[0], &stats[1]);
+                &stats[0], &stats[1], false);
     uint32_t v = p->S.result.id1;
     *idx = v;
     *dist = v == IMOMD_NONE ? INFINITY : haversine(p->lat[v], p->lon[v], lat, lon);
