@@ -328,6 +328,7 @@ struct Shared
     // connection gather: the other trees' (parent, cost) at conn_x (REQ_CONN / REQ_BFS)
     uint32_t conn_x;
     int32_t conn_pending;
+    double conn_cx;        // cost of conn_x in the tree being expanded
     uint32_t conn_par[IMOMD_KMAX];
     double conn_cost[IMOMD_KMAX];
     // jump-point search in flight
@@ -343,6 +344,8 @@ struct Shared
     // speculative no-op check of the next rewire calls
     uint32_t chk_hi, chk_lo, chk_skip;
     uint32_t chk_noop, chk_slot;
+    uint32_t chk_u, chk_e, chk_e1, chk_y, chk_py;   // the first call that re-parents
+    double chk_nc;
     int32_t chk_valid;
     // the query's K x K matrices, staged in shared memory for the duration of a launch
     double* mP;
@@ -473,6 +476,52 @@ IMOMD_HD inline void chl_store(uint32_t* rowp, const ChlRow<W>& r)
         t.w = r.v[4 * i + 3];
         dst[i] = t;
     }
+}
+
+template <int W>
+IMOMD_HD inline void chl_row_insert(ChlRow<W>& r, uint32_t x)
+{
+    int n = 0, at = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (r.v[i] != IMOMD_NONE)
+        {
+            if (r.v[i] == x) return;
+            if (at < 0 && r.v[i] % 13 == x % 13) at = i;
+            n = i + 1;
+        }
+    }
+    if (at < 0) at = 0;
+    if (n >= W) return;
+#pragma unroll
+    for (int i = W - 1; i > 0; --i)
+    {
+        if (i > at) r.v[i] = r.v[i - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (i == at) r.v[i] = x;
+    }
+}
+
+template <int W>
+IMOMD_HD inline void chl_row_erase(ChlRow<W>& r, uint32_t x)
+{
+    int at = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (r.v[i] == x) at = i;
+    }
+    if (at < 0) return;
+#pragma unroll
+    for (int i = 0; i < W - 1; ++i)
+    {
+        if (i >= at) r.v[i] = r.v[i + 1];
+    }
+    r.v[W - 1] = IMOMD_NONE;
 }
 
 template <int W>
@@ -694,10 +743,9 @@ struct Seq
     // updateConnectionTree_, src/imomd_rrt_star.cpp:645-706.  The other trees' parent
     // and cost at x were gathered into S.conn_par / S.conn_cost by the CTA
     // (svc_conn_gather); they cannot change while tree k is being expanded.
-    IMOMD_HD void apply_connection(int k, const TreeRef& T, uint32_t x)
+    IMOMD_HD void apply_connection(int k, const TreeRef& T, uint32_t x, double cx)
     {
         int K = Q->K;
-        double cx = T.cost(x);
         Q->stat[6] += 1;
         for (int o = 0; o < K; ++o)
         {
@@ -796,8 +844,10 @@ struct Seq
         if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
         T.set_parent(x_new, via);
         chl_assign_single(g, T, via, x_new);
-        T.set_cost(x_new, T.cost(via) + edge_weight(g, via, x_new));
+        double cnew = T.cost(via) + edge_weight(g, via, x_new);
+        T.set_cost(x_new, cnew);
         S.conn_x = x_new;
+        S.conn_cx = cnew;
         S.jps_next = next;
         return true;
     }
@@ -905,7 +955,9 @@ struct Seq
     // the list, almost all of which change nothing (REQ_CHECK).
     static constexpr uint32_t FR = 7;
 
-    IMOMD_HD bool push_frame(uint32_t x, uint32_t e)
+    IMOMD_HD bool push_frame(uint32_t x, uint32_t e) { return push_frame(x, e, P.g.row_ptr[x + 1]); }
+
+    IMOMD_HD bool push_frame(uint32_t x, uint32_t e, uint32_t e_end)
     {
         uint32_t top = S.rw_top;
         if (top + FR > P.arena_entries)
@@ -918,7 +970,7 @@ struct Seq
         f[0] = S.rw_fp;
         f[1] = x;
         f[2] = e;
-        f[3] = P.g.row_ptr[x + 1];
+        f[3] = e_end;
         f[4] = IMOMD_NONE;
         f[5] = IMOMD_NONE;
         f[6] = 0;
@@ -969,6 +1021,37 @@ struct Seq
         }
     }
 
+    // y leaves py's child row and joins x's (:579-581); both rows are fetched together
+    template <int W>
+    IMOMD_HD void move_child_w(const TreeRef& T, uint32_t y, uint32_t py, uint32_t x)
+    {
+        if (py == x)
+        {
+            chl_erase_w<W>(T.chl(py), y);
+            chl_insert_w<W>(T.chl(x), y);
+            return;
+        }
+        ChlRow<W> from = chl_load<W>(T.chl(py));
+        ChlRow<W> to = chl_load<W>(T.chl(x));
+        chl_row_erase<W>(from, y);
+        chl_row_insert<W>(to, y);
+        chl_store<W>(T.chl(py), from);
+        chl_store<W>(T.chl(x), to);
+    }
+
+    IMOMD_HD void reparent(const TreeRef& T, uint32_t y, uint32_t py, uint32_t x, double nc)
+    {
+        Q->stat[4] += 1;
+        if (P.g.width == 4) move_child_w<4>(T, y, py, x);
+        else if (P.g.width == 8) move_child_w<8>(T, y, py, x);
+        else move_child_w<16>(T, y, py, x);
+        T.set_parent(y, x);
+        S.bfs_node = y;
+        S.bfs_cost = nc;
+        S.bfs_lo = S.rw_top;
+        S.req = REQ_BFS;
+    }
+
     // returns true when the cascade is finished, false when a service was requested
     IMOMD_HD bool rewire_run(int k, const TreeRef& T)
     {
@@ -987,8 +1070,13 @@ struct Seq
                     f[6] -= S.chk_noop;          // calls that would have changed nothing
                     if (S.chk_slot != IMOMD_NONE)
                     {
-                        uint32_t u = arena[--f[6]];
-                        if (!push_frame(u, g.row_ptr[u] + S.chk_slot)) return true;
+                        // the examined call rewireTree_(u) re-parents y at slot chk_e: enter
+                        // its frame just behind that slot and do the re-parenting (:574-584)
+                        --f[6];
+                        uint32_t u = S.chk_u;
+                        if (!push_frame(u, S.chk_e + 1, S.chk_e1)) return true;
+                        reparent(T, S.chk_y, S.chk_py, u, S.chk_nc);
+                        return false;
                     }
                     continue;
                 }
@@ -1013,7 +1101,7 @@ struct Seq
                     Q->status = 3;
                     return true;
                 }
-                apply_connection(k, T, S.bfs_node);      // :586
+                apply_connection(k, T, S.bfs_node, S.bfs_cost);      // :586
                 f[4] = S.bfs_node;
                 f[5] = S.rw_top;
                 f[6] = S.bfs_hi;
@@ -1039,14 +1127,7 @@ struct Seq
                 continue;
             }
             f[2] = hit_e + 1;
-            Q->stat[4] += 1;
-            chl_erase(g, T, hit_py, hit_y);
-            T.set_parent(hit_y, f[1]);
-            chl_insert(g, T, f[1], hit_y);
-            S.bfs_node = hit_y;
-            S.bfs_cost = hit_nc;
-            S.bfs_lo = S.rw_top;
-            S.req = REQ_BFS;
+            reparent(T, hit_y, hit_py, f[1], hit_nc);
             return false;
         }
         return true;
@@ -1179,7 +1260,7 @@ struct Seq
                     if (S.conn_pending)
                     {
                         // the hop's updateConnectionTree_ (:446 / :456), then move on
-                        apply_connection(k, T, S.conn_x);
+                        apply_connection(k, T, S.conn_x, S.conn_cx);
                         S.conn_pending = 0;
                         S.x_new = S.jps_next;
                     }
@@ -1235,7 +1316,7 @@ struct Seq
                 }
                 case PH_LAST_CONN:
                 {
-                    apply_connection(k, T, S.x_new);         // :355
+                    apply_connection(k, T, S.x_new, T.cost(S.x_new));         // :355
                     Q->expansions += 1;
                     S.k = k + 1;
                     S.phase = PH_NEXT_TREE;
@@ -1806,6 +1887,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
     if (n > kCheckBatch) n = kCheckBatch;
     const uint32_t hi = S.chk_hi, skip = S.chk_skip;
     uint32_t key = IMOMD_NONE;
+    uint32_t my_u = 0, my_e = 0, my_e1 = 0, my_y = 0, my_py = 0;
+    double my_nc = 0.0;
     for (uint32_t idx = cta.tid(); idx < n * W; idx += cta.nt())
     {
         uint32_t i = idx / W, j = idx % W;
@@ -1819,9 +1902,28 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
         THead hy = T.head(y);
         if (hy.parent == IMOMD_NONE || y == hu.parent) continue;
         double nc = hu.cost + w;
-        if (hy.cost > nc && idx < key) key = idx;
+        if (hy.cost > nc && idx < key)
+        {
+            key = idx;
+            my_u = u;
+            my_e = e;
+            my_e1 = g.row_ptr[u + 1];
+            my_y = y;
+            my_py = hy.parent;
+            my_nc = nc;
+        }
     }
+    const uint32_t mine = key;
     key = cta.reduce_min_u32(key, S.scan);
+    if (key != IMOMD_NONE && mine == key)
+    {
+        S.chk_u = my_u;
+        S.chk_e = my_e;
+        S.chk_e1 = my_e1;
+        S.chk_y = my_y;
+        S.chk_py = my_py;
+        S.chk_nc = my_nc;
+    }
     if (cta.tid() == 0)
     {
         S.chk_noop = key == IMOMD_NONE ? n : key / W;
@@ -1938,7 +2040,24 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
         else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);
         else if (req == REQ_CONN) svc_conn_gather(cta, P, q, S.conn_x, S);
-        else if (req == REQ_BFS) svc_bfs(cta, P, q, k, S, lvl);
+        else if (req == REQ_BFS)
+        {
+            svc_bfs(cta, P, q, k, S, lvl);
+            cta.sync();
+            if (S.bfs_hi != IMOMD_NONE)
+            {
+                // the serial thread would ask for this next: examine the fresh list's calls
+                cta.sync();
+                if (cta.tid() == 0)
+                {
+                    S.chk_hi = S.bfs_hi;
+                    S.chk_lo = S.bfs_lo;
+                    S.chk_skip = S.bfs_node;
+                }
+                cta.sync();
+                svc_check(cta, P, q, k, S);
+            }
+        }
         else if (req == REQ_CHECK) svc_check(cta, P, q, k, S);
         cta.sync();
         if (cta.tid() == 0)
