@@ -74,7 +74,7 @@ enum Phase
 constexpr uint32_t kCheckBatch = 64;   // rewire calls examined per speculative check
 
 // include/osm_converter/compute_haversine.hpp:41-58, same expression order.
-IMOMD_HD inline double haversine(double lat1, double lon1, double lat2, double lon2)
+IMOMD_HD IMOMD_NOINLINE double haversine(double lat1, double lon1, double lat2, double lon2)
 {
     double lat1_rad = lat1 * kDeg2Rad;
     double lat2_rad = lat2 * kDeg2Rad;
@@ -97,7 +97,7 @@ IMOMD_HD inline double dist_of_a(double a)
 // Lower bound of haversine `a` between (qlat, qlon) and any point of hash cell c.
 // a = sin^2(dphi/2) + cos(phi_q) cos(phi_v) sin^2(dlam/2) is increasing in |dphi| and
 // |dlam| (both below pi here) and cos(phi_v) >= cosrow[row].
-IMOMD_HD inline double cell_lower_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
+IMOMD_HD IMOMD_NOINLINE double cell_lower_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
                                     double cos_qlat)
 {
     if (!g.prune) return 0.0;
@@ -120,7 +120,7 @@ IMOMD_HD inline double cell_lower_a(const GraphDev& g, uint32_t c, double qlat, 
 
 // Upper bound of haversine `a` between (qlat, qlon) and any point of hash cell c (the far
 // corner of the padded cell rectangle with the largest cos(lat) of the row).
-IMOMD_HD inline double cell_upper_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
+IMOMD_HD IMOMD_NOINLINE double cell_upper_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
                                     double cos_qlat)
 {
     if (!g.prune) return 1.0;
@@ -347,6 +347,8 @@ struct Shared
     uint32_t chk_u, chk_e, chk_e1, chk_y, chk_py;   // the first call that re-parents
     double chk_nc;
     int32_t chk_valid;
+    // hot header fields of the query (a shared-memory copy while a launch runs)
+    QueryDev* Q;
     // the query's K x K matrices, staged in shared memory for the duration of a launch
     double* mP;
     double* mD;
@@ -584,27 +586,6 @@ IMOMD_HD inline void chl_assign_single_w(uint32_t* rowp, uint32_t x)
     chl_store<W>(rowp, r);
 }
 
-IMOMD_HD inline void chl_insert(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
-{
-    if (g.width == 4) chl_insert_w<4>(T.chl(p), x);
-    else if (g.width == 8) chl_insert_w<8>(T.chl(p), x);
-    else chl_insert_w<16>(T.chl(p), x);
-}
-
-IMOMD_HD inline void chl_erase(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
-{
-    if (g.width == 4) chl_erase_w<4>(T.chl(p), x);
-    else if (g.width == 8) chl_erase_w<8>(T.chl(p), x);
-    else chl_erase_w<16>(T.chl(p), x);
-}
-
-IMOMD_HD inline void chl_assign_single(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
-{
-    if (g.width == 4) chl_assign_single_w<4>(T.chl(p), x);
-    else if (g.width == 8) chl_assign_single_w<8>(T.chl(p), x);
-    else chl_assign_single_w<16>(T.chl(p), x);
-}
-
 // (*connection_ptr_)[a][b]; the graph was validated symmetric at upload
 IMOMD_HD inline double edge_weight(const GraphDev& g, uint32_t a, uint32_t b)
 {
@@ -666,6 +647,7 @@ IMOMD_HD inline uint32_t ws_uniform_u32(WordStream& ws, uint32_t urange)
 
 // ===================================================== sequential stages =====
 
+template <int KW>
 struct Seq
 {
     const PlannerDev& P;
@@ -675,7 +657,7 @@ struct Seq
     uint32_t* arena;
 
     IMOMD_HD Seq(const PlannerDev& P_, int q_, Shared& S_)
-        : P(P_), Q(P_.query + q_), q(q_), S(S_), arena(P_.arena + (size_t)q_ * P_.arena_entries)
+        : P(P_), Q(S_.Q), q(q_), S(S_), arena(P_.arena + (size_t)q_ * P_.arena_entries)
     {
     }
 
@@ -843,7 +825,7 @@ struct Seq
         }
         if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
         T.set_parent(x_new, via);
-        chl_assign_single(g, T, via, x_new);
+        chl_assign_single_w<KW>(T.chl(via), x_new);
         double cnew = T.cost(via) + edge_weight(g, via, x_new);
         T.set_cost(x_new, cnew);
         S.conn_x = x_new;
@@ -896,16 +878,14 @@ struct Seq
         {
             if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
             T.set_parent(x_new, x_parent);
-            chl_insert(g, T, x_parent, x_new);
+            chl_insert_w<KW>(T.chl(x_parent), x_new);
             T.set_cost(x_new, min_cost);
         }
     }
 
     IMOMD_HD void connect_new_node(int k, const TreeRef& T, uint32_t x_new)
     {
-        if (P.g.width == 4) connect_new_node_w<4>(k, T, x_new);
-        else if (P.g.width == 8) connect_new_node_w<8>(k, T, x_new);
-        else connect_new_node_w<16>(k, T, x_new);
+        connect_new_node_w<KW>(k, T, x_new);
     }
 
     // neighbour part of updateExpandables, src/imomd_rrt_star.cpp:533-558 (the
@@ -941,9 +921,7 @@ struct Seq
 
     IMOMD_HD void insert_neighbours(int k, const TreeRef& T, uint32_t x_new)
     {
-        if (P.g.width == 4) insert_neighbours_w<4>(k, T, x_new);
-        else if (P.g.width == 8) insert_neighbours_w<8>(k, T, x_new);
-        else insert_neighbours_w<16>(k, T, x_new);
+        insert_neighbours_w<KW>(k, T, x_new);
     }
 
     // ---- rewireTree_, src/imomd_rrt_star.cpp:561-600 ------------------------------
@@ -1042,9 +1020,7 @@ struct Seq
     IMOMD_HD void reparent(const TreeRef& T, uint32_t y, uint32_t py, uint32_t x, double nc)
     {
         Q->stat[4] += 1;
-        if (P.g.width == 4) move_child_w<4>(T, y, py, x);
-        else if (P.g.width == 8) move_child_w<8>(T, y, py, x);
-        else move_child_w<16>(T, y, py, x);
+        move_child_w<KW>(T, y, py, x);
         T.set_parent(y, x);
         S.bfs_node = y;
         S.bfs_cost = nc;
@@ -1118,9 +1094,7 @@ struct Seq
             // together, the first one that re-parents is acted on
             uint32_t hit_e = IMOMD_NONE, hit_y = IMOMD_NONE, hit_py = IMOMD_NONE;
             double hit_nc = 0.0;
-            if (g.width == 4) scan_frame<4>(T, f, hit_e, hit_y, hit_py, hit_nc);
-            else if (g.width == 8) scan_frame<8>(T, f, hit_e, hit_y, hit_py, hit_nc);
-            else scan_frame<16>(T, f, hit_e, hit_y, hit_py, hit_nc);
+            scan_frame<KW>(T, f, hit_e, hit_y, hit_py, hit_nc);
             if (hit_e == IMOMD_NONE)
             {
                 f[2] = f[3];
@@ -1448,7 +1422,7 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
     }
     else if (t == 33)
     {
-        uint32_t ft = P.query[q].free_top[k];
+        uint32_t ft = S.Q->free_top[k];
         if (ft >= 2) acc += T.free_stack[ft - 1] + T.free_stack[ft - 2];
     }
     if (acc == 0x9E3779B9u) S.scan[39] = acc;   // keeps the loads alive, practically never taken
@@ -1481,7 +1455,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         S.n_recs = 0;
     }
     cta.sync();
-    Best b = pruned_argmin(cta, P, T, S, P.query[q].n_occ[k], lb, clist, lower, upper, eval, bound);
+    Best b = pruned_argmin(cta, P, T, S, S.Q->n_occ[k], lb, clist, lower, upper, eval, bound);
     int ambiguous = (b.id1 != IMOMD_NONE) && (b.v2 - b.v1 <= band(b.v1));
     if (ambiguous)
     {
@@ -1507,7 +1481,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     {
         S.result = b;
         S.ambiguous = ambiguous;
-        QueryDev* Qs = P.query + q;
+        QueryDev* Qs = S.Q;
         Qs->stat[0] += S.n_cells;
         Qs->stat[1] += S.n_recs;
     }
@@ -1519,7 +1493,7 @@ template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, double* lb)
 {
     const GraphDev& g = P.g;
-    QueryDev* Q = P.query + q;
+    QueryDev* Q = S.Q;
     TreeRef T = tree_ref(P, q, k);
     int K = Q->K;
     uint32_t cells = (uint32_t)g.G * (uint32_t)g.G;
@@ -1570,7 +1544,7 @@ template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
 {
     const GraphDev& g = P.g;
-    QueryDev* Q = P.query + q;
+    QueryDev* Q = S.Q;
     int K = Q->K;
     int m = S.n_ys;
     for (int i = cta.tid(); i < m * K; i += cta.nt())
@@ -1789,7 +1763,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                 }
                 if (cta.lane() == 0)
                 {
-                    P.query[q].prof_count[0] += levels;
+                    S.Q->prof_count[0] += levels;
                     S.lv_cur = cur;
                     S.lv_start = start;
                     S.lv_tail = tail;
@@ -1839,7 +1813,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
             cta.sync();
             if (cta.tid() == 0)
             {
-                P.query[q].prof_count[0] += 1;
+                S.Q->prof_count[0] += 1;
                 S.lv_cur = cur ^ 1u;
                 S.lv_start = tail;
                 S.lv_tail = tail + produced;
@@ -1854,8 +1828,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     if (cta.tid() == 0)
     {
         // statistics: [0] = subtree vertices (cycles slot) and levels... see imomd_get_profile
-        P.query[q].prof_cycles[0] += (uint64_t)(S.lv_tail - lo);
-        P.query[q].stat[5] += (uint64_t)(S.lv_tail - lo - 1);
+        S.Q->prof_cycles[0] += (uint64_t)(S.lv_tail - lo);
+        S.Q->stat[5] += (uint64_t)(S.lv_tail - lo - 1);
         bool overflow = S.lv_overflow != 0;
         if (!overflow) T.set_cost(rewired, new_cost);
         S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;
@@ -1863,26 +1837,18 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     }
 }
 
-template <class Cta>
-IMOMD_HD inline void svc_bfs(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, uint32_t* lvl)
-{
-    if (P.g.width == 4) svc_bfs_w<4>(cta, P, q, k, S, lvl);
-    else if (P.g.width == 8) svc_bfs_w<8>(cta, P, q, k, S, lvl);
-    else svc_bfs_w<16>(cta, P, q, k, S, lvl);
-}
-
 // Speculative examination of the next calls `rewireTree_(u)` of an updated_nodes list
 // (src/imomd_rrt_star.cpp:589-596): a call changes nothing unless some visited neighbour
 // y != parent[u] has cost[y] > cost[u] + w (:569-572).  All (call, adjacency slot) pairs of
 // a batch are tested at once against the current tree; the first pair that would re-parent
 // (in call order, then slot order) is reported, everything before it is skipped exactly.
-template <class Cta>
+template <int KW, class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
 {
     const GraphDev& g = P.g;
     TreeRef T = tree_ref(P, q, k);
     const uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
-    const uint32_t W = (uint32_t)g.width;
+    const uint32_t W = (uint32_t)KW;
     uint32_t n = S.chk_hi - S.chk_lo;
     if (n > kCheckBatch) n = kCheckBatch;
     const uint32_t hi = S.chk_hi, skip = S.chk_skip;
@@ -1980,14 +1946,21 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
 }
 
 // The per-query driver: the loop every CTA runs (device) / the host simulation runs.
-template <class Cta>
+template <int KW, class Cta>
 IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
-                               double* lb, uint32_t* lvl, double* mat)
+                               double* lb, uint32_t* lvl, double* mat, unsigned char* hot)
 {
-    QueryDev* Q = P.query + q;
+    QueryDev* Qg = P.query + q;
+    QueryDev* Q = reinterpret_cast<QueryDev*>(hot);
     const int KK = P.K * P.K;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Qg);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(hot);
+        for (uint32_t i = cta.tid(); i < IMOMD_QUERY_HOT_BYTES / 4; i += cta.nt()) dst[i] = src[i];
+    }
     if (cta.tid() == 0)
     {
+        S.Q = Q;
         S.mP = mat;
         S.mD = mat + KK;
         S.mMHv = mat + 2 * KK;
@@ -1997,11 +1970,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     cta.sync();
     for (int i = cta.tid(); i < KK; i += cta.nt())
     {
-        S.mP[i] = Q->P[i];
-        S.mD[i] = Q->D[i];
-        S.mMHv[i] = Q->MHv[i];
-        S.mMHi[i] = Q->MHi[i];
-        S.mCN[i] = Q->CN[i];
+        S.mP[i] = Qg->P[i];
+        S.mD[i] = Qg->D[i];
+        S.mMHv[i] = Qg->MHv[i];
+        S.mMHi[i] = Qg->MHi[i];
+        S.mCN[i] = Qg->CN[i];
     }
     if (cta.tid() == 0)
     {
@@ -2019,8 +1992,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         long long t0 = cta.clock();
         if (cta.tid() == 0)
         {
-            Seq seq(P, q, S);
+            int ph0 = S.phase & 7;
+            Seq<KW> seq(P, q, S);
             seq.step(iters);
+            Q->phase_cycles[ph0] += (uint64_t)(cta.clock() - t0);
+            Q->phase_count[ph0] += 1;
         }
         cta.sync();
         int req = S.req;
@@ -2042,7 +2018,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         else if (req == REQ_CONN) svc_conn_gather(cta, P, q, S.conn_x, S);
         else if (req == REQ_BFS)
         {
-            svc_bfs(cta, P, q, k, S, lvl);
+            svc_bfs_w<KW>(cta, P, q, k, S, lvl);
             cta.sync();
             if (S.bfs_hi != IMOMD_NONE)
             {
@@ -2055,10 +2031,10 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
                     S.chk_skip = S.bfs_node;
                 }
                 cta.sync();
-                svc_check(cta, P, q, k, S);
+                svc_check<KW>(cta, P, q, k, S);
             }
         }
-        else if (req == REQ_CHECK) svc_check(cta, P, q, k, S);
+        else if (req == REQ_CHECK) svc_check<KW>(cta, P, q, k, S);
         cta.sync();
         if (cta.tid() == 0)
         {
@@ -2068,11 +2044,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     }
     for (int i = cta.tid(); i < KK; i += cta.nt())
     {
-        Q->P[i] = S.mP[i];
-        Q->D[i] = S.mD[i];
-        Q->MHv[i] = S.mMHv[i];
-        Q->MHi[i] = S.mMHi[i];
-        Q->CN[i] = S.mCN[i];
+        Qg->P[i] = S.mP[i];
+        Qg->D[i] = S.mD[i];
+        Qg->MHv[i] = S.mMHv[i];
+        Qg->MHi[i] = S.mMHi[i];
+        Qg->CN[i] = S.mCN[i];
     }
     if (cta.tid() == 0)
     {
@@ -2100,6 +2076,13 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         R->unresolved_ties = Q->unresolved_ties;
         R->log_entries = (int64_t)Q->log_count;
     }
+    cta.sync();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(hot);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(Qg);
+        for (uint32_t i = cta.tid(); i < IMOMD_QUERY_HOT_BYTES / 4; i += cta.nt()) dst[i] = src[i];
+    }
+    cta.sync();
 }
 
 }  // namespace imomd

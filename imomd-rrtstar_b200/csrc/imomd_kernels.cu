@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -253,7 +254,7 @@ __global__ void k_init_trees(PlannerDev P)
 // 255 registers, no spills) for planners with few queries, and a throughput build (four
 // CTAs per SM) whose point is to hide each query's dependent-load latency behind the
 // other resident queries.
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, int KW>
 __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_expand(PlannerDev P, int iters)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -261,10 +262,11 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_expand(PlannerDev P, i
     double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
     uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + (size_t)P.g.G * P.g.G);
     double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
+    unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev cta;
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
-        run_query(cta, P, q, iters, S, lb, lvl, mat);
+        run_query<KW>(cta, P, q, iters, S, lb, lvl, mat, hot);
         __syncthreads();
     }
 }
@@ -290,6 +292,7 @@ k_nearest(PlannerDev P, int n, const imomd_nn_query* __restrict__ qs, uint32_t* 
         imomd_nn_query nq = qs[i];
         if (threadIdx.x == 0)
         {
+            S.Q = P.query + nq.query;
             S.qlat = nq.lat;
             S.qlon = nq.lon;
         }
@@ -600,13 +603,20 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
         fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
     }
     p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
-                    2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32;
-    CU(cudaFuncSetAttribute(k_expand<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)p->smem_bytes));
-    CU(cudaFuncSetAttribute(k_expand<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)p->smem_bytes));
-    CU(cudaFuncSetAttribute(k_expand<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)p->smem_bytes));
+                    2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32 +
+                    ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16;
+    {
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* f) {
+            cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)p->smem_bytes);
+            if (r != cudaSuccess) e = r;
+        };
+        set((const void*)k_expand<1, 4>); set((const void*)k_expand<2, 4>); set((const void*)k_expand<4, 4>);
+        set((const void*)k_expand<1, 8>); set((const void*)k_expand<2, 8>); set((const void*)k_expand<4, 8>);
+        set((const void*)k_expand<1, 16>); set((const void*)k_expand<2, 16>); set((const void*)k_expand<4, 16>);
+        CU(e);
+    }
     CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)p->smem_bytes));
     int rc = planner_fill_initial(p);
@@ -737,12 +747,16 @@ int imomd_expand_async(imomd_planner* p, int iters)
     if (iters < 0) return fail(IMOMD_ERR_ARG, "negative iteration count");
     CU(cudaSetDevice(p->g->device));
     CU(cudaEventRecord(p->ev0, p->stream));
-    if (p->d.Q <= 148)
-        k_expand<1><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
-    else if (p->d.Q <= 2 * 148)
-        k_expand<2><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
-    else
-        k_expand<4><<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+    {
+        // register budget by the number of resident queries, adjacency width by the graph
+        const int mb = p->d.Q <= 148 ? 1 : (p->d.Q <= 2 * 148 ? 2 : 4);
+        const int w = p->d.g.width;
+        void (*kern)(PlannerDev, int) = nullptr;
+        if (w == 4) kern = mb == 1 ? k_expand<1, 4> : (mb == 2 ? k_expand<2, 4> : k_expand<4, 4>);
+        else if (w == 8) kern = mb == 1 ? k_expand<1, 8> : (mb == 2 ? k_expand<2, 8> : k_expand<4, 8>);
+        else kern = mb == 1 ? k_expand<1, 16> : (mb == 2 ? k_expand<2, 16> : k_expand<4, 16>);
+        kern<<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     p->pending = true;
@@ -827,6 +841,15 @@ int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* c
     QueryDev* qd = p->d.query + query;
     CU(cudaMemcpy(cycles, qd->prof_cycles, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(counts, qd->prof_count, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (getenv("IMOMD_PHASE_PROFILE"))
+    {
+        uint64_t pc[16];
+        CU(cudaMemcpy(pc, qd->phase_cycles, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        const char* names[8] = {"next_tree", "after_nn", "jps", "insert", "finish", "rewire", "last_conn", "-"};
+        for (int i = 0; i < 7; ++i)
+            fprintf(stderr, "  phase %-10s steps %10llu  cycles/step %8.0f\n", names[i],
+                    (unsigned long long)pc[8 + i], pc[8 + i] ? (double)pc[i] / (double)pc[8 + i] : 0.0);
+    }
     return IMOMD_OK;
 }
 

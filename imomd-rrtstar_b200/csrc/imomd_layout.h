@@ -22,6 +22,7 @@
 #ifndef IMOMD_LAYOUT_H
 #define IMOMD_LAYOUT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifndef IMOMD_KMAX
@@ -78,11 +79,6 @@ struct QueryDev
     uint32_t free_top[IMOMD_KMAX];        // free chunks left on the tree's stack
     uint32_t n_occ[IMOMD_KMAX];           // occupied cells of the tree's frontier hash
     uint64_t tree_size[IMOMD_KMAX];       // parent.size()
-    double P[IMOMD_KMAX * IMOMD_KMAX];    // probability_matrix_
-    double D[IMOMD_KMAX * IMOMD_KMAX];    // distance_matrix_
-    double MHv[IMOMD_KMAX * IMOMD_KMAX];  // expandables_min_heuristic_matrix_ .second
-    uint32_t MHi[IMOMD_KMAX * IMOMD_KMAX];// ... .first
-    uint32_t CN[IMOMD_KMAX * IMOMD_KMAX]; // connection_node_matrix_
     uint8_t contact[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2 + 8];   // connection_nodes_set_[i] non-empty
     uint64_t word_cursor;                 // next word of the injected stream
     int64_t iterations;                   // cumulative
@@ -104,7 +100,17 @@ struct QueryDev
     // 3 adjacency slots read by serial scans, 4 re-parentings, 5 cost-propagated
     // descendants, 6 connection-checked vertices, 7 frontier records ranked (rescans)
     uint64_t stat[8];
+    uint64_t phase_cycles[8];   // serial-step cycles by the phase the step started in
+    uint64_t phase_count[8];
+    // ---- everything above is staged in shared memory while a launch runs (hot fields);
+    // ---- the K x K matrices below are staged separately, compacted to stride K
+    double P[IMOMD_KMAX * IMOMD_KMAX];    // probability_matrix_
+    double D[IMOMD_KMAX * IMOMD_KMAX];    // distance_matrix_
+    double MHv[IMOMD_KMAX * IMOMD_KMAX];  // expandables_min_heuristic_matrix_ .second
+    uint32_t MHi[IMOMD_KMAX * IMOMD_KMAX];// ... .first
+    uint32_t CN[IMOMD_KMAX * IMOMD_KMAX]; // connection_node_matrix_
 };
+#define IMOMD_QUERY_HOT_BYTES (offsetof(QueryDev, P))
 
 // mirrors imomd_query_report (include/imomd_b200.h)
 struct ReportDev

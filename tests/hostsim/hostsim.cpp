@@ -75,6 +75,7 @@ struct HsPlanner
     std::vector<double> lb;
     std::vector<uint32_t> lvl;
     std::vector<double> mat;
+    std::vector<unsigned char> hot;
     Shared S;
 };
 
@@ -142,6 +143,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->lb.resize(cells);
     p->lvl.resize(2 * kLevelCap);
     p->mat.resize((size_t)K * K * 4);
+    p->hot.resize(IMOMD_QUERY_HOT_BYTES + 64);
     d.query = p->query.data();
     d.trec = reinterpret_cast<unsigned char*>(((uintptr_t)p->trec.data() + 15) & ~(uintptr_t)15);
     d.cell_head = p->cell_head.data();
@@ -187,7 +189,16 @@ void hs_expand(void* hp, int iters, ReportDev* reports)
 {
     HsPlanner* p = (HsPlanner*)hp;
     CtaHost cta;
-    for (int q = 0; q < p->d.Q; ++q) run_query(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data());
+    unsigned char* hot = reinterpret_cast<unsigned char*>(((uintptr_t)p->hot.data() + 15) & ~(uintptr_t)15);
+    for (int q = 0; q < p->d.Q; ++q)
+    {
+        if (p->d.g.width == 4)
+            run_query<4>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+        else if (p->d.g.width == 8)
+            run_query<8>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+        else
+            run_query<16>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+    }
     if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
 }
 
@@ -276,6 +287,7 @@ void hs_nearest(void* hp, int q, int k, double lat, double lon, uint32_t* idx, d
 {
     HsPlanner* p = (HsPlanner*)hp;
     CtaHost cta;
+    p->S.Q = &p->query[q];
     p->S.qlat = lat;
     p->S.qlon = lon;
     svc_nearest(cta, p->d, q, k, p->S, p->lb.data(), p->clist.data() + (size_t)q * 2 * p->d.chunks,
