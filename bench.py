@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries", type=int, default=64, help="independent queries per GPU")
+    ap.add_argument("--queries", type=int, default=296, help="independent queries per GPU")
     ap.add_argument("--iters", type=int, default=3000, help="expandTreeLayers_ passes per query")
     ap.add_argument("--grid", type=int, default=1000, help="grid width (1000 = 1 M vertices)")
     ap.add_argument("--cpu-sample-iters", type=int, default=0,

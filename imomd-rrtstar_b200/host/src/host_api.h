@@ -14,5 +14,33 @@ extern "C" {
 /* K x K row-major selection-probability matrix for destinations at (lat[i], lon[i]) */
 void imomd_host_selection_probabilities(int K, const double* lat, const double* lon, double* P);
 double imomd_host_great_circle_m(double lat_a, double lon_a, double lat_b, double lon_b);
+
+/* One complete planner run through the C++ facade (ImomdRRT constructor + findShortestPath
+ * on a pthread, exactly like the reference's main.cpp:219-229).  The road graph is handed
+ * over as an edge list and rebuilt into the reference's two containers with the parser's
+ * two inserts per edge.  Results: log rows (time, cost, tree size, iteration), the final
+ * vertex path, the visiting sequence.  Returns 0, or -1 with a message in err. */
+typedef struct imomd_host_row
+{
+    double time_s;
+    double path_cost;
+    long long tree_size;
+    long long iteration;
+} imomd_host_row;
+
+int imomd_host_run(int device, uint64_t n, const double* lat, const double* lon, uint64_t m,
+                   const uint64_t* eu, const uint64_t* ev, const double* ew, int K, const uint64_t* dest,
+                   double goal_bias, int max_iter, int max_time, int ga_mutation_iter, int ga_population,
+                   int ga_generation, imomd_host_row* rows, int row_cap, int* n_rows, uint64_t* path,
+                   uint64_t path_cap, uint64_t* path_len, int32_t* seq, int seq_cap, int* seq_len,
+                   double* final_cost, long long* iterations, long long* expansions, char* err,
+                   int errlen);
+
+/* EciGenSolver of the facade on a row-major K x K matrix (GA fitness on the GPU) */
+void* imomd_host_solver_create(int device, int swapping, int genetic, int ga_mutation_iter,
+                               int ga_population, int ga_generation);
+void imomd_host_solver_destroy(void* s);
+int imomd_host_solver_solve(void* s, int K, const double* D, int source, int target, double* cost,
+                            int32_t* seq, int cap, uint64_t* evaluated, char* err, int errlen);
 }
 #endif

@@ -1,0 +1,339 @@
+// host/src/imomd_rrt_star.cpp -- host side of the drop-in planner.
+//
+// What the reference's ImomdRRT does per pass on the CPU (expandTreeLayers_ and everything
+// below it, src/imomd_rrt_star.cpp:329-742 upstream) happens on the GPU behind
+// include/imomd_b200.h.  This file keeps the parts that stay on the host:
+//   * construction: containers -> CSR (native iteration order) + SoA upload, the
+//     destination-selection probabilities (:84-185, see probability.cpp), RNG seeding
+//     (:193-201), CSV log file (:203-222);
+//   * the anytime loop of findShortestPath (:225-291): expansion passes in batches that end
+//     exactly where the reference calls solveRTSP_ (every 100 passes), max_iter / max_time;
+//   * solveRTSP_ (:966-1003), updatePath_ (:918-964), logData_ (:1005-1029), printPath
+//     (:293-322).
+// One deliberate deviation: max_time is checked between batches (every 100 passes), not
+// after every pass.
+#include "imomd_rrt_star/imomd_rrt_star.h"
+
+#include <algorithm>
+#include <cmath>
+#include <ctime>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+#include <unistd.h>
+
+#include "host_api.h"
+#include "imomd_b200.h"
+
+namespace {
+
+int g_default_device = 0;
+
+std::string fixed4(double v)
+{
+    std::ostringstream out;
+    out.precision(4);
+    out << std::fixed << v;
+    return out.str();
+}
+
+void check(int rc, const char* what)
+{
+    if (rc != IMOMD_OK)
+        throw std::runtime_error(std::string("ImomdRRT: ") + what + ": " + imomd_last_error());
+}
+
+}  // namespace
+
+void ImomdRRT::setDefaultDevice(int device) { g_default_device = device; }
+
+ImomdRRT::ImomdRRT(size_t source, size_t target, std::vector<size_t> objectives,
+                   const std::shared_ptr<std::vector<location_t>> map,
+                   const std::shared_ptr<std::vector<std::unordered_map<size_t, double>>> connection,
+                   const imomd_setting_t& setting)
+    : setting_(setting), map_(map), connection_(connection), device_(g_default_device)
+{
+    if (setting_.pseudo_mode)
+        throw std::invalid_argument(
+            "ImomdRRT (B200): pseudo_mode needs the pseudo-tree merge, which is not built yet");
+    destinations_.push_back(source);
+    for (size_t o : objectives) destinations_.push_back(o);
+    destinations_.push_back(target);
+    K_ = static_cast<int>(destinations_.size());
+    if (K_ > static_cast<int>(IMOMD_KMAX))
+        throw std::invalid_argument("ImomdRRT (B200): more than 30 objectives");
+    const size_t n = map_->size();
+    if (n == 0 || n > 0xFFFFFFF0ull || connection_->size() != n)
+        throw std::invalid_argument("ImomdRRT (B200): bad map / connection sizes");
+    for (size_t d : destinations_)
+        if (d >= n) throw std::invalid_argument("ImomdRRT (B200): destination id out of range");
+
+    // road graph -> CSR in the containers' own iteration order, coordinates -> SoA
+    std::vector<uint32_t> row_ptr(n + 1), col;
+    std::vector<double> w, lat(n), lon(n);
+    size_t arcs = 0;
+    for (const auto& row : *connection_) arcs += row.size();
+    col.reserve(arcs);
+    w.reserve(arcs);
+    for (size_t v = 0; v < n; ++v)
+    {
+        const location_t& loc = (*map_)[v];
+        if (loc.id != v)
+            throw std::invalid_argument(
+                "ImomdRRT (B200): location ids must equal their index (as OSMParser / FakeMap produce)");
+        lat[v] = loc.latitude;
+        lon[v] = loc.longitude;
+        row_ptr[v] = static_cast<uint32_t>(col.size());
+        for (const auto& kv : (*connection_)[v])
+        {
+            col.push_back(static_cast<uint32_t>(kv.first));
+            w.push_back(kv.second);
+        }
+    }
+    row_ptr[n] = static_cast<uint32_t>(col.size());
+    check(imomd_graph_create(device_, static_cast<uint32_t>(n), row_ptr.data(), col.data(), w.data(),
+                             lat.data(), lon.data(), &graph_),
+          "graph upload");
+
+    std::vector<uint32_t> dest(K_);
+    std::vector<double> dlat(K_), dlon(K_), prob(static_cast<size_t>(K_) * K_);
+    for (int i = 0; i < K_; ++i)
+    {
+        dest[i] = static_cast<uint32_t>(destinations_[i]);
+        dlat[i] = lat[destinations_[i]];
+        dlon[i] = lon[destinations_[i]];
+    }
+    imomd_host::selection_probabilities(K_, dlat.data(), dlon.data(), prob.data());
+    imomd_params params{};
+    params.goal_bias = setting_.goal_bias;
+    params.pseudo_mode = 0;
+    check(imomd_planner_create(graph_, 1, K_, dest.data(), prob.data(), &params, &planner_),
+          "planner creation");
+
+    solver_ = EciGenSolver(setting_.rtsp_setting, device_);
+    shortest_path_cost_ = INFINITY;
+    if (setting_.random_seed)
+    {
+        std::random_device rd;
+        rng_ = std::mt19937{rd()};
+    }
+    else
+    {
+        rng_ = std::mt19937{0};
+    }
+    start_ = std::chrono::steady_clock::now();
+    if (setting_.log_data)
+    {
+        std::time_t t = std::time(nullptr);
+        std::tm tm = *std::localtime(&t);
+        std::ostringstream stamp;
+        stamp << std::put_time(&tm, "%Y-%d-%m-%H-%M-%S");
+        char cwd[4096];
+        std::string dir = getcwd(cwd, sizeof(cwd)) ? cwd : ".";
+        csv_.open(dir + "/experiments/IMOMD_" + stamp.str() + "_command_history.csv");
+        if (csv_.good())
+            csv_ << "\"CPU_time\";\"path_cost\";\"tree_size\";" << std::endl;
+        else
+            std::cout << "Exception was thrown: cannot open the log file" << std::endl;
+    }
+}
+
+ImomdRRT::~ImomdRRT()
+{
+    if (planner_) imomd_planner_destroy(planner_);
+    if (graph_) imomd_graph_destroy(graph_);
+}
+
+void ImomdRRT::feedWords(size_t n)
+{
+    std::vector<uint32_t> words(n);
+    for (uint32_t& x : words) x = static_cast<uint32_t>(rng_());
+    check(imomd_planner_feed_words(planner_, words.data(), words.size()), "sample stream");
+    words_fed_ += n;
+}
+
+// `passes` calls of expandTreeLayers_ on the device
+bool ImomdRRT::expandBatch(int passes)
+{
+    int left = passes;
+    while (left > 0)
+    {
+        // every expansion draws 4 or 6 words (a few more for the rare Lemire rejection)
+        feedWords(static_cast<size_t>(left) * K_ * 8 + 256);
+        imomd_query_report rep{};
+        check(imomd_expand(planner_, left, &rep), "expansion");
+        left -= static_cast<int>(rep.iterations);
+        iteration_count_ += rep.iterations;
+        expansions_ += rep.expansions;
+        tree_vertices_ = rep.tree_vertices;
+        active_trees_ = rep.active_trees;
+        connected_ = rep.connected != 0;
+        dm_updated_ = rep.dm_updated != 0;
+        if (rep.status != IMOMD_RUN_OK && rep.status != IMOMD_RUN_NEED_WORDS)
+            throw std::runtime_error("ImomdRRT (B200): device run status " + std::to_string(rep.status));
+    }
+    return true;
+}
+
+void ImomdRRT::run()
+{
+    bool done_iter = false, done_time = false, done_expansion = false;
+    while (!done_iter && !done_time && !done_expansion)
+    {
+        // the reference solves the RTSP after the pass that starts with
+        // iteration_count_ % 100 == 0 and stops after the pass that starts with
+        // iteration_count_ > max_iter: batch up to whichever comes first
+        long long to_rtsp = (iteration_count_ % 100 == 0) ? 1 : 101 - (iteration_count_ % 100);
+        long long to_stop = static_cast<long long>(setting_.max_iter) + 2 - iteration_count_;
+        long long passes = std::max(1LL, std::min(to_rtsp, to_stop));
+        const long long before = iteration_count_;
+        expandBatch(static_cast<int>(passes));
+        if ((iteration_count_ - 1) % 100 == 0)
+        {
+            solveRTSP();
+            std::vector<int32_t> done(K_);
+            check(imomd_get_state(planner_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, done.data(),
+                                  nullptr),
+                  "state readback");
+            done_expansion = std::all_of(done.begin(), done.end(), [](int32_t d) { return d != 0; });
+        }
+        if (iteration_count_ - 1 > setting_.max_iter)
+            done_iter = true;
+        else if (std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count() >
+                 setting_.max_time)
+            done_time = true;
+        if (iteration_count_ == before) break;   // defensive: the device made no progress
+    }
+    if (done_iter) std::cout << "[IMOMD] Reached Max Iteration" << std::endl;
+    else if (done_time) std::cout << "[IMOMD] Reached Max Time" << std::endl;
+    if (done_expansion) std::cout << "[IMOMD] Tree Exploration Done" << std::endl;
+    for (int i = 0; i < 10; ++i) solveRTSP();
+
+    pthread_mutex_lock(&lock_);
+    finished_ = true;
+    pthread_mutex_unlock(&lock_);
+    pthread_cond_signal(&cond_);
+}
+
+void* ImomdRRT::findShortestPath(void* arg)
+{
+    static_cast<ImomdRRT*>(arg)->run();
+    pthread_exit(NULL);
+}
+
+void* ImomdRRT::printPath(void* arg)
+{
+    ImomdRRT* self = static_cast<ImomdRRT*>(arg);
+    int count = 0;
+    while (!self->finished_)
+    {
+        pthread_mutex_lock(&self->lock_);
+        while (!self->path_updated_ && !self->finished_) pthread_cond_wait(&self->cond_, &self->lock_);
+        std::cout << "[main] print path: " << count++ << std::endl;
+        for (size_t node : self->shortest_path_) std::cout << node << " -> ";
+        std::cout << "#" << std::endl;
+        self->path_updated_ = false;
+        pthread_mutex_unlock(&self->lock_);
+    }
+    pthread_exit(NULL);
+}
+
+std::shared_ptr<std::vector<std::vector<double>>> ImomdRRT::getDistanceMatrix()
+{
+    std::vector<double> flat(static_cast<size_t>(K_) * K_);
+    check(imomd_get_state(planner_, 0, flat.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
+          "distance matrix readback");
+    auto m = std::make_shared<std::vector<std::vector<double>>>(K_, std::vector<double>(K_));
+    for (int i = 0; i < K_; ++i)
+        for (int j = 0; j < K_; ++j) (*m)[i][j] = flat[static_cast<size_t>(i) * K_ + j];
+    return m;
+}
+
+void ImomdRRT::solveRTSP()
+{
+    if (!(connected_ && dm_updated_)) return;
+    auto result = solver_.solveRTSP(getDistanceMatrix(), 0, K_ - 1);
+    if (result.first < shortest_path_cost_)
+    {
+        sequence_ = result.second;
+        shortest_path_cost_ = result.first;
+        updatePath();
+        logData();
+    }
+}
+
+// Stitches the tree branches along the visiting sequence into one vertex path.
+void ImomdRRT::updatePath()
+{
+    std::vector<uint32_t> cn(static_cast<size_t>(K_) * K_);
+    check(imomd_get_state(planner_, 0, nullptr, cn.data(), nullptr, nullptr, nullptr, nullptr, nullptr),
+          "connection nodes readback");
+    std::vector<size_t> path;
+    std::vector<uint32_t> buf(1 << 16);
+    auto walk = [&](int tree, uint32_t from) {
+        uint32_t len = 0;
+        for (;;)
+        {
+            check(imomd_walk_to_root(planner_, 0, tree, from, buf.data(), static_cast<uint32_t>(buf.size()),
+                                     &len),
+                  "path walk");
+            if (len <= buf.size()) break;
+            buf.resize(len);
+        }
+        return len;
+    };
+    for (size_t s = 0; s + 1 < sequence_->size(); ++s)
+    {
+        const int cur = (*sequence_)[s], nxt = (*sequence_)[s + 1];
+        const uint32_t meet = cn[static_cast<size_t>(cur) * K_ + nxt];
+        // root of `cur` ... up to (excluding) the meeting vertex
+        uint32_t len = walk(cur, meet);
+        for (uint32_t i = len; i-- > 1;) path.push_back((*map_)[buf[i]].id);
+        // the meeting vertex ... up to (excluding) the root of `nxt`
+        len = walk(nxt, meet);
+        for (uint32_t i = 0; i + 1 < len; ++i) path.push_back((*map_)[buf[i]].id);
+    }
+    path.push_back(destinations_.back());
+
+    pthread_mutex_lock(&lock_);
+    shortest_path_.swap(path);
+    path_updated_ = true;
+    dm_updated_ = false;
+    pthread_mutex_unlock(&lock_);
+    check(imomd_clear_dm_updated(planner_, 0), "flag reset");
+    pthread_cond_signal(&cond_);
+}
+
+void ImomdRRT::logData()
+{
+    const double elapsed =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count();
+    std::cout << "Elapsed time[s]: " << std::setw(10) << elapsed << " | "
+              << "Path Cost[m]: " << std::setw(10) << shortest_path_cost_ << " | "
+              << "Tree Size: " << std::setw(10) << tree_vertices_ << std::endl;
+    log_.push_back({elapsed, shortest_path_cost_, tree_vertices_, iteration_count_ - 1});
+    if (setting_.log_data && csv_.good())
+    {
+        // three quoted fields like the reference's CSVFile (utils/csv.h:85-95); tree_size is
+        // an int there, so it prints without decimals
+        csv_ << '"' << fixed4(elapsed) << "\";\"" << fixed4(shortest_path_cost_) << "\";\""
+             << tree_vertices_ << "\";" << std::endl;
+    }
+}
+
+std::vector<size_t> ImomdRRT::getShortestPath()
+{
+    pthread_mutex_lock(&lock_);
+    std::vector<size_t> copy = shortest_path_;
+    pthread_mutex_unlock(&lock_);
+    return copy;
+}
+
+double ImomdRRT::getShortestPathCost() { return shortest_path_cost_; }
+
+std::vector<int> ImomdRRT::getVisitingSequence()
+{
+    return sequence_ ? *sequence_ : std::vector<int>{};
+}

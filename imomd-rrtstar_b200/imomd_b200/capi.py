@@ -105,6 +105,19 @@ def host_lib():
         L.imomd_host_selection_probabilities.argtypes = [C.c_int, f64p, f64p, f64p]
         L.imomd_host_great_circle_m.restype = C.c_double
         L.imomd_host_great_circle_m.argtypes = [C.c_double] * 4
+        u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+        L.imomd_host_run.argtypes = [C.c_int, C.c_uint64, f64p, f64p, C.c_uint64, u64p, u64p, f64p,
+                                     C.c_int, u64p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), u64p, C.c_uint64,
+                                     C.POINTER(C.c_uint64), i32p, C.c_int, C.POINTER(C.c_int),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_longlong),
+                                     C.POINTER(C.c_longlong), C.c_char_p, C.c_int]
+        L.imomd_host_solver_create.restype = C.c_void_p
+        L.imomd_host_solver_create.argtypes = [C.c_int] * 6
+        L.imomd_host_solver_destroy.argtypes = [C.c_void_p]
+        L.imomd_host_solver_solve.argtypes = [C.c_void_p, C.c_int, f64p, C.c_int, C.c_int,
+                                              C.POINTER(C.c_double), i32p, C.c_int,
+                                              C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
         _host = L
     return _host
 
@@ -287,3 +300,53 @@ class GaContext:
         _check(cuda_lib().imomd_ga_eval(self.h, K, D.ravel(), tours.shape[0], tours.shape[1],
                                         tours.ravel(), lens, out))
         return out
+
+
+class HostRow(C.Structure):
+    _fields_ = [("time_s", C.c_double), ("path_cost", C.c_double), ("tree_size", C.c_longlong),
+                ("iteration", C.c_longlong)]
+
+
+def facade_run(g, dest, goal_bias=1.0, max_iter=1000000, max_time=60, ga=(10000, 1000, 5), device=0):
+    """One full planner run through the C++ facade (ImomdRRT + findShortestPath on a pthread)."""
+    L = host_lib()
+    eu, ev, ew = g.edge_list()
+    eu = np.ascontiguousarray(eu, np.uint64); ev = np.ascontiguousarray(ev, np.uint64)
+    ew = np.ascontiguousarray(ew, np.float64)
+    rows = (HostRow * 4096)()
+    n_rows = C.c_int(); path = np.empty(1 << 22, np.uint64); path_len = C.c_uint64()
+    seq = np.empty(256, np.int32); seq_len = C.c_int(); cost = C.c_double()
+    its = C.c_longlong(); exps = C.c_longlong(); err = C.create_string_buffer(512)
+    rc = L.imomd_host_run(device, g.n, g.lat, g.lon, len(eu), eu, ev, ew, len(dest),
+                          np.asarray(dest, np.uint64), goal_bias, max_iter, max_time, ga[0], ga[1], ga[2],
+                          C.cast(rows, C.c_void_p), 4096, C.byref(n_rows), path, path.size,
+                          C.byref(path_len), seq, 256, C.byref(seq_len), C.byref(cost), C.byref(its),
+                          C.byref(exps), err, 512)
+    if rc != 0:
+        raise ImomdError(err.value.decode())
+    return dict(rows=[(r.time_s, r.path_cost, r.tree_size, r.iteration) for r in rows[:n_rows.value]],
+                path=path[:path_len.value].copy(), sequence=seq[:seq_len.value].copy(),
+                final_cost=cost.value, iterations=its.value, expansions=exps.value)
+
+
+class FacadeSolver:
+    """EciGenSolver of the host facade (GA fitness evaluated on the GPU)."""
+
+    def __init__(self, device=0, swapping=True, genetic=True, ga=(10000, 1000, 5)):
+        self.h = host_lib().imomd_host_solver_create(device, int(swapping), int(genetic), *ga)
+
+    def solve(self, D, source, target):
+        D = np.ascontiguousarray(D, np.float64)
+        K = D.shape[0]
+        cost = C.c_double(); seq = np.empty(256, np.int32); ev = C.c_uint64()
+        err = C.create_string_buffer(512)
+        n = host_lib().imomd_host_solver_solve(self.h, K, D.ravel(), source, target, C.byref(cost), seq,
+                                               256, C.byref(ev), err, 512)
+        if n < 0:
+            raise ImomdError(err.value.decode())
+        return cost.value, seq[:n].copy(), ev.value
+
+    def close(self):
+        if self.h:
+            host_lib().imomd_host_solver_destroy(self.h)
+            self.h = None

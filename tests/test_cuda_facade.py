@@ -1,0 +1,76 @@
+"""The C++ host facade (reference library API: ImomdRRT constructor + findShortestPath pthread,
+EciGenSolver::solveRTSP) on top of the CUDA path, against the unmodified reference run the
+same way (oracle/_ref, travels prebuilt to the GPU box)."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oraclelib as ol
+from imomd_b200 import capi, graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_pseudo_complete(K, rng, p_missing):
+    D = rng.uniform(100.0, 5000.0, (K, K)); D = (D + D.T) / 2
+    miss = np.triu(rng.random((K, K)) < p_missing, 1)
+    D[miss | miss.T] = np.inf
+    perm = rng.permutation(K)
+    for a, b in zip(perm[:-1], perm[1:]):
+        if np.isinf(D[a, b]):
+            D[a, b] = D[b, a] = rng.uniform(100.0, 5000.0)
+    np.fill_diagonal(D, 0.0)
+    return np.ascontiguousarray(D)
+
+
+@pytest.mark.parametrize("K,p_missing", [(4, 0.0), (7, 0.3), (12, 0.5), (22, 0.6), (12, 0.0)])
+def test_eci_gen_solver_with_gpu_fitness(K, p_missing):
+    """Same (cost, tour) as the oracle restatement over a sequence of solves (the solver-owned
+    RNG persists), with every GA fitness evaluated by the device kernel."""
+    O = ol.oracle()
+    os_ = O.orc_solver_create(1, 1, 2000, 300, 5)
+    fs = capi.FacadeSolver(0, ga=(2000, 300, 5))
+    rng = np.random.default_rng(K * 100 + int(p_missing * 10))
+    for trial in range(6):
+        D = _random_pseudo_complete(K, rng, p_missing)
+        c2 = ol.C.c_double(); s2 = np.empty(256, np.int32)
+        n2 = O.orc_solver_solve(os_, K, D.ravel(), 0, K - 1, ol.C.byref(c2), s2, 256)
+        c1, s1, evaluated = fs.solve(D, 0, K - 1)
+        assert np.array_equal(s1, s2[:n2]), (trial, s1, s2[:n2])
+        assert c1 == c2.value
+        assert evaluated > 0
+    fs.close(); O.orc_solver_destroy(os_)
+
+
+def _probe_run(g, dest, max_iter, ga):
+    with tempfile.TemporaryDirectory() as td:
+        gp = os.path.join(td, "g.bin")
+        g.write_probe_file(gp)
+        out = subprocess.check_output(
+            [ol.REF_PROBE, "--graph", gp, "--dest", ",".join(map(str, dest)), "--mode", "run",
+             "--max-iter", str(max_iter), "--max-time", "600", "--ga", ",".join(map(str, ga))], text=True)
+    return json.loads(out.strip().splitlines()[-1])
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("kind,K,max_iter", [("grid", 5, 1500), ("road", 4, 2500), ("grid", 8, 2500)])
+def test_anytime_run_matches_reference(kind, K, max_iter):
+    """Whole planner run: every logged improvement (iteration, path cost, tree size) and the
+    final vertex path equal the reference's."""
+    g = graphs.jittered_grid(70, seed=21) if kind == "grid" else graphs.road_like(5000, seed=4)
+    dest = graphs.pick_destinations(g, K, seed=K + 1)
+    ga = (3000, 400, 5)
+    ref = _probe_run(g, dest, max_iter, ga)
+    got = capi.facade_run(g, dest, max_iter=max_iter, max_time=600, ga=ga)
+    assert got["iterations"] == ref["iterations"]
+    assert got["expansions"] == ref["expansions"]
+    assert len(ref["rows"]) > 0, "the reference found no path: pick another scenario"
+    assert [(r[3], r[2]) for r in got["rows"]] == [(r[3], r[2]) for r in ref["rows"]]
+    for a, b in zip(got["rows"], ref["rows"]):
+        assert a[1] == b[1], (a, b)              # path cost, bit for bit
+    assert got["final_cost"] == ref["final_cost"]
+    assert list(got["path"]) == ref["path"]
