@@ -37,6 +37,11 @@ public:
         std::shared_ptr<std::vector<std::vector<double>>> adjacency_matrix_ptr, int source_id,
         int target_id);
 
+    // shortest chain source -> target only (used by the reference's baseline planners)
+    std::pair<double, std::shared_ptr<std::vector<int>>> solveDijkstra(
+        std::shared_ptr<std::vector<std::vector<double>>> adjacency_matrix_ptr, int source_id,
+        int target_id);
+
     // number of tours the GPU ranked during the last solve (for tests / reports)
     size_t lastEvaluatedTours() const { return evaluated_; }
 

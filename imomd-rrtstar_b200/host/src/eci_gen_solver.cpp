@@ -503,3 +503,21 @@ std::pair<double, std::shared_ptr<std::vector<int>>> EciGenSolver::solveRTSP(
     }
     return {best_cost_, std::make_shared<std::vector<int>>(best_)};
 }
+
+// solveDijkstra upstream (:55-74): the chain alone, no insertion, no GA
+std::pair<double, std::shared_ptr<std::vector<int>>> EciGenSolver::solveDijkstra(
+    std::shared_ptr<std::vector<std::vector<double>>> matrix, int source_id, int target_id)
+{
+    K_ = static_cast<int>(matrix->size());
+    D_.resize(static_cast<size_t>(K_) * K_);
+    for (int i = 0; i < K_; ++i)
+        for (int j = 0; j < K_; ++j) D_[static_cast<size_t>(i) * K_ + j] = (*matrix)[i][j];
+    source_ = source_id;
+    target_ = target_id;
+    best_.clear();
+    pool_.clear();
+    fitness_.clear();
+    Tour chain;
+    best_cost_ = shortestChain(chain);
+    return {best_cost_, std::make_shared<std::vector<int>>(chain)};
+}

@@ -1,0 +1,73 @@
+"""Drop-in proof: the reference's own, unmodified main.cpp compiled against this repository's
+planner (oracle/_ref/main_b200, see oracle/Makefile `dropin`) prints the same path as the
+reference's own binary (oracle/_ref/main_ref) for the same YAML configuration.  The bundled
+toy map -2 is used because OSM files do not travel to the GPU box."""
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+import oraclelib as ol
+
+pytestmark = [pytest.mark.gpu, pytest.mark.ref]
+
+CONFIG = """general:
+  system: 0
+  pseudo: 0
+  log_data: 1
+  print_path: 1
+  max_iter: 2000
+  max_time: 60
+rrt_params:
+  goal_bias: 1.0
+  random_seed: 0
+destinations:
+  source_id: 0
+  objective_ids: [3, 4]
+  target_id: 6
+map:
+  type: -2
+  path: none
+  name: none
+rtsp_settings:
+  shortcut: 1
+  swapping: 1
+  genetic: 1
+  ga:
+    random_seed: 0
+    mutation_iter: 10000
+    population: 1000
+    generation: 5
+"""
+
+
+def _run(binary):
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "config")); os.makedirs(os.path.join(td, "experiments"))
+        open(os.path.join(td, "config", "algorithm_config.yaml"), "w").write(CONFIG)
+        open(os.path.join(td, "config", "osm_way_config.yaml"), "w").write("osm_show_ways: 0\n")
+        out = subprocess.run([binary], cwd=td, capture_output=True, text=True, timeout=300)
+        csvs = [f for f in os.listdir(os.path.join(td, "experiments")) if f.endswith(".csv")]
+        rows = open(os.path.join(td, "experiments", csvs[0])).read().splitlines() if csvs else []
+    return out, rows
+
+
+def test_reference_main_runs_on_the_b200_planner():
+    ref_bin = os.path.join(ol.ORACLE_DIR, "_ref", "main_ref")
+    new_bin = os.path.join(ol.ORACLE_DIR, "_ref", "main_b200")
+    if not (os.path.exists(ref_bin) and os.path.exists(new_bin)):
+        pytest.skip("drop-in binaries not built")
+    a, rows_a = _run(ref_bin)
+    b, rows_b = _run(new_bin)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr[-400:], b.stderr[-400:])
+    paths_a = [l for l in a.stdout.splitlines() if l.strip().endswith("#")]
+    paths_b = [l for l in b.stdout.splitlines() if l.strip().endswith("#")]
+    assert paths_a and paths_a[-1] == paths_b[-1]              # e.g. 0 -> 2 -> 4 -> 5 -> 3 -> 5 -> 6 -> #
+    cost = lambda out: [re.search(r"Path Cost\[m\]:\s*([0-9.e+]+)", l).group(1)
+                        for l in out.splitlines() if "Path Cost[m]" in l]
+    assert cost(a.stdout) == cost(b.stdout)
+    # CSV: same header, same cost / tree-size columns (the time column differs)
+    assert rows_a[0] == rows_b[0] == '"CPU_time";"path_cost";"tree_size";'
+    assert [r.split(";")[1:] for r in rows_a[1:]] == [r.split(";")[1:] for r in rows_b[1:]]
