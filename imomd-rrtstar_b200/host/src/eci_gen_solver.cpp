@@ -161,16 +161,13 @@ void EciGenSolver::cheapestInsertion()
 {
     Tour tour;
     double cost = shortestChain(tour);
-    std::vector<char> placed(K_, 0);
-    int missing = K_;
-    for (int v : tour)
-    {
-        if (!placed[v])
-        {
-            placed[v] = 1;
-            --missing;
-        }
-    }
+    // Candidates are visited in the order upstream's `std::unordered_set<int> not_visited`
+    // iterates (:112-121): exact cost ties between different destinations go to the first one
+    // met, and symmetric maps do produce such ties.  Same libstdc++ here, so the real container
+    // is used (filled 0..K-1, then the chain's members erased).
+    std::unordered_set<int> waiting;
+    for (int v = 0; v < K_; ++v) waiting.insert(v);
+    for (int v : tour) waiting.erase(v);
     auto cheapest = [&](int v) {
         Placement best;
         const int n = static_cast<int>(tour.size());
@@ -226,15 +223,12 @@ void EciGenSolver::cheapestInsertion()
         }
         return best;
     };
-    while (missing > 0)
+    while (!waiting.empty())
     {
         Placement pick;
         int who = -1;
-        // upstream walks an unordered_set<int>; only exact cost ties between different
-        // destinations could expose that order (ascending ids here)
-        for (int v = 0; v < K_; ++v)
+        for (int v : waiting)
         {
-            if (placed[v]) continue;
             const Placement p = cheapest(v);
             if (p.extra < pick.extra)
             {
@@ -270,8 +264,7 @@ void EciGenSolver::cheapestInsertion()
                 break;
         }
         cost += pick.extra;
-        placed[who] = 1;
-        --missing;
+        waiting.erase(who);
     }
     best_cost_ = cost;
     best_ = tour;

@@ -1196,14 +1196,32 @@ struct orc_solver
                 --remaining;
             }
         }
+        // Iteration order of upstream's unordered_set<int> filled with 0..K-1 (:112-116):
+        // identity hash, every key lands in an empty bucket and goes to the list head, the
+        // list is reversed by each rehash (13 -> 29 -> 59 buckets).  Erasing keeps the order.
+        std::vector<int> order;
+        if (K <= 13)
+        {
+            for (int v = K - 1; v >= 0; --v) order.push_back(v);
+        }
+        else if (K <= 29)
+        {
+            for (int v = K - 1; v >= 13; --v) order.push_back(v);
+            for (int v = 0; v <= 12; ++v) order.push_back(v);
+        }
+        else
+        {
+            for (int v = K - 1; v >= 29; --v) order.push_back(v);
+            for (int v = 12; v >= 0; --v) order.push_back(v);
+            for (int v = 13; v <= 28; ++v) order.push_back(v);
+        }
         while (remaining > 0)
         {
             double min_ins = INFINITY;
             int left_idx = -1, id_insert = -1;
             Ins method = REVISIT;
-            // the reference walks an unordered_set<int>; only exact cost ties between
-            // different destinations could make the order visible (ascending here)
-            for (int cand = 0; cand < K; ++cand)
+            // exact cost ties between different destinations go to the first one met
+            for (int cand : order)
             {
                 if (!not_visited[cand]) continue;
                 double c;

@@ -74,3 +74,20 @@ def test_anytime_run_matches_reference(kind, K, max_iter):
         assert a[1] == b[1], (a, b)              # path cost, bit for bit
     assert got["final_cost"] == ref["final_cost"]
     assert list(got["path"]) == ref["path"]
+
+
+@pytest.mark.parametrize("K", [4, 13, 14, 30])
+def test_eci_gen_solver_exact_ties(K):
+    O = ol.oracle()
+    os_ = O.orc_solver_create(1, 1, 500, 100, 3)
+    fs = capi.FacadeSolver(0, ga=(500, 100, 3))
+    rng = np.random.default_rng(K)
+    for trial in range(6):
+        D = rng.integers(1, 4, (K, K)).astype(np.float64) * 100.0
+        D = np.ascontiguousarray((D + D.T) / 2)
+        np.fill_diagonal(D, 0.0)
+        c2 = ol.C.c_double(); s2 = np.empty(512, np.int32)
+        n2 = O.orc_solver_solve(os_, K, D.ravel(), 0, K - 1, ol.C.byref(c2), s2, 512)
+        c1, s1, _ = fs.solve(D, 0, K - 1)
+        assert np.array_equal(s1, s2[:n2]) and c1 == c2.value
+    fs.close(); O.orc_solver_destroy(os_)

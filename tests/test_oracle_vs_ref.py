@@ -283,3 +283,24 @@ def test_path_costs_batch():
     R.ref_path_costs(K, D.ravel(), n, stride, tours.ravel(), lens, a)
     O.orc_path_costs(K, D.ravel(), n, stride, tours.ravel(), lens, b)
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+@pytest.mark.parametrize("K", [4, 9, 13, 14, 20, 29, 30, 32])
+def test_eci_gen_solver_exact_ties(K):
+    """Integer-valued symmetric matrices are full of exact cost ties: the candidate order of
+    the cheapest insertion (an unordered_set<int> upstream) becomes visible."""
+    R, O = ol.ref(), ol.oracle()
+    rs = R.ref_solver_create(1, 1, 500, 100, 3)
+    os_ = O.orc_solver_create(1, 1, 500, 100, 3)
+    rng = np.random.default_rng(K)
+    for trial in range(8):
+        D = rng.integers(1, 4, (K, K)).astype(np.float64) * 100.0
+        D = np.ascontiguousarray((D + D.T) / 2)
+        np.fill_diagonal(D, 0.0)
+        c1 = ol.C.c_double(); c2 = ol.C.c_double()
+        s1 = np.empty(512, np.int32); s2 = np.empty(512, np.int32)
+        n1 = R.ref_solver_solve(rs, K, D.ravel(), 0, K - 1, ol.C.byref(c1), s1, 512)
+        n2 = O.orc_solver_solve(os_, K, D.ravel(), 0, K - 1, ol.C.byref(c2), s2, 512)
+        assert n1 == n2 and np.array_equal(s1[:n1], s2[:n2]), (trial, s1[:n1], s2[:n2])
+        assert c1.value == c2.value
+    O.orc_solver_destroy(os_)
