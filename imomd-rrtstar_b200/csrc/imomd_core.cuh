@@ -1473,7 +1473,13 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         if (cta.tid() == 0)
         {
             *near_ties += 1;
-            if (e.v2 - e.v1 <= kTieRel * e.v1) *unresolved_ties += 1;
+            if (e.v2 - e.v1 <= kTieRel * e.v1)
+            {
+                *unresolved_ties += 1;
+                double* ti = S.Q->tie_info;
+                ti[0] = 1; ti[1] = k; ti[2] = -1; ti[3] = e.v1; ti[4] = e.v2; ti[5] = e.id1;
+                ti[6] = qlat; ti[7] = qlon;
+            }
         }
     }
     if (warm) warm_expansion(cta, P, T, q, k, b.id1, S);
@@ -1532,7 +1538,13 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
             Q->stat[7] += S.n_recs;
             S.mMHi[k * K + o] = b.id1;
             S.mMHv[k * K + o] = b.v1;
-            if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1) Q->unresolved_ties += 1;
+            if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1)
+            {
+                Q->unresolved_ties += 1;
+                double* ti = Q->tie_info;
+                ti[0] = 2; ti[1] = k; ti[2] = o; ti[3] = b.v1; ti[4] = b.v2; ti[5] = b.id1;
+                ti[6] = 0; ti[7] = 0;
+            }
         }
         cta.sync();
     }

@@ -680,6 +680,15 @@ int imomd_planner_set_queries(imomd_planner* p, const uint32_t* dest, const doub
     return IMOMD_OK;
 }
 
+int imomd_get_tie_info(imomd_planner* p, int query, double* out)
+{
+    if (!p || query < 0 || query >= p->d.Q || !out) return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaMemcpy(out, p->d.query[query].tie_info, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+    return IMOMD_OK;
+}
+
 int imomd_get_counters(imomd_planner* p, uint64_t* out)
 {
     if (!p || !out) return fail(IMOMD_ERR_ARG, "null argument");

@@ -100,6 +100,8 @@ struct QueryDev
     // 3 adjacency slots read by serial scans, 4 re-parentings, 5 cost-propagated
     // descendants, 6 connection-checked vertices, 7 frontier records ranked (rescans)
     uint64_t stat[8];
+    double tie_info[8];         // last undecidable comparison: kind (1 nearest, 2 rescan), tree,
+                                // other, best, runner-up, vertex, sample lat, sample lon
     uint64_t phase_cycles[8];   // serial-step cycles by the phase the step started in
     uint64_t phase_count[8];
     // ---- everything above is staged in shared memory while a launch runs (hot fields);

@@ -72,6 +72,7 @@ def cuda_lib():
         L.imomd_planner_set_queries.argtypes = [vp, u32p, f64p]
         L.imomd_planner_clear_words.argtypes = [vp]
         L.imomd_get_counters.argtypes = [vp, np.ctypeslib.ndpointer(np.uint64, flags="C")]
+        L.imomd_get_tie_info.argtypes = [vp, C.c_int, f64p]
         L.imomd_planner_feed_words.argtypes = [vp, u32p, C.c_size_t]
         L.imomd_planner_words_available.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.imomd_expand.argtypes = [vp, C.c_int, C.POINTER(Report)]
@@ -200,6 +201,11 @@ class DevicePlanner:
     def set_queries(self, dests_u32, probs_f64):
         """dests_u32: contiguous u32[Q*K]; probs_f64: contiguous f64[Q*K*K] (host buffers)."""
         _check(cuda_lib().imomd_planner_set_queries(self.h, dests_u32, probs_f64))
+
+    def tie_info(self, q=0):
+        out = np.zeros(8)
+        _check(cuda_lib().imomd_get_tie_info(self.h, q, out))
+        return out
 
     def counters(self):
         out = np.zeros((self.Q, 8), np.uint64)

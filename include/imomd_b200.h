@@ -140,6 +140,10 @@ int imomd_sync(imomd_planner* p, imomd_query_report* reports);
  * nearest search, heuristic rescan, heuristic insert, connection gather, cost propagation,
  * rewire batch check; index 7 = the serial steps in between (development / profiling aid) */
 int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts);
+/* the last comparison the device could not decide within 1e-12 relative (see
+ * imomd_query_report.unresolved_ties): {kind 1 nearest / 2 heuristic rescan, tree, other tree,
+ * best value, runner-up value, vertex taken, sample lat, sample lon} */
+int imomd_get_tie_info(imomd_planner* p, int query, double* out);
 /* cumulative work counters of every query, out[Q][8]: hash cells bounded, frontier records
  * ranked by nearest searches, rewireTree_ calls, adjacency slots read by serial scans,
  * re-parentings, cost-propagated descendants, connection-checked vertices, frontier
