@@ -42,6 +42,19 @@ public:
         std::shared_ptr<std::vector<std::vector<double>>> adjacency_matrix_ptr, int source_id,
         int target_id);
 
+    // ---- GA islands (BASELINE config 4; not in the reference, which has one population) ----
+    // Several solvers ("islands", one per GPU) evolve their own population from their own seed
+    // and exchange their best tour between generations; the exchange itself is the caller's
+    // (imomd_b200/sharding.py: one NCCL all-gather of 272 bytes per rank and generation).
+    // islandBegin = insertion + seeding pass with mt19937{seed}; seed 0 reproduces upstream.
+    void islandBegin(std::shared_ptr<std::vector<std::vector<double>>> adjacency_matrix_ptr,
+                     int source_id, int target_id, unsigned seed);
+    bool islandStep();                                   // one generation; false: population < 2
+    std::pair<double, std::vector<int>> islandBest() const { return {best_cost_, best_}; }
+    // a migrant replaces the least fit chromosome when it is fitter; keeps the incumbent
+    void islandAccept(const std::vector<int>& tour, double cost);
+    size_t islandPopulation() const { return pool_.size(); }
+
     // number of tours the GPU ranked during the last solve (for tests / reports)
     size_t lastEvaluatedTours() const { return evaluated_; }
 
@@ -69,6 +82,7 @@ private:
     void evaluate(const std::vector<Tour>& tours, std::vector<double>& costs);
     void seedPopulation();
     void evolve();
+    bool evolveOnce();
     int drawInt(int lo, int hi);
     double drawReal(double lo, double hi);
 };

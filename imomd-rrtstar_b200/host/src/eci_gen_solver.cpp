@@ -391,7 +391,12 @@ void EciGenSolver::seedPopulation()
 // launch per generation.
 void EciGenSolver::evolve()
 {
-    for (int gen = 0; gen < setting_.ga_generation && pool_.size() >= 2; ++gen)
+    for (int gen = 0; gen < setting_.ga_generation && pool_.size() >= 2; ++gen) evolveOnce();
+}
+
+bool EciGenSolver::evolveOnce()
+{
+    if (pool_.size() < 2) return false;
     {
         const double total = std::accumulate(fitness_.begin(), fitness_.end(), 0.0);
         auto spin = [&]() -> const Tour& {
@@ -469,6 +474,55 @@ void EciGenSolver::evolve()
             best_cost_ = lowest;
             best_ = pool_[lowest_at];
         }
+    }
+    return true;
+}
+
+void EciGenSolver::islandBegin(std::shared_ptr<std::vector<std::vector<double>>> matrix,
+                               int source_id, int target_id, unsigned seed)
+{
+    K_ = static_cast<int>(matrix->size());
+    if (K_ < 2 || K_ > static_cast<int>(IMOMD_KMAX))
+        throw std::invalid_argument("EciGenSolver: matrix size out of range");
+    D_.resize(static_cast<size_t>(K_) * K_);
+    for (int i = 0; i < K_; ++i)
+        for (int j = 0; j < K_; ++j) D_[static_cast<size_t>(i) * K_ + j] = (*matrix)[i][j];
+    source_ = source_id;
+    target_ = target_id;
+    rng_ = std::mt19937{seed};
+    best_cost_ = 0;
+    best_.clear();
+    pool_.clear();
+    fitness_.clear();
+    evaluated_ = 0;
+    cheapestInsertion();
+    seedPopulation();
+}
+
+bool EciGenSolver::islandStep() { return evolveOnce(); }
+
+void EciGenSolver::islandAccept(const std::vector<int>& tour, double cost)
+{
+    if (pool_.empty())
+    {
+        pool_.push_back(tour);
+        fitness_.push_back(1 / cost);
+    }
+    else
+    {
+        size_t worst = 0;
+        for (size_t i = 1; i < fitness_.size(); ++i)
+            if (fitness_[i] < fitness_[worst]) worst = i;
+        if (1 / cost > fitness_[worst])
+        {
+            pool_[worst] = tour;
+            fitness_[worst] = 1 / cost;
+        }
+    }
+    if (cost < best_cost_)
+    {
+        best_cost_ = cost;
+        best_ = tour;
     }
 }
 

@@ -42,5 +42,12 @@ void* imomd_host_solver_create(int device, int swapping, int genetic, int ga_mut
 void imomd_host_solver_destroy(void* s);
 int imomd_host_solver_solve(void* s, int K, const double* D, int source, int target, double* cost,
                             int32_t* seq, int cap, uint64_t* evaluated, char* err, int errlen);
+/* GA islands: begin (insertion + seeding with mt19937{seed}), one generation, best tour, migrant */
+int imomd_host_island_begin(void* s, int K, const double* D, int source, int target, unsigned seed,
+                            char* err, int errlen);
+int imomd_host_island_step(void* s, char* err, int errlen);   /* 1 = stepped, 0 = population < 2 */
+int imomd_host_island_best(void* s, double* cost, int32_t* seq, int cap);
+void imomd_host_island_accept(void* s, double cost, const int32_t* seq, int len);
+uint64_t imomd_host_island_evaluated(void* s);
 }
 #endif

@@ -121,3 +121,53 @@ extern "C" int imomd_host_solver_solve(void* s, int K, const double* D, int sour
         return -1;
     }
 }
+
+extern "C" int imomd_host_island_begin(void* s, int K, const double* D, int source, int target,
+                                       unsigned seed, char* err, int errlen)
+{
+    try
+    {
+        auto m = std::make_shared<std::vector<std::vector<double>>>(K, std::vector<double>(K));
+        for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) (*m)[i][j] = D[static_cast<size_t>(i) * K + j];
+        static_cast<EciGenSolver*>(s)->islandBegin(m, source, target, seed);
+        return 0;
+    }
+    catch (const std::exception& ex)
+    {
+        put_err(err, errlen, ex.what());
+        return -1;
+    }
+}
+
+extern "C" int imomd_host_island_step(void* s, char* err, int errlen)
+{
+    try
+    {
+        return static_cast<EciGenSolver*>(s)->islandStep() ? 1 : 0;
+    }
+    catch (const std::exception& ex)
+    {
+        put_err(err, errlen, ex.what());
+        return -1;
+    }
+}
+
+extern "C" int imomd_host_island_best(void* s, double* cost, int32_t* seq, int cap)
+{
+    auto best = static_cast<EciGenSolver*>(s)->islandBest();
+    *cost = best.first;
+    int n = static_cast<int>(best.second.size());
+    for (int i = 0; i < n && i < cap; ++i) seq[i] = best.second[i];
+    return n;
+}
+
+extern "C" void imomd_host_island_accept(void* s, double cost, const int32_t* seq, int len)
+{
+    static_cast<EciGenSolver*>(s)->islandAccept(std::vector<int>(seq, seq + len), cost);
+}
+
+extern "C" uint64_t imomd_host_island_evaluated(void* s)
+{
+    return static_cast<EciGenSolver*>(s)->lastEvaluatedTours();
+}

@@ -119,6 +119,13 @@ def host_lib():
         L.imomd_host_solver_solve.argtypes = [C.c_void_p, C.c_int, f64p, C.c_int, C.c_int,
                                               C.POINTER(C.c_double), i32p, C.c_int,
                                               C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+        L.imomd_host_island_begin.argtypes = [C.c_void_p, C.c_int, f64p, C.c_int, C.c_int, C.c_uint,
+                                              C.c_char_p, C.c_int]
+        L.imomd_host_island_step.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.imomd_host_island_best.argtypes = [C.c_void_p, C.POINTER(C.c_double), i32p, C.c_int]
+        L.imomd_host_island_accept.argtypes = [C.c_void_p, C.c_double, i32p, C.c_int]
+        L.imomd_host_island_evaluated.restype = C.c_uint64
+        L.imomd_host_island_evaluated.argtypes = [C.c_void_p]
         _host = L
     return _host
 
@@ -351,6 +358,31 @@ class FacadeSolver:
         if n < 0:
             raise ImomdError(err.value.decode())
         return cost.value, seq[:n].copy(), ev.value
+
+    def island_begin(self, D, source, target, seed):
+        D = np.ascontiguousarray(D, np.float64)
+        err = C.create_string_buffer(512)
+        if host_lib().imomd_host_island_begin(self.h, D.shape[0], D.ravel(), source, target, seed, err, 512):
+            raise ImomdError(err.value.decode())
+
+    def island_step(self):
+        err = C.create_string_buffer(512)
+        rc = host_lib().imomd_host_island_step(self.h, err, 512)
+        if rc < 0:
+            raise ImomdError(err.value.decode())
+        return rc == 1
+
+    def island_best(self):
+        cost = C.c_double(); seq = np.empty(256, np.int32)
+        n = host_lib().imomd_host_island_best(self.h, C.byref(cost), seq, 256)
+        return cost.value, [int(v) for v in seq[:n]]
+
+    def island_accept(self, cost, tour):
+        t = np.ascontiguousarray(tour, np.int32)
+        host_lib().imomd_host_island_accept(self.h, cost, t, len(t))
+
+    def island_evaluated(self):
+        return int(host_lib().imomd_host_island_evaluated(self.h))
 
     def close(self):
         if self.h:

@@ -91,3 +91,17 @@ def test_eci_gen_solver_exact_ties(K):
         c1, s1, _ = fs.solve(D, 0, K - 1)
         assert np.array_equal(s1, s2[:n2]) and c1 == c2.value
     fs.close(); O.orc_solver_destroy(os_)
+
+
+def test_ga_island_single_rank_matches_plain_solve():
+    """One island with seed 0 and no migration partner is the reference's GA: same tour."""
+    from imomd_b200 import sharding
+    rng = np.random.default_rng(5)
+    K = 14
+    D = _random_pseudo_complete(K, rng, 0.3)
+    fs = capi.FacadeSolver(0, ga=(2000, 300, 5))
+    want_cost, want_seq, _ = fs.solve(D, 0, K - 1)
+    fs.close()
+    cost, tour, hist, evaluated = sharding.run_islands(D, 0, K - 1, 5, ga=(2000, 300, 5))
+    assert cost == want_cost and tour == [int(v) for v in want_seq]
+    assert evaluated > 0 and [h["best"] for h in hist] == sorted([h["best"] for h in hist], reverse=True)
