@@ -28,6 +28,7 @@
 #include "../../include/imomd_b200.h"
 #include "imomd_core.cuh"
 #include "imomd_setup.h"
+#include "imomd_nn_tiles.cuh"
 
 using namespace imomd;
 
@@ -1008,6 +1009,103 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
     cudaFree(dq);
     cudaFree(didx);
     cudaFree(ddist);
+    return IMOMD_OK;
+}
+
+int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* idx, double* dist,
+                        float* kernel_ms, uint64_t* bytes_streamed, uint32_t* n_refined)
+{
+    if (!p || !q || !idx || !dist || n < 0) return fail(IMOMD_ERR_ARG, "bad argument");
+    if (n == 0) return IMOMD_OK;
+    const int QK = p->d.Q * p->d.K;
+    for (int i = 0; i < n; ++i)
+    {
+        if (q[i].query < 0 || q[i].query >= p->d.Q || q[i].tree < 0 || q[i].tree >= p->d.K)
+            return fail(IMOMD_ERR_ARG, "lookup %d: query/tree out of range", i);
+    }
+    CU(cudaSetDevice(p->g->device));
+    // tiles: lookups grouped by (query, tree), at most kTileLookups per tile
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return q[a].query * p->d.K + q[a].tree < q[b].query * p->d.K + q[b].tree;
+    });
+    std::vector<NnTile> tiles;
+    for (int i = 0; i < n;)
+    {
+        NnTile t{};
+        t.qt = q[order[i]].query * p->d.K + q[order[i]].tree;
+        while (i < n && t.n < kTileLookups && q[order[i]].query * p->d.K + q[order[i]].tree == t.qt)
+            t.lookup[t.n++] = order[i++];
+        tiles.push_back(t);
+    }
+    uint32_t *lists = nullptr, *counts = nullptr, *didx = nullptr, *damb = nullptr;
+    double* ddist = nullptr;
+    imomd_nn_query* dq = nullptr;
+    NnTile* dtiles = nullptr;
+    int* derr = nullptr;
+    CU(dmalloc(&lists, (size_t)QK * 2 * p->d.chunks));
+    CU(dmalloc(&counts, (size_t)QK));
+    CU(dmalloc(&didx, (size_t)n));
+    CU(dmalloc(&damb, (size_t)n));
+    CU(dmalloc(&ddist, (size_t)n));
+    CU(dmalloc(&dq, (size_t)n));
+    CU(dmalloc(&dtiles, tiles.size()));
+    CU(dmalloc(&derr, 1));
+    CU(cudaMemsetAsync(derr, 0, sizeof(int), p->stream));
+    CU(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(imomd_nn_query), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(dtiles, tiles.data(), tiles.size() * sizeof(NnTile), cudaMemcpyHostToDevice,
+                       p->stream));
+    k_tree_chunk_lists<<<(QK + 3) / 4, 128, 0, p->stream>>>(p->d, lists, counts);
+    CU(cudaGetLastError());
+    const size_t smem = sizeof(NnShared) + 128;
+    CU(cudaFuncSetAttribute(k_nearest_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<size_t>(tiles.size(), 148 * 4);
+    CU(cudaEventRecord(p->ev0, p->stream));
+    k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, (int)tiles.size(), dtiles, dq, lists,
+                                                             counts, didx, ddist, damb, derr);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev1, p->stream));
+    std::vector<uint32_t> amb(n), hcounts(QK);
+    int herr = 0;
+    CU(cudaMemcpyAsync(idx, didx, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(amb.data(), damb, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(hcounts.data(), counts, (size_t)QK * 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    cudaFree(lists); cudaFree(counts); cudaFree(didx); cudaFree(damb); cudaFree(ddist);
+    cudaFree(dq); cudaFree(dtiles); cudaFree(derr);
+    if (herr) return fail(IMOMD_ERR_CUDA, "imomd_nearest_batch: pipeline barrier timed out");
+    if (kernel_ms) *kernel_ms = ms;
+    if (bytes_streamed)
+    {
+        uint64_t b = 0;
+        for (const NnTile& t : tiles)
+            b += (uint64_t)hcounts[t.qt] * IMOMD_CHUNK * sizeof(VRec) + (uint64_t)t.n * 36;
+        *bytes_streamed = b;
+    }
+    // lookups the chord ranking could not decide go through the exact path
+    std::vector<int> redo;
+    for (int i = 0; i < n; ++i)
+        if (amb[i]) redo.push_back(i);
+    if (n_refined) *n_refined = (uint32_t)redo.size();
+    if (!redo.empty())
+    {
+        std::vector<imomd_nn_query> rq(redo.size());
+        std::vector<uint32_t> ri(redo.size());
+        std::vector<double> rd(redo.size());
+        for (size_t j = 0; j < redo.size(); ++j) rq[j] = q[redo[j]];
+        int rc = imomd_nearest(p, (int)redo.size(), rq.data(), ri.data(), rd.data());
+        if (rc != IMOMD_OK) return rc;
+        for (size_t j = 0; j < redo.size(); ++j)
+        {
+            idx[redo[j]] = ri[j];
+            dist[redo[j]] = rd[j];
+        }
+    }
     return IMOMD_OK;
 }
 

@@ -90,6 +90,8 @@ def cuda_lib():
                                          C.POINTER(C.c_uint32)]
         L.imomd_get_connection_log.argtypes = [vp, C.c_int, u32p, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.imomd_nearest.argtypes = [vp, C.c_int, C.c_void_p, u32p, f64p]
+        L.imomd_nearest_batch.argtypes = [vp, C.c_int, C.c_void_p, u32p, f64p, C.POINTER(C.c_float),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.imomd_ctx_create.argtypes = [C.c_int, vpp]
         L.imomd_ctx_destroy.argtypes = [vp]
         L.imomd_ga_eval.argtypes = [vp, C.c_int, f64p, C.c_int, C.c_int, i32p, i32p, f64p]
@@ -292,6 +294,17 @@ class DevicePlanner:
         idx = np.empty(n, np.uint32); dist = np.empty(n)
         _check(cuda_lib().imomd_nearest(self.h, n, lk.ctypes.data_as(C.c_void_p), idx, dist))
         return idx, dist
+
+
+def nearest_batch(dp, lookups):
+    """imomd_nearest_batch: (idx, dist, dict(kernel_ms, bytes, refined))."""
+    lk = np.ascontiguousarray(lookups, NN_DTYPE)
+    n = lk.shape[0]
+    idx = np.empty(n, np.uint32); dist = np.empty(n)
+    ms, by, nr = C.c_float(), C.c_uint64(), C.c_uint32()
+    _check(cuda_lib().imomd_nearest_batch(dp.h, n, lk.ctypes.data_as(C.c_void_p), idx, dist,
+                                          C.byref(ms), C.byref(by), C.byref(nr)))
+    return idx, dist, dict(kernel_ms=ms.value, bytes=by.value, refined=nr.value)
 
 
 class GaContext:

@@ -191,3 +191,32 @@ def test_full_size_grid_1m_matches_oracle_prefix():
         nb = np.unique(np.concatenate([g.col[g.row_ptr[x]:g.row_ptr[x + 1]] for x in np.nonzero(vis)[0]]))
         assert np.array_equal(np.sort(nb[~vis[nb]]).astype(np.uint64), fr)
     dp.close(); dg.close(); op.close()
+
+
+def test_nearest_batch_tile_kernel_matches_exact_path():
+    """imomd_nearest_batch (bulk-async staged brute-force tiles) returns the same indices as the
+    pruned exact path and the oracle, over several queries / trees and ragged tile sizes."""
+    g = graphs.jittered_grid(150, seed=8)
+    rng = np.random.default_rng(5)
+    Q, K = 5, 6
+    dests = [graphs.pick_destinations(g, K, seed=int(s)) for s in rng.integers(0, 10**6, Q)]
+    dg = capi.DeviceGraph(g)
+    dp = capi.DevicePlanner(dg, dests)
+    dp.feed(capi.mt19937_words(0, 300000))
+    dp.expand(1200)
+    n = 4000
+    lk = np.empty(n, capi.NN_DTYPE)
+    lk["query"] = rng.integers(0, Q, n); lk["tree"] = rng.integers(0, K, n)
+    lk["lat"] = rng.uniform(g.lat.min(), g.lat.max(), n); lk["lon"] = rng.uniform(g.lon.min(), g.lon.max(), n)
+    # some trees get a single lookup, one gets hundreds (ragged tiles)
+    lk["query"][:600] = 2; lk["tree"][:600] = 3
+    idx_a, dist_a = dp.nearest(lk)
+    idx_b, dist_b, info = capi.nearest_batch(dp, lk)
+    assert np.array_equal(idx_a, idx_b)
+    assert np.array_equal(dist_a.view(np.uint64), dist_b.view(np.uint64))
+    assert info["bytes"] > 0 and info["kernel_ms"] > 0
+    o = ol.OraclePlanner(g, dests[2]); o.iterate(1200)
+    for i in range(0, 600, 7):
+        ok, want, d, ties, _ = o.nearest(3, float(lk["lat"][i]), float(lk["lon"][i]))
+        assert int(idx_b[i]) == want
+    o.close(); dp.close(); dg.close()
