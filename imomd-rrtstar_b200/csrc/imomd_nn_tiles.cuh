@@ -2,7 +2,7 @@
 // lookups (imomd_nearest_batch): the bandwidth-shaped variant of steerNewNode_'s arg-min
 // (src/imomd_rrt_star.cpp:406-418 upstream).
 //
-// A tile = one (query, tree) frontier and up to kTileLookups samples against it.  The
+// A tile = one (query, tree) frontier and up to kTileLookups (4) samples against it.  The
 // frontier lives in 1 KB chunks of 32 records (csrc/imomd_layout.h); a producer warp streams
 // the tree's chunks into a 4-stage shared-memory ring with bulk asynchronous copies
 // (cp.async.bulk ... mbarrier::complete_tx, the TMA engine; one 1 KB copy per chunk because
@@ -12,7 +12,7 @@
 // mbarriers hand the stages back and forth; the kernel is persistent over tiles.
 //
 // Algorithmic bytes: 32 B per frontier record per tile + 24 B per lookup + 12 B per answer
-// (brute-force variant).  With kTileLookups = 8 the FP64 work per staged byte
+// (brute-force variant).  With kTileLookups = 4 the FP64 work per staged byte
 // stays below the machine balance, so the kernel is HBM-bound when the frontiers do not fit
 // in L2.  Lookups whose two best candidates are closer than the rounding band are flagged
 // and re-done by the exact path (k_nearest).
@@ -23,7 +23,7 @@
 
 namespace imomd {
 
-constexpr int kTileLookups = 8;        // samples per tile
+constexpr int kTileLookups = 4;        // samples per tile
 constexpr int kStageChunks = 8;        // 1 KB chunks per pipeline stage
 constexpr int kStages = 4;
 constexpr int kConsumerWarps = 4;
@@ -135,7 +135,7 @@ struct __align__(16) NnShared
     int error;
 };
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
 k_nearest_tiles(PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
                 const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
                 const uint32_t* __restrict__ counts, uint32_t* __restrict__ idx,
@@ -176,63 +176,109 @@ k_nearest_tiles(PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
         if (warp == 0)
         {
             // ---------------- producer: bulk copies chunk -> stage ----------------
+            // lane j of the producer warp owns chunk j of every stage: it fetches the chunk id
+            // (prefetched one stage ahead) and issues its own 1 KB bulk copy
+            uint32_t my_chunk = IMOMD_NONE, my_valid = 0;
+            if (n_stages > 0 && lane < kStageChunks && (uint32_t)lane < n_chunks)
+            {
+                my_chunk = list[2 * lane];
+                my_valid = list[2 * lane + 1];
+            }
             for (uint32_t s = 0; s < n_stages; ++s)
             {
                 const uint32_t slot = (it + s) % kStages, round = (it + s) / kStages;
+                const uint32_t c0 = s * kStageChunks;
+                const uint32_t nc = min((uint32_t)kStageChunks, n_chunks - c0);
+                const uint32_t chunk = my_chunk, valid = my_valid;
+                // next stage's ids are requested before this stage's barrier wait
+                const uint32_t nxt = c0 + kStageChunks + lane;
+                if (lane < kStageChunks && nxt < n_chunks)
+                {
+                    my_chunk = list[2 * nxt];
+                    my_valid = list[2 * nxt + 1];
+                }
                 if (lane == 0)
                 {
                     if (round > 0 && !mbar_wait(&sh.empty[slot], (round - 1) & 1)) sh.error = 1;
-                    const uint32_t c0 = s * kStageChunks;
-                    const uint32_t nc = min((uint32_t)kStageChunks, n_chunks - c0);
-                    for (uint32_t j = 0; j < (uint32_t)kStageChunks; ++j)
-                        sh.valid[slot][j] = j < nc ? list[2 * (c0 + j) + 1] : 0u;
-                    mbar_expect_tx(&sh.full[slot], nc * (uint32_t)(IMOMD_CHUNK * sizeof(VRec)));
-                    for (uint32_t j = 0; j < nc; ++j)
-                    {
-                        const uint32_t chunk = list[2 * (c0 + j)];
-                        bulk_g2s(&sh.stage[slot][j * IMOMD_CHUNK], rec + (size_t)chunk * IMOMD_CHUNK,
-                                 (uint32_t)(IMOMD_CHUNK * sizeof(VRec)), &sh.full[slot]);
-                    }
                 }
+                __syncwarp();
+                if (lane < kStageChunks) sh.valid[slot][lane] = (uint32_t)lane < nc ? valid : 0u;
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(&sh.full[slot], nc * (uint32_t)(IMOMD_CHUNK * sizeof(VRec)));
+                __syncwarp();
+                if ((uint32_t)lane < nc)
+                    bulk_g2s(&sh.stage[slot][lane * IMOMD_CHUNK], rec + (size_t)chunk * IMOMD_CHUNK,
+                             (uint32_t)(IMOMD_CHUNK * sizeof(VRec)), &sh.full[slot]);
                 __syncwarp();
             }
         }
         else
         {
             // ---------------- consumers: rank the staged records ----------------
+            // each thread takes records c, c+128, ... of a stage and ranks them against ALL
+            // samples of the tile (one record load feeds kTileLookups chord evaluations)
             const int c = threadIdx.x - 32;                 // 0 .. 127
-            const int l = c % kTileLookups;                 // sample handled by this thread
-            const int grp = c / kTileLookups;               // record phase 0 .. 15
-            constexpr int kGroups = kConsumerWarps * 32 / kTileLookups;
-            const double qx = sh.qx[l], qy = sh.qy[l], qz = sh.qz[l];
-            Best b = best_empty();
+            double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
+            Best b[kTileLookups];
+#pragma unroll
+            for (int l = 0; l < kTileLookups; ++l)
+            {
+                qx[l] = sh.qx[l];
+                qy[l] = sh.qy[l];
+                qz[l] = sh.qz[l];
+                b[l] = best_empty();
+            }
             for (uint32_t s = 0; s < n_stages; ++s)
             {
                 const uint32_t slot = (it + s) % kStages, round = (it + s) / kStages;
                 if (!mbar_wait(&sh.full[slot], round & 1)) sh.error = 1;
                 const VRec* st = sh.stage[slot];
-#pragma unroll 4
-                for (int r = grp; r < kStageChunks * IMOMD_CHUNK; r += kGroups)
+#pragma unroll
+                for (int r = c; r < kStageChunks * IMOMD_CHUNK; r += kConsumerWarps * 32)
                 {
                     if ((uint32_t)(r % IMOMD_CHUNK) < sh.valid[slot][r / IMOMD_CHUNK])
                     {
                         const VRec v = st[r];
-                        double dx = v.x - qx, dy = v.y - qy, dz = v.z - qz;
-                        best_add(b, dx * dx + dy * dy + dz * dz, v.id);
+#pragma unroll
+                        for (int l = 0; l < kTileLookups; ++l)
+                        {
+                            double dx = v.x - qx[l], dy = v.y - qy[l], dz = v.z - qz[l];
+                            double c2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                            // common case first: not better than the incumbent -> only the
+                            // runner-up can move
+                            if (c2 > b[l].v1)
+                                b[l].v2 = fmin(b[l].v2, c2);
+                            else
+                                best_add(b[l], c2, v.id);
+                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.empty[slot]);
             }
-            sh.part[c] = b;
+            // per-sample merge over the warp, one partial per (warp, sample)
+#pragma unroll
+            for (int l = 0; l < kTileLookups; ++l)
+            {
+                Best x = b[l];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+                {
+                    Best o;
+                    o.v1 = __shfl_down_sync(0xFFFFFFFFu, x.v1, off);
+                    o.id1 = __shfl_down_sync(0xFFFFFFFFu, x.id1, off);
+                    o.v2 = __shfl_down_sync(0xFFFFFFFFu, x.v2, off);
+                    x = best_merge(x, o);
+                }
+                if (lane == 0) sh.part[(warp - 1) * kTileLookups + l] = x;
+            }
         }
         it += n_stages;
         __syncthreads();
         if (threadIdx.x < (unsigned)t.n)
         {
-            constexpr int kGroups = kConsumerWarps * 32 / kTileLookups;
             Best b = best_empty();
-            for (int gI = 0; gI < kGroups; ++gI) b = best_merge(b, sh.part[gI * kTileLookups + threadIdx.x]);
+            for (int w = 0; w < kConsumerWarps; ++w) b = best_merge(b, sh.part[w * kTileLookups + threadIdx.x]);
             const int li = t.lookup[threadIdx.x];
             const imomd_nn_query nq = qs[li];
             idx[li] = b.id1;

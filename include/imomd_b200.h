@@ -180,7 +180,7 @@ int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uin
  * frontiers; idx = IMOMD_NONE when the frontier is empty; dist = haversine metres. */
 int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* idx, double* dist);
 
-/* Same answers for LARGE batches: lookups are grouped into tiles of one frontier x 8 samples
+/* Same answers for LARGE batches: lookups are grouped into tiles of one frontier x 4 samples
  * and every frontier is streamed once per tile through a shared-memory ring filled by bulk
  * asynchronous copies (the bandwidth-shaped brute-force variant).  Optional outputs: device
  * time of the tile kernel, algorithmic bytes it streamed (32 B per frontier record per tile
