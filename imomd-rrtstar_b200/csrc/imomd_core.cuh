@@ -193,30 +193,17 @@ struct __attribute__((aligned(16))) U4
     uint32_t x, y, z, w;
 };
 
-// Vertex record of one tree, 16 bytes when the graph's degree is at most 8:
-//   tag  u32   parent id when visited | 0x80000000 + frontier slot when in the frontier |
-//              NONE when neither (a vertex is never both: it leaves the frontier when it is
-//              visited)
-//   chl  u32   the child row: up to 8 four-bit adjacency-slot numbers in container order,
-//              0xF = end (children of p are neighbours of p, so a slot number into p's
-//              adjacency row names the child)
-//   cost f64
-// One 128-bit load answers "visited? parent? cost? in the frontier? which children?".
-// Degree 9..13 graphs use 32-byte records with a 64-bit child word.
-constexpr uint32_t kFrontierTag = 0x80000000u;
-
 struct THead
 {
     uint32_t parent;   // NONE = not visited
     uint32_t fslot;    // frontier slot, NONE = not in the frontier
     double cost;
-    uint32_t chl32;    // packed child row (low 8 nibbles)
 };
 
 struct TreeRef
 {
     unsigned char* base;
-    uint32_t stride;          // bytes per vertex record: 16 (width <= 8) or 32
+    uint32_t stride;          // bytes per vertex record: 16 + 4 * width
     uint32_t* cell_head;
     uint32_t* cell_cnt;
     uint32_t* occ;        // [cells] occupied cells, then [cells] cell -> position
@@ -224,45 +211,29 @@ struct TreeRef
     uint32_t* chunk_next;
     uint32_t* free_stack;
 
-    IMOMD_HD unsigned char* at(uint32_t v) const { return base + (size_t)v * stride; }
-    IMOMD_HD static uint32_t tag_parent(uint32_t tag) { return (tag & kFrontierTag) ? IMOMD_NONE : tag; }
-    IMOMD_HD static uint32_t tag_fslot(uint32_t tag)
+    IMOMD_HD THead* hp(uint32_t v) const
     {
-        return (tag != IMOMD_NONE && (tag & kFrontierTag)) ? (tag & ~kFrontierTag) : IMOMD_NONE;
+        return reinterpret_cast<THead*>(base + (size_t)v * stride);
     }
     IMOMD_HD THead head(uint32_t v) const   // one 128-bit load
     {
-        U4 t = *reinterpret_cast<const U4*>(at(v));
+        U4 t = *reinterpret_cast<const U4*>(base + (size_t)v * stride);
         THead h;
-        h.parent = tag_parent(t.x);
-        h.fslot = tag_fslot(t.x);
-        h.chl32 = t.y;
+        h.parent = t.x;
+        h.fslot = t.y;
         unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
         memcpy(&h.cost, &bits, 8);
         return h;
     }
-    IMOMD_HD uint32_t tag(uint32_t v) const { return *reinterpret_cast<const uint32_t*>(at(v)); }
-    IMOMD_HD uint32_t parent(uint32_t v) const { return tag_parent(tag(v)); }
-    IMOMD_HD uint32_t fslot(uint32_t v) const { return tag_fslot(tag(v)); }
-    IMOMD_HD double cost(uint32_t v) const { return *reinterpret_cast<const double*>(at(v) + 8); }
-    IMOMD_HD void set_parent(uint32_t v, uint32_t p) const { *reinterpret_cast<uint32_t*>(at(v)) = p; }
-    IMOMD_HD void set_fslot(uint32_t v, uint32_t f) const
+    IMOMD_HD uint32_t parent(uint32_t v) const { return hp(v)->parent; }
+    IMOMD_HD uint32_t fslot(uint32_t v) const { return hp(v)->fslot; }
+    IMOMD_HD double cost(uint32_t v) const { return hp(v)->cost; }
+    IMOMD_HD void set_parent(uint32_t v, uint32_t p) const { hp(v)->parent = p; }
+    IMOMD_HD void set_fslot(uint32_t v, uint32_t f) const { hp(v)->fslot = f; }
+    IMOMD_HD void set_cost(uint32_t v, double c) const { hp(v)->cost = c; }
+    IMOMD_HD uint32_t* chl(uint32_t v) const
     {
-        *reinterpret_cast<uint32_t*>(at(v)) = f == IMOMD_NONE ? IMOMD_NONE : (f | kFrontierTag);
-    }
-    IMOMD_HD void set_cost(uint32_t v, double c) const { *reinterpret_cast<double*>(at(v) + 8) = c; }
-    // packed child row as a 64-bit word (nibble i = adjacency slot of the i-th child, 0xF = end)
-    template <int W>
-    IMOMD_HD uint64_t chl_bits(uint32_t v) const
-    {
-        if (W <= 8) return 0xFFFFFFFF00000000ull | *reinterpret_cast<const uint32_t*>(at(v) + 4);
-        return *reinterpret_cast<const uint64_t*>(at(v) + 16);
-    }
-    template <int W>
-    IMOMD_HD void set_chl_bits(uint32_t v, uint64_t bits) const
-    {
-        if (W <= 8) *reinterpret_cast<uint32_t*>(at(v) + 4) = (uint32_t)bits;
-        else *reinterpret_cast<uint64_t*>(at(v) + 16) = bits;
+        return reinterpret_cast<uint32_t*>(base + (size_t)v * stride + 16);
     }
 };
 
@@ -473,15 +444,14 @@ IMOMD_HD inline void fr_erase(const PlannerDev& P, QueryDev* Q, const TreeRef& T
 template <int W>
 struct ChlRow
 {
-    uint32_t v[W];   // child vertex ids in container order, NONE-terminated
+    uint32_t v[W];
 };
 
-// adjacency row of p in the padded table (W ids, NONE padded): W/4 128-bit loads
 template <int W>
-IMOMD_HD inline ChlRow<W> ell_load(const GraphDev& g, uint32_t p)
+IMOMD_HD inline ChlRow<W> chl_load(const uint32_t* rowp)
 {
     ChlRow<W> r;
-    const U4* src = reinterpret_cast<const U4*>(g.ell + (size_t)p * W);
+    const U4* src = reinterpret_cast<const U4*>(rowp);
 #pragma unroll
     for (int i = 0; i < W / 4; ++i)
     {
@@ -495,62 +465,19 @@ IMOMD_HD inline ChlRow<W> ell_load(const GraphDev& g, uint32_t p)
 }
 
 template <int W>
-IMOMD_HD inline ChlRow<W> chl_decode(uint64_t bits, const ChlRow<W>& adj)
+IMOMD_HD inline void chl_store(uint32_t* rowp, const ChlRow<W>& r)
 {
-    ChlRow<W> r;
-    bool ended = false;
+    U4* dst = reinterpret_cast<U4*>(rowp);
 #pragma unroll
-    for (int i = 0; i < W; ++i)
+    for (int i = 0; i < W / 4; ++i)
     {
-        uint32_t slot = i < 16 ? (uint32_t)((bits >> (4 * i)) & 0xFu) : 0xFu;
-        if (slot == 0xFu) ended = true;
-        uint32_t id = IMOMD_NONE;
-        if (!ended)
-        {
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-            {
-                if ((uint32_t)j == slot) id = adj.v[j];
-            }
-        }
-        r.v[i] = id;
+        U4 t;
+        t.x = r.v[4 * i];
+        t.y = r.v[4 * i + 1];
+        t.z = r.v[4 * i + 2];
+        t.w = r.v[4 * i + 3];
+        dst[i] = t;
     }
-    return r;
-}
-
-template <int W>
-IMOMD_HD inline uint64_t chl_encode(const ChlRow<W>& r, const ChlRow<W>& adj)
-{
-    uint64_t bits = ~0ull;
-#pragma unroll
-    for (int i = 0; i < W; ++i)
-    {
-        if (i < 16 && r.v[i] != IMOMD_NONE)
-        {
-            uint64_t slot = 0xFull;
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-            {
-                if (adj.v[j] == r.v[i]) slot = (uint64_t)j;
-            }
-            bits = (bits & ~(0xFull << (4 * i))) | (slot << (4 * i));
-        }
-    }
-    return bits;
-}
-
-template <int W>
-IMOMD_HD inline ChlRow<W> chl_load(const GraphDev& g, const TreeRef& T, uint32_t p)
-{
-    ChlRow<W> adj = ell_load<W>(g, p);
-    return chl_decode<W>(T.chl_bits<W>(p), adj);
-}
-
-template <int W>
-IMOMD_HD inline void chl_store(const GraphDev& g, const TreeRef& T, uint32_t p, const ChlRow<W>& r)
-{
-    ChlRow<W> adj = ell_load<W>(g, p);
-    T.set_chl_bits<W>(p, chl_encode<W>(r, adj));
 }
 
 template <int W>
@@ -600,32 +527,63 @@ IMOMD_HD inline void chl_row_erase(ChlRow<W>& r, uint32_t x)
 }
 
 template <int W>
-IMOMD_HD inline void chl_insert_w(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
+IMOMD_HD inline void chl_insert_w(uint32_t* rowp, uint32_t x)
 {
-    ChlRow<W> adj = ell_load<W>(g, p);
-    ChlRow<W> r = chl_decode<W>(T.chl_bits<W>(p), adj);
-    chl_row_insert<W>(r, x);
-    T.set_chl_bits<W>(p, chl_encode<W>(r, adj));
+    ChlRow<W> r = chl_load<W>(rowp);
+    int n = 0, at = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (r.v[i] != IMOMD_NONE)
+        {
+            if (r.v[i] == x) return;
+            if (at < 0 && r.v[i] % 13 == x % 13) at = i;
+            n = i + 1;
+        }
+    }
+    if (at < 0) at = 0;
+    if (n >= W) return;   // cannot happen: children are distinct neighbours, W >= degree
+#pragma unroll
+    for (int i = W - 1; i > 0; --i)
+    {
+        if (i > at) r.v[i] = r.v[i - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (i == at) r.v[i] = x;
+    }
+    chl_store<W>(rowp, r);
 }
 
 template <int W>
-IMOMD_HD inline void chl_erase_w(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
+IMOMD_HD inline void chl_erase_w(uint32_t* rowp, uint32_t x)
 {
-    ChlRow<W> adj = ell_load<W>(g, p);
-    ChlRow<W> r = chl_decode<W>(T.chl_bits<W>(p), adj);
-    chl_row_erase<W>(r, x);
-    T.set_chl_bits<W>(p, chl_encode<W>(r, adj));
+    ChlRow<W> r = chl_load<W>(rowp);
+    int at = -1;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if (r.v[i] == x) at = i;
+    }
+    if (at < 0) return;
+#pragma unroll
+    for (int i = 0; i < W - 1; ++i)
+    {
+        if (i >= at) r.v[i] = r.v[i + 1];
+    }
+    r.v[W - 1] = IMOMD_NONE;
+    chl_store<W>(rowp, r);
 }
 
 template <int W>
-IMOMD_HD inline void chl_assign_single_w(const GraphDev& g, const TreeRef& T, uint32_t p, uint32_t x)
+IMOMD_HD inline void chl_assign_single_w(uint32_t* rowp, uint32_t x)
 {
-    ChlRow<W> adj = ell_load<W>(g, p);
     ChlRow<W> r;
 #pragma unroll
     for (int i = 0; i < W; ++i) r.v[i] = IMOMD_NONE;
     r.v[0] = x;
-    T.set_chl_bits<W>(p, chl_encode<W>(r, adj));
+    chl_store<W>(rowp, r);
 }
 
 // (*connection_ptr_)[a][b]; the graph was validated symmetric at upload
@@ -867,7 +825,7 @@ struct Seq
         }
         if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
         T.set_parent(x_new, via);
-        chl_assign_single_w<KW>(g, T, via, x_new);
+        chl_assign_single_w<KW>(T.chl(via), x_new);
         double cnew = T.cost(via) + edge_weight(g, via, x_new);
         T.set_cost(x_new, cnew);
         S.conn_x = x_new;
@@ -920,7 +878,7 @@ struct Seq
         {
             if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
             T.set_parent(x_new, x_parent);
-            chl_insert_w<KW>(g, T, x_parent, x_new);
+            chl_insert_w<KW>(T.chl(x_parent), x_new);
             T.set_cost(x_new, min_cost);
         }
     }
@@ -1045,23 +1003,18 @@ struct Seq
     template <int W>
     IMOMD_HD void move_child_w(const TreeRef& T, uint32_t y, uint32_t py, uint32_t x)
     {
-        const GraphDev& g = P.g;
         if (py == x)
         {
-            chl_erase_w<W>(g, T, py, y);
-            chl_insert_w<W>(g, T, x, y);
+            chl_erase_w<W>(T.chl(py), y);
+            chl_insert_w<W>(T.chl(x), y);
             return;
         }
-        ChlRow<W> adj_from = ell_load<W>(g, py);
-        ChlRow<W> adj_to = ell_load<W>(g, x);
-        uint64_t bits_from = T.chl_bits<W>(py);
-        uint64_t bits_to = T.chl_bits<W>(x);
-        ChlRow<W> from = chl_decode<W>(bits_from, adj_from);
-        ChlRow<W> to = chl_decode<W>(bits_to, adj_to);
+        ChlRow<W> from = chl_load<W>(T.chl(py));
+        ChlRow<W> to = chl_load<W>(T.chl(x));
         chl_row_erase<W>(from, y);
         chl_row_insert<W>(to, y);
-        T.set_chl_bits<W>(py, chl_encode<W>(from, adj_from));
-        T.set_chl_bits<W>(x, chl_encode<W>(to, adj_to));
+        chl_store<W>(T.chl(py), from);
+        chl_store<W>(T.chl(x), to);
     }
 
     IMOMD_HD void reparent(const TreeRef& T, uint32_t y, uint32_t py, uint32_t x, double nc)
@@ -1292,11 +1245,9 @@ struct Seq
                         return;
                     }
                     uint32_t x_new = S.x_new;
-                    // updateExpandables(tree, x_new, true), first half -- done before
-                    // connectNewNode_ here (the two do not interact) because a record's tag
-                    // holds either the frontier slot or the parent
-                    fr_erase(P, Q, T, k, x_new);
                     connect_new_node(k, T, x_new);
+                    // updateExpandables(tree, x_new, true), first half
+                    fr_erase(P, Q, T, k, x_new);
                     collect_rescans(k, x_new);
                     S.phase = PH_INSERT;
                     if (S.n_rescan > 0)
@@ -1456,7 +1407,7 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
         uint32_t y = g.col[e0 + t];
         double w = g.w[e0 + t];
         THead h = T.head(y);
-        acc += h.chl32 + h.parent + (w > 0.0 ? 1u : 0u) + g.ell[(size_t)y * g.width];
+        acc += T.chl(y)[0] + h.parent + (w > 0.0 ? 1u : 0u);
         VRec v = g.vrec[y];
         acc += T.cell_cnt[v.cell] + T.cell_head[v.cell];
         acc += g.row_ptr[y] + g.row_ptr[y + 1];
@@ -1467,7 +1418,7 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
         uint32_t c = g.vrec[x].cell;
         uint32_t cnt = T.cell_cnt[c], hd = T.cell_head[c];
         if (cnt != 0 && hd != IMOMD_NONE) acc += T.rec[(size_t)hd * IMOMD_CHUNK + (cnt - 1) % IMOMD_CHUNK].id;
-        acc += h.fslot + h.chl32 + g.ell[(size_t)x * g.width];
+        acc += h.fslot + T.chl(x)[0];
     }
     else if (t == 33)
     {
@@ -1648,7 +1599,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_conn_gather(Cta& cta, const PlannerDev& P, int 
         unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
         double c;
         memcpy(&c, &bits, 8);
-        S.conn_par[o] = TreeRef::tag_parent(t.x);   // a frontier tag is not a parent
+        S.conn_par[o] = t.x;
         S.conn_cost[o] = c;
     }
 }
@@ -1680,18 +1631,15 @@ IMOMD_HD inline void bfs_flush(const TreeRef&, BfsPending<W>&, double, double)
 // one vertex of the current level: a single record load returns its cost (updated in
 // place, include/imomd_rrt_star/imomd_rrt_star.h:116) and its child row
 template <int W>
-IMOMD_HD inline int bfs_expand(const GraphDev& g, const TreeRef& T, uint32_t node, bool active,
-                               BfsPending<W>&, double new_cost, double old, ChlRow<W>& row,
-                               uint32_t rewired)
+IMOMD_HD inline int bfs_expand(const TreeRef& T, uint32_t node, bool active, BfsPending<W>&,
+                               double new_cost, double old, ChlRow<W>& row, uint32_t rewired)
 {
     int cnt = 0;
     if (active)
     {
-        ChlRow<W> adj = ell_load<W>(g, node);          // shared graph table, independent address
-        THead h = T.head(node);                        // cost + packed child row in one load
-        uint64_t bits = W <= 8 ? (0xFFFFFFFF00000000ull | h.chl32) : T.chl_bits<W>(node);
+        THead h = T.head(node);
+        row = chl_load<W>(T.chl(node));
         if (node != rewired) T.set_cost(node, new_cost + h.cost - old);
-        row = chl_decode<W>(bits, adj);
 #pragma unroll
         for (int i = 0; i < W; ++i)
         {
@@ -1755,7 +1703,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                             for (;;)
                             {
                                 ChlRow<W> row;
-                                int cnt = bfs_expand<W>(P.g, T, node, true, pd, new_cost, old, row, rewired);
+                                int cnt = bfs_expand<W>(T, node, true, pd, new_cost, old, row, rewired);
                                 if (tail + (uint32_t)cnt > cap)
                                 {
                                     ovf = 1;
@@ -1799,7 +1747,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                     bool active = (uint32_t)cta.lane() < n;
                     uint32_t node = active ? cl[cta.lane()] : 0u;
                     ChlRow<W> row;
-                    int cnt = bfs_expand<W>(P.g, T, node, active, pd, new_cost, old, row, rewired);
+                    int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row, rewired);
                     uint32_t total = 0;
                     uint32_t off = cta.warp_scan_small((uint32_t)cnt, W, &total);
                     if (tail + total > cap)
@@ -1852,7 +1800,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                 uint32_t node = 0u;
                 if (active) node = idx < kLevelCap ? cl[idx] : arena[start + idx];
                 ChlRow<W> row;
-                int cnt = bfs_expand<W>(P.g, T, node, active, pd, new_cost, old, row, rewired);
+                int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row, rewired);
                 uint32_t total = 0;
                 uint32_t off = cta.scan_exclusive((uint32_t)cnt, &total, S.scan);
                 if (tail + produced + total > cap)

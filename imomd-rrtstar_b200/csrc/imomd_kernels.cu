@@ -328,7 +328,6 @@ __global__ void k_walk(const unsigned char* __restrict__ trec, uint32_t stride, 
     while (v != root && v != IMOMD_NONE)
     {
         v = *reinterpret_cast<const uint32_t*>(trec + (size_t)v * stride);
-        if (v & kFrontierTag) v = IMOMD_NONE;
         if (n < cap) out[n] = v;
         ++n;
         if (n > 0x7FFFFFF0u) break;
@@ -389,7 +388,6 @@ struct imomd_graph
     double* lat;
     double* lon;
     VRec* vrec;
-    uint32_t* ell;
     double* cosrow;
     uint32_t max_degree;
 };
@@ -495,18 +493,12 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     CU(dmalloc(&g->lat, n));
     CU(dmalloc(&g->lon, n));
     CU(dmalloc(&g->vrec, n));
-    CU(dmalloc(&g->ell, (size_t)n * d.width));
     CU(dmalloc(&g->cosrow, 2 * (size_t)G));
     CU(cudaMemcpy(g->row_ptr, row_ptr, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->col, col, (size_t)arcs * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->w, w, (size_t)arcs * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->lat, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->lon, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
-    {
-        std::vector<uint32_t> ell;
-        build_ell(n, row_ptr, col, d.width, &ell);
-        CU(cudaMemcpy(g->ell, ell.data(), ell.size() * 4, cudaMemcpyHostToDevice));
-    }
     CU(cudaMemcpy(g->cosrow, cosrow.data(), 2 * (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
     d.row_ptr = g->row_ptr;
     d.col = g->col;
@@ -514,7 +506,6 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     d.lat = g->lat;
     d.lon = g->lon;
     d.vrec = g->vrec;
-    d.ell = g->ell;
     d.cosrow = g->cosrow;
     k_build_vrec<<<(n + 255) / 256, 256>>>(n, g->lat, g->lon, g->vrec, G, d.lat0, d.lon0, d.hlat,
                                            d.hlon);
@@ -534,7 +525,6 @@ int imomd_graph_destroy(imomd_graph* g)
     cudaFree(g->lat);
     cudaFree(g->lon);
     cudaFree(g->vrec);
-    cudaFree(g->ell);
     cudaFree(g->cosrow);
     delete g;
     return IMOMD_OK;
@@ -591,7 +581,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     CU(cudaEventCreate(&p->ev0));
     CU(cudaEventCreate(&p->ev1));
     CU(dmalloc(&d.query, (size_t)n_queries));
-    d.trec_stride = tree_record_stride(g->d.width);
+    d.trec_stride = 16u + 4u * (uint32_t)g->d.width;
     CU(dmalloc(&d.trec, qk * n * d.trec_stride));
     CU(dmalloc(&d.cell_head, qk * cells));
     CU(dmalloc(&d.cell_cnt, qk * cells));
@@ -897,11 +887,10 @@ int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, doub
     if (cost)
     {
         CU(cudaMemcpy2D(cost, 8, base + 8, p->d.trec_stride, 8, n, cudaMemcpyDeviceToHost));
-    }
-    for (size_t v = 0; v < n; ++v)
-    {
-        if (parent[v] & kFrontierTag) parent[v] = IMOMD_NONE;   // frontier slot or nothing
-        if (cost && parent[v] == IMOMD_NONE) cost[v] = INFINITY;
+        for (size_t v = 0; v < n; ++v)
+        {
+            if (parent[v] == IMOMD_NONE) cost[v] = INFINITY;
+        }
     }
     return IMOMD_OK;
 }
@@ -916,12 +905,12 @@ int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uin
     size_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
     std::vector<uint32_t> slot(n);
-    CU(cudaMemcpy2D(slot.data(), 4, p->d.trec + qt * n * p->d.trec_stride, p->d.trec_stride, 4, n,
+    CU(cudaMemcpy2D(slot.data(), 4, p->d.trec + qt * n * p->d.trec_stride + 4, p->d.trec_stride, 4, n,
                     cudaMemcpyDeviceToHost));
     uint32_t c = 0;
     for (size_t v = 0; v < n; ++v)
     {
-        if (slot[v] != IMOMD_NONE && (slot[v] & kFrontierTag))
+        if (slot[v] != IMOMD_NONE)
         {
             if (out && c < cap) out[c] = (uint32_t)v;
             ++c;

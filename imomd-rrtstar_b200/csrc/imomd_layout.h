@@ -14,8 +14,8 @@
 //   arena u32[arena_entries]                   rewire scratch (updateCost lists, frames)
 //   clist u32x2[chunks_per_tree]               chunk work list of the pruned searches
 // Per (query, tree):
-//   trec[N]: 16-byte records {tag u32 = parent | frontier slot | NONE, packed child row u32
-//             (4-bit adjacency slots, container order), cost f64}; 32 B when degree > 8
+//   trec[N]: {parent u32 (NONE = not visited), frontier slot u32, cost f64,
+//             child[width] u32 (NONE-terminated, container order)}  -- 32 B when width = 4
 //   cell_head u32[G*G], cell_cnt u32[G*G]      frontier hash: per-cell chunk chain
 //   occ u32[2*G*G]                             occupied cells (list + inverse)
 //   rec VRec[chunks*32], chunk_next u32[chunks], free_stack u32[chunks]
@@ -53,7 +53,6 @@ struct GraphDev
     const double* lat;
     const double* lon;
     const VRec* vrec;
-    const uint32_t* ell;  // [n][width] padded adjacency (same order as the CSR rows, NONE padded)
     int32_t G;            // cells per axis
     int32_t prune;        // 0 = map too large for the cell bound: scan every cell
     int32_t width;        // adjacency slots per vertex in the batched checks: pow2 >= max degree
@@ -143,8 +142,9 @@ struct PlannerDev
     uint32_t log_entries;
     QueryDev* query;           // [Q]
     // per (query, tree), index qt = q*K + k
-    unsigned char* trec;       // [Q*K][n] vertex records of trec_stride bytes (imomd_core.cuh)
-    uint32_t trec_stride;      // 16 (width <= 8) or 32
+    unsigned char* trec;       // [Q*K][n] vertex records of trec_stride bytes:
+                               //   {u32 parent, u32 frontier slot, f64 cost, u32 child[width]}
+    uint32_t trec_stride;      // 16 + 4 * width
     uint32_t pad1_;
     uint32_t* cell_head;       // [Q*K][G*G]
     uint32_t* cell_cnt;        // [Q*K][G*G]

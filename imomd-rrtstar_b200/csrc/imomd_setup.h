@@ -119,27 +119,14 @@ inline void setup_grid(GraphDev& d, uint32_t n, const double* lat, const double*
     }
 }
 
-// padded adjacency table: row v = the CSR row of v, NONE padded to `width` entries
-inline void build_ell(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, int width,
-                      std::vector<uint32_t>* ell)
-{
-    ell->assign((size_t)n * width, IMOMD_NONE);
-    for (uint32_t v = 0; v < n; ++v)
-    {
-        for (uint32_t e = row_ptr[v]; e < row_ptr[v + 1]; ++e) (*ell)[(size_t)v * width + (e - row_ptr[v])] = col[e];
-    }
-}
-
-inline uint32_t tree_record_stride(int width) { return width <= 8 ? 16u : 32u; }
-
 inline void default_sizes(PlannerDev& d, uint32_t frontier_chunks, uint32_t arena_entries,
                           uint32_t log_entries)
 {
     const size_t n = d.g.n;
     const size_t cells = (size_t)d.g.G * d.g.G;
     // a tree's frontier needs at most (occupied cells + entries / 32) chunks; the default
-    // covers frontiers of up to ~N/32 vertices (the run stops with FRONTIER_FULL beyond it)
-    size_t chunks = frontier_chunks ? frontier_chunks : cells + n / 1024 + 64;
+    // covers frontiers of up to ~N/8 vertices (the run stops with FRONTIER_FULL beyond it)
+    size_t chunks = frontier_chunks ? frontier_chunks : cells + n / 256 + 64;
     d.chunks = (int32_t)chunks;
     // rewire scratch: update lists are bounded by the tree size, frames by the depth
     d.arena_entries = arena_entries

@@ -65,7 +65,7 @@ ImomdRRT::ImomdRRT(size_t source, size_t target, std::vector<size_t> objectives,
     if (K_ > static_cast<int>(IMOMD_KMAX))
         throw std::invalid_argument("ImomdRRT (B200): more than 30 objectives");
     const size_t n = map_->size();
-    if (n == 0 || n > 0x7FFFFFF0ull || connection_->size() != n)
+    if (n == 0 || n > 0xFFFFFFF0ull || connection_->size() != n)
         throw std::invalid_argument("ImomdRRT (B200): bad map / connection sizes");
     for (size_t d : destinations_)
         if (d >= n) throw std::invalid_argument("ImomdRRT (B200): destination id out of range");

@@ -61,7 +61,7 @@ struct CtaHost
 struct HsPlanner
 {
     PlannerDev d;
-    std::vector<uint32_t> row_ptr, col, ell;
+    std::vector<uint32_t> row_ptr, col;
     std::vector<double> w, lat, lon, cosrow;
     std::vector<VRec> vrec;
     std::vector<QueryDev> query;
@@ -116,8 +116,6 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     d.g.lat = p->lat.data();
     d.g.lon = p->lon.data();
     d.g.vrec = p->vrec.data();
-    build_ell(n, row_ptr, col, d.g.width, &p->ell);
-    d.g.ell = p->ell.data();
     d.g.cosrow = p->cosrow.data();
     d.Q = Q;
     d.K = K;
@@ -128,7 +126,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->query.resize(Q);
     for (int q = 0; q < Q; ++q)
         fill_initial_header(p->query[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
-    d.trec_stride = tree_record_stride(d.g.width);
+    d.trec_stride = 16u + 4u * (uint32_t)d.g.width;
     p->trec.assign(qk * (size_t)n * d.trec_stride + 16, 0xFF);
     p->cell_head.assign(qk * cells, IMOMD_NONE);
     p->cell_cnt.assign(qk * cells, 0);
