@@ -290,6 +290,30 @@ def bugtrap_grid(width: int, seed: int = 123, name: str | None = None):
     return g2, int(source), int(target), [int(p) for p in pseudo]
 
 
+def hub_grid(width: int, seed: int = 3, hubs: int = 12, spokes: int = 9, name: str | None = None) -> RoadGraph:
+    """Jittered grid plus a few high-degree hubs (extra edges to random vertices nearby): max
+    degree up to 13, which exercises the widest child-row / adjacency-slot code paths."""
+    g = jittered_grid(width, seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    eu, ev = list(g.eu.astype(np.int64)), list(g.ev.astype(np.int64))
+    have = set(zip(eu, ev)) | set(zip(ev, eu))
+    deg = g.degree().copy()
+    for h in rng.choice(g.n, size=hubs, replace=False):
+        r, c = divmod(int(h), width)
+        added = 0
+        for _ in range(200):
+            if added >= spokes or deg[h] >= 13:
+                break
+            rr = int(np.clip(r + rng.integers(-4, 5), 0, width - 1))
+            cc = int(np.clip(c + rng.integers(-4, 5), 0, width - 1))
+            v = rr * width + cc
+            if v == h or (h, v) in have or deg[v] >= 12:
+                continue
+            eu.append(int(h)); ev.append(v); have.add((h, v)); have.add((v, h))
+            deg[h] += 1; deg[v] += 1; added += 1
+    return from_edges(g.lat, g.lon, np.asarray(eu), np.asarray(ev), name=name or f"hubgrid{width}")
+
+
 def pick_destinations(g: RoadGraph, count: int, seed: int = 7, same_component: bool = True):
     """`count` distinct vertices with non-empty adjacency (largest component when asked)."""
     rng = np.random.default_rng(seed)

@@ -220,3 +220,18 @@ def test_nearest_batch_tile_kernel_matches_exact_path():
         ok, want, d, ties, _ = o.nearest(3, float(lk["lat"][i]), float(lk["lon"][i]))
         assert int(idx_b[i]) == want
     o.close(); dp.close(); dg.close()
+
+
+@pytest.mark.parametrize("width,hubs,spokes", [(40, 10, 3), (40, 14, 9)])
+def test_wide_adjacency_rows(width, hubs, spokes):
+    """max degree 5..8 (8-slot kernels) and 9..13 (16-slot kernels)"""
+    g = graphs.hub_grid(width, seed=4, hubs=hubs, spokes=spokes)
+    assert g.degree().max() > (8 if spokes > 4 else 4)
+    dest = graphs.pick_destinations(g, 5, seed=2)
+    op, dg, dp = _pair(g, dest)
+    dp.feed(capi.mt19937_words(0, 200000))
+    for chunk in (100, 700):
+        rep = dp.expand(chunk)[0]
+        assert rep.status == 0 and rep.expansions == op.iterate(chunk)
+        compare_with_oracle(dp, op, 5, False)
+    dp.close(); dg.close(); op.close()

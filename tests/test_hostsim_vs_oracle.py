@@ -119,3 +119,18 @@ def test_multi_query_batch_independent():
         compare_with_oracle(hp, o, 2, True, q=q)
         o.close()
     hp.close()
+
+
+@pytest.mark.parametrize("width,hubs,spokes", [(40, 10, 3), (40, 14, 9)])
+def test_wide_adjacency_rows(width, hubs, spokes):
+    """max degree 5..8 (8-slot rows) and 9..13 (16-slot rows)"""
+    g = graphs.hub_grid(width, seed=4, hubs=hubs, spokes=spokes)
+    assert g.degree().max() > (8 if spokes > 4 else 4)
+    dest = graphs.pick_destinations(g, 5, seed=2)
+    op, hp = _pair(g, dest)
+    hp.feed(_words(200000))
+    for chunk in (100, 700):
+        rep = hp.expand(chunk)[0]
+        assert rep.status == 0 and rep.expansions == op.iterate(chunk)
+        compare_with_oracle(hp, op, 5, True)
+    op.close(); hp.close()

@@ -304,3 +304,20 @@ def test_eci_gen_solver_exact_ties(K):
         assert n1 == n2 and np.array_equal(s1[:n1], s2[:n2]), (trial, s1[:n1], s2[:n2])
         assert c1.value == c2.value
     O.orc_solver_destroy(os_)
+
+
+@pytest.mark.parametrize("hubs,spokes", [(10, 3), (14, 9)])
+def test_high_degree_graph(hubs, spokes):
+    """Degree up to 13: the adjacency-order emulation and the child-order rule at their limit,
+    against the real containers."""
+    R = ol.ref()
+    g = graphs.hub_grid(40, seed=4, hubs=hubs, spokes=spokes)
+    gh = R.ref_graph_from_edges(g.n, g.lat, g.lon, len(g.eu), g.eu, g.ev, g.ew.ctypes.data_as(ol.C.c_void_p))
+    gr = ol.ref_export_graph(gh)
+    assert np.array_equal(gr.row_ptr, g.row_ptr) and np.array_equal(gr.col, g.col)
+    dest = graphs.pick_destinations(g, 5, seed=2)
+    rp, op = ol.RefPlanner(gh, dest), ol.OraclePlanner(g, dest)
+    for chunk in (100, 700, 1200):
+        assert rp.iterate(chunk) == op.iterate(chunk)
+        _full_compare(rp, op, 5, g.n)
+    op.close()
