@@ -59,6 +59,10 @@ def parse():
     ap.add_argument("--queries", type=int, default=296, help="independent queries per GPU")
     ap.add_argument("--iters", type=int, default=3000, help="expandTreeLayers_ passes per query")
     ap.add_argument("--grid", type=int, default=1000, help="grid width (1000 = 1 M vertices)")
+    ap.add_argument("--workload", default="grid", choices=["grid", "san_pablo"],
+                    help="grid = BASELINE configs[2] (default); san_pablo = configs[4]: 1024 "
+                         "source/target queries (K = 2) on the bundled san_pablo road graph")
+    ap.add_argument("--no-ttfs", action="store_true", help="skip the time-to-first-solution side measurement")
     ap.add_argument("--cpu-sample-iters", type=int, default=0,
                     help="iterations of the CPU sample (0 = same as --iters)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -75,16 +79,32 @@ def dist_env():
 def make_workload(args, rank):
     from imomd_b200 import graphs
 
+    if getattr(args, "workload", "grid") == "san_pablo":
+        # configs[4]: the reference's san_pablo.osm as parsed by its own parser (fixture exported
+        # by tests/golden/make_golden.py), rebuilt from its edge list so that both arms see the
+        # same adjacency order; source/target pairs from the largest component
+        src = graphs.RoadGraph.load(os.path.join(ROOT, "tests", "golden", "graphs", "san_pablo.npz"))
+        g = graphs.from_edges(src.lat, src.lon, *src.edge_list(), name="san_pablo")
+        lab = g.components()
+        big = np.nonzero(lab == np.bincount(lab).argmax())[0]
+        rng = np.random.default_rng(11 + rank)
+        dests = [[int(v) for v in rng.choice(big, size=2, replace=False)] for _ in range(args.queries)]
+        return g, dests
     g = graphs.jittered_grid(args.grid, seed=123)
     # query q of rank r: destinations drawn with seed 1000 + r*queries + q (query 0 of rank 0
-    # is the survey's `mt19937{7}`-style pick, seed 7)
+    # uses seed 7)
     dests = []
-    lab = None
     for q in range(args.queries):
         seed = 7 if (rank == 0 and q == 0) else 1000 + rank * args.queries + q
         rng = np.random.default_rng(seed)
         dests.append([int(v) for v in rng.choice(g.n, size=K_TREES, replace=False)])
     return g, dests
+
+
+def workload_name(args, iters, K):
+    if getattr(args, "workload", "grid") == "san_pablo":
+        return f"san_pablo_osm_K{K}_iters{iters}"
+    return f"grid{args.grid}x{args.grid}_K{K}_iters{iters}"
 
 
 class ClockSampler(threading.Thread):
@@ -150,6 +170,31 @@ def run_reference_sample(g, dests, iters, cores, graph_file=None):
                         "toolchain": outs[0]["toolchain"]}
 
 
+def measure_ttfs(g, dest, device, max_iter=2500):
+    from imomd_b200 import capi
+    got = capi.facade_run(g, dest, max_iter=max_iter, max_time=300, device=device)
+    out = {"b200_s": got["rows"][0][0] if got["rows"] else None,
+           "b200_first_cost": got["rows"][0][1] if got["rows"] else None,
+           "b200_first_iteration": got["rows"][0][3] if got["rows"] else None, "max_iter": max_iter}
+    if os.path.exists(REF_PROBE):
+        fd, gf = tempfile.mkstemp(suffix=".bin", prefix="imomd_graph_")
+        os.close(fd)
+        try:
+            g.write_probe_file(gf)
+            res = json.loads(subprocess.check_output(
+                [REF_PROBE, "--graph", gf, "--dest", ",".join(map(str, dest)), "--mode", "run",
+                 "--max-iter", str(max_iter), "--max-time", "300"], text=True).strip().splitlines()[-1])
+        finally:
+            os.unlink(gf)
+        rows = res["rows"]
+        out.update({"reference_s": rows[0][0] if rows else None,
+                    "reference_first_cost": rows[0][1] if rows else None,
+                    "reference_first_iteration": rows[0][3] if rows else None,
+                    "same_first_solution": bool(rows and got["rows"] and rows[0][1] == got["rows"][0][1]
+                                                and rows[0][3] == got["rows"][0][3])})
+    return out
+
+
 def cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -169,7 +214,7 @@ def reference_arm(args):
     g, dests = make_workload(args, 0)
     while len(dests) < cores:      # more cores than queries: more queries of the same family
         rng = np.random.default_rng(5000 + len(dests))
-        dests.append([int(v) for v in rng.choice(g.n, size=K_TREES, replace=False)])
+        dests.append([int(v) for v in rng.choice(g.n, size=len(dests[0]), replace=False)])
     iters = args.cpu_sample_iters or args.iters
     fd, gf = tempfile.mkstemp(suffix=".bin", prefix="imomd_graph_")
     os.close(fd)
@@ -194,8 +239,8 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"grid{args.grid}x{args.grid}_K{K_TREES}_iters{iters}",
-                   "graph": "jittered 4-neighbour grid, seed 123", "trees_per_query": K_TREES,
+        "config": {"workload": workload_name(args, iters, len(dests[0])),
+                   "graph": g.name, "trees_per_query": len(dests[0]),
                    "iters_per_query": iters, "goal_bias": 1.0,
                    "queries_per_step": cores, "note": "one reference process per host core"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
@@ -234,7 +279,7 @@ def b200_arm(args):
     device = local
     torch.cuda.set_device(device)
     g, dests = make_workload(args, rank)
-    Q, K = args.queries, K_TREES
+    Q, K = args.queries, len(dests[0])
     dg = capi.DeviceGraph(g, device=device)
     probs = np.stack([capi.selection_probabilities(g, d) for d in dests])
     dp = capi.DevicePlanner(dg, dests, probs)
@@ -319,8 +364,8 @@ def b200_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"grid{args.grid}x{args.grid}_K{K}_iters{args.iters}",
-                   "graph": "jittered 4-neighbour grid, seed 123", "vertices": g.n,
+        "config": {"workload": workload_name(args, args.iters, K),
+                   "graph": g.name, "vertices": g.n,
                    "trees_per_query": K, "iters_per_query": args.iters, "goal_bias": 1.0,
                    "queries_per_gpu": Q, "l2": "inputs_larger_than_l2 (state rebuilt every step)",
                    "hash_cells_per_axis": dg.info()["grid_dim"]},
@@ -362,6 +407,13 @@ def b200_arm(args):
                                        "frontier records total larger than L2"}
     except Exception as ex:  # the headline line must survive a failure of the side measurement
         line["roofline_nn"] = {"error": str(ex)}
+    # time to first solution of ONE query through the drop-in C++ facade (planner construction ->
+    # first accepted RTSP tour, same 100-pass cadence) next to the unmodified reference
+    if not args.no_ttfs and not args.no_cpu_baseline and world == 1:
+        try:
+            line["ttfs"] = measure_ttfs(g, dests[0], device)
+        except Exception as ex:
+            line["ttfs"] = {"error": str(ex)}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         cd = list(dests)
