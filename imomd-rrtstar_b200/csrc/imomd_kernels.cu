@@ -255,8 +255,8 @@ __global__ void k_init_trees(PlannerDev P)
 // 255 registers, no spills) for planners with few queries, and a throughput build (four
 // CTAs per SM) whose point is to hide each query's dependent-load latency behind the
 // other resident queries.
-template <int MIN_BLOCKS, int KW>
-__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_expand(PlannerDev P, int iters)
+template <int THREADS, int MIN_BLOCKS, int KW>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand(PlannerDev P, int iters)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
@@ -613,9 +613,9 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
                                                  (int)p->smem_bytes);
             if (r != cudaSuccess) e = r;
         };
-        set((const void*)k_expand<1, 4>); set((const void*)k_expand<2, 4>); set((const void*)k_expand<4, 4>);
-        set((const void*)k_expand<1, 8>); set((const void*)k_expand<2, 8>); set((const void*)k_expand<4, 8>);
-        set((const void*)k_expand<1, 16>); set((const void*)k_expand<2, 16>); set((const void*)k_expand<4, 16>);
+#define IMOMD_SET_ALL(W) set((const void*)k_expand<256, 1, W>); set((const void*)k_expand<256, 2, W>);
+        IMOMD_SET_ALL(4) IMOMD_SET_ALL(8) IMOMD_SET_ALL(16)
+#undef IMOMD_SET_ALL
         CU(e);
     }
     CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -758,13 +758,18 @@ int imomd_expand_async(imomd_planner* p, int iters)
     CU(cudaSetDevice(p->g->device));
     CU(cudaEventRecord(p->ev0, p->stream));
     {
-        // register budget by the number of resident queries, adjacency width by the graph
-        const int mb = p->d.Q <= 148 ? 1 : (p->d.Q <= 2 * 148 ? 2 : 4);
+        // Register budget by the number of queries: up to one query per SM the latency build
+        // (255 registers, no spills); beyond that two CTAs per SM, whose dependent-load
+        // latencies overlap.  Measured on B200 (round 1): four or eight smaller CTAs per SM
+        // (128 threads and/or 64 registers) are 5-20 % slower than two -- the CTA-wide
+        // services lose more than the extra residency returns -- so larger query counts simply
+        // run in waves.  Adjacency width by the graph.
+        const bool two_per_sm = p->d.Q > 148;
         const int w = p->d.g.width;
         void (*kern)(PlannerDev, int) = nullptr;
-        if (w == 4) kern = mb == 1 ? k_expand<1, 4> : (mb == 2 ? k_expand<2, 4> : k_expand<4, 4>);
-        else if (w == 8) kern = mb == 1 ? k_expand<1, 8> : (mb == 2 ? k_expand<2, 8> : k_expand<4, 8>);
-        else kern = mb == 1 ? k_expand<1, 16> : (mb == 2 ? k_expand<2, 16> : k_expand<4, 16>);
+        if (w == 4) kern = two_per_sm ? k_expand<256, 2, 4> : k_expand<256, 1, 4>;
+        else if (w == 8) kern = two_per_sm ? k_expand<256, 2, 8> : k_expand<256, 1, 8>;
+        else kern = two_per_sm ? k_expand<256, 2, 16> : k_expand<256, 1, 16>;
         kern<<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
     }
     CU(cudaGetLastError());
