@@ -333,6 +333,7 @@ struct Shared
     double conn_cost[IMOMD_KMAX];
     // jump-point search in flight
     uint32_t jps_next;
+    int32_t attach_mode;   // 1: imomd_attach (pseudo-tree merge): no sampling, JPS, pruning
     // rewire machine: explicit LIFO in the arena
     uint32_t rw_fp, rw_top;
     // cost propagation request / result (tree_t::updateCost)
@@ -762,6 +763,14 @@ struct Seq
         }
     }
 
+    // pseudo mode: the order in which a tree visits its vertices is the insertion order of
+    // the reference's `tree.parent` map, which mergeTwoTree_ iterates (:860)
+    IMOMD_HD void log_visit(int k, uint32_t x)
+    {
+        if (!P.pseudo) return;
+        P.visit_log[((size_t)q * P.K + k) * P.g.n + (Q->tree_size[k] - 1)] = x;
+    }
+
     IMOMD_HD void log_connection(uint32_t set_idx, uint32_t x)
     {
         uint32_t* lg = P.log + (size_t)q * 2 * P.log_entries;
@@ -823,7 +832,11 @@ struct Seq
             via = x_2;
             next = x_1;
         }
-        if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
+        if (T.parent(x_new) == IMOMD_NONE)
+        {
+            Q->tree_size[k] += 1;
+            log_visit(k, x_new);
+        }
         T.set_parent(x_new, via);
         chl_assign_single_w<KW>(T.chl(via), x_new);
         double cnew = T.cost(via) + edge_weight(g, via, x_new);
@@ -876,7 +889,11 @@ struct Seq
         }
         if (x_parent != IMOMD_NONE)
         {
-            if (T.parent(x_new) == IMOMD_NONE) Q->tree_size[k] += 1;
+            if (T.parent(x_new) == IMOMD_NONE)
+            {
+                Q->tree_size[k] += 1;
+                log_visit(k, x_new);
+            }
             T.set_parent(x_new, x_parent);
             chl_insert_w<KW>(T.chl(x_parent), x_new);
             T.set_cost(x_new, min_cost);
@@ -1238,7 +1255,7 @@ struct Seq
                         S.conn_pending = 0;
                         S.x_new = S.jps_next;
                     }
-                    if (jps_hop(k, T))
+                    if (!S.attach_mode && jps_hop(k, T))
                     {
                         S.conn_pending = 1;
                         S.req = REQ_CONN;
@@ -1282,7 +1299,7 @@ struct Seq
                 {
                     if (!rewire_run(k, T)) return;   // REQ_BFS or REQ_CHECK posted
                     if (Q->status != 0) continue;
-                    update_selection_probability(k);
+                    if (!S.attach_mode) update_selection_probability(k);
                     S.conn_x = S.x_new;
                     S.req = REQ_CONN;
                     S.phase = PH_LAST_CONN;
@@ -1291,6 +1308,11 @@ struct Seq
                 case PH_LAST_CONN:
                 {
                     apply_connection(k, T, S.x_new, T.cost(S.x_new));         // :355
+                    if (S.attach_mode)
+                    {
+                        S.req = REQ_EXIT;
+                        return;
+                    }
                     Q->expansions += 1;
                     S.k = k + 1;
                     S.phase = PH_NEXT_TREE;
@@ -1932,6 +1954,7 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
         T.set_parent(root, root);
         T.set_cost(root, 0.0);
         Q->tree_size[i] = 1;
+        if (P.pseudo) P.visit_log[((size_t)q * K + i) * g.n] = root;
         Q->ds_parent[i] = i;
         // erase(root) is a no-op and no holder equals the root yet; neighbours:
         uint32_t e0 = g.row_ptr[root], e1 = g.row_ptr[root + 1];
@@ -1960,7 +1983,8 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
 // The per-query driver: the loop every CTA runs (device) / the host simulation runs.
 template <int KW, class Cta>
 IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
-                               double* lb, uint32_t* lvl, double* mat, unsigned char* hot)
+                               double* lb, uint32_t* lvl, double* mat, unsigned char* hot,
+                               int attach_tree = -1, uint32_t attach_vertex = IMOMD_NONE)
 {
     QueryDev* Qg = P.query + q;
     QueryDev* Q = reinterpret_cast<QueryDev*>(hot);
@@ -1993,6 +2017,17 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         S.phase = PH_NEXT_TREE;
         S.it = 0;
         S.k = Q->resume_k;         // resume point inside an interrupted pass
+        S.attach_mode = 0;
+        if (attach_tree >= 0)
+        {
+            // mergeTwoTree_ (:848-851): connectNewNode_, updateExpandables, rewireTree_,
+            // updateConnectionTree_ of one given vertex in one given tree
+            S.attach_mode = 1;
+            S.k = attach_tree;
+            S.x_new = attach_vertex;
+            S.conn_pending = 0;
+            S.phase = PH_JPS;
+        }
         S.req = REQ_EXIT;
         if (Q->status == 1) Q->status = 0;   // NEED_WORDS is resumable
         Q->last_iterations = Q->iterations;
@@ -2064,7 +2099,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     }
     if (cta.tid() == 0)
     {
-        Q->resume_k = S.k < Q->K ? S.k : 0;
+        if (attach_tree < 0) Q->resume_k = S.k < Q->K ? S.k : 0;
         Q->last_iterations = Q->iterations - Q->last_iterations;
         Q->last_expansions = Q->expansions - Q->last_expansions;
         int active = 0;

@@ -272,6 +272,20 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand(PlannerDev P, in
     }
 }
 
+// mergeTwoTree_'s per-vertex work (pseudo-tree merge driven by the host facade)
+template <int KW>
+__global__ void __launch_bounds__(kThreads) k_attach(PlannerDev P, int q, int tree, uint32_t vertex)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+    double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
+    uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + (size_t)P.g.G * P.g.G);
+    double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
+    unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
+    CtaDev cta;
+    run_query<KW>(cta, P, q, 0, S, lb, lvl, mat, hot, tree, vertex);
+}
+
 // One CTA per lookup slot (grid-stride over the lookups); scratch chunk lists are per CTA.
 __global__ void __launch_bounds__(kThreads)
 k_nearest(PlannerDev P, int n, const imomd_nn_query* __restrict__ qs, uint32_t* __restrict__ idx,
@@ -595,6 +609,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     CU(dmalloc(&d.clist, (size_t)n_queries * 2 * chunks));
     CU(dmalloc(&d.log, (size_t)n_queries * 2 * d.log_entries));
     CU(dmalloc(&d.reports, (size_t)n_queries));
+    d.visit_log = nullptr;
+    if (d.pseudo) CU(dmalloc(&d.visit_log, qk * n));
     d.words = nullptr;
     d.words_avail = 0;
     // initial headers
@@ -613,7 +629,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
                                                  (int)p->smem_bytes);
             if (r != cudaSuccess) e = r;
         };
-#define IMOMD_SET_ALL(W) set((const void*)k_expand<256, 1, W>); set((const void*)k_expand<256, 2, W>);
+#define IMOMD_SET_ALL(W) set((const void*)k_expand<256, 1, W>); set((const void*)k_expand<256, 2, W>); set((const void*)k_attach<W>);
         IMOMD_SET_ALL(4) IMOMD_SET_ALL(8) IMOMD_SET_ALL(16)
 #undef IMOMD_SET_ALL
         CU(e);
@@ -650,6 +666,7 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(d.clist);
     cudaFree(d.log);
     cudaFree(d.reports);
+    cudaFree(d.visit_log);
     cudaFree(p->words);
     cudaFree(p->nn_scratch);
     cudaFree(p->nn_stats);
@@ -678,6 +695,90 @@ int imomd_planner_set_queries(imomd_planner* p, const uint32_t* dest, const doub
     k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(p->d);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(p->stream));
+    return IMOMD_OK;
+}
+
+int imomd_attach(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* parent_out,
+                 imomd_query_report* report)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || vertex >= p->d.g.n)
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree/vertex");
+    CU(cudaSetDevice(p->g->device));
+    const int w = p->d.g.width;
+    if (w == 4) k_attach<4><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, vertex);
+    else if (w == 8) k_attach<8><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, vertex);
+    else k_attach<16><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, vertex);
+    CU(cudaGetLastError());
+    if (report)
+        CU(cudaMemcpyAsync(report, p->d.reports + query, sizeof(ReportDev), cudaMemcpyDeviceToHost,
+                           p->stream));
+    if (parent_out)
+    {
+        const size_t qt = (size_t)query * p->d.K + tree;
+        CU(cudaMemcpyAsync(parent_out, p->d.trec + (qt * p->d.g.n + vertex) * p->d.trec_stride, 4,
+                           cudaMemcpyDeviceToHost, p->stream));
+    }
+    CU(cudaStreamSynchronize(p->stream));
+    return IMOMD_OK;
+}
+
+int imomd_get_visit_order(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
+                          uint32_t* count)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !count)
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    if (!p->d.visit_log) return fail(IMOMD_ERR_ARG, "the visit order is only recorded in pseudo mode");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    QueryDev h;
+    CU(cudaMemcpy(&h, p->d.query + query, IMOMD_QUERY_HOT_BYTES, cudaMemcpyDeviceToHost));
+    uint32_t n = (uint32_t)h.tree_size[tree];
+    *count = n;
+    uint32_t take = std::min(n, cap);
+    const size_t qt = (size_t)query * p->d.K + tree;
+    if (take && out)
+        CU(cudaMemcpy(out, p->d.visit_log + qt * p->d.g.n, (size_t)take * 4, cudaMemcpyDeviceToHost));
+    return IMOMD_OK;
+}
+
+// host-side edits of a query's state the pseudo-tree merge needs (mergePseudoTrees_ :797-816,
+// mergeTwoTree_ :905-915): distance / connection-node entry, is_done flag, "set non-empty" flag
+int imomd_set_distance(imomd_planner* p, int query, int i, int j, double d, uint32_t conn_node)
+{
+    if (!p || query < 0 || query >= p->d.Q || i < 0 || j < 0 || i >= p->d.K || j >= p->d.K)
+        return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    QueryDev* qd = p->d.query + query;
+    const int K = p->d.K;
+    int32_t one = 1;
+    CU(cudaMemcpy(&qd->D[i * K + j], &d, 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(&qd->D[j * K + i], &d, 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(&qd->CN[i * K + j], &conn_node, 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(&qd->CN[j * K + i], &conn_node, 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(&qd->dm_updated, &one, 4, cudaMemcpyHostToDevice));
+    return IMOMD_OK;
+}
+
+int imomd_set_tree_done(imomd_planner* p, int query, int tree, int done)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K)
+        return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    int32_t v = done ? 1 : 0;
+    CU(cudaMemcpy(&p->d.query[query].is_done[tree], &v, 4, cudaMemcpyHostToDevice));
+    return IMOMD_OK;
+}
+
+int imomd_set_contact(imomd_planner* p, int query, int set_idx)
+{
+    if (!p || query < 0 || query >= p->d.Q || set_idx < 0 || set_idx >= p->d.K * (p->d.K - 1) / 2)
+        return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    uint8_t one = 1;
+    CU(cudaMemcpy(&p->d.query[query].contact[set_idx], &one, 1, cudaMemcpyHostToDevice));
     return IMOMD_OK;
 }
 
@@ -951,6 +1052,32 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
     *len = l;
     uint32_t take = std::min(l, cap);
     if (take) CU(cudaMemcpy(out, p->walk_buf + 1, (size_t)take * 4, cudaMemcpyDeviceToHost));
+    return IMOMD_OK;
+}
+
+int imomd_get_connection_log_from(imomd_planner* p, int query, uint32_t first, uint32_t* set_idx,
+                                  uint32_t* vertex, uint32_t cap, uint32_t* count)
+{
+    if (!p || query < 0 || query >= p->d.Q || !count) return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(cudaStreamSynchronize(p->stream));
+    uint32_t total = 0;
+    CU(cudaMemcpy(&total, &p->d.query[query].log_count, 4, cudaMemcpyDeviceToHost));
+    *count = total;
+    if (total > p->d.log_entries) return fail(IMOMD_ERR_ARG, "connection log overflow: raise log_entries");
+    if (first >= total) return IMOMD_OK;
+    uint32_t take = std::min(total - first, cap);
+    if (take && set_idx && vertex)
+    {
+        std::vector<uint32_t> buf((size_t)take * 2);
+        CU(cudaMemcpy(buf.data(), p->d.log + (size_t)query * 2 * p->d.log_entries + 2 * (size_t)first,
+                      (size_t)take * 8, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < take; ++i)
+        {
+            set_idx[i] = buf[2 * i];
+            vertex[i] = buf[2 * i + 1];
+        }
+    }
     return IMOMD_OK;
 }
 

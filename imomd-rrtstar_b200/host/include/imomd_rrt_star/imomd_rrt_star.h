@@ -7,8 +7,10 @@
 // include/imomd_b200.h; this class only keeps what the reference keeps on the host side
 // of that line: the RTSP trigger every 100 passes, path extraction and logging.
 //
-// Not supported yet: pseudo_mode's tree merge (mergePseudoTrees_) -- the
-// constructor throws std::invalid_argument for setting.pseudo_mode.
+// pseudo_mode: the trees rooted at pseudo destinations are merged into the source / target
+// trees once the graph of trees is connected (mergePseudoTrees_, :744-916 upstream).  The merge
+// is driven from here -- it iterates std containers whose order is part of the reference's
+// behaviour -- and performs every tree update on the device (imomd_attach).
 #ifndef IMOMD_B200_IMOMD_RRT_STAR_H
 #define IMOMD_B200_IMOMD_RRT_STAR_H
 
@@ -19,6 +21,7 @@
 #include <random>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include <pthread.h>
@@ -65,6 +68,11 @@ public:
     long long iterations() const { return iteration_count_; }
     long long expansions() const { return expansions_; }
     void setDevice(int device) { device_ = device; }   // before the first expansion
+    // stepwise driving (what findShortestPath's loop does): n x expandTreeLayers_, one
+    // solveRTSP_ ; the C-ABI planner handle for state readback
+    void stepPasses(int passes) { expandBatch(passes); }
+    void stepRTSP() { solveRTSP(); }
+    imomd_planner* nativeHandle() { return planner_; }
     static void setDefaultDevice(int device);
 
 private:
@@ -74,6 +82,11 @@ private:
     void updatePath();
     void logData();
     void feedWords(size_t n);
+    void drainConnectionLog();
+    void mergePseudoTrees();
+    void mergeTwoTrees(int parent_tree, int child_tree);
+    bool attach(int tree, size_t vertex, std::vector<char>& visited, std::vector<char>& frontier);
+    int setIndex(int a, int b) const { return a > b ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; }
 
     imomd_setting_t setting_{};
     std::shared_ptr<std::vector<location_t>> map_;
@@ -103,6 +116,12 @@ private:
     bool finished_ = false;
     pthread_cond_t cond_ = PTHREAD_COND_INITIALIZER;
     pthread_mutex_t lock_ = PTHREAD_MUTEX_INITIALIZER;
+
+    // pseudo mode: host mirrors of connection_nodes_set_ (real unordered_sets fed in the
+    // device's insertion order, so that they iterate like the reference's)
+    std::vector<std::unordered_set<size_t>> connection_sets_;
+    uint32_t log_consumed_ = 0;
+    bool merge_done_ = false;
 
     std::chrono::steady_clock::time_point start_;
     std::ofstream csv_;

@@ -30,11 +30,23 @@ typedef struct imomd_host_row
 
 int imomd_host_run(int device, uint64_t n, const double* lat, const double* lon, uint64_t m,
                    const uint64_t* eu, const uint64_t* ev, const double* ew, int K, const uint64_t* dest,
-                   double goal_bias, int max_iter, int max_time, int ga_mutation_iter, int ga_population,
+                   double goal_bias, int pseudo_mode, int max_iter, int max_time, int ga_mutation_iter, int ga_population,
                    int ga_generation, imomd_host_row* rows, int row_cap, int* n_rows, uint64_t* path,
                    uint64_t path_cap, uint64_t* path_len, int32_t* seq, int seq_cap, int* seq_len,
                    double* final_cost, long long* iterations, long long* expansions, char* err,
                    int errlen);
+
+/* the facade driven stepwise: passes x expandTreeLayers_, optionally one solveRTSP_ (in pseudo mode
+ * that is where the tree merge happens); _native returns the imomd_planner* for state readback */
+void* imomd_host_planner_create(int device, uint64_t n, const double* lat, const double* lon, uint64_t m,
+                                const uint64_t* eu, const uint64_t* ev, const double* ew, int K,
+                                const uint64_t* dest, double goal_bias, int pseudo_mode,
+                                int ga_mutation_iter, int ga_population, int ga_generation, char* err,
+                                int errlen);
+void imomd_host_planner_destroy(void* h);
+int imomd_host_planner_step(void* h, int passes, int solve_rtsp, char* err, int errlen);
+void* imomd_host_planner_native(void* h);
+double imomd_host_planner_cost(void* h);
 
 /* EciGenSolver of the facade on a row-major K x K matrix (GA fitness on the GPU) */
 void* imomd_host_solver_create(int device, int swapping, int genetic, int ga_mutation_iter,

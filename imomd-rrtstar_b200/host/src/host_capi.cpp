@@ -25,7 +25,8 @@ void put_err(char* err, int errlen, const std::string& msg)
 
 extern "C" int imomd_host_run(int device, uint64_t n, const double* lat, const double* lon, uint64_t m,
                               const uint64_t* eu, const uint64_t* ev, const double* ew, int K,
-                              const uint64_t* dest, double goal_bias, int max_iter, int max_time,
+                              const uint64_t* dest, double goal_bias, int pseudo_mode, int max_iter,
+                              int max_time,
                               int ga_mutation_iter, int ga_population, int ga_generation,
                               imomd_host_row* rows, int row_cap, int* n_rows, uint64_t* path,
                               uint64_t path_cap, uint64_t* path_len, int32_t* seq, int seq_cap,
@@ -47,7 +48,7 @@ extern "C" int imomd_host_run(int device, uint64_t n, const double* lat, const d
         st.max_iter = max_iter;
         st.max_time = max_time;
         st.random_seed = false;
-        st.pseudo_mode = false;
+        st.pseudo_mode = pseudo_mode != 0;
         st.log_data = 0;
         st.rtsp_setting.swapping = true;
         st.rtsp_setting.genetic = true;
@@ -82,6 +83,69 @@ extern "C" int imomd_host_run(int device, uint64_t n, const double* lat, const d
         return -1;
     }
 }
+
+// stepwise facade handle (tests: state after the pseudo-tree merge against the reference's)
+extern "C" void* imomd_host_planner_create(int device, uint64_t n, const double* lat, const double* lon,
+                                           uint64_t m, const uint64_t* eu, const uint64_t* ev,
+                                           const double* ew, int K, const uint64_t* dest, double goal_bias,
+                                           int pseudo_mode, int ga_mutation_iter, int ga_population,
+                                           int ga_generation, char* err, int errlen)
+{
+    try
+    {
+        auto map = std::make_shared<std::vector<location_t>>(n);
+        auto conn = std::make_shared<std::vector<std::unordered_map<size_t, double>>>(n);
+        for (uint64_t i = 0; i < n; ++i) (*map)[i] = location_t(i, lat[i], lon[i]);
+        for (uint64_t e = 0; e < m; ++e)
+        {
+            (*conn)[eu[e]].insert({ev[e], ew[e]});
+            (*conn)[ev[e]].insert({eu[e], ew[e]});
+        }
+        imomd_setting_t st{};
+        st.goal_bias = goal_bias;
+        st.max_iter = 1 << 30;
+        st.max_time = 1 << 30;
+        st.random_seed = false;
+        st.pseudo_mode = pseudo_mode != 0;
+        st.log_data = 0;
+        st.rtsp_setting.swapping = true;
+        st.rtsp_setting.genetic = true;
+        st.rtsp_setting.ga_mutation_iter = ga_mutation_iter;
+        st.rtsp_setting.ga_population = ga_population;
+        st.rtsp_setting.ga_generation = ga_generation;
+        st.rtsp_setting.ga_random_seed = false;
+        std::vector<size_t> objectives(dest + 1, dest + K - 1);
+        ImomdRRT::setDefaultDevice(device);
+        return new ImomdRRT(dest[0], dest[K - 1], objectives, map, conn, st);
+    }
+    catch (const std::exception& ex)
+    {
+        put_err(err, errlen, ex.what());
+        return nullptr;
+    }
+}
+
+extern "C" void imomd_host_planner_destroy(void* h) { delete static_cast<ImomdRRT*>(h); }
+
+extern "C" int imomd_host_planner_step(void* h, int passes, int solve_rtsp, char* err, int errlen)
+{
+    try
+    {
+        ImomdRRT* p = static_cast<ImomdRRT*>(h);
+        if (passes > 0) p->stepPasses(passes);
+        if (solve_rtsp) p->stepRTSP();
+        return 0;
+    }
+    catch (const std::exception& ex)
+    {
+        put_err(err, errlen, ex.what());
+        return -1;
+    }
+}
+
+extern "C" void* imomd_host_planner_native(void* h) { return static_cast<ImomdRRT*>(h)->nativeHandle(); }
+
+extern "C" double imomd_host_planner_cost(void* h) { return static_cast<ImomdRRT*>(h)->getShortestPathCost(); }
 
 extern "C" void* imomd_host_solver_create(int device, int swapping, int genetic, int ga_mutation_iter,
                                           int ga_population, int ga_generation)

@@ -55,9 +55,6 @@ ImomdRRT::ImomdRRT(size_t source, size_t target, std::vector<size_t> objectives,
                    const imomd_setting_t& setting)
     : setting_(setting), map_(map), connection_(connection), device_(g_default_device)
 {
-    if (setting_.pseudo_mode)
-        throw std::invalid_argument(
-            "ImomdRRT (B200): pseudo_mode needs the pseudo-tree merge, which is not built yet");
     destinations_.push_back(source);
     for (size_t o : objectives) destinations_.push_back(o);
     destinations_.push_back(target);
@@ -108,7 +105,8 @@ ImomdRRT::ImomdRRT(size_t source, size_t target, std::vector<size_t> objectives,
     imomd_host::selection_probabilities(K_, dlat.data(), dlon.data(), prob.data());
     imomd_params params{};
     params.goal_bias = setting_.goal_bias;
-    params.pseudo_mode = 0;
+    params.pseudo_mode = setting_.pseudo_mode ? 1 : 0;
+    if (setting_.pseudo_mode) connection_sets_.resize(static_cast<size_t>(K_) * (K_ - 1) / 2);
     check(imomd_planner_create(graph_, 1, K_, dest.data(), prob.data(), &params, &planner_),
           "planner creation");
 
@@ -174,7 +172,196 @@ bool ImomdRRT::expandBatch(int passes)
         if (rep.status != IMOMD_RUN_OK && rep.status != IMOMD_RUN_NEED_WORDS)
             throw std::runtime_error("ImomdRRT (B200): device run status " + std::to_string(rep.status));
     }
+    if (setting_.pseudo_mode) drainConnectionLog();
     return true;
+}
+
+// connection_nodes_set_ insertions the device logged since the last call, applied in order
+void ImomdRRT::drainConnectionLog()
+{
+    for (;;)
+    {
+        std::vector<uint32_t> idx(1 << 16), vx(1 << 16);
+        uint32_t total = 0;
+        check(imomd_get_connection_log_from(planner_, 0, log_consumed_, idx.data(), vx.data(),
+                                            static_cast<uint32_t>(idx.size()), &total),
+              "connection log");
+        const uint32_t got = std::min<uint32_t>(total - log_consumed_, static_cast<uint32_t>(idx.size()));
+        for (uint32_t i = 0; i < got; ++i) connection_sets_[idx[i]].insert(vx[i]);
+        log_consumed_ += got;
+        if (log_consumed_ >= total) break;
+    }
+}
+
+// connectNewNode_ + updateExpandables + rewireTree_ + updateConnectionTree_ of one vertex
+// (:848-851 / :883-886 upstream) on the device; the host mirrors of the tree's visited set and
+// frontier follow (the rewire cascade changes neither)
+bool ImomdRRT::attach(int tree, size_t vertex, std::vector<char>& visited, std::vector<char>& frontier)
+{
+    uint32_t parent = IMOMD_NONE;
+    imomd_query_report rep{};
+    check(imomd_attach(planner_, 0, tree, static_cast<uint32_t>(vertex), &parent, &rep), "tree merge");
+    if (rep.status != IMOMD_RUN_OK)
+        throw std::runtime_error("ImomdRRT (B200): device status " + std::to_string(rep.status) +
+                                 " during the tree merge");
+    tree_vertices_ = rep.tree_vertices;
+    if (rep.dm_updated) dm_updated_ = true;
+    frontier[vertex] = 0;
+    const bool connected = parent != IMOMD_NONE && !(parent & 0x80000000u);
+    if (connected) visited[vertex] = 1;
+    for (const auto& kv : (*connection_)[vertex])
+        if (!visited[kv.first]) frontier[kv.first] = 1;
+    drainConnectionLog();
+    return connected;
+}
+
+// mergeTwoTree_, src/imomd_rrt_star.cpp:819-916 upstream
+void ImomdRRT::mergeTwoTrees(int parent_tree, int child_tree)
+{
+    const size_t n = map_->size();
+    // mirrors of the parent tree: visited set and frontier ("expandables")
+    std::vector<uint32_t> par(n);
+    check(imomd_get_tree(planner_, 0, parent_tree, par.data(), nullptr), "tree readback");
+    std::vector<char> visited(n, 0), frontier(n, 0);
+    for (size_t v = 0; v < n; ++v) visited[v] = par[v] != IMOMD_NONE;
+    {
+        std::vector<uint32_t> fr(n);
+        uint32_t cnt = 0;
+        check(imomd_get_frontier(planner_, 0, parent_tree, fr.data(), static_cast<uint32_t>(n), &cnt),
+              "frontier readback");
+        for (uint32_t i = 0; i < cnt; ++i) frontier[fr[i]] = 1;
+    }
+    // the child tree's parent map, rebuilt with the reference's insertion history so that it
+    // iterates in the same order (:860): {root, root} first, then every vertex as visited
+    std::vector<uint32_t> cpar(n), order(n);
+    check(imomd_get_tree(planner_, 0, child_tree, cpar.data(), nullptr), "tree readback");
+    uint32_t visited_count = 0;
+    check(imomd_get_visit_order(planner_, 0, child_tree, order.data(), static_cast<uint32_t>(n),
+                                &visited_count),
+          "visit order readback");
+    const size_t child_root = destinations_[child_tree];
+    std::unordered_map<size_t, size_t> child_parent = {{child_root, child_root}};
+    for (uint32_t i = 1; i < visited_count; ++i) child_parent[order[i]] = cpar[order[i]];
+
+    const int idx = setIndex(parent_tree, child_tree);
+    std::unordered_set<int> merged;
+    // main branches: connection node ----> root of the child tree
+    for (size_t connection_node : connection_sets_[idx])
+    {
+        size_t current = connection_node;
+        bool optimal = true;
+        while (current != child_root && optimal)
+        {
+            const size_t x_new = child_parent[current];
+            if (visited[x_new])
+            {
+                if (merged.count(static_cast<int>(x_new))) optimal = false;
+            }
+            else
+            {
+                attach(parent_tree, x_new, visited, frontier);
+                merged.insert(static_cast<int>(x_new));
+            }
+            current = x_new;
+        }
+    }
+    // side branches, in the iteration order of the child's parent map
+    for (const auto& node : child_parent)
+    {
+        if (visited[node.first]) continue;
+        size_t current = node.first;
+        std::vector<size_t> branch = {current};
+        while (!frontier[current])
+        {
+            current = child_parent[current];
+            branch.push_back(current);
+        }
+        for (auto it = branch.rbegin(); it != branch.rend(); ++it)
+            if (!visited[*it]) attach(parent_tree, *it, visited, frontier);
+    }
+    // connection nodes of the child towards the other trees now belong to the parent
+    for (int t = 0; t < K_; ++t)
+    {
+        if (t == child_tree || t == parent_tree) continue;
+        const int from = setIndex(child_tree, t), to = setIndex(parent_tree, t);
+        for (size_t node : connection_sets_[from])
+        {
+            if (!visited[node])
+            {
+                connection_sets_[to].insert(node);
+                check(imomd_set_contact(planner_, 0, to), "contact flag");
+            }
+        }
+    }
+    check(imomd_set_tree_done(planner_, 0, child_tree, 1), "tree flag");
+}
+
+// mergePseudoTrees_, src/imomd_rrt_star.cpp:744-817 upstream
+void ImomdRRT::mergePseudoTrees()
+{
+    const int source = 0, target = K_ - 1;
+    std::unordered_set<int> unmerged;
+    for (int i = 1; i < K_ - 1; ++i) unmerged.insert(i);
+    int pick = -1;
+    while (!unmerged.empty())
+    {
+        bool progress = false;
+        size_t most = 0;
+        for (int id : unmerged)
+        {
+            const size_t c = connection_sets_[id * (id - 1) / 2].size();
+            if (c > most)
+            {
+                most = c;
+                pick = id;
+            }
+        }
+        if (most > 0)
+        {
+            mergeTwoTrees(source, pick);
+            unmerged.erase(pick);
+            progress = true;
+        }
+        most = 0;
+        for (int id : unmerged)
+        {
+            const size_t c = connection_sets_[target * (target - 1) / 2 + id].size();
+            if (c > most)
+            {
+                most = c;
+                pick = id;
+            }
+        }
+        if (most > 0)
+        {
+            mergeTwoTrees(target, pick);
+            unmerged.erase(pick);
+            progress = true;
+        }
+        if (!progress)
+            throw std::runtime_error("ImomdRRT (B200): a pseudo tree touches neither the source nor the "
+                                     "target tree (the reference loops forever here)");
+    }
+    // best direct connection between the merged source and target trees (:797-815; the
+    // threshold stays the initial distance, as upstream)
+    const size_t n = map_->size();
+    std::vector<uint32_t> par(n);
+    std::vector<double> cost_s(n), cost_t(n);
+    check(imomd_get_tree(planner_, 0, source, par.data(), cost_s.data()), "tree readback");
+    check(imomd_get_tree(planner_, 0, target, par.data(), cost_t.data()), "tree readback");
+    auto D = getDistanceMatrix();
+    const double threshold = (*D)[source][target];
+    for (size_t node : connection_sets_[target * (target - 1) / 2])
+    {
+        const double distance = cost_s[node] + cost_t[node];
+        if (distance < threshold)
+        {
+            check(imomd_set_distance(planner_, 0, source, target, distance, static_cast<uint32_t>(node)),
+                  "distance update");
+            dm_updated_ = true;
+        }
+    }
+    merge_done_ = true;
 }
 
 void ImomdRRT::run()
@@ -254,6 +441,19 @@ std::shared_ptr<std::vector<std::vector<double>>> ImomdRRT::getDistanceMatrix()
 void ImomdRRT::solveRTSP()
 {
     if (!(connected_ && dm_updated_)) return;
+    if (setting_.pseudo_mode)
+    {
+        // :990-1001 upstream: merge once, then the path is source -> target through the merged trees
+        if (!merge_done_)
+        {
+            mergePseudoTrees();
+            sequence_ = std::make_shared<std::vector<int>>(std::vector<int>{0, K_ - 1});
+        }
+        shortest_path_cost_ = (*getDistanceMatrix())[0][K_ - 1];
+        updatePath();
+        logData();
+        return;
+    }
     auto result = solver_.solveRTSP(getDistanceMatrix(), 0, K_ - 1);
     if (result.first < shortest_path_cost_)
     {

@@ -110,11 +110,21 @@ def host_lib():
         L.imomd_host_great_circle_m.argtypes = [C.c_double] * 4
         u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
         L.imomd_host_run.argtypes = [C.c_int, C.c_uint64, f64p, f64p, C.c_uint64, u64p, u64p, f64p,
-                                     C.c_int, u64p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, u64p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), u64p, C.c_uint64,
                                      C.POINTER(C.c_uint64), i32p, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_double), C.POINTER(C.c_longlong),
                                      C.POINTER(C.c_longlong), C.c_char_p, C.c_int]
+        L.imomd_host_planner_create.restype = C.c_void_p
+        L.imomd_host_planner_create.argtypes = [C.c_int, C.c_uint64, f64p, f64p, C.c_uint64, u64p, u64p,
+                                                f64p, C.c_int, u64p, C.c_double, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.imomd_host_planner_destroy.argtypes = [C.c_void_p]
+        L.imomd_host_planner_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.imomd_host_planner_native.restype = C.c_void_p
+        L.imomd_host_planner_native.argtypes = [C.c_void_p]
+        L.imomd_host_planner_cost.restype = C.c_double
+        L.imomd_host_planner_cost.argtypes = [C.c_void_p]
         L.imomd_host_solver_create.restype = C.c_void_p
         L.imomd_host_solver_create.argtypes = [C.c_int] * 6
         L.imomd_host_solver_destroy.argtypes = [C.c_void_p]
@@ -333,7 +343,8 @@ class HostRow(C.Structure):
                 ("iteration", C.c_longlong)]
 
 
-def facade_run(g, dest, goal_bias=1.0, max_iter=1000000, max_time=60, ga=(10000, 1000, 5), device=0):
+def facade_run(g, dest, goal_bias=1.0, max_iter=1000000, max_time=60, ga=(10000, 1000, 5), device=0,
+               pseudo=False):
     """One full planner run through the C++ facade (ImomdRRT + findShortestPath on a pthread)."""
     L = host_lib()
     eu, ev, ew = g.edge_list()
@@ -344,7 +355,7 @@ def facade_run(g, dest, goal_bias=1.0, max_iter=1000000, max_time=60, ga=(10000,
     seq = np.empty(256, np.int32); seq_len = C.c_int(); cost = C.c_double()
     its = C.c_longlong(); exps = C.c_longlong(); err = C.create_string_buffer(512)
     rc = L.imomd_host_run(device, g.n, g.lat, g.lon, len(eu), eu, ev, ew, len(dest),
-                          np.asarray(dest, np.uint64), goal_bias, max_iter, max_time, ga[0], ga[1], ga[2],
+                          np.asarray(dest, np.uint64), goal_bias, int(pseudo), max_iter, max_time, ga[0], ga[1], ga[2],
                           C.cast(rows, C.c_void_p), 4096, C.byref(n_rows), path, path.size,
                           C.byref(path_len), seq, 256, C.byref(seq_len), C.byref(cost), C.byref(its),
                           C.byref(exps), err, 512)
@@ -353,6 +364,42 @@ def facade_run(g, dest, goal_bias=1.0, max_iter=1000000, max_time=60, ga=(10000,
     return dict(rows=[(r.time_s, r.path_cost, r.tree_size, r.iteration) for r in rows[:n_rows.value]],
                 path=path[:path_len.value].copy(), sequence=seq[:seq_len.value].copy(),
                 final_cost=cost.value, iterations=its.value, expansions=exps.value)
+
+
+class FacadePlanner:
+    """The C++ facade driven stepwise: `passes` x expandTreeLayers_, then optionally one
+    solveRTSP_ (which, in pseudo mode, performs the tree merge).  `.dev` is a DevicePlanner view
+    of the facade's C-ABI planner for state readback."""
+
+    def __init__(self, g, dest, goal_bias=1.0, pseudo=False, ga=(10000, 1000, 5), device=0):
+        L = host_lib()
+        eu, ev, ew = g.edge_list()
+        eu = np.ascontiguousarray(eu, np.uint64); ev = np.ascontiguousarray(ev, np.uint64)
+        ew = np.ascontiguousarray(ew, np.float64)
+        err = C.create_string_buffer(512)
+        self.h = L.imomd_host_planner_create(device, g.n, g.lat, g.lon, len(eu), eu, ev, ew, len(dest),
+                                             np.asarray(dest, np.uint64), goal_bias, int(pseudo),
+                                             ga[0], ga[1], ga[2], err, 512)
+        if not self.h:
+            raise ImomdError(err.value.decode())
+        dev = DevicePlanner.__new__(DevicePlanner)
+        dev.h = C.c_void_p(L.imomd_host_planner_native(self.h))
+        dev.g, dev.dg, dev.Q, dev.K = g, None, 1, len(dest)
+        self.dev = dev
+
+    def step(self, passes, solve_rtsp=True):
+        err = C.create_string_buffer(512)
+        if host_lib().imomd_host_planner_step(self.h, passes, int(solve_rtsp), err, 512) != 0:
+            raise ImomdError(err.value.decode())
+
+    def cost(self):
+        return host_lib().imomd_host_planner_cost(self.h)
+
+    def close(self):
+        if self.h:
+            host_lib().imomd_host_planner_destroy(self.h)
+            self.h = None
+            self.dev.h = None
 
 
 class FacadeSolver:

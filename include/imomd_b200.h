@@ -174,6 +174,26 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
 /* pseudo mode: ordered (set index, vertex) insertions into connection_nodes_set_ (:692-703) */
 int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uint32_t* vertex,
                              uint32_t cap, uint32_t* count);
+/* same, starting at entry `first` (*count still receives the total length) */
+int imomd_get_connection_log_from(imomd_planner* p, int query, uint32_t first, uint32_t* set_idx,
+                                  uint32_t* vertex, uint32_t cap, uint32_t* count);
+
+/* Pseudo-tree merge support (mergePseudoTrees_ / mergeTwoTree_, :744-916; the merge itself is
+ * driven by the host facade because it iterates std containers in libstdc++ order):
+ *   imomd_attach          connectNewNode_ + updateExpandables + rewireTree_ +
+ *                         updateConnectionTree_ of `vertex` in `tree` (:848-851, :883-886);
+ *                         parent_out receives the parent chosen (IMOMD_NONE: not connectable)
+ *   imomd_get_visit_order vertices of a tree in the order they were visited = insertion order
+ *                         of the reference's tree.parent map (pseudo mode only)
+ *   imomd_set_distance    distance / connection-node entry (i,j) and (j,i), raises dm_updated
+ *   imomd_set_tree_done, imomd_set_contact   is_done flag; "connection set non-empty" flag */
+int imomd_attach(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* parent_out,
+                 imomd_query_report* report);
+int imomd_get_visit_order(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
+                          uint32_t* count);
+int imomd_set_distance(imomd_planner* p, int query, int i, int j, double d, uint32_t conn_node);
+int imomd_set_tree_done(imomd_planner* p, int query, int tree, int done);
+int imomd_set_contact(imomd_planner* p, int query, int set_idx);
 
 /* Parity hook for the nearest-frontier-vertex search (steerNewNode_ arg-min,
  * :406-418): n independent (query, tree, lat, lon) lookups against the current

@@ -541,9 +541,11 @@ struct ref_log_row_t
 };
 
 // The loop of ImomdRRT::findShortestPath (src/imomd_rrt_star.cpp:225-283) driven
-// from here (the original ends in pthread_exit and cannot return).  Every time
-// solveRTSP_ lowers shortest_path_cost_ one row is recorded -- the same moment
-// the reference calls logData_ (:978-984).  Returns the number of rows.
+// from here (the original ends in pthread_exit and cannot return).  One row is
+// recorded at every moment the reference calls logData_: when solveRTSP_ lowers
+// shortest_path_cost_ (:978-984) or, in pseudo mode, on every solveRTSP_ that
+// finds the graph connected and the distance matrix updated (:990-1001, the
+// cost may then stay the same).  Returns the number of rows.
 int ref_planner_run(void* pp, ref_log_row_t* rows, int cap, int64_t* iterations,
                     double* elapsed_s, int64_t* expansions)
 {
@@ -551,8 +553,8 @@ int ref_planner_run(void* pp, ref_log_row_t* rows, int cap, int64_t* iterations,
     ImomdRRT& r = *p->rrt;
     int n_rows = 0;
     int64_t n_exp = 0;
-    auto record = [&](double before) {
-        if (r.shortest_path_cost_ < before && n_rows < cap)
+    auto record = [&](double before, bool pseudo_log) {
+        if ((r.setting_.pseudo_mode ? pseudo_log : r.shortest_path_cost_ < before) && n_rows < cap)
         {
             int64_t ts = 0;
             for (const auto& t : r.tree_layers_) ts += (int64_t)t.parent.size();
@@ -577,8 +579,9 @@ int ref_planner_run(void* pp, ref_log_row_t* rows, int cap, int64_t* iterations,
         if (r.iteration_count_ % 100 == 0)
         {
             double before = r.shortest_path_cost_;
+            bool pseudo_log = r.is_connected_graph_ && r.is_distance_matrix_updated_;
             r.solveRTSP_();
-            record(before);
+            record(before, pseudo_log);
             done_exp = true;
             for (const tree_t& t : r.tree_layers_)
             {
@@ -597,8 +600,9 @@ int ref_planner_run(void* pp, ref_log_row_t* rows, int cap, int64_t* iterations,
     for (int c = 0; c < 10; ++c)
     {
         double before = r.shortest_path_cost_;
+        bool pseudo_log = r.is_connected_graph_ && r.is_distance_matrix_updated_;
         r.solveRTSP_();
-        record(before);
+        record(before, pseudo_log);
     }
     std::cout.rdbuf(old);
     if (iterations) *iterations = r.iteration_count_;

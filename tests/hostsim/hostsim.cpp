@@ -69,7 +69,7 @@ struct HsPlanner
     std::vector<uint32_t> cell_head, cell_cnt, chunk_next, free_stack, arena,
         clist, log, words;
     std::vector<double> lbd, ubd;
-    std::vector<uint32_t> occ;
+    std::vector<uint32_t> occ, visit_log;
     std::vector<VRec> rec;
     std::vector<ReportDev> reports;
     std::vector<double> lb;
@@ -154,6 +154,11 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     d.lbd = p->lbd.data();
     d.ubd = p->ubd.data();
     d.occ = p->occ.data();
+    if (pseudo)
+    {
+        p->visit_log.assign(qk * (size_t)n, IMOMD_NONE);
+        d.visit_log = p->visit_log.data();
+    }
     d.arena = p->arena.data();
     d.clist = p->clist.data();
     d.log = p->log.data();

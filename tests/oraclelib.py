@@ -302,3 +302,9 @@ class RefPlanner:
         out = np.empty(self.n, np.uint64)
         c = self.R.ref_planner_connection_set(self.ph, idx, out, self.n)
         return [int(x) for x in out[:c]]
+
+    def solve_rtsp(self):
+        return self.R.ref_planner_solve_rtsp(self.ph)
+
+    def path_cost(self):
+        return self.R.ref_planner_path_cost(self.ph)

@@ -46,13 +46,14 @@ def test_eci_gen_solver_with_gpu_fitness(K, p_missing):
     fs.close(); O.orc_solver_destroy(os_)
 
 
-def _probe_run(g, dest, max_iter, ga):
+def _probe_run(g, dest, max_iter, ga, pseudo=False):
     with tempfile.TemporaryDirectory() as td:
         gp = os.path.join(td, "g.bin")
         g.write_probe_file(gp)
         out = subprocess.check_output(
             [ol.REF_PROBE, "--graph", gp, "--dest", ",".join(map(str, dest)), "--mode", "run",
-             "--max-iter", str(max_iter), "--max-time", "600", "--ga", ",".join(map(str, ga))], text=True)
+             "--max-iter", str(max_iter), "--max-time", "600", "--ga", ",".join(map(str, ga))]
+            + (["--pseudo"] if pseudo else []), text=True)
     return json.loads(out.strip().splitlines()[-1])
 
 
@@ -74,6 +75,53 @@ def test_anytime_run_matches_reference(kind, K, max_iter):
         assert a[1] == b[1], (a, b)              # path cost, bit for bit
     assert got["final_cost"] == ref["final_cost"]
     assert list(got["path"]) == ref["path"]
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("kind,K,max_iter", [("grid", 5, 1500), ("road", 4, 2500), ("grid", 8, 2500),
+                                             ("grid", 3, 1200)])
+def test_pseudo_mode_run_matches_reference(kind, K, max_iter):
+    """pseudo_mode: the trees of the pseudo destinations are merged into the source / target
+    trees once everything is connected (mergePseudoTrees_, :744-916 upstream) and the planner
+    keeps improving the merged pair.  Rows, final cost and path equal the reference's."""
+    g = graphs.jittered_grid(70, seed=21) if kind == "grid" else graphs.road_like(5000, seed=4)
+    dest = graphs.pick_destinations(g, K, seed=K + 1)
+    ga = (3000, 400, 5)
+    ref = _probe_run(g, dest, max_iter, ga, pseudo=True)
+    got = capi.facade_run(g, dest, max_iter=max_iter, max_time=600, ga=ga, pseudo=True)
+    assert len(ref["rows"]) > 0, "the reference found no path: pick another scenario"
+    assert got["iterations"] == ref["iterations"]
+    assert got["expansions"] == ref["expansions"]
+    assert [(r[3], r[2]) for r in got["rows"]] == [(r[3], r[2]) for r in ref["rows"]]
+    for a, b in zip(got["rows"], ref["rows"]):
+        assert a[1] == b[1], (a, b)
+    assert got["final_cost"] == ref["final_cost"]
+    assert list(got["path"]) == ref["path"]
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("kind,K", [("grid", 5), ("road", 4), ("grid", 8)])
+def test_pseudo_merge_state_matches_reference(kind, K):
+    """Stepwise: 100 passes + solveRTSP_ at a time.  After the merge (the first solveRTSP_ on a
+    connected graph) and after every later step, every tree (parents, cost bits, frontier), the
+    matrices and the flags equal the reference's."""
+    from parity import compare_with_oracle
+    R = ol.ref()
+    g = graphs.jittered_grid(70, seed=21) if kind == "grid" else graphs.road_like(5000, seed=4)
+    dest = graphs.pick_destinations(g, K, seed=K + 1)
+    gh = R.ref_graph_from_edges(g.n, g.lat, g.lon, len(g.eu), g.eu, g.ev,
+                                g.ew.ctypes.data_as(ol.C.c_void_p))
+    rp = ol.RefPlanner(gh, dest, pseudo=True, ga=(3000, 400, 5))
+    fp = capi.FacadePlanner(g, dest, pseudo=True, ga=(3000, 400, 5))
+    merged = False
+    for step in range(8):
+        rp.iterate(100); rp.solve_rtsp()
+        fp.step(100, True)
+        compare_with_oracle(fp.dev, rp, K, exact_heuristics=False)
+        merged = merged or bool(rp.flags()["connected"])
+        assert fp.cost() == rp.path_cost() or not merged
+    assert merged, "the trees never connected: pick another scenario"
+    fp.close()
 
 
 @pytest.mark.parametrize("K", [4, 13, 14, 30])
