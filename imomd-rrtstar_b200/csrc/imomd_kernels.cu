@@ -1081,6 +1081,16 @@ int imomd_get_connection_log_from(imomd_planner* p, int query, uint32_t first, u
     return IMOMD_OK;
 }
 
+int imomd_clear_connection_log(imomd_planner* p, int query)
+{
+    if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
+    CU(cudaSetDevice(p->g->device));
+    uint32_t zero = 0;
+    CU(cudaMemcpyAsync(&p->d.query[query].log_count, &zero, 4, cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return IMOMD_OK;
+}
+
 int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uint32_t* vertex,
                              uint32_t cap, uint32_t* count)
 {

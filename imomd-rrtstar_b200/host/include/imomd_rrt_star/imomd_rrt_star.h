@@ -20,6 +20,7 @@
 #include <memory>
 #include <random>
 #include <string>
+#include <exception>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -68,6 +69,10 @@ public:
     long long iterations() const { return iteration_count_; }
     long long expansions() const { return expansions_; }
     void setDevice(int device) { device_ = device; }   // before the first expansion
+    // findShortestPath runs on a pthread and cannot throw: a failure (device capacity status,
+    // unmergeable pseudo tree) ends the run, is printed to stderr and kept here
+    bool failed() const { return static_cast<bool>(failure_); }
+    void rethrowFailure() const { if (failure_) std::rethrow_exception(failure_); }
     // stepwise driving (what findShortestPath's loop does): n x expandTreeLayers_, one
     // solveRTSP_ ; the C-ABI planner handle for state readback
     void stepPasses(int passes) { expandBatch(passes); }
@@ -122,6 +127,7 @@ private:
     std::vector<std::unordered_set<size_t>> connection_sets_;
     uint32_t log_consumed_ = 0;
     bool merge_done_ = false;
+    std::exception_ptr failure_;
 
     std::chrono::steady_clock::time_point start_;
     std::ofstream csv_;

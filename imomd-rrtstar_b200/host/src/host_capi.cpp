@@ -62,6 +62,7 @@ extern "C" int imomd_host_run(int device, uint64_t n, const double* lat, const d
         pthread_t tid;
         pthread_create(&tid, NULL, ImomdRRT::findShortestPath, &planner);
         pthread_join(tid, NULL);
+        planner.rethrowFailure();
         const auto& log = planner.getLog();
         *n_rows = static_cast<int>(log.size());
         for (int i = 0; i < *n_rows && i < row_cap; ++i)

@@ -179,6 +179,7 @@ bool ImomdRRT::expandBatch(int passes)
 // connection_nodes_set_ insertions the device logged since the last call, applied in order
 void ImomdRRT::drainConnectionLog()
 {
+    if (merge_done_) return;   // the sets are only read by the merge (as upstream)
     for (;;)
     {
         std::vector<uint32_t> idx(1 << 16), vx(1 << 16);
@@ -190,6 +191,11 @@ void ImomdRRT::drainConnectionLog()
         for (uint32_t i = 0; i < got; ++i) connection_sets_[idx[i]].insert(vx[i]);
         log_consumed_ += got;
         if (log_consumed_ >= total) break;
+    }
+    if (log_consumed_ > 0)
+    {
+        check(imomd_clear_connection_log(planner_, 0), "connection log");
+        log_consumed_ = 0;
     }
 }
 
@@ -406,7 +412,22 @@ void ImomdRRT::run()
 
 void* ImomdRRT::findShortestPath(void* arg)
 {
-    static_cast<ImomdRRT*>(arg)->run();
+    // An exception cannot leave a pthread entry point: keep it for failure() / rethrowFailure(),
+    // report it and release a printPath thread that may be waiting.
+    ImomdRRT* self = static_cast<ImomdRRT*>(arg);
+    try
+    {
+        self->run();
+    }
+    catch (const std::exception& ex)
+    {
+        self->failure_ = std::current_exception();
+        std::cerr << "[IMOMD] planner stopped: " << ex.what() << std::endl;
+        pthread_mutex_lock(&self->lock_);
+        self->finished_ = true;
+        pthread_mutex_unlock(&self->lock_);
+        pthread_cond_signal(&self->cond_);
+    }
     pthread_exit(NULL);
 }
 

@@ -174,6 +174,8 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
 /* pseudo mode: ordered (set index, vertex) insertions into connection_nodes_set_ (:692-703) */
 int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uint32_t* vertex,
                              uint32_t cap, uint32_t* count);
+/* forget the logged entries (a caller that has consumed them all keeps the log from filling up) */
+int imomd_clear_connection_log(imomd_planner* p, int query);
 /* same, starting at entry `first` (*count still receives the total length) */
 int imomd_get_connection_log_from(imomd_planner* p, int query, uint32_t first, uint32_t* set_idx,
                                   uint32_t* vertex, uint32_t cap, uint32_t* count);

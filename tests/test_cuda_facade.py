@@ -46,14 +46,14 @@ def test_eci_gen_solver_with_gpu_fitness(K, p_missing):
     fs.close(); O.orc_solver_destroy(os_)
 
 
-def _probe_run(g, dest, max_iter, ga, pseudo=False):
+def _probe_run(g, dest, max_iter, ga, pseudo=False, goal_bias=1.0):
     with tempfile.TemporaryDirectory() as td:
         gp = os.path.join(td, "g.bin")
         g.write_probe_file(gp)
         out = subprocess.check_output(
             [ol.REF_PROBE, "--graph", gp, "--dest", ",".join(map(str, dest)), "--mode", "run",
              "--max-iter", str(max_iter), "--max-time", "600", "--ga", ",".join(map(str, ga))]
-            + (["--pseudo"] if pseudo else []), text=True)
+            + (["--pseudo"] if pseudo else []) + ["--goal-bias", repr(goal_bias)], text=True)
     return json.loads(out.strip().splitlines()[-1])
 
 
@@ -89,6 +89,29 @@ def test_pseudo_mode_run_matches_reference(kind, K, max_iter):
     ga = (3000, 400, 5)
     ref = _probe_run(g, dest, max_iter, ga, pseudo=True)
     got = capi.facade_run(g, dest, max_iter=max_iter, max_time=600, ga=ga, pseudo=True)
+    assert len(ref["rows"]) > 0, "the reference found no path: pick another scenario"
+    assert got["iterations"] == ref["iterations"]
+    assert got["expansions"] == ref["expansions"]
+    assert [(r[3], r[2]) for r in got["rows"]] == [(r[3], r[2]) for r in ref["rows"]]
+    for a, b in zip(got["rows"], ref["rows"]):
+        assert a[1] == b[1], (a, b)
+    assert got["final_cost"] == ref["final_cost"]
+    assert list(got["path"]) == ref["path"]
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("width,goal_bias,max_iter", [(60, 0.3, 3000), (90, 0.3, 4000), (60, 1.0, 3000)])
+def test_bugtrap_pseudo_mode_matches_reference(width, goal_bias, max_iter):
+    """BASELINE configs[1] (stand-in for the missing sanf.osm): source inside a
+    U-shaped trap, target behind its closed side, 5 pseudo destinations around the opening,
+    pseudo mode, goal_bias 0.3 as in the README recipe.  Rows, cost and path equal the
+    reference's (run in its own process: goal_bias < 1 uses function-local static state)."""
+    g, source, target, pseudo = graphs.bugtrap_grid(width, seed=3)
+    dest = [source] + pseudo + [target]
+    ga = (3000, 400, 5)
+    ref = _probe_run(g, dest, max_iter, ga, pseudo=True, goal_bias=goal_bias)
+    got = capi.facade_run(g, dest, goal_bias=goal_bias, max_iter=max_iter, max_time=600, ga=ga,
+                          pseudo=True)
     assert len(ref["rows"]) > 0, "the reference found no path: pick another scenario"
     assert got["iterations"] == ref["iterations"]
     assert got["expansions"] == ref["expansions"]
