@@ -334,6 +334,7 @@ struct Shared
     // jump-point search in flight
     uint32_t jps_next;
     int32_t attach_mode;   // 1: imomd_attach (pseudo-tree merge): no sampling, JPS, pruning
+    uint32_t attach_i, attach_n;   // position in / length of P.attach_list
     // rewire machine: explicit LIFO in the arena
     uint32_t rw_fp, rw_top;
     // cost propagation request / result (tree_t::updateCost)
@@ -1310,6 +1311,16 @@ struct Seq
                     apply_connection(k, T, S.x_new, T.cost(S.x_new));         // :355
                     if (S.attach_mode)
                     {
+                        // report the parent this vertex received, then take the next one
+                        P.attach_list[S.attach_i] = T.parent(S.x_new);
+                        S.attach_i += 1;
+                        if (S.attach_i < S.attach_n && Q->status == 0)
+                        {
+                            S.x_new = P.attach_list[S.attach_i];
+                            S.conn_pending = 0;
+                            S.phase = PH_JPS;
+                            continue;
+                        }
                         S.req = REQ_EXIT;
                         return;
                     }
@@ -1984,7 +1995,7 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
 template <int KW, class Cta>
 IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
                                double* lb, uint32_t* lvl, double* mat, unsigned char* hot,
-                               int attach_tree = -1, uint32_t attach_vertex = IMOMD_NONE)
+                               int attach_tree = -1, uint32_t attach_count = 0)
 {
     QueryDev* Qg = P.query + q;
     QueryDev* Q = reinterpret_cast<QueryDev*>(hot);
@@ -2021,10 +2032,12 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         if (attach_tree >= 0)
         {
             // mergeTwoTree_ (:848-851): connectNewNode_, updateExpandables, rewireTree_,
-            // updateConnectionTree_ of one given vertex in one given tree
+            // updateConnectionTree_ of the listed vertices, in order, in one given tree
             S.attach_mode = 1;
             S.k = attach_tree;
-            S.x_new = attach_vertex;
+            S.attach_i = 0;
+            S.attach_n = attach_count;
+            S.x_new = P.attach_list[0];
             S.conn_pending = 0;
             S.phase = PH_JPS;
         }

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand(PlannerDev P, in
 
 // mergeTwoTree_'s per-vertex work (pseudo-tree merge driven by the host facade)
 template <int KW>
-__global__ void __launch_bounds__(kThreads) k_attach(PlannerDev P, int q, int tree, uint32_t vertex)
+__global__ void __launch_bounds__(kThreads) k_attach(PlannerDev P, int q, int tree, uint32_t count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
@@ -283,7 +283,34 @@ __global__ void __launch_bounds__(kThreads) k_attach(PlannerDev P, int q, int tr
     double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev cta;
-    run_query<KW>(cta, P, q, 0, S, lb, lvl, mat, hot, tree, vertex);
+    run_query<KW>(cta, P, q, 0, S, lb, lvl, mat, hot, tree, count);
+}
+
+// Sparse readback: parent and cost of the listed vertices of one tree (ids in, parents out, in place).
+__global__ void k_gather_tree(PlannerDev P, size_t qt, uint32_t* ids, double* cost, uint32_t count)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned char* rec = P.trec + (qt * P.g.n + ids[i]) * P.trec_stride;
+    uint32_t par = *reinterpret_cast<const uint32_t*>(rec);
+    ids[i] = par;
+    cost[i] = par == IMOMD_NONE ? INFINITY : *reinterpret_cast<const double*>(rec + 8);
+}
+
+// Frontier of one tree as a compact id list (order unspecified): out[0] = count, ids from out[1].
+__global__ void k_frontier_list(PlannerDev P, size_t qt, uint32_t* out)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    if (v < P.g.n)
+        in = *reinterpret_cast<const uint32_t*>(P.trec + (qt * P.g.n + v) * P.trec_stride + 4) != IMOMD_NONE;
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    if (m == 0) return;
+    int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(out, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (in) out[1 + base + __popc(m & ((1u << lane) - 1))] = v;
 }
 
 // One CTA per lookup slot (grid-stride over the lookups); scratch chunk lists are per CTA.
@@ -424,6 +451,9 @@ struct imomd_planner
     int64_t* nn_stats;
     uint32_t* walk_buf;
     uint32_t walk_cap;
+    // sparse readback scratch (imomd_gather_tree, imomd_get_frontier): ids / values, n + 1 each
+    uint32_t* gather_u32;
+    double* gather_f64;
 };
 
 struct imomd_ctx
@@ -579,6 +609,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     p->nn_ctas = 0;
     p->nn_stats = nullptr;
     p->walk_buf = nullptr;
+    p->gather_u32 = nullptr;
+    p->gather_f64 = nullptr;
     p->walk_cap = 0;
     PlannerDev& d = p->d;
     d.g = g->d;
@@ -610,7 +642,9 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     CU(dmalloc(&d.log, (size_t)n_queries * 2 * d.log_entries));
     CU(dmalloc(&d.reports, (size_t)n_queries));
     d.visit_log = nullptr;
+    d.attach_list = nullptr;
     if (d.pseudo) CU(dmalloc(&d.visit_log, qk * n));
+    if (d.pseudo) CU(dmalloc(&d.attach_list, n));
     d.words = nullptr;
     d.words_avail = 0;
     // initial headers
@@ -667,10 +701,13 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(d.log);
     cudaFree(d.reports);
     cudaFree(d.visit_log);
+    cudaFree(d.attach_list);
     cudaFree(p->words);
     cudaFree(p->nn_scratch);
     cudaFree(p->nn_stats);
     cudaFree(p->walk_buf);
+    cudaFree(p->gather_u32);
+    cudaFree(p->gather_f64);
     cudaEventDestroy(p->ev0);
     cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->stream);
@@ -698,28 +735,37 @@ int imomd_planner_set_queries(imomd_planner* p, const uint32_t* dest, const doub
     return IMOMD_OK;
 }
 
-int imomd_attach(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* parent_out,
-                 imomd_query_report* report)
+int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* vertices, uint32_t count,
+                      uint32_t* parents_out, imomd_query_report* report)
 {
-    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || vertex >= p->d.g.n)
-        return fail(IMOMD_ERR_ARG, "bad planner/query/tree/vertex");
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !vertices)
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree/list");
+    if (!p->d.attach_list) return fail(IMOMD_ERR_ARG, "imomd_attach needs a pseudo-mode planner");
+    if (count == 0) return IMOMD_OK;
+    if (count > p->d.g.n) return fail(IMOMD_ERR_ARG, "attach list longer than the graph");
+    for (uint32_t i = 0; i < count; ++i)
+        if (vertices[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "attach list: vertex id out of range");
     CU(cudaSetDevice(p->g->device));
+    CU(cudaMemcpyAsync(p->d.attach_list, vertices, (size_t)count * 4, cudaMemcpyHostToDevice, p->stream));
     const int w = p->d.g.width;
-    if (w == 4) k_attach<4><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, vertex);
-    else if (w == 8) k_attach<8><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, vertex);
-    else k_attach<16><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, vertex);
+    if (w == 4) k_attach<4><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
+    else if (w == 8) k_attach<8><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
+    else k_attach<16><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
     CU(cudaGetLastError());
     if (report)
         CU(cudaMemcpyAsync(report, p->d.reports + query, sizeof(ReportDev), cudaMemcpyDeviceToHost,
                            p->stream));
-    if (parent_out)
-    {
-        const size_t qt = (size_t)query * p->d.K + tree;
-        CU(cudaMemcpyAsync(parent_out, p->d.trec + (qt * p->d.g.n + vertex) * p->d.trec_stride, 4,
-                           cudaMemcpyDeviceToHost, p->stream));
-    }
+    if (parents_out)
+        CU(cudaMemcpyAsync(parents_out, p->d.attach_list, (size_t)count * 4, cudaMemcpyDeviceToHost,
+                           p->stream));
     CU(cudaStreamSynchronize(p->stream));
     return IMOMD_OK;
+}
+
+int imomd_attach(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* parent_out,
+                 imomd_query_report* report)
+{
+    return imomd_attach_list(p, query, tree, &vertex, 1, parent_out, report);
 }
 
 int imomd_get_visit_order(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
@@ -1001,28 +1047,58 @@ int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, doub
     return IMOMD_OK;
 }
 
+static int ensure_gather(imomd_planner* p)
+{
+    if (!p->gather_u32) CU(dmalloc(&p->gather_u32, (size_t)p->d.g.n + 1));
+    if (!p->gather_f64) CU(dmalloc(&p->gather_f64, (size_t)p->d.g.n + 1));
+    return IMOMD_OK;
+}
+
 int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
                        uint32_t* count)
 {
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !count)
         return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
-    size_t n = p->d.g.n;
+    if (int rc = ensure_gather(p)) return rc;
+    const uint32_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
-    std::vector<uint32_t> slot(n);
-    CU(cudaMemcpy2D(slot.data(), 4, p->d.trec + qt * n * p->d.trec_stride + 4, p->d.trec_stride, 4, n,
-                    cudaMemcpyDeviceToHost));
+    CU(cudaMemsetAsync(p->gather_u32, 0, 4, p->stream));
+    k_frontier_list<<<(n + 255) / 256, 256, 0, p->stream>>>(p->d, qt, p->gather_u32);
+    CU(cudaGetLastError());
     uint32_t c = 0;
-    for (size_t v = 0; v < n; ++v)
-    {
-        if (slot[v] != IMOMD_NONE)
-        {
-            if (out && c < cap) out[c] = (uint32_t)v;
-            ++c;
-        }
-    }
+    CU(cudaMemcpyAsync(&c, p->gather_u32, 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
     *count = c;
+    uint32_t take = std::min(c, cap);
+    if (take && out)
+    {
+        CU(cudaMemcpy(out, p->gather_u32 + 1, (size_t)take * 4, cudaMemcpyDeviceToHost));
+        std::sort(out, out + take);   // ascending ids, as the dense scan used to return them
+    }
+    return IMOMD_OK;
+}
+
+int imomd_gather_tree(imomd_planner* p, int query, int tree, const uint32_t* vertices, uint32_t count,
+                      uint32_t* parent, double* cost)
+{
+    if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || (count && !vertices))
+        return fail(IMOMD_ERR_ARG, "bad planner/query/tree/list");
+    if (count > p->d.g.n) return fail(IMOMD_ERR_ARG, "gather list longer than the graph");
+    if (count == 0) return IMOMD_OK;
+    for (uint32_t i = 0; i < count; ++i)
+        if (vertices[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "gather list: vertex id out of range");
+    CU(cudaSetDevice(p->g->device));
+    if (int rc = ensure_gather(p)) return rc;
+    size_t qt = (size_t)query * p->d.K + tree;
+    CU(cudaMemcpyAsync(p->gather_u32, vertices, (size_t)count * 4, cudaMemcpyHostToDevice, p->stream));
+    k_gather_tree<<<(count + 255) / 256, 256, 0, p->stream>>>(p->d, qt, p->gather_u32, p->gather_f64, count);
+    CU(cudaGetLastError());
+    if (parent)
+        CU(cudaMemcpyAsync(parent, p->gather_u32, (size_t)count * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (cost)
+        CU(cudaMemcpyAsync(cost, p->gather_f64, (size_t)count * 8, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
     return IMOMD_OK;
 }
 

@@ -159,6 +159,8 @@ struct PlannerDev
     uint32_t* clist;           // [Q][2*chunks]   (chunk id, valid count)
     uint32_t* log;             // [Q][2*log_entries] (set idx, vertex)
     uint32_t* visit_log;       // pseudo mode: [Q*K][n] vertices in the order they were visited
+    uint32_t* attach_list;     // pseudo mode: [n] vertices imomd_attach_list works through; each entry is
+                               // overwritten with the parent the vertex received
     struct ReportDev* reports; // [Q] compact per-launch report (copied back to the host)
     // injected random words
     const uint32_t* words;

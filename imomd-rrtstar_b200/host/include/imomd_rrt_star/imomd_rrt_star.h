@@ -90,7 +90,7 @@ private:
     void drainConnectionLog();
     void mergePseudoTrees();
     void mergeTwoTrees(int parent_tree, int child_tree);
-    bool attach(int tree, size_t vertex, std::vector<char>& visited, std::vector<char>& frontier);
+    void attachList(int tree, const std::vector<uint32_t>& vertices);
     int setIndex(int a, int b) const { return a > b ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; }
 
     imomd_setting_t setting_{};

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <ctime>
 #include <iomanip>
+#include <cstdlib>
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
@@ -38,6 +39,22 @@ std::string fixed4(double v)
     out << std::fixed << v;
     return out.str();
 }
+
+// IMOMD_FACADE_TIMING=1: wall time of the facade's stages on stderr (development aid)
+struct StageTimer
+{
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    explicit StageTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    ~StageTimer()
+    {
+        static const bool on = std::getenv("IMOMD_FACADE_TIMING") != nullptr;
+        if (on)
+            std::cerr << "[facade] " << name << " "
+                      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()
+                      << " ms" << std::endl;
+    }
+};
 
 void check(int rc, const char* what)
 {
@@ -155,6 +172,7 @@ void ImomdRRT::feedWords(size_t n)
 // `passes` calls of expandTreeLayers_ on the device
 bool ImomdRRT::expandBatch(int passes)
 {
+    StageTimer timer("expandBatch");
     int left = passes;
     while (left > 0)
     {
@@ -199,37 +217,42 @@ void ImomdRRT::drainConnectionLog()
     }
 }
 
-// connectNewNode_ + updateExpandables + rewireTree_ + updateConnectionTree_ of one vertex
-// (:848-851 / :883-886 upstream) on the device; the host mirrors of the tree's visited set and
-// frontier follow (the rewire cascade changes neither)
-bool ImomdRRT::attach(int tree, size_t vertex, std::vector<char>& visited, std::vector<char>& frontier)
+// connectNewNode_ + updateExpandables + rewireTree_ + updateConnectionTree_ (:848-851 /
+// :883-886 upstream) of the listed vertices, one after the other, in one device launch; then the
+// connection-set insertions they made are applied to the host mirrors.
+void ImomdRRT::attachList(int tree, const std::vector<uint32_t>& vertices)
 {
-    uint32_t parent = IMOMD_NONE;
+    if (vertices.empty()) return;
+    std::vector<uint32_t> got(vertices.size());
     imomd_query_report rep{};
-    check(imomd_attach(planner_, 0, tree, static_cast<uint32_t>(vertex), &parent, &rep), "tree merge");
+    check(imomd_attach_list(planner_, 0, tree, vertices.data(), static_cast<uint32_t>(vertices.size()),
+                            got.data(), &rep),
+          "tree merge");
     if (rep.status != IMOMD_RUN_OK)
         throw std::runtime_error("ImomdRRT (B200): device status " + std::to_string(rep.status) +
                                  " during the tree merge");
+    for (uint32_t parent : got)
+        if (parent == IMOMD_NONE)
+            throw std::runtime_error("ImomdRRT (B200): a vertex did not connect during the tree merge");
     tree_vertices_ = rep.tree_vertices;
     if (rep.dm_updated) dm_updated_ = true;
-    frontier[vertex] = 0;
-    const bool connected = parent != IMOMD_NONE && !(parent & 0x80000000u);
-    if (connected) visited[vertex] = 1;
-    for (const auto& kv : (*connection_)[vertex])
-        if (!visited[kv.first]) frontier[kv.first] = 1;
     drainConnectionLog();
-    return connected;
 }
 
 // mergeTwoTree_, src/imomd_rrt_star.cpp:819-916 upstream
 void ImomdRRT::mergeTwoTrees(int parent_tree, int child_tree)
 {
+    StageTimer timer("mergeTwoTrees");
     const size_t n = map_->size();
-    // mirrors of the parent tree: visited set and frontier ("expandables")
-    std::vector<uint32_t> par(n);
-    check(imomd_get_tree(planner_, 0, parent_tree, par.data(), nullptr), "tree readback");
+    // mirrors of the parent tree: visited set (= its visit order) and frontier ("expandables");
+    // all readbacks are sparse, nothing of size n crosses the bus
     std::vector<char> visited(n, 0), frontier(n, 0);
-    for (size_t v = 0; v < n; ++v) visited[v] = par[v] != IMOMD_NONE;
+    std::vector<uint32_t> order(n);
+    uint32_t visited_count = 0;
+    check(imomd_get_visit_order(planner_, 0, parent_tree, order.data(), static_cast<uint32_t>(n),
+                                &visited_count),
+          "visit order readback");
+    for (uint32_t i = 0; i < visited_count; ++i) visited[order[i]] = 1;
     {
         std::vector<uint32_t> fr(n);
         uint32_t cnt = 0;
@@ -239,23 +262,30 @@ void ImomdRRT::mergeTwoTrees(int parent_tree, int child_tree)
     }
     // the child tree's parent map, rebuilt with the reference's insertion history so that it
     // iterates in the same order (:860): {root, root} first, then every vertex as visited
-    std::vector<uint32_t> cpar(n), order(n);
-    check(imomd_get_tree(planner_, 0, child_tree, cpar.data(), nullptr), "tree readback");
-    uint32_t visited_count = 0;
     check(imomd_get_visit_order(planner_, 0, child_tree, order.data(), static_cast<uint32_t>(n),
                                 &visited_count),
           "visit order readback");
+    std::vector<uint32_t> cpar(visited_count);
+    check(imomd_gather_tree(planner_, 0, child_tree, order.data(), visited_count, cpar.data(), nullptr),
+          "tree readback");
     const size_t child_root = destinations_[child_tree];
     std::unordered_map<size_t, size_t> child_parent = {{child_root, child_root}};
-    for (uint32_t i = 1; i < visited_count; ++i) child_parent[order[i]] = cpar[order[i]];
+    for (uint32_t i = 1; i < visited_count; ++i) child_parent[order[i]] = cpar[i];
 
     const int idx = setIndex(parent_tree, child_tree);
     std::unordered_set<int> merged;
+    StageTimer timer2("  mergeTwoTrees after readback");
     // main branches: connection node ----> root of the child tree
+    // Which vertices a chain attaches follows from the child's parent map and the visited
+    // mirror alone, so each chain is ONE device launch; the set insertions its attaches made
+    // are applied, in order, before the set iterator advances (the state it then sees is the
+    // one upstream's in-loop insertions produce).
+    std::vector<uint32_t> chain;
     for (size_t connection_node : connection_sets_[idx])
     {
         size_t current = connection_node;
         bool optimal = true;
+        chain.clear();
         while (current != child_root && optimal)
         {
             const size_t x_new = child_parent[current];
@@ -265,13 +295,22 @@ void ImomdRRT::mergeTwoTrees(int parent_tree, int child_tree)
             }
             else
             {
-                attach(parent_tree, x_new, visited, frontier);
+                chain.push_back(static_cast<uint32_t>(x_new));
+                visited[x_new] = 1;
+                frontier[x_new] = 0;
+                for (const auto& kv : (*connection_)[x_new])
+                    if (!visited[kv.first]) frontier[kv.first] = 1;
                 merged.insert(static_cast<int>(x_new));
             }
             current = x_new;
         }
+        attachList(parent_tree, chain);
     }
-    // side branches, in the iteration order of the child's parent map
+    // side branches, in the iteration order of the child's parent map.  Nothing in this loop
+    // reads what the attaches compute (each vertex is adjacent to a visited one, so it always
+    // connects; the visited set and the frontier follow from the adjacency alone), so the
+    // whole sequence is worked out here and performed by ONE device launch.
+    std::vector<uint32_t> todo;
     for (const auto& node : child_parent)
     {
         if (visited[node.first]) continue;
@@ -283,8 +322,17 @@ void ImomdRRT::mergeTwoTrees(int parent_tree, int child_tree)
             branch.push_back(current);
         }
         for (auto it = branch.rbegin(); it != branch.rend(); ++it)
-            if (!visited[*it]) attach(parent_tree, *it, visited, frontier);
+        {
+            const size_t x = *it;
+            if (visited[x]) continue;
+            todo.push_back(static_cast<uint32_t>(x));
+            visited[x] = 1;
+            frontier[x] = 0;
+            for (const auto& kv : (*connection_)[x])
+                if (!visited[kv.first]) frontier[kv.first] = 1;
+        }
     }
+    attachList(parent_tree, todo);
     // connection nodes of the child towards the other trees now belong to the parent
     for (int t = 0; t < K_; ++t)
     {
@@ -305,6 +353,7 @@ void ImomdRRT::mergeTwoTrees(int parent_tree, int child_tree)
 // mergePseudoTrees_, src/imomd_rrt_star.cpp:744-817 upstream
 void ImomdRRT::mergePseudoTrees()
 {
+    StageTimer timer("mergePseudoTrees");
     const int source = 0, target = K_ - 1;
     std::unordered_set<int> unmerged;
     for (int i = 1; i < K_ - 1; ++i) unmerged.insert(i);
@@ -350,16 +399,22 @@ void ImomdRRT::mergePseudoTrees()
     }
     // best direct connection between the merged source and target trees (:797-815; the
     // threshold stays the initial distance, as upstream)
-    const size_t n = map_->size();
-    std::vector<uint32_t> par(n);
-    std::vector<double> cost_s(n), cost_t(n);
-    check(imomd_get_tree(planner_, 0, source, par.data(), cost_s.data()), "tree readback");
-    check(imomd_get_tree(planner_, 0, target, par.data(), cost_t.data()), "tree readback");
+    const auto& direct = connection_sets_[target * (target - 1) / 2];
+    std::vector<uint32_t> nodes;
+    for (size_t node : direct) nodes.push_back(static_cast<uint32_t>(node));
+    std::vector<double> cost_s(nodes.size()), cost_t(nodes.size());
+    check(imomd_gather_tree(planner_, 0, source, nodes.data(), static_cast<uint32_t>(nodes.size()), nullptr,
+                            cost_s.data()),
+          "tree readback");
+    check(imomd_gather_tree(planner_, 0, target, nodes.data(), static_cast<uint32_t>(nodes.size()), nullptr,
+                            cost_t.data()),
+          "tree readback");
     auto D = getDistanceMatrix();
     const double threshold = (*D)[source][target];
-    for (size_t node : connection_sets_[target * (target - 1) / 2])
+    for (size_t i = 0; i < nodes.size(); ++i)
     {
-        const double distance = cost_s[node] + cost_t[node];
+        const size_t node = nodes[i];
+        const double distance = cost_s[i] + cost_t[i];
         if (distance < threshold)
         {
             check(imomd_set_distance(planner_, 0, source, target, distance, static_cast<uint32_t>(node)),
@@ -488,6 +543,7 @@ void ImomdRRT::solveRTSP()
 // Stitches the tree branches along the visiting sequence into one vertex path.
 void ImomdRRT::updatePath()
 {
+    StageTimer timer("updatePath");
     std::vector<uint32_t> cn(static_cast<size_t>(K_) * K_);
     check(imomd_get_state(planner_, 0, nullptr, cn.data(), nullptr, nullptr, nullptr, nullptr, nullptr),
           "connection nodes readback");

@@ -168,6 +168,10 @@ int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, doub
 /* frontier ("expandables") of one tree, unordered; *count receives its size */
 int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
                        uint32_t* count);
+/* sparse readback: parent (IMOMD_NONE = not visited) and cost (INFINITY then) of the listed
+ * vertices of one tree; either output may be NULL */
+int imomd_gather_tree(imomd_planner* p, int query, int tree, const uint32_t* vertices, uint32_t count,
+                      uint32_t* parent, double* cost);
 /* parent-pointer walk vertex -> root of `tree` (updatePath_, :936-954); out[0] = vertex */
 int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* out,
                        uint32_t cap, uint32_t* len);
@@ -185,12 +189,17 @@ int imomd_get_connection_log_from(imomd_planner* p, int query, uint32_t first, u
  *   imomd_attach          connectNewNode_ + updateExpandables + rewireTree_ +
  *                         updateConnectionTree_ of `vertex` in `tree` (:848-851, :883-886);
  *                         parent_out receives the parent chosen (IMOMD_NONE: not connectable)
+ *   imomd_attach_list     the same for `count` vertices one after the other in ONE launch
+ *                         (each sees the tree as the previous ones left it); parents_out[i]
+ *                         = parent of vertices[i] after the whole list
  *   imomd_get_visit_order vertices of a tree in the order they were visited = insertion order
  *                         of the reference's tree.parent map (pseudo mode only)
  *   imomd_set_distance    distance / connection-node entry (i,j) and (j,i), raises dm_updated
  *   imomd_set_tree_done, imomd_set_contact   is_done flag; "connection set non-empty" flag */
 int imomd_attach(imomd_planner* p, int query, int tree, uint32_t vertex, uint32_t* parent_out,
                  imomd_query_report* report);
+int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* vertices, uint32_t count,
+                      uint32_t* parents_out, imomd_query_report* report);
 int imomd_get_visit_order(imomd_planner* p, int query, int tree, uint32_t* out, uint32_t cap,
                           uint32_t* count);
 int imomd_set_distance(imomd_planner* p, int query, int i, int j, double d, uint32_t conn_node);
