@@ -170,9 +170,25 @@ def run_reference_sample(g, dests, iters, cores, graph_file=None):
                         "toolchain": outs[0]["toolchain"]}
 
 
+class _stdout_to_stderr:
+    """The facade prints the reference's progress rows on stdout (C++ iostream); keep the bench's
+    stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def measure_ttfs(g, dest, device, max_iter=2500):
     from imomd_b200 import capi
-    got = capi.facade_run(g, dest, max_iter=max_iter, max_time=300, device=device)
+    with _stdout_to_stderr():
+        got = capi.facade_run(g, dest, max_iter=max_iter, max_time=300, device=device)
     out = {"b200_s": got["rows"][0][0] if got["rows"] else None,
            "b200_first_cost": got["rows"][0][1] if got["rows"] else None,
            "b200_first_iteration": got["rows"][0][3] if got["rows"] else None, "max_iter": max_iter}
@@ -192,6 +208,43 @@ def measure_ttfs(g, dest, device, max_iter=2500):
                     "reference_first_iteration": rows[0][3] if rows else None,
                     "same_first_solution": bool(rows and got["rows"] and rows[0][1] == got["rows"][0][1]
                                                 and rows[0][3] == got["rows"][0][3])})
+    return out
+
+
+def measure_ttfs_bugtrap(device, width=1131, max_iter=10000):
+    """BASELINE configs[1] (stand-in for the missing sanf.osm): bug-trap grid, pseudo
+    mode, 5 pseudo destinations, goal_bias 0.3; the drop-in facade next to the unmodified
+    reference: time to first solution, and the time and cost after `max_iter` passes."""
+    from imomd_b200 import capi, graphs
+    g, s, t, ps = graphs.bugtrap_grid(width, seed=123)
+    dest = [s] + ps + [t]
+    with _stdout_to_stderr():
+        got = capi.facade_run(g, dest, goal_bias=0.3, max_iter=max_iter, max_time=600, pseudo=True,
+                              device=device)
+    rows = got["rows"]
+    out = {"workload": f"bugtrap grid {width}x{width} ({g.n} vertices), pseudo mode, 5 pseudo destinations, "
+                       f"goal_bias 0.3, {max_iter} passes",
+           "b200_first_s": rows[0][0] if rows else None, "b200_first_cost": rows[0][1] if rows else None,
+           "b200_last_s": rows[-1][0] if rows else None, "b200_final_cost": got["final_cost"],
+           "expansions": got["expansions"]}
+    if os.path.exists(REF_PROBE):
+        fd, gf = tempfile.mkstemp(suffix=".bin", prefix="imomd_graph_")
+        os.close(fd)
+        try:
+            g.write_probe_file(gf)
+            res = json.loads(subprocess.check_output(
+                [REF_PROBE, "--graph", gf, "--dest", ",".join(map(str, dest)), "--mode", "run", "--pseudo",
+                 "--goal-bias", "0.3", "--max-iter", str(max_iter), "--max-time", "600"],
+                text=True).strip().splitlines()[-1])
+        finally:
+            os.unlink(gf)
+        rr = res["rows"]
+        out.update({"reference_first_s": rr[0][0] if rr else None,
+                    "reference_first_cost": rr[0][1] if rr else None,
+                    "reference_last_s": rr[-1][0] if rr else None,
+                    "reference_final_cost": res["final_cost"],
+                    "identical_rows": [(r[3], r[2], r[1]) for r in rows] == [(r[3], r[2], r[1]) for r in rr],
+                    "identical_path": list(got["path"]) == res["path"]})
     return out
 
 
@@ -414,6 +467,10 @@ def b200_arm(args):
             line["ttfs"] = measure_ttfs(g, dests[0], device)
         except Exception as ex:
             line["ttfs"] = {"error": str(ex)}
+        try:
+            line["ttfs_bugtrap"] = measure_ttfs_bugtrap(device)
+        except Exception as ex:
+            line["ttfs_bugtrap"] = {"error": str(ex)}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         cd = list(dests)

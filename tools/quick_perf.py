@@ -43,6 +43,14 @@ if __name__ == "__main__":
         rng = np.random.default_rng(1)
         dests = [graphs.pick_destinations(g, 2, seed=int(s)) for s in rng.integers(0, 1 << 30, 1024)]
         run("roadlike7k_Q1024_K2", g, dests, [100, 900, 2000])
+    if "bugtrap" in which:
+        g, s_, t_, ps = graphs.bugtrap_grid(1131, seed=123)
+        run("bugtrap1131_K7_pseudo", g, [[s_] + ps + [t_]], [100] * 8, goal_bias=0.3, pseudo=True)
+    if "bench" in which:
+        g = graphs.jittered_grid(1000, seed=123)
+        rng = np.random.default_rng(2)
+        dests = [graphs.pick_destinations(g, 12, seed=int(s)) for s in rng.integers(0, 1 << 30, 296)]
+        run("grid1000_K12_Q296", g, dests, [3000])
     if "multi" in which:
         g = graphs.jittered_grid(1000, seed=123)
         rng = np.random.default_rng(2)
