@@ -22,6 +22,14 @@ def run(name, g, dests, iters_list, **kw):
                         exp_per_s=round(ex / (ms / 1e3), 1), status=[r.status for r in reps][:4],
                         tree_vertices=sum(r.tree_vertices for r in reps),
                         near=sum(r.near_ties for r in reps), unres=sum(r.unresolved_ties for r in reps)))
+    if len(dests) > 1:
+        tot = []
+        for q in range(len(dests)):
+            pr = dp.profile(q); pr.pop("bfs_vertices_levels")
+            tot.append(sum(c for c, _ in pr.values()))
+        tot = np.array(tot, float)
+        print("  per-query busy cycles: min %.3g  p50 %.3g  p90 %.3g  max %.3g  mean %.3g  (max/mean %.2f)" % (
+            tot.min(), np.median(tot), np.percentile(tot, 90), tot.max(), tot.mean(), tot.max() / tot.mean()))
     prof = dp.profile(0)
     print("  bfs vertices, levels:", prof.pop("bfs_vertices_levels"))
     tot = sum(c for c, _ in prof.values()) or 1
@@ -49,8 +57,16 @@ if __name__ == "__main__":
     if "bench" in which:
         g = graphs.jittered_grid(1000, seed=123)
         rng = np.random.default_rng(2)
-        dests = [graphs.pick_destinations(g, 12, seed=int(s)) for s in rng.integers(0, 1 << 30, 296)]
-        run("grid1000_K12_Q296", g, dests, [3000])
+        Q = int(os.environ.get("QP_Q", "296"))
+        dests = [graphs.pick_destinations(g, 12, seed=int(s)) for s in rng.integers(0, 1 << 30, Q)]
+        run(f"grid1000_K12_Q{Q}", g, dests, [3000])
+    if "occ" in which:
+        # residency experiment: same per-query work, 296 vs 592 queries on a graph small enough for both
+        g = graphs.jittered_grid(700, seed=123)
+        rng = np.random.default_rng(2)
+        Q = int(os.environ.get("QP_Q", "296"))
+        dests = [graphs.pick_destinations(g, 12, seed=int(s)) for s in rng.integers(0, 1 << 30, Q)]
+        run(f"grid700_K12_Q{Q}", g, dests, [3000])
     if "multi" in which:
         g = graphs.jittered_grid(1000, seed=123)
         rng = np.random.default_rng(2)
