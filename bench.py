@@ -451,8 +451,18 @@ def b200_arm(args):
             if best is None or info["kernel_ms"] < best["kernel_ms"]:
                 best = info
         nn_gbs = best["bytes"] / (best["kernel_ms"] / 1e3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed
+        # `ncu --set full` capture (profiles/r01_nn_tiles_traffic.json), when the shape matches
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_nn_tiles_traffic.json")) as f:
+                cap = json.load(f)
+            if cap["lookups"] == n_lk and abs(cap["algorithmic_bytes"] - best["bytes"]) < 0.02 * best["bytes"]:
+                traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         line["roofline_nn"] = {"bound": "hbm", "achieved": nn_gbs, "peak": peak, "unit": "GB/s",
-                               "frac": nn_gbs / peak, "traffic": None, "kernel": "k_nearest_tiles",
+                               "frac": nn_gbs / peak, "traffic": traffic, "kernel": "k_nearest_tiles",
                                "algorithmic_bytes_per_launch": int(best["bytes"]),
                                "launch_ms": best["kernel_ms"], "lookups": n_lk,
                                "lookups_per_s": n_lk / (best["kernel_ms"] / 1e3),
