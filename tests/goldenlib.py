@@ -22,6 +22,10 @@ def runs():
     return json.load(open(os.path.join(GOLDEN, "runs.json")))["runs"]
 
 
+def runs_pseudo():
+    return json.load(open(os.path.join(GOLDEN, "runs_pseudo.json")))["runs"]
+
+
 def rtsp():
     return json.load(open(os.path.join(GOLDEN, "rtsp.json")))["solvers"]
 

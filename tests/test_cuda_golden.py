@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import goldenlib as gl
-from imomd_b200 import capi
+from imomd_b200 import capi, graphs
 
 pytestmark = pytest.mark.gpu
 
@@ -58,6 +58,24 @@ def test_nearest_golden(name):
 def test_facade_anytime_runs(run):
     g = gl.graph(run["graph"])
     got = capi.facade_run(g, run["dest"], max_iter=run["max_iter"], max_time=600, ga=tuple(run["ga"]))
+    assert got["iterations"] == run["iterations"] and got["expansions"] == run["expansions"]
+    rows = [[int(np.array([r[1]]).view(np.uint64)[0]), r[2], r[3]] for r in got["rows"]]
+    assert rows == run["rows"]
+    assert int(np.array([got["final_cost"]]).view(np.uint64)[0]) == run["final_cost"]
+    assert [int(v) for v in got["path"]] == run["path"]
+
+
+@pytest.mark.parametrize("run", gl.runs_pseudo(), ids=lambda r: r["graph"])
+def test_facade_pseudo_mode_runs(run):
+    """pseudo_mode runs (tree merge, src/imomd_rrt_star.cpp:744-916 upstream) recorded from the
+    unmodified reference by tests/golden/make_golden_pseudo.py: every logged row (cost bits, tree
+    size, iteration), the final cost and the printed path."""
+    if run["kind"] == "bugtrap":
+        g = graphs.bugtrap_grid(80, seed=3)[0]
+    else:
+        g = gl.graph(run["graph"])
+    got = capi.facade_run(g, run["dest"], goal_bias=run["goal_bias"], max_iter=run["max_iter"],
+                          max_time=600, ga=tuple(run["ga"]), pseudo=True)
     assert got["iterations"] == run["iterations"] and got["expansions"] == run["expansions"]
     rows = [[int(np.array([r[1]]).view(np.uint64)[0]), r[2], r[3]] for r in got["rows"]]
     assert rows == run["rows"]
