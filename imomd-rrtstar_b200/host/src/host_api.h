@@ -48,6 +48,15 @@ int imomd_host_planner_step(void* h, int passes, int solve_rtsp, char* err, int 
 void* imomd_host_planner_native(void* h);
 double imomd_host_planner_cost(void* h);
 
+/* GraphCache (imomd_rrt_star/graph_cache.h) round trip: save + load + order check; CSR of the
+ * loaded containers out */
+int imomd_host_cache_roundtrip(const char* path, uint64_t n, const double* lat, const double* lon, uint64_t m,
+                               const uint64_t* eu, const uint64_t* ev, const double* ew, uint32_t* row_ptr,
+                               uint32_t* col, double* w, double* lat_out, double* lon_out, char* err,
+                               int errlen);
+
+int imomd_host_cache_load_check(const char* path, char* err, int errlen);
+
 /* EciGenSolver of the facade on a row-major K x K matrix (GA fitness on the GPU) */
 void* imomd_host_solver_create(int device, int swapping, int genetic, int ga_mutation_iter,
                                int ga_population, int ga_generation);

@@ -8,6 +8,7 @@
 #include <pthread.h>
 
 #include "host_api.h"
+#include "imomd_rrt_star/graph_cache.h"
 #include "imomd_rrt_star/imomd_rrt_star.h"
 
 namespace {
@@ -235,4 +236,72 @@ extern "C" void imomd_host_island_accept(void* s, double cost, const int32_t* se
 extern "C" uint64_t imomd_host_island_evaluated(void* s)
 {
     return static_cast<EciGenSolver*>(s)->lastEvaluatedTours();
+}
+
+// GraphCache round trip for the tests: containers built from the edge list (insertion order =
+// list order, as every other wrapper here), saved, loaded; the loaded containers' iteration
+// order is written out as CSR.  Returns 0, or -1 with a message.
+extern "C" int imomd_host_cache_roundtrip(const char* path, uint64_t n, const double* lat, const double* lon,
+                                          uint64_t m, const uint64_t* eu, const uint64_t* ev,
+                                          const double* ew, uint32_t* row_ptr, uint32_t* col, double* w,
+                                          double* lat_out, double* lon_out, char* err, int errlen)
+{
+    try
+    {
+        imomd_b200::GraphCache::Map map(n);
+        imomd_b200::GraphCache::Connection conn(n);
+        for (uint64_t i = 0; i < n; ++i) map[i] = location_t(i, lat[i], lon[i]);
+        for (uint64_t e = 0; e < m; ++e)
+        {
+            conn[eu[e]].insert({ev[e], ew[e]});
+            conn[ev[e]].insert({eu[e], ew[e]});
+        }
+        imomd_b200::GraphCache::save(path, map, conn);
+        std::shared_ptr<imomd_b200::GraphCache::Map> m2;
+        std::shared_ptr<imomd_b200::GraphCache::Connection> c2;
+        if (!imomd_b200::GraphCache::load(path, m2, c2)) throw std::runtime_error("cache file vanished");
+        if (m2->size() != n || c2->size() != n) throw std::runtime_error("size mismatch after load");
+        uint32_t at = 0;
+        for (uint64_t v = 0; v < n; ++v)
+        {
+            lat_out[v] = (*m2)[v].latitude;
+            lon_out[v] = (*m2)[v].longitude;
+            row_ptr[v] = at;
+            // must equal the ORIGINAL containers' order, element by element
+            auto it = conn[v].begin();
+            for (const auto& kv : (*c2)[v])
+            {
+                if (it == conn[v].end() || it->first != kv.first || it->second != kv.second)
+                    throw std::runtime_error("iteration order differs after load");
+                ++it;
+                col[at] = static_cast<uint32_t>(kv.first);
+                w[at] = kv.second;
+                ++at;
+            }
+            if (it != conn[v].end()) throw std::runtime_error("row shorter after load");
+        }
+        row_ptr[n] = at;
+        return 0;
+    }
+    catch (const std::exception& ex)
+    {
+        put_err(err, errlen, ex.what());
+        return -1;
+    }
+}
+
+// 0 = loaded and verified, 1 = no such file, -1 = rejected (message in err)
+extern "C" int imomd_host_cache_load_check(const char* path, char* err, int errlen)
+{
+    try
+    {
+        std::shared_ptr<imomd_b200::GraphCache::Map> m;
+        std::shared_ptr<imomd_b200::GraphCache::Connection> c;
+        return imomd_b200::GraphCache::load(path, m, c) ? 0 : 1;
+    }
+    catch (const std::exception& ex)
+    {
+        put_err(err, errlen, ex.what());
+        return -1;
+    }
 }

@@ -125,6 +125,8 @@ def host_lib():
         L.imomd_host_planner_native.argtypes = [C.c_void_p]
         L.imomd_host_planner_cost.restype = C.c_double
         L.imomd_host_planner_cost.argtypes = [C.c_void_p]
+        L.imomd_host_cache_roundtrip.argtypes = [C.c_char_p, C.c_uint64, f64p, f64p, C.c_uint64, u64p, u64p,
+                                                 f64p, u32p, u32p, f64p, f64p, f64p, C.c_char_p, C.c_int]
         L.imomd_host_solver_create.restype = C.c_void_p
         L.imomd_host_solver_create.argtypes = [C.c_int] * 6
         L.imomd_host_solver_destroy.argtypes = [C.c_void_p]
@@ -364,6 +366,23 @@ def facade_run(g, dest, goal_bias=1.0, max_iter=1000000, max_time=60, ga=(10000,
     return dict(rows=[(r.time_s, r.path_cost, r.tree_size, r.iteration) for r in rows[:n_rows.value]],
                 path=path[:path_len.value].copy(), sequence=seq[:seq_len.value].copy(),
                 final_cost=cost.value, iterations=its.value, expansions=exps.value)
+
+
+def graph_cache_roundtrip(g, path):
+    """GraphCache::save + load of the containers built from g's edge list (C++ facade library); returns
+    (row_ptr, col, w, lat, lon) of the LOADED containers in their iteration order."""
+    L = host_lib()
+    eu, ev, ew = g.edge_list()
+    eu = np.ascontiguousarray(eu, np.uint64); ev = np.ascontiguousarray(ev, np.uint64)
+    ew = np.ascontiguousarray(ew, np.float64)
+    row_ptr = np.empty(g.n + 1, np.uint32); col = np.empty(2 * len(eu), np.uint32); w = np.empty(2 * len(eu))
+    lat = np.empty(g.n); lon = np.empty(g.n)
+    err = C.create_string_buffer(512)
+    rc = L.imomd_host_cache_roundtrip(path.encode(), g.n, g.lat, g.lon, len(eu), eu, ev, ew, row_ptr, col, w,
+                                      lat, lon, err, 512)
+    if rc != 0:
+        raise ImomdError(err.value.decode())
+    return row_ptr, col[:row_ptr[-1]], w[:row_ptr[-1]], lat, lon
 
 
 class FacadePlanner:
