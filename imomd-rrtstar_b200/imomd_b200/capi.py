@@ -81,6 +81,7 @@ def cuda_lib():
         L.imomd_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.imomd_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p]
         L.imomd_clear_dm_updated.argtypes = [vp, C.c_int]
+        L.imomd_get_visit_order.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.imomd_get_profile.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
                                         np.ctypeslib.ndpointer(np.uint64, flags="C")]
         L.imomd_get_flags.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -287,6 +288,12 @@ class DevicePlanner:
         out = np.empty(self.g.n, np.uint32); c = C.c_uint32()
         _check(cuda_lib().imomd_get_frontier(self.h, q, k, out, self.g.n, C.byref(c)))
         return np.sort(out[:c.value]).astype(np.uint64)
+
+    def visit_order(self, k, q=0):
+        """pseudo-mode planners: the tree's vertices in the order they were visited (root first)."""
+        out = np.empty(self.g.n, np.uint32); c = C.c_uint32()
+        _check(cuda_lib().imomd_get_visit_order(self.h, q, k, out, self.g.n, C.byref(c)))
+        return out[:c.value].copy()
 
     def walk_to_root(self, k, vertex, q=0, cap=1 << 20):
         out = np.empty(cap, np.uint32); ln = C.c_uint32()

@@ -1,7 +1,7 @@
 """Ad-hoc device timing of the expansion kernel (development aid, not the bench)."""
 import sys, os, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "imomd-rrtstar_b200"))
+sys.path.insert(0, os.path.join(ROOT, "imomd-rrtstar_b200")); sys.path.insert(0, ROOT)
 import numpy as np
 from imomd_b200 import capi, graphs
 
@@ -67,6 +67,11 @@ if __name__ == "__main__":
         Q = int(os.environ.get("QP_Q", "296"))
         dests = [graphs.pick_destinations(g, 12, seed=int(s)) for s in rng.integers(0, 1 << 30, Q)]
         run(f"grid700_K12_Q{Q}", g, dests, [3000])
+    if "sanpablo" in which:
+        import bench
+        class A: workload = "san_pablo"; queries = int(os.environ.get("QP_Q", "1024")); grid = 0
+        g, dests = bench.make_workload(A, 0)
+        run(f"san_pablo_Q{A.queries}_K2", g, dests, [100, 900, 2000])
     if "multi" in which:
         g = graphs.jittered_grid(1000, seed=123)
         rng = np.random.default_rng(2)
