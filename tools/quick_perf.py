@@ -28,6 +28,10 @@ def run(name, g, dests, iters_list, **kw):
             pr = dp.profile(q); pr.pop("bfs_vertices_levels")
             tot.append(sum(c for c, _ in pr.values()))
         tot = np.array(tot, float)
+        qs = int(np.argmax(tot))
+        prs = dp.profile(qs); bvs = prs.pop("bfs_vertices_levels"); ts = sum(c for c, _ in prs.values()) or 1
+        print(f"  slowest query {qs}: expansions {reps[qs].expansions} tree_vertices {reps[qs].tree_vertices} bfs vertices/levels {bvs}",
+              {k: f"{100*c/ts:.1f}% n={n} {c/max(n,1):.0f}cyc" for k, (c, n) in prs.items()})
         print("  per-query busy cycles: min %.3g  p50 %.3g  p90 %.3g  max %.3g  mean %.3g  (max/mean %.2f)" % (
             tot.min(), np.median(tot), np.percentile(tot, 90), tot.max(), tot.mean(), tot.max() / tot.mean()))
     prof = dp.profile(0)
