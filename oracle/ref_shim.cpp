@@ -611,6 +611,31 @@ int ref_planner_run(void* pp, ref_log_row_t* rows, int cap, int64_t* iterations,
     return n_rows;
 }
 
+// The per-vertex work of mergeTwoTree_ (src/imomd_rrt_star.cpp:848-851 / :883-886) on tree k:
+// connectNewNode_, updateExpandables(.., true), rewireTree_, updateConnectionTree_.
+void ref_planner_attach(void* pp, int k, uint64_t x)
+{
+    RefPlanner* p = (RefPlanner*)pp;
+    tree_t& t = p->rrt->tree_layers_[k];
+    p->rrt->connectNewNode_(t, x);
+    p->rrt->updateExpandables(t, x, true);
+    p->rrt->rewireTree_(t, x);
+    p->rrt->updateConnectionTree_(t, x);
+}
+
+// keys of tree k's parent map in iteration order (what mergeTwoTree_ :860 walks)
+uint64_t ref_planner_parent_order(void* pp, int k, uint64_t* out, uint64_t cap)
+{
+    RefPlanner* p = (RefPlanner*)pp;
+    uint64_t c = 0;
+    for (const auto& kv : p->rrt->tree_layers_[k].parent)
+    {
+        if (c < cap) out[c] = kv.first;
+        ++c;
+    }
+    return c;
+}
+
 // One solveRTSP_ call (src/imomd_rrt_star.cpp:966-1003); returns 1 when the
 // path improved.
 int ref_planner_solve_rtsp(void* pp)

@@ -69,7 +69,7 @@ struct HsPlanner
     std::vector<uint32_t> cell_head, cell_cnt, chunk_next, free_stack, arena,
         clist, log, words;
     std::vector<double> lbd, ubd;
-    std::vector<uint32_t> occ, visit_log;
+    std::vector<uint32_t> occ, visit_log, attach_list;
     std::vector<VRec> rec;
     std::vector<ReportDev> reports;
     std::vector<double> lb;
@@ -158,6 +158,8 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     {
         p->visit_log.assign(qk * (size_t)n, IMOMD_NONE);
         d.visit_log = p->visit_log.data();
+        p->attach_list.assign(n, 0);
+        d.attach_list = p->attach_list.data();
     }
     d.arena = p->arena.data();
     d.clist = p->clist.data();
@@ -205,6 +207,32 @@ void hs_expand(void* hp, int iters, ReportDev* reports)
             run_query<16>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
     }
     if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
+}
+
+// imomd_attach_list on the host simulation (pseudo-mode planners): the merge's per-vertex work
+void hs_attach_list(void* hp, int q, int k, const uint32_t* vertices, uint32_t count, uint32_t* parents_out)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    if (!p->d.attach_list || count == 0) return;
+    std::memcpy(p->d.attach_list, vertices, (size_t)count * 4);
+    CtaHost cta;
+    unsigned char* hot = reinterpret_cast<unsigned char*>(((uintptr_t)p->hot.data() + 15) & ~(uintptr_t)15);
+    if (p->d.g.width == 4)
+        run_query<4>(cta, p->d, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
+    else if (p->d.g.width == 8)
+        run_query<8>(cta, p->d, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
+    else
+        run_query<16>(cta, p->d, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
+    if (parents_out) std::memcpy(parents_out, p->d.attach_list, (size_t)count * 4);
+}
+
+uint32_t hs_visit_order(void* hp, int q, int k, uint32_t* out)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    if (!p->d.visit_log) return 0;
+    uint32_t n = (uint32_t)p->query[q].tree_size[k];
+    std::memcpy(out, p->d.visit_log + ((size_t)q * p->d.K + k) * p->d.g.n, (size_t)n * 4);
+    return n;
 }
 
 void hs_get_tree(void* hp, int q, int k, uint32_t* parent, double* cost)

@@ -59,6 +59,9 @@ def lib():
         L.hs_check_hash.argtypes = [vp, C.c_int, C.c_int]
         L.hs_nearest.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                  C.POINTER(C.c_uint32), C.POINTER(C.c_double), i64p]
+        L.hs_attach_list.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, u32p]
+        L.hs_visit_order.restype = C.c_uint32
+        L.hs_visit_order.argtypes = [vp, C.c_int, C.c_int, u32p]
         L.hs_connection_log.restype = C.c_uint32
         L.hs_connection_log.argtypes = [vp, C.c_int, u32p, u32p, C.c_uint32]
         _lib = L
@@ -118,6 +121,17 @@ class HostSimPlanner:
         idx = C.c_uint32(); d = C.c_double(); st = np.zeros(3, np.int64)
         self.L.hs_nearest(self.h, q, k, lat, lon, C.byref(idx), C.byref(d), st)
         return idx.value, d.value, st
+
+    def attach_list(self, k, vertices, q=0):
+        v = np.ascontiguousarray(vertices, np.uint32)
+        out = np.empty(v.size, np.uint32)
+        self.L.hs_attach_list(self.h, q, k, v, v.size, out)
+        return out
+
+    def visit_order(self, k, q=0):
+        out = np.empty(self.g.n, np.uint32)
+        c = self.L.hs_visit_order(self.h, q, k, out)
+        return out[:c].copy()
 
     def connection_log(self, q=0):
         cap = 1 << 20

@@ -132,6 +132,8 @@ def ref():
         _sig(L.ref_planner_nearest, C.c_int,
              [vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_double),
               C.POINTER(C.c_int32), C.POINTER(C.c_double)])
+        _sig(L.ref_planner_attach, None, [vp, C.c_int, C.c_uint64])
+        _sig(L.ref_planner_parent_order, C.c_uint64, [vp, C.c_int, u64p, C.c_uint64])
         _sig(L.ref_planner_solve_rtsp, C.c_int, [vp])
         _sig(L.ref_planner_path_cost, C.c_double, [vp])
         _sig(L.ref_planner_path, C.c_uint64, [vp, u64p, C.c_uint64])
@@ -302,6 +304,14 @@ class RefPlanner:
         out = np.empty(self.n, np.uint64)
         c = self.R.ref_planner_connection_set(self.ph, idx, out, self.n)
         return [int(x) for x in out[:c]]
+
+    def attach(self, k, x):
+        self.R.ref_planner_attach(self.ph, k, int(x))
+
+    def parent_order(self, k):
+        out = np.empty(self.n, np.uint64)
+        c = self.R.ref_planner_parent_order(self.ph, k, out, self.n)
+        return out[:c].copy()
 
     def solve_rtsp(self):
         return self.R.ref_planner_solve_rtsp(self.ph)

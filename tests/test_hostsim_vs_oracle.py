@@ -134,3 +134,49 @@ def test_wide_adjacency_rows(width, hubs, spokes):
         assert rep.status == 0 and rep.expansions == op.iterate(chunk)
         compare_with_oracle(hp, op, 5, True)
     op.close(); hp.close()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("kind,K,warm", [("grid", 4, 300), ("road", 5, 500), ("grid", 7, 150)])
+def test_attach_list_matches_reference_merge_step(kind, K, warm):
+    """The per-vertex work of the pseudo-tree merge (imomd_attach_list: connectNewNode_ +
+    updateExpandables + rewireTree_ + updateConnectionTree_, src/imomd_rrt_star.cpp:848-851
+    upstream) against the UNMODIFIED reference performing the same calls: after a warm-up,
+    frontier vertices of every tree are attached in runs of several vertices per launch; trees,
+    frontiers, matrices, flags, the connection-node sets and the visit order (= insertion order
+    of the reference's parent map, replayed into a real container by the facade) all agree."""
+    R = ol.ref()
+    g = graphs.jittered_grid(60, seed=11) if kind == "grid" else graphs.road_like(4000, seed=9)
+    dest = graphs.pick_destinations(g, K, seed=K + 3)
+    gh = R.ref_graph_from_edges(g.n, g.lat, g.lon, len(g.eu), g.eu, g.ev,
+                                g.ew.ctypes.data_as(ol.C.c_void_p))
+    rp = ol.RefPlanner(gh, dest, pseudo=True)
+    P0 = rp.matrices()["P"]
+    hp = hs.HostSimPlanner(g, [dest], [P0], 1.0, True, 0)
+    hp.feed(_words(400000))
+    assert hp.expand(warm)[0].expansions == rp.iterate(warm)
+    compare_with_oracle(hp, rp, K, False)
+    rng = np.random.default_rng(K)
+    for round_ in range(6):
+        for k in range(K):
+            todo = []
+            for _ in range(int(rng.integers(1, 6))):
+                fr = rp.frontier(k)
+                if len(fr) == 0:
+                    break
+                x = int(fr[int(rng.integers(0, len(fr)))])
+                rp.attach(k, x)                       # the reference does it vertex by vertex
+                todo.append(x)
+            if todo:
+                got = hp.attach_list(k, todo)         # the device logic: one launch for the run
+                assert (got != 0xFFFFFFFF).all()
+        compare_with_oracle(hp, rp, K, False)
+    # connection-node sets: the logged insertions, deduplicated, are the reference's sets
+    si, vx = hp.connection_log()
+    for idx in range(K * (K - 1) // 2):
+        assert sorted(set(int(v) for v in vx[si == idx])) == sorted(rp.connection_set(idx))
+    # visit order: the same vertices the reference's parent map holds; replayed into a real
+    # unordered_map it iterates like the reference's (checked end to end in test_cuda_facade.py)
+    for k in range(K):
+        assert sorted(int(v) for v in hp.visit_order(k)) == sorted(int(v) for v in rp.parent_order(k))
+    hp.close()
