@@ -58,3 +58,12 @@ def test_argument_validation_needs_no_gpu():
     out = ctypes.c_void_p()
     rc = L.imomd_graph_create(0, g.n, g.row_ptr, col, g.w, g.lat, g.lon, ctypes.byref(out))
     assert rc == 3 and b"arc" in L.imomd_last_error() or b"self loop" in L.imomd_last_error()
+
+
+def test_facade_constructor_rejects_bad_input_before_touching_the_device():
+    """ImomdRRT's constructor (the reference reports nothing here: out-of-range ids are UB upstream)"""
+    g = graphs.jittered_grid(12)
+    with pytest.raises(capi.ImomdError, match="more than 30 objectives"):
+        capi.FacadePlanner(g, list(range(33)))
+    with pytest.raises(capi.ImomdError, match="destination id out of range"):
+        capi.FacadePlanner(g, [0, g.n + 5, 7])
