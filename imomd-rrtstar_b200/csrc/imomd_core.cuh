@@ -311,6 +311,8 @@ struct Shared
     int32_t k;             // tree being expanded
     // sample (selectRandomVertex_)
     uint64_t rand_id;
+    int32_t sample_is_vertex;   // the sample's coordinates are exactly those of vertex rand_id
+    int32_t pad_sample;
     double qlat, qlon;
     // search results
     Best result;
@@ -689,8 +691,10 @@ struct Seq
             uint32_t random_dest = Q->view_root[i - 1];
             double rlat = g.lat[random_dest];
             double rlon = g.lon[random_dest];
+            S.sample_is_vertex = 1;
             if (T.parent(random_dest) != IMOMD_NONE)
             {
+                S.sample_is_vertex = 0;   // the sample is moved towards the root (:383-390)
                 double ratio = ws_uniform_real(ws, 0.0, 0.5);
                 uint32_t root = Q->view_root[k];
                 rlat *= ratio;
@@ -705,6 +709,7 @@ struct Seq
         else
         {
             uint32_t v = ws_uniform_u32(ws, g.n - 1);
+            S.sample_is_vertex = 1;
             S.rand_id = v;
             S.qlat = g.lat[v];
             S.qlon = g.lon[v];
@@ -1470,9 +1475,26 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     const GraphDev& g = P.g;
     TreeRef T = tree_ref(P, q, k);
     double qlat = S.qlat, qlon = S.qlon;
-    double cl = cos(qlat * kDeg2Rad), sl = sin(qlat * kDeg2Rad);
-    double co = cos(qlon * kDeg2Rad), so = sin(qlon * kDeg2Rad);
-    double qx = cl * co, qy = cl * so, qz = sl;
+    double cl = cos(qlat * kDeg2Rad);
+    double qx, qy, qz;
+    if (warm && S.sample_is_vertex && S.rand_id < (uint64_t)g.n)
+    {
+        // the planner's samples are graph vertices (selectRandomVertex_): their unit vector was
+        // computed at upload with the very expressions below (make_vrec), so one 32-byte load
+        // replaces three double-precision sin / cos evaluations in every thread
+        const VRec me = g.vrec[(uint32_t)S.rand_id];
+        qx = me.x;
+        qy = me.y;
+        qz = me.z;
+    }
+    else
+    {
+        double sl = sin(qlat * kDeg2Rad);
+        double co = cos(qlon * kDeg2Rad), so = sin(qlon * kDeg2Rad);
+        qx = cl * co;
+        qy = cl * so;
+        qz = sl;
+    }
     auto lower = [&](uint32_t c) { return 4.0 * cell_lower_a(g, c, qlat, qlon, cl); };
     auto upper = [&](uint32_t c) { return 4.0 * cell_upper_a(g, c, qlat, qlon, cl); };
     auto eval = [&](const VRec& r) {
