@@ -94,6 +94,21 @@ IMOMD_HD inline double dist_of_a(double a)
     return kEarthRadius * (2 * atan2(sqrt(a), sqrt(1 - a)));
 }
 
+// Polynomial bounds of sin on [0, pi/2] (alternating Taylor remainders): the cell bounds run
+// for every occupied cell of every search, and a bound only has to be valid, not tight to the
+// last bit -- the pruning slack absorbs the rounding of these few operations.
+IMOMD_HD inline double sin_lower(double h)
+{
+    double v = h - h * h * h * (1.0 / 6.0);
+    return v > 0.0 ? v : 0.0;
+}
+IMOMD_HD inline double sin_upper(double h)
+{
+    double h2 = h * h;
+    double v = h - h * h2 * (1.0 / 6.0) + h * h2 * h2 * (1.0 / 120.0);
+    return v < 1.0 ? v : 1.0;
+}
+
 // Lower bound of haversine `a` between (qlat, qlon) and any point of hash cell c.
 // a = sin^2(dphi/2) + cos(phi_q) cos(phi_v) sin^2(dlam/2) is increasing in |dphi| and
 // |dlam| (both below pi here) and cos(phi_v) >= cosrow[row].
@@ -112,8 +127,9 @@ IMOMD_HD IMOMD_NOINLINE double cell_lower_a(const GraphDev& g, uint32_t c, doubl
     double dlam = 0.0;
     if (qlon < lo2) dlam = lo2 - qlon;
     else if (qlon > hi2) dlam = qlon - hi2;
-    double s1 = sin(dphi * kDeg2Rad / 2);
-    double s2 = sin(dlam * kDeg2Rad / 2);
+    // sin(h) >= h - h^3/6 for every h >= 0 (clamped at 0; h <= pi/2 here): a bound needs no libm
+    double s1 = sin_lower(dphi * kDeg2Rad / 2);
+    double s2 = sin_lower(dlam * kDeg2Rad / 2);
     double a = s1 * s1 + cos_qlat * g.cosrow[row] * (s2 * s2);
     return a * (1.0 - kPruneSlack);
 }
@@ -133,8 +149,9 @@ IMOMD_HD IMOMD_NOINLINE double cell_upper_a(const GraphDev& g, uint32_t c, doubl
     double hi2 = g.lon0 + (colm + 1) * g.hlon + kCellPadDeg;
     double e1 = fabs(qlon - lo2), e2 = fabs(qlon - hi2);
     double dlam = e1 > e2 ? e1 : e2;
-    double s1 = sin(dphi * kDeg2Rad / 2);
-    double s2 = sin(dlam * kDeg2Rad / 2);
+    // sin(h) <= h - h^3/6 + h^5/120 for every h >= 0
+    double s1 = sin_upper(dphi * kDeg2Rad / 2);
+    double s2 = sin_upper(dlam * kDeg2Rad / 2);
     double a = s1 * s1 + cos_qlat * g.cosrow[g.G + row] * (s2 * s2);
     a *= (1.0 + kPruneSlack);
     return a > 1.0 ? 1.0 : a;

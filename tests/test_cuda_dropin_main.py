@@ -62,15 +62,15 @@ def test_reference_main_runs_on_the_b200_planner():
     a, rows_a = _run(ref_bin)
     b, rows_b = _run(new_bin)
     assert a.returncode == 0 and b.returncode == 0, (a.stderr[-400:], b.stderr[-400:])
-    paths_a = [l for l in a.stdout.splitlines() if l.strip().endswith("#")]
-    paths_b = [l for l in b.stdout.splitlines() if l.strip().endswith("#")]
-    # e.g. 0 -> 2 -> 4 -> 5 -> 3 -> 5 -> 6 -> #.  The print thread is woken per improvement and may
-    # miss one when the planner finishes first (same race upstream), so: the last path either binary
-    # printed is one the other printed too; the improvements themselves are compared exactly below.
+    # Both binaries print from two threads at once (progress rows from the planner thread, paths from
+    # the print thread -- as upstream), so stdout lines can interleave: only well-formed path lines
+    # are used, and the print thread may miss the last improvement when the planner finishes first.
+    # The improvements themselves are compared exactly through the CSV below.
+    well_formed = re.compile(r"^(\d+ -> )+#$")
+    paths_a = [l.strip() for l in a.stdout.splitlines() if well_formed.match(l.strip())]
+    paths_b = [l.strip() for l in b.stdout.splitlines() if well_formed.match(l.strip())]
     assert paths_a and paths_b and (paths_b[-1] in paths_a or paths_a[-1] in paths_b)
-    cost = lambda out: [re.search(r"Path Cost\[m\]:\s*([0-9.e+]+)", l).group(1)
-                        for l in out.splitlines() if "Path Cost[m]" in l]
-    assert cost(a.stdout) == cost(b.stdout)
+    assert "Path Cost[m]" in b.stdout and "Tree Size" in b.stdout and "[main] print path" in b.stdout
     # CSV: same header, same cost / tree-size columns (the time column differs)
     assert rows_a[0] == rows_b[0] == '"CPU_time";"path_cost";"tree_size";'
     assert [r.split(";")[1:] for r in rows_a[1:]] == [r.split(";")[1:] for r in rows_b[1:]]
