@@ -1764,86 +1764,58 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
                 {
                     uint32_t* cl = lvl + cur * kLevelCap;
                     uint32_t* nl = lvl + (cur ^ 1u) * kLevelCap;
-                    if (n == 1)
+                    const bool active = (uint32_t)cta.lane() < n;
+                    uint32_t node = active ? cl[cta.lane()] : 0u;
+                    // Lockstep run: a rewired subtree is mostly a handful of parallel chains
+                    // (1.4 vertices per level on a grid).  While every vertex of the level has
+                    // exactly one child the next level has the same shape -- lane i's vertex is
+                    // replaced by its child -- so the walk stays in registers: one record load,
+                    // one vote, one store per level, no scan and no shared-memory round trip.
+                    for (;;)
                     {
-                        // chain walk: most levels of a rewired subtree hold a single vertex
-                        // (1.4 on average on a grid), so lane 0 follows child pointers with
-                        // nothing but the child-row load on the critical path
-                        if (cta.lane() == 0)
+                        ChlRow<W> row;
+                        int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row, rewired);
+                        if (cta.warp_all(!active || cnt == 1))
                         {
-                            uint32_t node = cl[0];
-                            for (;;)
+                            if (tail + n > cap)
                             {
-                                ChlRow<W> row;
-                                int cnt = bfs_expand<W>(T, node, true, pd, new_cost, old, row, rewired);
-                                if (tail + (uint32_t)cnt > cap)
-                                {
-                                    ovf = 1;
-                                    break;
-                                }
+                                ovf = 1;
+                                break;
+                            }
+                            if (active) arena[tail + (uint32_t)cta.lane()] = row.v[0];
+                            start = tail;
+                            tail += n;
+                            ++levels;
+                            node = row.v[0];
+                            continue;
+                        }
+                        // mixed level: place the children behind everything queued before
+                        uint32_t total = 0;
+                        uint32_t off = cta.warp_scan_small((uint32_t)cnt, W, &total);
+                        if (tail + total > cap)
+                        {
+                            ovf = 1;
+                            break;
+                        }
 #pragma unroll
-                                for (int i = 0; i < W; ++i)
-                                {
-                                    if (i < cnt)
-                                    {
-                                        arena[tail + i] = row.v[i];
-                                    }
-                                }
-                                pd.n = cnt;
-                                start = tail;
-                                tail += (uint32_t)cnt;
-                                ++levels;
-                                if (cnt != 1)
-                                {
-#pragma unroll
-                                    for (int i = 0; i < W; ++i)
-                                    {
-                                        if (i < cnt) nl[i] = row.v[i];
-                                    }
-                                    n = (uint32_t)cnt;
-                                    cur ^= 1u;
-                                    break;
-                                }
-                                node = row.v[0];
+                        for (int i = 0; i < W; ++i)
+                        {
+                            if (i < cnt)
+                            {
+                                uint32_t child = row.v[i];
+                                arena[tail + off + i] = child;
+                                if (off + i < kLevelCap) nl[off + i] = child;
                             }
                         }
-                        n = cta.warp_bcast(n);
-                        cur = cta.warp_bcast(cur);
-                        start = cta.warp_bcast(start);
-                        tail = cta.warp_bcast(tail);
-                        ovf = cta.warp_bcast(ovf);
-                        levels = cta.warp_bcast(levels);
+                        pd.n = cnt;
+                        start = tail;
+                        tail += total;
+                        n = total;
+                        cur ^= 1u;
+                        ++levels;
                         cta.warp_sync();
-                        continue;
-                    }
-                    bool active = (uint32_t)cta.lane() < n;
-                    uint32_t node = active ? cl[cta.lane()] : 0u;
-                    ChlRow<W> row;
-                    int cnt = bfs_expand<W>(T, node, active, pd, new_cost, old, row, rewired);
-                    uint32_t total = 0;
-                    uint32_t off = cta.warp_scan_small((uint32_t)cnt, W, &total);
-                    if (tail + total > cap)
-                    {
-                        ovf = 1;
                         break;
                     }
-#pragma unroll
-                    for (int i = 0; i < W; ++i)
-                    {
-                        if (i < cnt)
-                        {
-                            uint32_t child = row.v[i];
-                            arena[tail + off + i] = child;
-                            if (off + i < kLevelCap) nl[off + i] = child;
-                        }
-                    }
-                    pd.n = cnt;
-                    start = tail;
-                    tail += total;
-                    n = total;
-                    cur ^= 1u;
-                    ++levels;
-                    cta.warp_sync();
                 }
                 if (cta.lane() == 0)
                 {

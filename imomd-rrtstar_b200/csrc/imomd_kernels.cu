@@ -69,6 +69,7 @@ struct CtaDev
     __device__ __forceinline__ int warp_width() const { return 32; }
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ uint32_t warp_bcast(uint32_t v) const { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+    __device__ __forceinline__ bool warp_all(bool p) const { return __all_sync(0xFFFFFFFFu, p) != 0; }
     // exclusive scan of per-lane counts in [0, maxv]: one ballot per possible count
     __device__ __forceinline__ uint32_t warp_scan_small(uint32_t v, int maxv, uint32_t* total) const
     {

@@ -32,6 +32,7 @@ struct CtaHost
     int warp_width() const { return 1; }
     void warp_sync() const {}
     uint32_t warp_bcast(uint32_t v) const { return v; }
+    bool warp_all(bool p) const { return p; }
     uint32_t warp_scan_small(uint32_t v, int, uint32_t* total) const
     {
         *total = v;
