@@ -1658,22 +1658,23 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
     }
 }
 
+IMOMD_HD inline void conn_gather_one(const PlannerDev& P, int q, uint32_t x, int o, Shared& S)
+{
+    const size_t qt = (size_t)q * P.K + o;
+    const U4 t = *reinterpret_cast<const U4*>(P.trec + (qt * (size_t)P.g.n + x) * (size_t)P.trec_stride);
+    unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
+    double c;
+    memcpy(&c, &bits, 8);
+    S.conn_par[o] = t.x;
+    S.conn_cost[o] = c;
+}
+
 // the other trees' parent / cost at vertex x, one tree per thread
 template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_conn_gather(Cta& cta, const PlannerDev& P, int q, uint32_t x, Shared& S)
 {
     int K = P.K;
-    const size_t n = P.g.n;
-    for (int o = cta.tid(); o < K; o += cta.nt())
-    {
-        size_t qt = (size_t)q * K + o;
-        const U4 t = *reinterpret_cast<const U4*>(P.trec + (qt * n + x) * (size_t)P.trec_stride);
-        unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
-        double c;
-        memcpy(&c, &bits, 8);
-        S.conn_par[o] = t.x;
-        S.conn_cost[o] = c;
-    }
+    for (int o = cta.tid(); o < K; o += cta.nt()) conn_gather_one(P, q, x, o, S);
 }
 
 // tree_t::updateCost (include/imomd_rrt_star/imomd_rrt_star.h:102-123) as a level-wise
@@ -1734,6 +1735,20 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     const double old = T.cost(rewired);
     BfsPending<W> pd;
     pd.n = 0;
+    // The connection check that follows the propagation needs the OTHER trees' records of
+    // `rewired` (untouched by this walk): the second warp fetches them while the first one walks.
+    const bool early_gather = cta.nt() >= 64;
+    if (early_gather)
+    {
+        const int o = cta.tid() - 32;
+        if (o >= 0)
+        {
+            for (int oo = o; oo < P.K; oo += cta.nt() - 32)
+            {
+                if (oo != k) conn_gather_one(P, q, rewired, oo, S);
+            }
+        }
+    }
     if (cta.tid() == 0)
     {
         S.lv_overflow = lo >= cap ? 1 : 0;
@@ -1880,7 +1895,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
         }
     }
     bfs_flush<W>(T, pd, new_cost, old);
-    svc_conn_gather(cta, P, q, rewired, S);
+    if (!early_gather) svc_conn_gather(cta, P, q, rewired, S);
     if (cta.tid() == 0)
     {
         // statistics: [0] = subtree vertices (cycles slot) and levels... see imomd_get_profile
