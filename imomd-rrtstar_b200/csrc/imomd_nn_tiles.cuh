@@ -82,7 +82,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // flat (chunk id, valid records) list of every tree: one warp per tree walks the occupied
 // cells and their chunk chains
-__global__ void k_tree_chunk_lists(PlannerDev P, uint32_t* lists, uint32_t* counts)
+__global__ void k_tree_chunk_lists(const __grid_constant__ PlannerDev P, uint32_t* lists, uint32_t* counts)
 {
     int qt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -136,7 +136,7 @@ struct __align__(16) NnShared
 };
 
 __global__ void __launch_bounds__(kTileThreads, 4)
-k_nearest_tiles(PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
+k_nearest_tiles(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
                 const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
                 const uint32_t* __restrict__ counts, uint32_t* __restrict__ idx,
                 double* __restrict__ dist, uint32_t* __restrict__ ambiguous, int* __restrict__ error)
