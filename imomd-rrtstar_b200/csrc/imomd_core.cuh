@@ -43,6 +43,18 @@
 #define IMOMD_NOINLINE
 #endif
 
+// Address-space facts the compiler cannot see through structs and references: with them the
+// generic LD / ST of the device logic become LDG / LDS (no address-window resolution on the
+// serial thread's critical path).  No-ops in the host simulation.
+#ifdef __CUDA_ARCH__
+#define IMOMD_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#define IMOMD_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define IMOMD_ASSUME_GLOBAL(p) ((void)0)
+#define IMOMD_ASSUME_SHARED(p) ((void)0)
+#endif
+
+
 namespace imomd {
 
 constexpr double kDeg2Rad = 3.14159265358979323846 / 180;
@@ -267,7 +279,36 @@ IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
     t.rec = P.rec + qt * (size_t)P.chunks * IMOMD_CHUNK;
     t.chunk_next = P.chunk_next + qt * P.chunks;
     t.free_stack = P.free_stack + qt * P.chunks;
+    IMOMD_ASSUME_GLOBAL(t.base);
+    IMOMD_ASSUME_GLOBAL(t.cell_head);
+    IMOMD_ASSUME_GLOBAL(t.cell_cnt);
+    IMOMD_ASSUME_GLOBAL(t.occ);
+    IMOMD_ASSUME_GLOBAL(t.rec);
+    IMOMD_ASSUME_GLOBAL(t.chunk_next);
+    IMOMD_ASSUME_GLOBAL(t.free_stack);
     return t;
+}
+
+// every pointer of the planner descriptor is device-global memory
+IMOMD_HD inline void assume_planner(const PlannerDev& P)
+{
+    IMOMD_ASSUME_GLOBAL(P.g.row_ptr);
+    IMOMD_ASSUME_GLOBAL(P.g.col);
+    IMOMD_ASSUME_GLOBAL(P.g.w);
+    IMOMD_ASSUME_GLOBAL(P.g.lat);
+    IMOMD_ASSUME_GLOBAL(P.g.lon);
+    IMOMD_ASSUME_GLOBAL(P.g.vrec);
+    IMOMD_ASSUME_GLOBAL(P.g.cosrow);
+    IMOMD_ASSUME_GLOBAL(P.query);
+    IMOMD_ASSUME_GLOBAL(P.trec);
+    IMOMD_ASSUME_GLOBAL(P.lbd);
+    IMOMD_ASSUME_GLOBAL(P.ubd);
+    IMOMD_ASSUME_GLOBAL(P.arena);
+    IMOMD_ASSUME_GLOBAL(P.clist);
+    IMOMD_ASSUME_GLOBAL(P.log);
+    IMOMD_ASSUME_GLOBAL(P.reports);
+    IMOMD_ASSUME_GLOBAL(P.words);
+    (void)P;
 }
 
 struct Best
@@ -680,6 +721,15 @@ struct Seq
     IMOMD_HD Seq(const PlannerDev& P_, int q_, Shared& S_)
         : P(P_), Q(S_.Q), q(q_), S(S_), arena(P_.arena + (size_t)q_ * P_.arena_entries)
     {
+        assume_planner(P);
+        IMOMD_ASSUME_SHARED(&S);
+        IMOMD_ASSUME_SHARED(Q);      // the launch-staged copy of the hot header
+        IMOMD_ASSUME_SHARED(S.mP);
+        IMOMD_ASSUME_SHARED(S.mD);
+        IMOMD_ASSUME_SHARED(S.mMHv);
+        IMOMD_ASSUME_SHARED(S.mMHi);
+        IMOMD_ASSUME_SHARED(S.mCN);
+        IMOMD_ASSUME_GLOBAL(arena);
     }
 
     IMOMD_HD uint32_t deg(uint32_t v) const { return P.g.row_ptr[v + 1] - P.g.row_ptr[v]; }
@@ -1190,7 +1240,7 @@ struct Seq
 
     // Runs the serial part of expandTree_ (:337-356) until it needs the CTA or the
     // launch is over; S.req tells the CTA what to do next.
-    IMOMD_HD IMOMD_NOINLINE void step(int iters)
+    IMOMD_HD void step(int iters)
     {
         int K = Q->K;
         for (;;)
@@ -1489,6 +1539,9 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
                                  double* lb, uint32_t* clist, int64_t* near_ties,
                                  int64_t* unresolved_ties, bool warm)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
+    IMOMD_ASSUME_SHARED(lb);
     const GraphDev& g = P.g;
     TreeRef T = tree_ref(P, q, k);
     double qlat = S.qlat, qlon = S.qlon;
@@ -1570,6 +1623,9 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
 template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, int k, Shared& S, double* lb)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
+    IMOMD_ASSUME_SHARED(lb);
     const GraphDev& g = P.g;
     QueryDev* Q = S.Q;
     TreeRef T = tree_ref(P, q, k);
@@ -1627,6 +1683,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
 template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
     const GraphDev& g = P.g;
     QueryDev* Q = S.Q;
     int K = Q->K;
@@ -1673,6 +1731,8 @@ IMOMD_HD inline void conn_gather_one(const PlannerDev& P, int q, uint32_t x, int
 template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_conn_gather(Cta& cta, const PlannerDev& P, int q, uint32_t x, Shared& S)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
     int K = P.K;
     for (int o = cta.tid(); o < K; o += cta.nt()) conn_gather_one(P, q, x, o, S);
 }
@@ -1726,6 +1786,9 @@ template <int W, class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
                                uint32_t* lvl)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
+    IMOMD_ASSUME_SHARED(lvl);
     TreeRef T = tree_ref(P, q, k);
     uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
     const uint32_t cap = P.arena_entries;
@@ -1916,6 +1979,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
 template <int KW, class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int k, Shared& S)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
     const GraphDev& g = P.g;
     TreeRef T = tree_ref(P, q, k);
     const uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
@@ -2023,6 +2088,12 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
                                double* lb, uint32_t* lvl, double* mat, unsigned char* hot,
                                int attach_tree = -1, uint32_t attach_count = 0)
 {
+    assume_planner(P);
+    IMOMD_ASSUME_SHARED(&S);
+    IMOMD_ASSUME_SHARED(lb);
+    IMOMD_ASSUME_SHARED(lvl);
+    IMOMD_ASSUME_SHARED(mat);
+    IMOMD_ASSUME_SHARED(hot);
     QueryDev* Qg = P.query + q;
     QueryDev* Q = reinterpret_cast<QueryDev*>(hot);
     const int KK = P.K * P.K;
