@@ -709,6 +709,14 @@ IMOMD_HD inline uint32_t ws_uniform_u32(WordStream& ws, uint32_t urange)
 
 // ===================================================== sequential stages =====
 
+// The staged K x K matrices live in shared memory; their pointers are re-read from `Shared`, so
+// the address space is asserted at every use (see IMOMD_ASSUME_SHARED).
+IMOMD_HD inline double* sm_P(const Shared& S) { double* p = S.mP; IMOMD_ASSUME_SHARED(p); return p; }
+IMOMD_HD inline double* sm_D(const Shared& S) { double* p = S.mD; IMOMD_ASSUME_SHARED(p); return p; }
+IMOMD_HD inline double* sm_MHv(const Shared& S) { double* p = S.mMHv; IMOMD_ASSUME_SHARED(p); return p; }
+IMOMD_HD inline uint32_t* sm_MHi(const Shared& S) { uint32_t* p = S.mMHi; IMOMD_ASSUME_SHARED(p); return p; }
+IMOMD_HD inline uint32_t* sm_CN(const Shared& S) { uint32_t* p = S.mCN; IMOMD_ASSUME_SHARED(p); return p; }
+
 template <int KW>
 struct Seq
 {
@@ -753,7 +761,7 @@ struct Seq
                     Q->status = 4;   // IMOMD_RUN_CDF_OVERRUN
                     break;
                 }
-                rnd -= S.mP[k * K + i++];
+                rnd -= sm_P(S)[k * K + i++];
             }
             uint32_t random_dest = Q->view_root[i - 1];
             double rlat = g.lat[random_dest];
@@ -792,7 +800,7 @@ struct Seq
         for (int o = 0; o < K; ++o)
         {
             if (o == k) continue;
-            if (S.mMHi[k * K + o] == x) S.rescan_o[S.n_rescan++] = o;
+            if (sm_MHi(S)[k * K + o] == x) S.rescan_o[S.n_rescan++] = o;
         }
     }
 
@@ -815,12 +823,12 @@ struct Seq
                 connect_two_trees(k, o);
             }
             double distance = cx + S.conn_cost[o];
-            if (distance < S.mD[k * K + o] - 0.1)
+            if (distance < sm_D(S)[k * K + o] - 0.1)
             {
-                S.mD[k * K + o] = distance;
-                S.mD[o * K + k] = distance;
-                S.mCN[k * K + o] = x;
-                S.mCN[o * K + k] = x;
+                sm_D(S)[k * K + o] = distance;
+                sm_D(S)[o * K + k] = distance;
+                sm_CN(S)[k * K + o] = x;
+                sm_CN(S)[o * K + k] = x;
                 Q->dm_updated = 1;
             }
             if (P.pseudo)
@@ -1211,9 +1219,9 @@ struct Seq
             }
         }
         if (other == K) return;
-        if (S.mMHv[k * K + other] > S.mD[k * K + other])
+        if (sm_MHv(S)[k * K + other] > sm_D(S)[k * K + other])
         {
-            double* Pm = S.mP;
+            double* Pm = sm_P(S);
             Pm[k * K + other] = 0.0;
             Pm[other * K + k] = 0.0;
             int dk = 1, dother = 1;
@@ -1664,8 +1672,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
         {
             Q->stat[0] += S.n_cells;
             Q->stat[7] += S.n_recs;
-            S.mMHi[k * K + o] = b.id1;
-            S.mMHv[k * K + o] = b.v1;
+            sm_MHi(S)[k * K + o] = b.id1;
+            sm_MHv(S)[k * K + o] = b.v1;
             if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1)
             {
                 Q->unresolved_ties += 1;
@@ -1700,8 +1708,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
     for (int o = cta.tid(); o < K; o += cta.nt())
     {
         if (o == k) continue;
-        double best = S.mMHv[k * K + o];
-        uint32_t arg = S.mMHi[k * K + o];
+        double best = sm_MHv(S)[k * K + o];
+        uint32_t arg = sm_MHi(S)[k * K + o];
         for (int yi = 0; yi < m; ++yi)
         {
             double h = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
@@ -1711,8 +1719,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
                 arg = S.ys[yi];
             }
         }
-        S.mMHv[k * K + o] = best;
-        S.mMHi[k * K + o] = arg;
+        sm_MHv(S)[k * K + o] = best;
+        sm_MHi(S)[k * K + o] = arg;
     }
 }
 
@@ -2114,11 +2122,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     cta.sync();
     for (int i = cta.tid(); i < KK; i += cta.nt())
     {
-        S.mP[i] = Qg->P[i];
-        S.mD[i] = Qg->D[i];
-        S.mMHv[i] = Qg->MHv[i];
-        S.mMHi[i] = Qg->MHi[i];
-        S.mCN[i] = Qg->CN[i];
+        sm_P(S)[i] = Qg->P[i];
+        sm_D(S)[i] = Qg->D[i];
+        sm_MHv(S)[i] = Qg->MHv[i];
+        sm_MHi(S)[i] = Qg->MHi[i];
+        sm_CN(S)[i] = Qg->CN[i];
     }
     if (cta.tid() == 0)
     {
@@ -2201,11 +2209,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     }
     for (int i = cta.tid(); i < KK; i += cta.nt())
     {
-        Qg->P[i] = S.mP[i];
-        Qg->D[i] = S.mD[i];
-        Qg->MHv[i] = S.mMHv[i];
-        Qg->MHi[i] = S.mMHi[i];
-        Qg->CN[i] = S.mCN[i];
+        Qg->P[i] = sm_P(S)[i];
+        Qg->D[i] = sm_D(S)[i];
+        Qg->MHv[i] = sm_MHv(S)[i];
+        Qg->MHi[i] = sm_MHi(S)[i];
+        Qg->CN[i] = sm_CN(S)[i];
     }
     if (cta.tid() == 0)
     {
