@@ -1976,6 +1976,9 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
         if (!overflow) T.set_cost(rewired, new_cost);
         S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;
         S.bfs_valid = 1;
+        S.chk_hi = S.lv_tail;     // the examination request that follows (run_query)
+        S.chk_lo = lo;
+        S.chk_skip = rewired;
     }
 }
 
@@ -2185,19 +2188,9 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         {
             svc_bfs_w<KW>(cta, P, q, k, S, lvl);
             cta.sync();
-            if (S.bfs_hi != IMOMD_NONE)
-            {
-                // the serial thread would ask for this next: examine the fresh list's calls
-                cta.sync();
-                if (cta.tid() == 0)
-                {
-                    S.chk_hi = S.bfs_hi;
-                    S.chk_lo = S.bfs_lo;
-                    S.chk_skip = S.bfs_node;
-                }
-                cta.sync();
-                svc_check<KW>(cta, P, q, k, S);
-            }
+            // the serial thread would ask for this next: examine the fresh list's calls (the
+            // request was filled in by svc_bfs_w's last step)
+            if (S.bfs_hi != IMOMD_NONE) svc_check<KW>(cta, P, q, k, S);
         }
         else if (req == REQ_CHECK) svc_check<KW>(cta, P, q, k, S);
         cta.sync();
