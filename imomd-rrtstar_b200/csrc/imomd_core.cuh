@@ -289,6 +289,11 @@ IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
     return t;
 }
 
+// The view of tree k inside run_query: read back from the per-launch table in shared memory
+// (64 bytes, four 128-bit loads) instead of eight 64-bit multiply-adds per call.
+struct Shared;
+IMOMD_HD inline TreeRef tree_ref_of(const PlannerDev& P, int q, int k, const Shared& S);
+
 // every pointer of the planner descriptor is device-global memory
 IMOMD_HD inline void assume_planner(const PlannerDev& P)
 {
@@ -411,6 +416,8 @@ struct Shared
     int32_t chk_valid;
     // hot header fields of the query (a shared-memory copy while a launch runs)
     QueryDev* Q;
+    // the K tree views of the query, computed once per launch (null outside run_query)
+    TreeRef* tref;
     // the query's K x K matrices, staged in shared memory for the duration of a launch
     double* mP;
     double* mD;
@@ -709,6 +716,22 @@ IMOMD_HD inline uint32_t ws_uniform_u32(WordStream& ws, uint32_t urange)
 
 // ===================================================== sequential stages =====
 
+IMOMD_HD inline TreeRef tree_ref_of(const PlannerDev& P, int q, int k, const Shared& S)
+{
+    const TreeRef* table = S.tref;
+    if (table == nullptr) return tree_ref(P, q, k);
+    IMOMD_ASSUME_SHARED(table);
+    TreeRef t = table[k];
+    IMOMD_ASSUME_GLOBAL(t.base);
+    IMOMD_ASSUME_GLOBAL(t.cell_head);
+    IMOMD_ASSUME_GLOBAL(t.cell_cnt);
+    IMOMD_ASSUME_GLOBAL(t.occ);
+    IMOMD_ASSUME_GLOBAL(t.rec);
+    IMOMD_ASSUME_GLOBAL(t.chunk_next);
+    IMOMD_ASSUME_GLOBAL(t.free_stack);
+    return t;
+}
+
 // The staged K x K matrices live in shared memory; their pointers are re-read from `Shared`, so
 // the address space is asserted at every use (see IMOMD_ASSUME_SHARED).
 IMOMD_HD inline double* sm_P(const Shared& S) { double* p = S.mP; IMOMD_ASSUME_SHARED(p); return p; }
@@ -833,7 +856,7 @@ struct Seq
             }
             if (P.pseudo)
             {
-                TreeRef O = tree_ref(P, q, o);
+                TreeRef O = tree_ref_of(P, q, o, S);
                 uint32_t x_parent = T.parent(x);
                 uint32_t opp = O.parent(x_parent);
                 if (opp == IMOMD_NONE || (opp != x && S.conn_par[o] != x_parent))
@@ -1259,7 +1282,7 @@ struct Seq
                 return;
             }
             int k = S.k;
-            TreeRef T = tree_ref(P, q, k < K ? k : 0);
+            TreeRef T = tree_ref_of(P, q, k < K ? k : 0, S);
             switch (S.phase)
             {
                 case PH_NEXT_TREE:
@@ -1551,7 +1574,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     IMOMD_ASSUME_SHARED(&S);
     IMOMD_ASSUME_SHARED(lb);
     const GraphDev& g = P.g;
-    TreeRef T = tree_ref(P, q, k);
+    TreeRef T = tree_ref_of(P, q, k, S);
     double qlat = S.qlat, qlon = S.qlon;
     double cl = cos(qlat * kDeg2Rad);
     double qx, qy, qz;
@@ -1636,7 +1659,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
     IMOMD_ASSUME_SHARED(lb);
     const GraphDev& g = P.g;
     QueryDev* Q = S.Q;
-    TreeRef T = tree_ref(P, q, k);
+    TreeRef T = tree_ref_of(P, q, k, S);
     int K = Q->K;
     uint32_t cells = (uint32_t)g.G * (uint32_t)g.G;
     uint32_t* clist = P.clist + (size_t)q * 2 * P.chunks;
@@ -1797,7 +1820,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     assume_planner(P);
     IMOMD_ASSUME_SHARED(&S);
     IMOMD_ASSUME_SHARED(lvl);
-    TreeRef T = tree_ref(P, q, k);
+    TreeRef T = tree_ref_of(P, q, k, S);
     uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
     const uint32_t cap = P.arena_entries;
     const uint32_t rewired = S.bfs_node;
@@ -1993,7 +2016,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
     assume_planner(P);
     IMOMD_ASSUME_SHARED(&S);
     const GraphDev& g = P.g;
-    TreeRef T = tree_ref(P, q, k);
+    TreeRef T = tree_ref_of(P, q, k, S);
     const uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
     const uint32_t W = (uint32_t)KW;
     uint32_t n = S.chk_hi - S.chk_lo;
@@ -2113,9 +2136,12 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         uint32_t* dst = reinterpret_cast<uint32_t*>(hot);
         for (uint32_t i = cta.tid(); i < IMOMD_QUERY_HOT_BYTES / 4; i += cta.nt()) dst[i] = src[i];
     }
+    TreeRef* tref = reinterpret_cast<TreeRef*>(hot + ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16);
+    for (int k = cta.tid(); k < P.K; k += cta.nt()) tref[k] = tree_ref(P, q, k);
     if (cta.tid() == 0)
     {
         S.Q = Q;
+        S.tref = tref;
         S.mP = mat;
         S.mD = mat + KK;
         S.mMHv = mat + 2 * KK;

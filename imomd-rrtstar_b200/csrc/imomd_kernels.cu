@@ -330,6 +330,7 @@ k_nearest(const __grid_constant__ PlannerDev P, int n, const imomd_nn_query* __r
     __shared__ int64_t near_ties, unresolved;
     if (threadIdx.x == 0)
     {
+        S.tref = nullptr;   // no per-launch table of tree views here
         near_ties = 0;
         unresolved = 0;
     }
@@ -659,7 +660,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     }
     p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
                     2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32 +
-                    ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16;
+                    ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)K * sizeof(TreeRef);
     {
         cudaError_t e = cudaSuccess;
         auto set = [&](const void* f) {

@@ -144,7 +144,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->lb.resize(cells);
     p->lvl.resize(2 * kLevelCap);
     p->mat.resize((size_t)K * K * 4);
-    p->hot.resize(IMOMD_QUERY_HOT_BYTES + 64);
+    p->hot.resize(IMOMD_QUERY_HOT_BYTES + 64 + (size_t)K * sizeof(TreeRef));
     d.query = p->query.data();
     d.trec = reinterpret_cast<unsigned char*>(((uintptr_t)p->trec.data() + 15) & ~(uintptr_t)15);
     d.cell_head = p->cell_head.data();
@@ -322,6 +322,7 @@ void hs_nearest(void* hp, int q, int k, double lat, double lon, uint32_t* idx, d
     HsPlanner* p = (HsPlanner*)hp;
     CtaHost cta;
     p->S.Q = &p->query[q];
+    p->S.tref = nullptr;
     p->S.qlat = lat;
     p->S.qlon = lon;
     svc_nearest(cta, p->d, q, k, p->S, p->lb.data(), p->clist.data() + (size_t)q * 2 * p->d.chunks,
