@@ -169,6 +169,43 @@ IMOMD_HD IMOMD_NOINLINE double cell_upper_a(const GraphDev& g, uint32_t c, doubl
     return a > 1.0 ? 1.0 : a;
 }
 
+// Both bounds of one cell at once (the per-search path: the row / column decoding and the cell
+// rectangle are shared).
+IMOMD_HD IMOMD_NOINLINE void cell_bounds_a(const GraphDev& g, uint32_t c, double qlat, double qlon,
+                                           double cos_qlat, double* lower, double* upper)
+{
+    if (!g.prune)
+    {
+        *lower = 0.0;
+        *upper = 1.0;
+        return;
+    }
+    int row = (int)(c / (uint32_t)g.G), colm = (int)(c % (uint32_t)g.G);
+    double lo = g.lat0 + row * g.hlat - kCellPadDeg;
+    double hi = g.lat0 + (row + 1) * g.hlat + kCellPadDeg;
+    double lo2 = g.lon0 + colm * g.hlon - kCellPadDeg;
+    double hi2 = g.lon0 + (colm + 1) * g.hlon + kCellPadDeg;
+    double dphi = 0.0;
+    if (qlat < lo) dphi = lo - qlat;
+    else if (qlat > hi) dphi = qlat - hi;
+    double dlam = 0.0;
+    if (qlon < lo2) dlam = lo2 - qlon;
+    else if (qlon > hi2) dlam = qlon - hi2;
+    double s1 = sin_lower(dphi * kDeg2Rad / 2);
+    double s2 = sin_lower(dlam * kDeg2Rad / 2);
+    double a = s1 * s1 + cos_qlat * g.cosrow[row] * (s2 * s2);
+    *lower = a * (1.0 - kPruneSlack);
+    double d1 = fabs(qlat - lo), d2 = fabs(qlat - hi);
+    double fphi = d1 > d2 ? d1 : d2;
+    double e1 = fabs(qlon - lo2), e2 = fabs(qlon - hi2);
+    double flam = e1 > e2 ? e1 : e2;
+    double t1 = sin_upper(fphi * kDeg2Rad / 2);
+    double t2 = sin_upper(flam * kDeg2Rad / 2);
+    double b = t1 * t1 + cos_qlat * g.cosrow[g.G + row] * (t2 * t2);
+    b *= (1.0 + kPruneSlack);
+    *upper = b > 1.0 ? 1.0 : b;
+}
+
 // unit vector + hash cell of one vertex (graph upload)
 IMOMD_HD inline VRec make_vrec(uint32_t v, double lat, double lon, int G, double lat0, double lon0,
                                double hlat, double hlon)
@@ -1482,25 +1519,26 @@ IMOMD_HD inline void list_cell(Cta& cta, const TreeRef& T, uint32_t* clist, uint
 }
 
 // Pruned arg-min over the frontier hash of one tree.
-//   lower(c) / upper(c)  conservative bounds of the objective over cell c
+//   bounds(c, lo, hi)    conservative bounds of the objective over cell c
 //   eval(r)              objective of a frontier record
 //   bound(m)             largest lower bound a cell may have and still matter when the
 //                        minimum is known to be at most m
 // The smallest upper bound over the occupied cells caps the minimum, every occupied cell
 // whose lower bound does not exceed that cap is listed, its 32-record chunks are ranked one
 // record per thread.  Returns the same Best on every thread.  `lb` holds G*G doubles.
-template <class Cta, class Lower, class Upper, class Eval, class Bound>
+template <class Cta, class Bounds, class Eval, class Bound>
 IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef& T, Shared& S,
-                                   uint32_t n_occ, double* lb, uint32_t* clist, Lower lower,
-                                   Upper upper, Eval eval, Bound bound)
+                                   uint32_t n_occ, double* lb, uint32_t* clist, Bounds bounds,
+                                   Eval eval, Bound bound)
 {
     if (n_occ == 0) return best_empty();
     double mub = INFINITY;
     for (uint32_t i = cta.tid(); i < n_occ; i += cta.nt())
     {
         uint32_t c = T.occ[i];
-        lb[i] = lower(c);
-        double u = upper(c);
+        double l, u;
+        bounds(c, l, u);
+        lb[i] = l;
         if (u < mub) mub = u;
     }
     if (cta.tid() == 0)
@@ -1576,7 +1614,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     const GraphDev& g = P.g;
     TreeRef T = tree_ref_of(P, q, k, S);
     double qlat = S.qlat, qlon = S.qlon;
-    double cl = cos(qlat * kDeg2Rad);
+    double cl;
     double qx, qy, qz;
     if (warm && S.sample_is_vertex && S.rand_id < (uint64_t)g.n)
     {
@@ -1587,17 +1625,23 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         qx = me.x;
         qy = me.y;
         qz = me.z;
+        // cos(lat) = |(x, y)| to a few ulps: it only scales the cell bounds, whose slack is 1e-9
+        cl = sqrt(qx * qx + qy * qy);
     }
     else
     {
+        cl = cos(qlat * kDeg2Rad);
         double sl = sin(qlat * kDeg2Rad);
         double co = cos(qlon * kDeg2Rad), so = sin(qlon * kDeg2Rad);
         qx = cl * co;
         qy = cl * so;
         qz = sl;
     }
-    auto lower = [&](uint32_t c) { return 4.0 * cell_lower_a(g, c, qlat, qlon, cl); };
-    auto upper = [&](uint32_t c) { return 4.0 * cell_upper_a(g, c, qlat, qlon, cl); };
+    auto bounds = [&](uint32_t c, double& lo, double& hi) {
+        cell_bounds_a(g, c, qlat, qlon, cl, &lo, &hi);
+        lo *= 4.0;
+        hi *= 4.0;
+    };
     auto eval = [&](const VRec& r) {
         double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
         return dx * dx + dy * dy + dz * dz;
@@ -1611,7 +1655,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         S.n_recs = 0;
     }
     cta.sync();
-    Best b = pruned_argmin(cta, P, T, S, S.Q->n_occ[k], lb, clist, lower, upper, eval, bound);
+    Best b = pruned_argmin(cta, P, T, S, S.Q->n_occ[k], lb, clist, bounds, eval, bound);
     int ambiguous = (b.id1 != IMOMD_NONE) && (b.v2 - b.v1 <= band(b.v1));
     if (ambiguous)
     {
@@ -1677,8 +1721,10 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
         const double* lo = lbd + (size_t)o * cells;
         const double* uk = ubd + (size_t)k * cells;
         const double* uo = ubd + (size_t)o * cells;
-        auto lower = [&](uint32_t c) { return lk[c] + lo[c]; };
-        auto upper = [&](uint32_t c) { return uk[c] + uo[c]; };
+        auto bounds = [&](uint32_t c, double& lower, double& upper) {
+            lower = lk[c] + lo[c];
+            upper = uk[c] + uo[c];
+        };
         auto eval = [&](const VRec& r) {
             double vlat = g.lat[r.id], vlon = g.lon[r.id];
             return haversine(vlat, vlon, klat, klon) + haversine(vlat, vlon, olat, olon);
@@ -1690,7 +1736,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
             S.n_recs = 0;
         }
         cta.sync();
-        Best b = pruned_argmin(cta, P, T, S, Q->n_occ[k], lb, clist, lower, upper, eval, bound);
+        Best b = pruned_argmin(cta, P, T, S, Q->n_occ[k], lb, clist, bounds, eval, bound);
         if (cta.tid() == 0)
         {
             Q->stat[0] += S.n_cells;
