@@ -266,6 +266,10 @@ struct THead
     double cost;
 };
 
+// padded adjacency rows (see GraphDev)
+IMOMD_HD inline uint32_t row_begin(const GraphDev& g, uint32_t v) { return v * (uint32_t)g.width; }
+IMOMD_HD inline uint32_t row_end(const GraphDev& g, uint32_t v) { return v * (uint32_t)g.width + g.deg[v]; }
+
 struct TreeRef
 {
     unsigned char* base;
@@ -334,7 +338,7 @@ IMOMD_HD inline TreeRef tree_ref_of(const PlannerDev& P, int q, int k, const Sha
 // every pointer of the planner descriptor is device-global memory
 IMOMD_HD inline void assume_planner(const PlannerDev& P)
 {
-    IMOMD_ASSUME_GLOBAL(P.g.row_ptr);
+    IMOMD_ASSUME_GLOBAL(P.g.deg);
     IMOMD_ASSUME_GLOBAL(P.g.col);
     IMOMD_ASSUME_GLOBAL(P.g.w);
     IMOMD_ASSUME_GLOBAL(P.g.lat);
@@ -695,7 +699,7 @@ IMOMD_HD inline void chl_assign_single_w(uint32_t* rowp, uint32_t x)
 // (*connection_ptr_)[a][b]; the graph was validated symmetric at upload
 IMOMD_HD inline double edge_weight(const GraphDev& g, uint32_t a, uint32_t b)
 {
-    uint32_t e0 = g.row_ptr[a], e1 = g.row_ptr[a + 1];
+    uint32_t e0 = row_begin(g, a), e1 = row_end(g, a);
     for (uint32_t e = e0; e < e1; ++e)
     {
         if (g.col[e] == b) return g.w[e];
@@ -800,7 +804,7 @@ struct Seq
         IMOMD_ASSUME_GLOBAL(arena);
     }
 
-    IMOMD_HD uint32_t deg(uint32_t v) const { return P.g.row_ptr[v + 1] - P.g.row_ptr[v]; }
+    IMOMD_HD uint32_t deg(uint32_t v) const { return P.g.deg[v]; }
 
     // selectRandomVertex_, src/imomd_rrt_star.cpp:358-400
     IMOMD_HD void sample(int k, const TreeRef& T)
@@ -958,7 +962,7 @@ struct Seq
         const GraphDev& g = P.g;
         uint32_t x_new = S.x_new;
         if (deg(x_new) != 2) return false;
-        uint32_t e = g.row_ptr[x_new];
+        uint32_t e = row_begin(g, x_new);
         uint32_t x_1 = g.col[e];
         uint32_t x_2 = g.col[e + 1];
         uint32_t via, next;
@@ -995,7 +999,7 @@ struct Seq
     IMOMD_HD void connect_new_node_w(int k, const TreeRef& T, uint32_t x_new)
     {
         const GraphDev& g = P.g;
-        uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
+        uint32_t e0 = row_begin(g, x_new), e1 = row_end(g, x_new);
         uint32_t ys[W];
         double ws[W];
         THead hs[W];
@@ -1053,7 +1057,7 @@ struct Seq
     {
         const GraphDev& g = P.g;
         S.n_ys = 0;
-        uint32_t e0 = g.row_ptr[x_new], e1 = g.row_ptr[x_new + 1];
+        uint32_t e0 = row_begin(g, x_new), e1 = row_end(g, x_new);
         uint32_t ys[W];
         uint32_t par[W];
 #pragma unroll
@@ -1091,7 +1095,7 @@ struct Seq
     // the list, almost all of which change nothing (REQ_CHECK).
     static constexpr uint32_t FR = 7;
 
-    IMOMD_HD bool push_frame(uint32_t x, uint32_t e) { return push_frame(x, e, P.g.row_ptr[x + 1]); }
+    IMOMD_HD bool push_frame(uint32_t x, uint32_t e) { return push_frame(x, e, row_end(P.g, x)); }
 
     IMOMD_HD bool push_frame(uint32_t x, uint32_t e, uint32_t e_end)
     {
@@ -1432,7 +1436,7 @@ struct Seq
                     S.rw_top = 0;
                     S.bfs_valid = 0;
                     S.chk_valid = 0;
-                    push_frame(S.x_new, P.g.row_ptr[S.x_new]);
+                    push_frame(S.x_new, row_begin(P.g, S.x_new));
                     S.phase = PH_REWIRE;
                     continue;
                 }
@@ -1573,7 +1577,7 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
 {
     const GraphDev& g = P.g;
     if (x == IMOMD_NONE || cta.nt() < 64) return;
-    const uint32_t e0 = g.row_ptr[x], e1 = g.row_ptr[x + 1];
+    const uint32_t e0 = row_begin(g, x), e1 = row_end(g, x);
     uint32_t acc = 0;
     const uint32_t t = (uint32_t)cta.tid();
     if (t < e1 - e0)
@@ -1584,7 +1588,7 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
         acc += T.chl(y)[0] + h.parent + (w > 0.0 ? 1u : 0u);
         VRec v = g.vrec[y];
         acc += T.cell_cnt[v.cell] + T.cell_head[v.cell];
-        acc += g.row_ptr[y] + g.row_ptr[y + 1];
+        acc += g.deg[y] + g.col[row_begin(g, y)];
     }
     else if (t == 32)
     {
@@ -2076,10 +2080,11 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
         uint32_t i = idx / W, j = idx % W;
         uint32_t u = arena[hi - 1 - i];
         if (u == skip) continue;
-        uint32_t e = g.row_ptr[u] + j;
-        if (e >= g.row_ptr[u + 1]) continue;
+        // padded rows: the slot's address follows from u alone, empty slots hold NONE
+        uint32_t e = row_begin(g, u) + j;
         uint32_t y = g.col[e];
         double w = g.w[e];
+        if (y == IMOMD_NONE) continue;
         THead hu = T.head(u);
         THead hy = T.head(y);
         if (hy.parent == IMOMD_NONE || y == hu.parent) continue;
@@ -2089,7 +2094,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
             key = idx;
             my_u = u;
             my_e = e;
-            my_e1 = g.row_ptr[u + 1];
+            my_e1 = row_end(g, u);
             my_y = y;
             my_py = hy.parent;
             my_nc = nc;
@@ -2139,7 +2144,7 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
         if (P.pseudo) P.visit_log[((size_t)q * K + i) * g.n] = root;
         Q->ds_parent[i] = i;
         // erase(root) is a no-op and no holder equals the root yet; neighbours:
-        uint32_t e0 = g.row_ptr[root], e1 = g.row_ptr[root + 1];
+        uint32_t e0 = row_begin(g, root), e1 = row_end(g, root);
         for (uint32_t e = e0; e < e1; ++e)
         {
             uint32_t y = g.col[e];

@@ -428,7 +428,7 @@ struct imomd_graph
 {
     int device;
     GraphDev d;
-    uint32_t* row_ptr;
+    uint8_t* deg;
     uint32_t* col;
     double* w;
     double* lat;
@@ -536,20 +536,30 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     std::vector<double> cosrow;
     setup_grid(d, n, lat, lon, grid_dim, max_deg, &cosrow);
     const int G = d.G;
-    CU(dmalloc(&g->row_ptr, (size_t)n + 1));
-    CU(dmalloc(&g->col, arcs));
-    CU(dmalloc(&g->w, arcs));
+    // adjacency as padded rows of d.width slots (GraphDev)
+    if ((uint64_t)n * (uint64_t)d.width > 0xFFFFFFF0ull)
+    {
+        delete g;
+        return fail(IMOMD_ERR_GRAPH, "graph too large for 32-bit adjacency slots (n * width)");
+    }
+    std::vector<uint32_t> pcol;
+    std::vector<double> pw;
+    std::vector<uint8_t> pdeg;
+    build_padded_rows(n, row_ptr, col, w, d.width, &pcol, &pw, &pdeg);
+    CU(dmalloc(&g->deg, (size_t)n));
+    CU(dmalloc(&g->col, pcol.size()));
+    CU(dmalloc(&g->w, pw.size()));
     CU(dmalloc(&g->lat, n));
     CU(dmalloc(&g->lon, n));
     CU(dmalloc(&g->vrec, n));
     CU(dmalloc(&g->cosrow, 2 * (size_t)G));
-    CU(cudaMemcpy(g->row_ptr, row_ptr, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->col, col, (size_t)arcs * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->w, w, (size_t)arcs * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->deg, pdeg.data(), (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->col, pcol.data(), pcol.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->w, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->lat, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->lon, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->cosrow, cosrow.data(), 2 * (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
-    d.row_ptr = g->row_ptr;
+    d.deg = g->deg;
     d.col = g->col;
     d.w = g->w;
     d.lat = g->lat;
@@ -568,7 +578,7 @@ int imomd_graph_destroy(imomd_graph* g)
 {
     if (!g) return IMOMD_OK;
     cudaSetDevice(g->device);
-    cudaFree(g->row_ptr);
+    cudaFree(g->deg);
     cudaFree(g->col);
     cudaFree(g->w);
     cudaFree(g->lat);

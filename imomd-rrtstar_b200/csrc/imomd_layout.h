@@ -47,7 +47,11 @@ struct GraphDev
 {
     uint32_t n;
     uint32_t arcs;
-    const uint32_t* row_ptr;
+    // Adjacency in PADDED rows of `width` slots (width = power of two >= the maximum degree):
+    // the neighbours of v are col[v*width .. v*width + deg[v]) in the reference containers'
+    // iteration order, the remaining slots hold IMOMD_NONE / 0.  A row's address follows from
+    // the vertex id alone -- no row_ptr load in front of every neighbourhood access.
+    const uint8_t* deg;
     const uint32_t* col;
     const double* w;
     const double* lat;

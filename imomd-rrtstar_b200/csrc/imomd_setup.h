@@ -119,6 +119,26 @@ inline void setup_grid(GraphDev& d, uint32_t n, const double* lat, const double*
     }
 }
 
+// CSR -> padded rows (GraphDev::col / w / deg)
+inline void build_padded_rows(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const double* w,
+                              int width, std::vector<uint32_t>* pcol, std::vector<double>* pw,
+                              std::vector<uint8_t>* deg)
+{
+    pcol->assign((size_t)n * width, IMOMD_NONE);
+    pw->assign((size_t)n * width, 0.0);
+    deg->assign(n, 0);
+    for (uint32_t v = 0; v < n; ++v)
+    {
+        const uint32_t d = row_ptr[v + 1] - row_ptr[v];
+        (*deg)[v] = (uint8_t)d;
+        for (uint32_t j = 0; j < d; ++j)
+        {
+            (*pcol)[(size_t)v * width + j] = col[row_ptr[v] + j];
+            (*pw)[(size_t)v * width + j] = w[row_ptr[v] + j];
+        }
+    }
+}
+
 inline void default_sizes(PlannerDev& d, uint32_t frontier_chunks, uint32_t arena_entries,
                           uint32_t log_entries)
 {

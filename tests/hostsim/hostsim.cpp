@@ -62,7 +62,9 @@ struct CtaHost
 struct HsPlanner
 {
     PlannerDev d;
-    std::vector<uint32_t> row_ptr, col;
+    std::vector<uint32_t> row_ptr, col, pcol;
+    std::vector<double> pw;
+    std::vector<uint8_t> pdeg;
     std::vector<double> w, lat, lon, cosrow;
     std::vector<VRec> vrec;
     std::vector<QueryDev> query;
@@ -111,9 +113,10 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->vrec.resize(n);
     for (uint32_t v = 0; v < n; ++v)
         p->vrec[v] = make_vrec(v, lat[v], lon[v], d.g.G, d.g.lat0, d.g.lon0, d.g.hlat, d.g.hlon);
-    d.g.row_ptr = p->row_ptr.data();
-    d.g.col = p->col.data();
-    d.g.w = p->w.data();
+    build_padded_rows(n, row_ptr, col, w, d.g.width, &p->pcol, &p->pw, &p->pdeg);
+    d.g.deg = p->pdeg.data();
+    d.g.col = p->pcol.data();
+    d.g.w = p->pw.data();
     d.g.lat = p->lat.data();
     d.g.lon = p->lon.data();
     d.g.vrec = p->vrec.data();
