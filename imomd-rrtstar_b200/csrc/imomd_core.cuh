@@ -99,6 +99,20 @@ IMOMD_HD IMOMD_NOINLINE double haversine(double lat1, double lon1, double lat2, 
     return kEarthRadius * c;
 }
 
+// The same value from the per-vertex cosines precomputed at upload (GraphDev::coslat holds
+// cos(lat * kDeg2Rad), the very operand of the two cos() calls above).
+IMOMD_HD IMOMD_NOINLINE double haversine_pc(double lat1, double lon1, double cos1, double lat2, double lon2,
+                                            double cos2)
+{
+    double diff_lat_rad = (lat2 - lat1) * kDeg2Rad;
+    double diff_long_rad = (lon2 - lon1) * kDeg2Rad;
+    double s1 = sin(diff_lat_rad / 2);
+    double s2 = sin(diff_long_rad / 2);
+    double a = s1 * s1 + cos1 * cos2 * (s2 * s2);
+    double c = 2 * atan2(sqrt(a), sqrt(1 - a));
+    return kEarthRadius * c;
+}
+
 // distance for a haversine `a` value (used for the cell lower bounds)
 IMOMD_HD inline double dist_of_a(double a)
 {
@@ -344,6 +358,7 @@ IMOMD_HD inline void assume_planner(const PlannerDev& P)
     IMOMD_ASSUME_GLOBAL(P.g.lat);
     IMOMD_ASSUME_GLOBAL(P.g.lon);
     IMOMD_ASSUME_GLOBAL(P.g.vrec);
+    IMOMD_ASSUME_GLOBAL(P.g.coslat);
     IMOMD_ASSUME_GLOBAL(P.g.cosrow);
     IMOMD_ASSUME_GLOBAL(P.query);
     IMOMD_ASSUME_GLOBAL(P.trec);
@@ -1729,9 +1744,10 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
             lower = lk[c] + lo[c];
             upper = uk[c] + uo[c];
         };
+        const double kcos = g.coslat[rk], ocos = g.coslat[ro];
         auto eval = [&](const VRec& r) {
-            double vlat = g.lat[r.id], vlon = g.lon[r.id];
-            return haversine(vlat, vlon, klat, klon) + haversine(vlat, vlon, olat, olon);
+            double vlat = g.lat[r.id], vlon = g.lon[r.id], vcos = g.coslat[r.id];
+            return haversine_pc(vlat, vlon, vcos, klat, klon, kcos) + haversine_pc(vlat, vlon, vcos, olat, olon, ocos);
         };
         auto bound = [&](double m) { return m * (1.0 + kPruneSlack); };
         if (cta.tid() == 0)
@@ -1775,7 +1791,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
         int yi = i / K, o = i % K;
         uint32_t y = S.ys[yi];
         uint32_t r = Q->view_root[o];
-        S.h[yi * IMOMD_KMAX + o] = haversine(g.lat[y], g.lon[y], g.lat[r], g.lon[r]);
+        S.h[yi * IMOMD_KMAX + o] = haversine_pc(g.lat[y], g.lon[y], g.coslat[y], g.lat[r], g.lon[r], g.coslat[r]);
     }
     cta.sync();
     for (int o = cta.tid(); o < K; o += cta.nt())

@@ -215,12 +215,14 @@ struct CtaDev
 // ---------------------------------------------------------------- kernels ---
 
 __global__ void k_build_vrec(uint32_t n, const double* __restrict__ lat,
-                             const double* __restrict__ lon, VRec* __restrict__ vrec, int G,
-                             double lat0, double lon0, double hlat, double hlon)
+                             const double* __restrict__ lon, VRec* __restrict__ vrec,
+                             double* __restrict__ coslat, int G, double lat0, double lon0, double hlat,
+                             double hlon)
 {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     vrec[v] = make_vrec(v, lat[v], lon[v], G, lat0, lon0, hlat, hlon);
+    coslat[v] = cos(lat[v] * kDeg2Rad);   // the operand of imomd::haversine's cos() calls
 }
 
 // lbd[q][t][c] = lower bound (metres) of haversine(root of tree t, any point of cell c)
@@ -434,6 +436,7 @@ struct imomd_graph
     double* lat;
     double* lon;
     VRec* vrec;
+    double* coslat;
     double* cosrow;
     uint32_t max_degree;
 };
@@ -552,6 +555,7 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     CU(dmalloc(&g->lat, n));
     CU(dmalloc(&g->lon, n));
     CU(dmalloc(&g->vrec, n));
+    CU(dmalloc(&g->coslat, n));
     CU(dmalloc(&g->cosrow, 2 * (size_t)G));
     CU(cudaMemcpy(g->deg, pdeg.data(), (size_t)n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->col, pcol.data(), pcol.size() * 4, cudaMemcpyHostToDevice));
@@ -565,9 +569,10 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     d.lat = g->lat;
     d.lon = g->lon;
     d.vrec = g->vrec;
+    d.coslat = g->coslat;
     d.cosrow = g->cosrow;
-    k_build_vrec<<<(n + 255) / 256, 256>>>(n, g->lat, g->lon, g->vrec, G, d.lat0, d.lon0, d.hlat,
-                                           d.hlon);
+    k_build_vrec<<<(n + 255) / 256, 256>>>(n, g->lat, g->lon, g->vrec, g->coslat, G, d.lat0, d.lon0,
+                                           d.hlat, d.hlon);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     *out = g;
@@ -584,6 +589,7 @@ int imomd_graph_destroy(imomd_graph* g)
     cudaFree(g->lat);
     cudaFree(g->lon);
     cudaFree(g->vrec);
+    cudaFree(g->coslat);
     cudaFree(g->cosrow);
     delete g;
     return IMOMD_OK;

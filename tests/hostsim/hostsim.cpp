@@ -63,7 +63,7 @@ struct HsPlanner
 {
     PlannerDev d;
     std::vector<uint32_t> row_ptr, col, pcol;
-    std::vector<double> pw;
+    std::vector<double> pw, coslat;
     std::vector<uint8_t> pdeg;
     std::vector<double> w, lat, lon, cosrow;
     std::vector<VRec> vrec;
@@ -113,6 +113,9 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->vrec.resize(n);
     for (uint32_t v = 0; v < n; ++v)
         p->vrec[v] = make_vrec(v, lat[v], lon[v], d.g.G, d.g.lat0, d.g.lon0, d.g.hlat, d.g.hlon);
+    p->coslat.resize(n);
+    for (uint32_t v = 0; v < n; ++v) p->coslat[v] = std::cos(lat[v] * kDeg2Rad);
+    d.g.coslat = p->coslat.data();
     build_padded_rows(n, row_ptr, col, w, d.g.width, &p->pcol, &p->pw, &p->pdeg);
     d.g.deg = p->pdeg.data();
     d.g.col = p->pcol.data();
