@@ -1644,8 +1644,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         qx = me.x;
         qy = me.y;
         qz = me.z;
-        // cos(lat) = |(x, y)| to a few ulps: it only scales the cell bounds, whose slack is 1e-9
-        cl = sqrt(qx * qx + qy * qy);
+        cl = g.coslat[(uint32_t)S.rand_id];
     }
     else
     {
@@ -1666,7 +1665,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         return dx * dx + dy * dy + dz * dz;
     };
     // rounding band of a squared chord m: unit-vector components carry ~1e-16 each
-    auto band = [](double m) { return 2e-12 * m + 4e-15 * sqrt(m); };
+    // (an upper bound of 2e-12 m + 4e-15 sqrt(m): single-precision root, rounded up)
+    auto band = [](double m) { return 2e-12 * m + 4.00001e-15 * (double)sqrtf((float)m) + 1e-33; };
     auto bound = [&](double m) { return m * (1.0 + kPruneSlack) + 4.0 * band(m); };
     if (cta.tid() == 0)
     {
