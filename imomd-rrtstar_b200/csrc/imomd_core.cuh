@@ -1580,7 +1580,9 @@ IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef&
     return cta.reduce(b, S.red);
 }
 
-// Helper-thread prefetch.  The serial bookkeeping that follows a nearest search touches
+// Helper-thread prefetch, run by the second warp WHILE the serial thread processes the result
+// of a nearest search (the other warps would only wait at the barrier).  The serial bookkeeping
+// that follows a nearest search touches
 // lines nobody has looked at yet (records of unvisited neighbours, their hash cells, the
 // chunk that gives up its last record): one dependent DRAM round trip each when thread 0
 // meets them alone.  Here the idle threads of the CTA fetch those lines in parallel --
@@ -1591,10 +1593,10 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
                                     uint32_t x, Shared& S)
 {
     const GraphDev& g = P.g;
-    if (x == IMOMD_NONE || cta.nt() < 64) return;
+    if (x == IMOMD_NONE || cta.nt() < 64 || cta.tid() < 32) return;   // helpers: the second warp on
     const uint32_t e0 = row_begin(g, x), e1 = row_end(g, x);
     uint32_t acc = 0;
-    const uint32_t t = (uint32_t)cta.tid();
+    const uint32_t t = (uint32_t)cta.tid() - 32u;
     if (t < e1 - e0)
     {
         uint32_t y = g.col[e0 + t];
@@ -1701,7 +1703,6 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
             }
         }
     }
-    if (warm) warm_expansion(cta, P, T, q, k, b.id1, S);
     if (cta.tid() == 0)
     {
         S.result = b;
@@ -2248,9 +2249,12 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         Q->last_expansions = Q->expansions;
     }
     cta.sync();
+    int warm_k = -1;              // tree whose nearest search has just finished (helpers prefetch)
+    uint32_t warm_x = IMOMD_NONE;
     for (;;)
     {
         long long t0 = cta.clock();
+        if (warm_k >= 0) warm_x = S.result.id1;
         if (cta.tid() == 0)
         {
             int ph0 = S.phase & 7;
@@ -2259,9 +2263,15 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
             Q->phase_cycles[ph0] += (uint64_t)(cta.clock() - t0);
             Q->phase_count[ph0] += 1;
         }
+        else if (warm_k >= 0)
+        {
+            // a nearest search has just finished: fetch what the serial thread is about to touch
+            warm_expansion(cta, P, tree_ref_of(P, q, warm_k, S), q, warm_k, warm_x, S);
+        }
         cta.sync();
         int req = S.req;
         int k = S.k;
+        warm_k = -1;
         long long t1 = cta.clock();
         if (cta.tid() == 0)
         {
@@ -2273,6 +2283,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         {
             svc_nearest(cta, P, q, k, S, lb, P.clist + (size_t)q * 2 * P.chunks, &Q->near_ties,
                         &Q->unresolved_ties, true);
+            warm_k = k;
         }
         else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
         else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);
