@@ -466,8 +466,15 @@ def b200_arm(args):
                                "algorithmic_bytes_per_launch": int(best["bytes"]),
                                "launch_ms": best["kernel_ms"], "lookups": n_lk,
                                "lookups_per_s": n_lk / (best["kernel_ms"] / 1e3),
+                               "segments": int(best["segments"]),
+                               "prep_ms": best["prep_ms"], "merge_ms": best["merge_ms"],
+                               "lookups_per_s_pipeline": n_lk / ((best["prep_ms"] + best["kernel_ms"] +
+                                                                  best["merge_ms"]) / 1e3),
                                "note": "imomd_nearest_batch, 4 samples per frontier, best of 5 launches; "
-                                       "frontier records total larger than L2"}
+                                       "frontier records total larger than L2; algorithmic bytes = 32 B per "
+                                       "OCCUPIED frontier record + 8 B per chunk-list entry + 36 B per lookup; "
+                                       "prep_ms = chunk lists + seeds + segment scan, merge_ms = fold of the "
+                                       "segment partials (device times of the same call)"}
     except Exception as ex:  # the headline line must survive a failure of the side measurement
         line["roofline_nn"] = {"error": str(ex)}
     # time to first solution of ONE query through the drop-in C++ facade (planner construction ->

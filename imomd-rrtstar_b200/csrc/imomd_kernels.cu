@@ -462,6 +462,9 @@ struct imomd_planner
     // sparse readback scratch (imomd_gather_tree, imomd_get_frontier): ids / values, n + 1 each
     uint32_t* gather_u32;
     double* gather_f64;
+    // device times of the last imomd_nearest_batch call
+    float nn_prep_ms = 0.f, nn_tiles_ms = 0.f, nn_merge_ms = 0.f;
+    uint32_t nn_segments = 0;
 };
 
 struct imomd_ctx
@@ -482,6 +485,26 @@ cudaError_t dmalloc(T** p, size_t count)
 {
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
 }
+
+// device scratch of one imomd_nearest_batch call; released on every exit path
+struct NnScratch
+{
+    std::vector<void*> ptrs;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~NnScratch()
+    {
+        for (void* x : ptrs) cudaFree(x);
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    template <class T>
+    cudaError_t get(T** x, size_t count)
+    {
+        cudaError_t rc = dmalloc(x, count);
+        if (rc == cudaSuccess) ptrs.push_back(*x);
+        return rc;
+    }
+};
 
 int planner_fill_initial(imomd_planner* p)
 {
@@ -1278,52 +1301,93 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
             t.lookup[t.n++] = order[i++];
         tiles.push_back(t);
     }
-    uint32_t *lists = nullptr, *counts = nullptr, *didx = nullptr, *damb = nullptr;
+    NnScratch sc;
+    const int n_tiles = (int)tiles.size();
+    uint32_t *lists = nullptr, *counts = nullptr, *didx = nullptr, *damb = nullptr, *tile_valid = nullptr,
+             *nseg = nullptr, *seg_start = nullptr, *next_work = nullptr;
     double* ddist = nullptr;
     imomd_nn_query* dq = nullptr;
     NnTile* dtiles = nullptr;
+    NnSeed* seed = nullptr;
+    NnWork* work = nullptr;
+    Best* part = nullptr;
     int* derr = nullptr;
-    CU(dmalloc(&lists, (size_t)QK * 2 * p->d.chunks));
-    CU(dmalloc(&counts, (size_t)QK));
-    CU(dmalloc(&didx, (size_t)n));
-    CU(dmalloc(&damb, (size_t)n));
-    CU(dmalloc(&ddist, (size_t)n));
-    CU(dmalloc(&dq, (size_t)n));
-    CU(dmalloc(&dtiles, tiles.size()));
-    CU(dmalloc(&derr, 1));
+    for (cudaEvent_t& e : sc.ev) CU(cudaEventCreate(&e));
+    CU(sc.get(&lists, (size_t)QK * 2 * p->d.chunks));
+    CU(sc.get(&counts, (size_t)QK));
+    CU(sc.get(&didx, (size_t)n));
+    CU(sc.get(&damb, (size_t)n));
+    CU(sc.get(&ddist, (size_t)n));
+    CU(sc.get(&dq, (size_t)n));
+    CU(sc.get(&dtiles, (size_t)n_tiles));
+    CU(sc.get(&seed, (size_t)n_tiles));
+    CU(sc.get(&tile_valid, (size_t)n_tiles));
+    CU(sc.get(&nseg, (size_t)n_tiles));
+    CU(sc.get(&seg_start, (size_t)n_tiles + 1));
+    CU(sc.get(&next_work, 1));
+    CU(sc.get(&derr, 1));
     CU(cudaMemsetAsync(derr, 0, sizeof(int), p->stream));
+    CU(cudaMemsetAsync(next_work, 0, sizeof(uint32_t), p->stream));
     CU(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(imomd_nn_query), cudaMemcpyHostToDevice, p->stream));
     CU(cudaMemcpyAsync(dtiles, tiles.data(), tiles.size() * sizeof(NnTile), cudaMemcpyHostToDevice,
                        p->stream));
-    k_tree_chunk_lists<<<(QK + 3) / 4, 128, 0, p->stream>>>(p->d, lists, counts);
+    // preparation: chunk lists of the trees, seeds and segment counts of the tiles, segment scan
+    CU(cudaEventRecord(sc.ev[0], p->stream));
+    k_tree_chunk_lists<<<QK, kListThreads, 0, p->stream>>>(p->d, lists, counts);
     CU(cudaGetLastError());
+    k_nn_seed<<<(n_tiles + 3) / 4, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, dq, lists, counts, seed,
+                                                        tile_valid, nseg);
+    CU(cudaGetLastError());
+    k_nn_segments<<<1, 1024, 0, p->stream>>>(n_tiles, nseg, seg_start);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(sc.ev[1], p->stream));
+    uint32_t n_work = 0;
+    CU(cudaMemcpyAsync(&n_work, seg_start + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(sc.get(&work, (size_t)n_work));
+    CU(sc.get(&part, (size_t)n_work * kConsumerWarps * kTileLookups));
+    k_nn_fill_work<<<(n_work + 127) / 128 + 1, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, lists, counts,
+                                                                    seg_start, work);
+    CU(cudaGetLastError());
+    // the tile kernel: persistent CTAs over the segments
     const size_t smem = sizeof(NnShared) + 128;
     CU(cudaFuncSetAttribute(k_nearest_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<size_t>(tiles.size(), 148 * 4);
-    CU(cudaEventRecord(p->ev0, p->stream));
-    k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, (int)tiles.size(), dtiles, dq, lists,
-                                                             counts, didx, ddist, damb, derr);
+    CU(cudaEventRecord(sc.ev[2], p->stream));
+    if (n_work > 0)
+    {
+        const int grid = (int)std::min<size_t>(n_work, (size_t)148 * kTileCtasPerSm);
+        k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, dtiles, seed, work, seg_start + n_tiles,
+                                                                 next_work, lists, part, derr);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(sc.ev[3], p->stream));
+    k_nn_merge<<<(n_tiles * kTileLookups + 255) / 256, 256, 0, p->stream>>>(p->d, n_tiles, dtiles, dq, seg_start,
+                                                                            part, didx, ddist, damb);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(p->ev1, p->stream));
-    std::vector<uint32_t> amb(n), hcounts(QK);
+    CU(cudaEventRecord(sc.ev[4], p->stream));
+    std::vector<uint32_t> amb(n), hcounts(QK), hvalid(n_tiles);
     int herr = 0;
     CU(cudaMemcpyAsync(idx, didx, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(amb.data(), damb, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(hcounts.data(), counts, (size_t)QK * 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(hvalid.data(), tile_valid, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
-    cudaFree(lists); cudaFree(counts); cudaFree(didx); cudaFree(damb); cudaFree(ddist);
-    cudaFree(dq); cudaFree(dtiles); cudaFree(derr);
+    CU(cudaEventElapsedTime(&ms, sc.ev[2], sc.ev[3]));
+    CU(cudaEventElapsedTime(&p->nn_prep_ms, sc.ev[0], sc.ev[1]));
+    CU(cudaEventElapsedTime(&p->nn_merge_ms, sc.ev[3], sc.ev[4]));
+    p->nn_tiles_ms = ms;
+    p->nn_segments = n_work;
     if (herr) return fail(IMOMD_ERR_CUDA, "imomd_nearest_batch: pipeline barrier timed out");
     if (kernel_ms) *kernel_ms = ms;
     if (bytes_streamed)
     {
         uint64_t b = 0;
-        for (const NnTile& t : tiles)
-            b += (uint64_t)hcounts[t.qt] * IMOMD_CHUNK * sizeof(VRec) + (uint64_t)t.n * 36;
+        for (int t = 0; t < n_tiles; ++t)
+            b += (uint64_t)hvalid[t] * sizeof(VRec) + (uint64_t)hcounts[tiles[t].qt] * 8 +
+                 (uint64_t)tiles[t].n * 36;
         *bytes_streamed = b;
     }
     // lookups the chord ranking could not decide go through the exact path
@@ -1345,6 +1409,17 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
             dist[redo[j]] = rd[j];
         }
     }
+    return IMOMD_OK;
+}
+
+int imomd_nearest_batch_last_timing(imomd_planner* p, float* prep_ms, float* tiles_ms, float* merge_ms,
+                                    uint32_t* n_segments)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null argument");
+    if (prep_ms) *prep_ms = p->nn_prep_ms;
+    if (tiles_ms) *tiles_ms = p->nn_tiles_ms;
+    if (merge_ms) *merge_ms = p->nn_merge_ms;
+    if (n_segments) *n_segments = p->nn_segments;
     return IMOMD_OK;
 }
 

@@ -3,19 +3,27 @@
 // (src/imomd_rrt_star.cpp:406-418 upstream).
 //
 // A tile = one (query, tree) frontier and up to kTileLookups (4) samples against it.  The
-// frontier lives in 1 KB chunks of 32 records (csrc/imomd_layout.h); a producer warp streams
-// the tree's chunks into a 4-stage shared-memory ring with bulk asynchronous copies
-// (cp.async.bulk ... mbarrier::complete_tx, the TMA engine; one 1 KB copy per chunk because
-// chunks of a cell chain are not contiguous), four consumer warps rank the staged records
-// against the tile's samples by squared chord (every shared-memory read is a broadcast or
-// conflict free) and keep (best, lowest id on ties, runner-up) per sample.  Full/empty
-// mbarriers hand the stages back and forth; the kernel is persistent over tiles.
+// frontier lives in 1 KB chunks of 32 records (csrc/imomd_layout.h) of which only the first
+// `valid` are occupied.  The launch is cut into SEGMENTS of kSegChunks chunks of one tile
+// (k_nn_segments / k_nn_fill_work); persistent CTAs take segments from an atomic counter, so
+// the launch ends within one segment (~40 KB) of perfect balance whatever the frontier sizes.
+// Per CTA a producer warp streams the segment into a 3-stage shared-memory ring with bulk
+// asynchronous copies (cp.async.bulk ... mbarrier::complete_tx, the TMA engine): one copy per
+// chunk, of its VALID records only, packed back to back in the stage -- no padding crosses
+// the memory system and no consumer lane idles on an empty slot.  Four consumer warps rank the
+// staged records against the tile's samples and keep (best, lowest id on ties, runner-up) per
+// sample.  A record is first screened by its dot product with the sample (3 FP64 operations):
+// chord^2 = |v|^2 + |q|^2 - 2 v.q, so v.q < 1 - cap/2 - margin proves chord^2 > cap, where cap
+// is an upper bound of the runner-up (seeded by k_nn_seed from the first record of every
+// chunk, tightened by what the thread has seen); only survivors get the exact squared chord
+// of the pruned path.  The screen never changes an answer: every record whose chord^2 does
+// not exceed the final runner-up passes it.  Full/empty mbarriers hand the stages back and
+// forth; k_nn_merge folds the per-segment partials and writes the answers.
 //
-// Algorithmic bytes: 32 B per frontier record per tile + 24 B per lookup + 12 B per answer
-// (brute-force variant).  With kTileLookups = 4 the FP64 work per staged byte
-// stays below the machine balance, so the kernel is HBM-bound when the frontiers do not fit
-// in L2.  Lookups whose two best candidates are closer than the rounding band are flagged
-// and re-done by the exact path (k_nearest).
+// Algorithmic bytes: 32 B per occupied frontier record per tile + 8 B per chunk-list entry +
+// 24 B per lookup + 12 B per answer (brute-force variant).  Lookups whose two
+// best candidates are closer than the rounding band are flagged and re-done by the exact path
+// (k_nearest).
 #ifndef IMOMD_NN_TILES_CUH
 #define IMOMD_NN_TILES_CUH
 
@@ -24,10 +32,15 @@
 namespace imomd {
 
 constexpr int kTileLookups = 4;        // samples per tile
-constexpr int kStageChunks = 8;        // 1 KB chunks per pipeline stage
-constexpr int kStages = 4;
+constexpr int kStageChunks = 16;       // at most this many chunks per pipeline stage (one producer lane each)
+constexpr int kStageRecs = 256;        // records per pipeline stage (8 KB)
+constexpr int kStages = 6;
+constexpr int kSegChunks = 64;         // chunks per segment (work item)
+constexpr int kSegStagesMax = kSegChunks * IMOMD_CHUNK / kStageRecs;   // 8: a stage short of the end holds > 256 - 32 records or 16 chunks
 constexpr int kConsumerWarps = 4;
 constexpr int kTileThreads = 32 * (kConsumerWarps + 1);   // warp 0 = producer
+constexpr int kTileCtasPerSm = 4;
+constexpr double kDotMargin = 1e-14;   // >= 4x the rounding of |v|^2, |q|^2 and the dot product
 
 struct NnTile
 {
@@ -35,6 +48,27 @@ struct NnTile
     int32_t n;                 // lookups in this tile (<= kTileLookups)
     int32_t lookup[kTileLookups];
 };
+
+// per tile, written by k_nn_seed: unit vectors of the samples and an upper bound of each
+// sample's runner-up chord^2 (unused sample slots: zero vector, bound 1 -> always screened out)
+struct __align__(16) NnSeed
+{
+    double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups], ub[kTileLookups];
+};
+
+// one segment: kSegChunks consecutive entries of a tile's chunk list, packed greedily into stages
+// of <= kStageRecs occupied records and <= kStageChunks chunks (k_nn_fill_work).  64 bytes: the
+// producer warp fetches a segment with one load per lane.
+struct __align__(16) NnWork
+{
+    int32_t tile;
+    int32_t qt;                // query * K + tree
+    uint32_t chunk0;           // first entry of the tile's chunk list
+    uint32_t n_stages;
+    uint32_t stage[12];        // [0, n_stages): first entry (bits 0-6, relative to chunk0) | chunks << 7
+};
+static_assert(sizeof(NnWork) == 64, "NnWork is fetched as 16 words");
+static_assert(kSegStagesMax <= 12, "stage table of a segment");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
@@ -80,25 +114,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
-// flat (chunk id, valid records) list of every tree: one warp per tree walks the occupied
-// cells and their chunk chains
-__global__ void k_tree_chunk_lists(const __grid_constant__ PlannerDev P, uint32_t* lists, uint32_t* counts)
+// flat (chunk id, occupied records) list of every tree: one CTA per tree, one thread per occupied
+// cell walks the cell's chunk chain (the dependent loads of 128 chains overlap)
+constexpr int kListThreads = 128;
+__global__ void __launch_bounds__(kListThreads)
+k_tree_chunk_lists(const __grid_constant__ PlannerDev P, uint32_t* lists, uint32_t* counts)
 {
-    int qt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (qt >= P.Q * P.K) return;
-    int q = qt / P.K, k = qt % P.K;
+    __shared__ uint32_t warp_sum[kListThreads / 32];
+    const int qt = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = qt / P.K, k = qt % P.K;
     TreeRef T = tree_ref(P, q, k);
-    uint32_t n_occ = P.query[q].n_occ[k];
+    const uint32_t n_occ = P.query[q].n_occ[k];
     uint32_t* out = lists + (size_t)qt * 2 * P.chunks;
     uint32_t total = 0;
-    for (uint32_t base = 0; base < n_occ; base += 32)
+    for (uint32_t base = 0; base < n_occ; base += kListThreads)
     {
-        uint32_t i = base + lane;
+        const uint32_t i = base + threadIdx.x;
         uint32_t cnt = 0, head = IMOMD_NONE, nch = 0;
         if (i < n_occ)
         {
-            uint32_t c = T.occ[i];
+            const uint32_t c = T.occ[i];
             cnt = T.cell_cnt[c];
             head = T.cell_head[c];
             nch = (cnt + IMOMD_CHUNK - 1) / IMOMD_CHUNK;
@@ -109,7 +145,18 @@ __global__ void k_tree_chunk_lists(const __grid_constant__ PlannerDev P, uint32_
             uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
             if (lane >= off) inc += t;
         }
-        uint32_t at = total + inc - nch;
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < kListThreads / 32; ++w)
+        {
+            const uint32_t x = warp_sum[w];
+            if (w < warp) before += x;
+            all += x;
+        }
+        __syncthreads();
+        const uint32_t at = total + before + inc - nch;
         uint32_t n = cnt ? (cnt - 1) % IMOMD_CHUNK + 1 : 0;
         uint32_t chunk = head;
         for (uint32_t j = 0; j < nch; ++j)
@@ -119,27 +166,250 @@ __global__ void k_tree_chunk_lists(const __grid_constant__ PlannerDev P, uint32_
             n = IMOMD_CHUNK;
             chunk = T.chunk_next[chunk];
         }
-        total += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        total += all;
     }
-    if (lane == 0) counts[qt] = total;
+    if (threadIdx.x == 0) counts[qt] = total;
 }
+
+__device__ __forceinline__ double chord2(const VRec& v, double qx, double qy, double qz)
+{
+    double dx = v.x - qx, dy = v.y - qy, dz = v.z - qz;
+    return fma(dz, dz, fma(dy, dy, dx * dx));
+}
+
+__device__ __forceinline__ Best warp_best(Best x)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        Best o;
+        o.v1 = __shfl_down_sync(0xFFFFFFFFu, x.v1, off);
+        o.id1 = __shfl_down_sync(0xFFFFFFFFu, x.id1, off);
+        o.v2 = __shfl_down_sync(0xFFFFFFFFu, x.v2, off);
+        x = best_merge(x, o);
+    }
+    return x;
+}
+
+// one warp per tile: unit vectors of the samples, runner-up bound from the first record of
+// every chunk (a spatially uniform subsample of the frontier: the chunks follow the hash
+// cells), occupied records and segments of the tile
+__global__ void k_nn_seed(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
+                          const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
+                          const uint32_t* __restrict__ counts, NnSeed* __restrict__ seed,
+                          uint32_t* __restrict__ tile_valid, uint32_t* __restrict__ nseg)
+{
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
+    const NnTile t = tiles[tile];
+    double mx = 0, my = 0, mz = 0;
+    if (lane < t.n)
+    {
+        imomd_nn_query nq = qs[t.lookup[lane]];
+        double la = nq.lat * kDeg2Rad, lo = nq.lon * kDeg2Rad;
+        double cl = cos(la);
+        mx = cl * cos(lo);
+        my = cl * sin(lo);
+        mz = sin(la);
+    }
+    double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
+    Best b[kTileLookups];
+#pragma unroll
+    for (int l = 0; l < kTileLookups; ++l)
+    {
+        qx[l] = __shfl_sync(0xFFFFFFFFu, mx, l);
+        qy[l] = __shfl_sync(0xFFFFFFFFu, my, l);
+        qz[l] = __shfl_sync(0xFFFFFFFFu, mz, l);
+        b[l] = best_empty();
+    }
+    const uint32_t n_chunks = counts[t.qt];
+    const uint32_t* list = lists + (size_t)t.qt * 2 * P.chunks;
+    const VRec* rec = P.rec + (size_t)t.qt * (size_t)P.chunks * IMOMD_CHUNK;
+    uint32_t valid = 0;
+    // four chunks per lane and round: the list entries, then the records, are requested together
+    for (uint32_t base = lane; base < n_chunks; base += 128)
+    {
+        uint2 e[4];
+        VRec v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const uint32_t i = base + 32 * j;
+            e[j] = i < n_chunks ? *reinterpret_cast<const uint2*>(list + 2 * i) : make_uint2(IMOMD_NONE, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (e[j].y) v[j] = rec[(size_t)e[j].x * IMOMD_CHUNK];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            valid += e[j].y;
+            if (e[j].y)
+            {
+#pragma unroll
+                for (int l = 0; l < kTileLookups; ++l)
+                    best_add(b[l], chord2(v[j], qx[l], qy[l], qz[l]), v[j].id);
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) valid += __shfl_down_sync(0xFFFFFFFFu, valid, off);
+    double ub = INFINITY;
+#pragma unroll
+    for (int l = 0; l < kTileLookups; ++l)
+    {
+        Best x = warp_best(b[l]);
+        double u = __shfl_sync(0xFFFFFFFFu, x.v2, 0);
+        if (lane == l) ub = u;
+    }
+    if (lane < kTileLookups)
+    {
+        seed[tile].qx[lane] = mx;
+        seed[tile].qy[lane] = my;
+        seed[tile].qz[lane] = mz;
+        seed[tile].ub[lane] = ub;
+    }
+    if (lane == 0)
+    {
+        tile_valid[tile] = valid;
+        nseg[tile] = (n_chunks + kSegChunks - 1) / kSegChunks;
+    }
+}
+
+// exclusive scan of the segment counts (one CTA): seg_start[0 .. n_tiles], total last
+__global__ void __launch_bounds__(1024) k_nn_segments(int n_tiles, const uint32_t* __restrict__ nseg,
+                                                      uint32_t* __restrict__ seg_start)
+{
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024)
+    {
+        const int i = base + threadIdx.x;
+        const uint32_t x = i < n_tiles ? nseg[i] : 0u;
+        uint32_t inc = x;
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0)
+        {
+            uint32_t w = warp_sum[lane], winc = w;
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, off);
+                if (lane >= off) winc += t;
+            }
+            warp_sum[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sum[warp] + inc - x;
+        if (i < n_tiles) seg_start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg_start[n_tiles] = carry;
+}
+
+// one thread per segment slot of a tile: greedy packing of its chunks into stages
+__global__ void k_nn_fill_work(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
+                               const uint32_t* __restrict__ lists, const uint32_t* __restrict__ counts,
+                               const uint32_t* __restrict__ seg_start, NnWork* __restrict__ work)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_work = seg_start[n_tiles];
+    if (w >= n_work) return;
+    // tile of this segment: last tile whose first segment is <= w
+    int lo = 0, hi = n_tiles - 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (seg_start[mid] <= w)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const int tile = lo;
+    const int32_t qt = tiles[tile].qt;
+    const uint32_t n_chunks = counts[qt];
+    NnWork x;
+    x.tile = tile;
+    x.qt = qt;
+    x.chunk0 = (w - seg_start[tile]) * kSegChunks;
+    const uint32_t n = min((uint32_t)kSegChunks, n_chunks - x.chunk0);
+    const uint32_t* list = lists + (size_t)qt * 2 * P.chunks + 2 * (size_t)x.chunk0;
+    for (int j = 0; j < 12; ++j) x.stage[j] = 0;
+    uint32_t ns = 0, first = 0, recs = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t v = list[2 * i + 1];
+        if (recs + v > (uint32_t)kStageRecs || i - first == (uint32_t)kStageChunks)
+        {
+            x.stage[ns++] = first | ((i - first) << 7);
+            first = i;
+            recs = 0;
+        }
+        recs += v;
+    }
+    x.stage[ns++] = first | ((n - first) << 7);
+    x.n_stages = ns;
+    work[w] = x;
+}
+
+// Rare path of the consumers (a few percent of the records): exact squared chord of a record
+// that passed the screen of at least one sample.  Out of line on purpose, with the running
+// results in local memory: the screening loop then carries nothing but the thresholds.
+struct Thr4
+{
+    double t[kTileLookups];
+};
+__device__ __noinline__ Thr4 nn_rank_exact(const VRec v, const double* q /*[3][kTileLookups], shared*/, Thr4 thr,
+                                           Best* b)
+{
+#pragma unroll
+    for (int l = 0; l < kTileLookups; ++l)
+    {
+        const double qx = q[l], qy = q[kTileLookups + l], qz = q[2 * kTileLookups + l];
+        const double dot = fma(v.z, qz, fma(v.y, qy, v.x * qx));      // the screening loop's own value
+        if (!(dot < thr.t[l]))
+        {
+            best_add(b[l], chord2(v, qx, qy, qz), v.id);
+            thr.t[l] = fmax(thr.t[l], 1.0 - 0.5 * b[l].v2 - kDotMargin);
+        }
+    }
+    return thr;
+}
+
+struct NnStageMeta
+{
+    int32_t work;              // segment staged here, -1 = no more work
+    int32_t flags;             // 1 = first stage of its segment, 2 = last
+    uint32_t n_rec;            // occupied records packed in the stage
+    int32_t pad;
+};
 
 struct __align__(16) NnShared
 {
-    VRec stage[kStages][kStageChunks * IMOMD_CHUNK];   // 4 x 8 KB
-    uint32_t valid[kStages][kStageChunks];
+    VRec stage[kStages][kStageRecs];                   // 6 x 8 KB
+    NnSeed seed[kStages];                              // meaningful in a segment's first stage
+    double cur[kConsumerWarps][3 * kTileLookups];      // samples of the segment a consumer warp is in
+    NnStageMeta meta[kStages];
     uint64_t full[kStages];
     uint64_t empty[kStages];
-    double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
-    Best part[kConsumerWarps * 32];
     int error;
 };
 
-__global__ void __launch_bounds__(kTileThreads, 4)
-k_nearest_tiles(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
-                const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
-                const uint32_t* __restrict__ counts, uint32_t* __restrict__ idx,
-                double* __restrict__ dist, uint32_t* __restrict__ ambiguous, int* __restrict__ error)
+__global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm)
+k_nearest_tiles(const __grid_constant__ PlannerDev P, const NnTile* __restrict__ tiles,
+                const NnSeed* __restrict__ seed, const NnWork* __restrict__ work,
+                const uint32_t* __restrict__ n_work_ptr, uint32_t* __restrict__ next_work,
+                const uint32_t* __restrict__ lists, Best* __restrict__ part, int* __restrict__ error)
 {
     extern __shared__ __align__(128) unsigned char nn_smem_raw[];
     NnShared& sh = *reinterpret_cast<NnShared*>(nn_smem_raw);
@@ -156,141 +426,218 @@ k_nearest_tiles(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile*
     }
     __syncthreads();
     uint32_t it = 0;                 // stages produced / consumed so far (same on both sides)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    if (warp == 0)
     {
-        const NnTile t = tiles[tile];
-        const uint32_t n_chunks = counts[t.qt];
-        const uint32_t n_stages = (n_chunks + kStageChunks - 1) / kStageChunks;
-        const uint32_t* list = lists + (size_t)t.qt * 2 * P.chunks;
-        const VRec* rec = P.rec + (size_t)t.qt * (size_t)P.chunks * IMOMD_CHUNK;
-        if (threadIdx.x < (unsigned)t.n)
+        // ---------------- producer: bulk copies chunk -> stage ----------------
+        // Segments come from an atomic counter two ahead (the counter's answer, the segment
+        // record and the first chunk ids of the next segment are all requested one segment /
+        // one stage before they are needed: no dependent global load sits between two stages).
+        // Lane j < 16 owns chunk j of a stage and issues the copy of its occupied records,
+        // packed behind lane j-1's.
+        const uint32_t n_work = *n_work_ptr;
+        uint32_t w0 = 0, w1 = 0;
+        if (lane == 0)
         {
-            imomd_nn_query nq = qs[t.lookup[threadIdx.x]];
-            double la = nq.lat * kDeg2Rad, lo = nq.lon * kDeg2Rad;
-            double cl = cos(la);
-            sh.qx[threadIdx.x] = cl * cos(lo);
-            sh.qy[threadIdx.x] = cl * sin(lo);
-            sh.qz[threadIdx.x] = sin(la);
+            w0 = atomicAdd(next_work, 1u);
+            w1 = atomicAdd(next_work, 1u);
         }
-        __syncthreads();
-        if (warp == 0)
+        w0 = __shfl_sync(0xFFFFFFFFu, w0, 0);
+        w1 = __shfl_sync(0xFFFFFFFFu, w1, 0);
+        // lane l < 16 holds word l of the segment record
+        auto fetch_work = [&](uint32_t w) -> uint32_t {
+            return (w < n_work && lane < 16) ? reinterpret_cast<const uint32_t*>(work + w)[lane] : 0u;
+        };
+        auto fetch_entry = [&](uint32_t qt, uint32_t chunk0, uint32_t desc) -> uint2 {
+            const uint32_t off = desc & 127u, nc = desc >> 7;
+            if ((uint32_t)lane >= nc) return make_uint2(IMOMD_NONE, 0u);
+            return *reinterpret_cast<const uint2*>(lists + (size_t)qt * 2 * P.chunks +
+                                                   2 * ((size_t)chunk0 + off + lane));
+        };
+        uint32_t X0 = fetch_work(w0), X1 = fetch_work(w1);
+        uint2 mine = make_uint2(IMOMD_NONE, 0u);
+        double seed_word = 0;
+        if (w0 < n_work)
         {
-            // ---------------- producer: bulk copies chunk -> stage ----------------
-            // lane j of the producer warp owns chunk j of every stage: it fetches the chunk id
-            // (prefetched one stage ahead) and issues its own 1 KB bulk copy
-            uint32_t my_chunk = IMOMD_NONE, my_valid = 0;
-            if (n_stages > 0 && lane < kStageChunks && (uint32_t)lane < n_chunks)
-            {
-                my_chunk = list[2 * lane];
-                my_valid = list[2 * lane + 1];
-            }
+            const uint32_t tile = __shfl_sync(0xFFFFFFFFu, X0, 0), qt = __shfl_sync(0xFFFFFFFFu, X0, 1);
+            mine = fetch_entry(qt, __shfl_sync(0xFFFFFFFFu, X0, 2), __shfl_sync(0xFFFFFFFFu, X0, 4));
+            if (lane < 16) seed_word = reinterpret_cast<const double*>(seed + tile)[lane];
+        }
+        while (w0 < n_work)
+        {
+            uint32_t w2 = 0;
+            if (lane == 0) w2 = atomicAdd(next_work, 1u);       // consumed after this segment
+            const uint32_t qt = __shfl_sync(0xFFFFFFFFu, X0, 1);
+            const uint32_t chunk0 = __shfl_sync(0xFFFFFFFFu, X0, 2);
+            const uint32_t n_stages = __shfl_sync(0xFFFFFFFFu, X0, 3);
+            const VRec* rec = P.rec + (size_t)qt * (size_t)P.chunks * IMOMD_CHUNK;
             for (uint32_t s = 0; s < n_stages; ++s)
             {
                 const uint32_t slot = (it + s) % kStages, round = (it + s) / kStages;
-                const uint32_t c0 = s * kStageChunks;
-                const uint32_t nc = min((uint32_t)kStageChunks, n_chunks - c0);
-                const uint32_t chunk = my_chunk, valid = my_valid;
-                // next stage's ids are requested before this stage's barrier wait
-                const uint32_t nxt = c0 + kStageChunks + lane;
-                if (lane < kStageChunks && nxt < n_chunks)
+                const uint32_t chunk = mine.x, valid = mine.y;
+                const double seed_now = seed_word;
+                // what the next stage needs is requested before this stage's barrier wait
+                if (s + 1 < n_stages)
+                    mine = fetch_entry(qt, chunk0, __shfl_sync(0xFFFFFFFFu, X0, 4 + s + 1));
+                else if (w1 < n_work)
                 {
-                    my_chunk = list[2 * nxt];
-                    my_valid = list[2 * nxt + 1];
+                    const uint32_t tile1 = __shfl_sync(0xFFFFFFFFu, X1, 0);
+                    mine = fetch_entry(__shfl_sync(0xFFFFFFFFu, X1, 1), __shfl_sync(0xFFFFFFFFu, X1, 2),
+                                       __shfl_sync(0xFFFFFFFFu, X1, 4));
+                    if (lane < 16) seed_word = reinterpret_cast<const double*>(seed + tile1)[lane];
                 }
+                uint32_t inc = valid;                    // packed position of this lane's records
+                for (int off = 1; off < kStageChunks; off <<= 1)
+                {
+                    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+                    if (lane >= off) inc += t;
+                }
+                const uint32_t n_rec = __shfl_sync(0xFFFFFFFFu, inc, kStageChunks - 1);
                 if (lane == 0)
                 {
                     if (round > 0 && !mbar_wait(&sh.empty[slot], (round - 1) & 1)) sh.error = 1;
                 }
                 __syncwarp();
-                if (lane < kStageChunks) sh.valid[slot][lane] = (uint32_t)lane < nc ? valid : 0u;
-                __syncwarp();
-                if (lane == 0) mbar_expect_tx(&sh.full[slot], nc * (uint32_t)(IMOMD_CHUNK * sizeof(VRec)));
-                __syncwarp();
-                if ((uint32_t)lane < nc)
-                    bulk_g2s(&sh.stage[slot][lane * IMOMD_CHUNK], rec + (size_t)chunk * IMOMD_CHUNK,
-                             (uint32_t)(IMOMD_CHUNK * sizeof(VRec)), &sh.full[slot]);
-                __syncwarp();
-            }
-        }
-        else
-        {
-            // ---------------- consumers: rank the staged records ----------------
-            // each thread takes records c, c+128, ... of a stage and ranks them against ALL
-            // samples of the tile (one record load feeds kTileLookups chord evaluations)
-            const int c = threadIdx.x - 32;                 // 0 .. 127
-            double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
-            Best b[kTileLookups];
-#pragma unroll
-            for (int l = 0; l < kTileLookups; ++l)
-            {
-                qx[l] = sh.qx[l];
-                qy[l] = sh.qy[l];
-                qz[l] = sh.qz[l];
-                b[l] = best_empty();
-            }
-            for (uint32_t s = 0; s < n_stages; ++s)
-            {
-                const uint32_t slot = (it + s) % kStages, round = (it + s) / kStages;
-                if (!mbar_wait(&sh.full[slot], round & 1)) sh.error = 1;
-                const VRec* st = sh.stage[slot];
-#pragma unroll
-                for (int r = c; r < kStageChunks * IMOMD_CHUNK; r += kConsumerWarps * 32)
+                if (s == 0 && lane < 16) reinterpret_cast<double*>(&sh.seed[slot])[lane] = seed_now;
+                if (lane == 0)
                 {
-                    if ((uint32_t)(r % IMOMD_CHUNK) < sh.valid[slot][r / IMOMD_CHUNK])
-                    {
-                        const VRec v = st[r];
-#pragma unroll
-                        for (int l = 0; l < kTileLookups; ++l)
-                        {
-                            double dx = v.x - qx[l], dy = v.y - qy[l], dz = v.z - qz[l];
-                            double c2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                            // common case first: not better than the incumbent -> only the
-                            // runner-up can move
-                            if (c2 > b[l].v1)
-                                b[l].v2 = fmin(b[l].v2, c2);
-                            else
-                                best_add(b[l], c2, v.id);
-                        }
-                    }
+                    NnStageMeta m;
+                    m.work = (int32_t)w0;
+                    m.flags = (s == 0 ? 1 : 0) | (s + 1 == n_stages ? 2 : 0);
+                    m.n_rec = n_rec;
+                    m.pad = 0;
+                    sh.meta[slot] = m;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.empty[slot]);
+                if (lane == 0) mbar_expect_tx(&sh.full[slot], n_rec * (uint32_t)sizeof(VRec));
+                __syncwarp();
+                if (valid)
+                    bulk_g2s(&sh.stage[slot][inc - valid], rec + (size_t)chunk * IMOMD_CHUNK,
+                             valid * (uint32_t)sizeof(VRec), &sh.full[slot]);
+                __syncwarp();
             }
-            // per-sample merge over the warp, one partial per (warp, sample)
-#pragma unroll
-            for (int l = 0; l < kTileLookups; ++l)
-            {
-                Best x = b[l];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-                {
-                    Best o;
-                    o.v1 = __shfl_down_sync(0xFFFFFFFFu, x.v1, off);
-                    o.id1 = __shfl_down_sync(0xFFFFFFFFu, x.id1, off);
-                    o.v2 = __shfl_down_sync(0xFFFFFFFFu, x.v2, off);
-                    x = best_merge(x, o);
-                }
-                if (lane == 0) sh.part[(warp - 1) * kTileLookups + l] = x;
-            }
+            it += n_stages;
+            w0 = w1;
+            X0 = X1;
+            w1 = __shfl_sync(0xFFFFFFFFu, w2, 0);
+            X1 = fetch_work(w1);
         }
-        it += n_stages;
-        __syncthreads();
-        if (threadIdx.x < (unsigned)t.n)
+        // end marker for the consumers
         {
-            Best b = best_empty();
-            for (int w = 0; w < kConsumerWarps; ++w) b = best_merge(b, sh.part[w * kTileLookups + threadIdx.x]);
-            const int li = t.lookup[threadIdx.x];
-            const imomd_nn_query nq = qs[li];
-            idx[li] = b.id1;
-            dist[li] = b.id1 == IMOMD_NONE
-                           ? INFINITY
-                           : haversine(P.g.lat[b.id1], P.g.lon[b.id1], nq.lat, nq.lon);
-            const double band = 2e-12 * b.v1 + 4e-15 * sqrt(b.v1);
-            ambiguous[li] = (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= band) ? 1u : 0u;
+            const uint32_t slot = it % kStages, round = it / kStages;
+            if (lane == 0)
+            {
+                if (round > 0 && !mbar_wait(&sh.empty[slot], (round - 1) & 1)) sh.error = 1;
+                NnStageMeta m;
+                m.work = -1; m.flags = 0; m.n_rec = 0; m.pad = 0;
+                sh.meta[slot] = m;
+                mbar_arrive(&sh.full[slot]);
+            }
         }
-        __syncthreads();
     }
+    else
+    {
+        // ---------------- consumers: screen and rank the staged records ----------------
+        const int c = threadIdx.x - 32;                 // 0 .. 127
+        double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
+        Thr4 thr;
+        Best b[kTileLookups];                           // local memory: touched by the rare path only
+        bool any = false;                               // this thread ranked something in this segment
+        const double* qsh = sh.seed[0].qx;
+#pragma unroll
+        for (int l = 0; l < kTileLookups; ++l)
+        {
+            qx[l] = qy[l] = qz[l] = 0;
+            thr.t[l] = -INFINITY;
+            b[l] = best_empty();
+        }
+        for (;; ++it)
+        {
+            const uint32_t slot = it % kStages, round = it / kStages;
+            if (!mbar_wait(&sh.full[slot], round & 1))
+            {
+                sh.error = 1;
+                break;
+            }
+            const NnStageMeta m = sh.meta[slot];
+            if (m.work < 0) break;
+            if (m.flags & 1)
+            {
+                // the rare path reads the samples from the warp's own copy in shared memory
+#pragma unroll
+                for (int l = 0; l < kTileLookups; ++l)
+                {
+                    qx[l] = sh.seed[slot].qx[l];
+                    qy[l] = sh.seed[slot].qy[l];
+                    qz[l] = sh.seed[slot].qz[l];
+                    thr.t[l] = 1.0 - 0.5 * sh.seed[slot].ub[l] - kDotMargin;
+                    b[l] = best_empty();
+                }
+                any = false;
+                if (lane < 3 * kTileLookups)
+                    sh.cur[warp - 1][lane] = reinterpret_cast<const double*>(&sh.seed[slot])[lane];
+                __syncwarp();
+                qsh = sh.cur[warp - 1];
+            }
+            const VRec* st = sh.stage[slot];
+#pragma unroll 1
+            for (uint32_t r = c; r < m.n_rec; r += kConsumerWarps * 32)
+            {
+                const VRec v = st[r];
+                bool pass = false;
+#pragma unroll
+                for (int l = 0; l < kTileLookups; ++l)
+                {
+                    const double dot = fma(v.z, qz[l], fma(v.y, qy[l], v.x * qx[l]));
+                    pass |= !(dot < thr.t[l]);
+                }
+                if (pass)
+                {
+                    thr = nn_rank_exact(v, qsh, thr, b);
+                    any = true;
+                }
+            }
+            if (m.flags & 2)
+            {
+                // most segments are far from most samples: nothing passed the screen in the whole warp
+                const bool warp_any = __any_sync(0xFFFFFFFFu, any);
+#pragma unroll
+                for (int l = 0; l < kTileLookups; ++l)
+                {
+                    Best x = best_empty();
+                    if (warp_any) x = warp_best(b[l]);
+                    if (lane == 0) part[((size_t)m.work * kConsumerWarps + (warp - 1)) * kTileLookups + l] = x;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty[slot]);
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0 && sh.error) *error = 1;
+}
+
+// one thread per (tile, sample): fold the segment partials, write the answer
+__global__ void k_nn_merge(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
+                           const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ seg_start,
+                           const Best* __restrict__ part, uint32_t* __restrict__ idx,
+                           double* __restrict__ dist, uint32_t* __restrict__ ambiguous)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile = i / kTileLookups, l = i % kTileLookups;
+    if (tile >= n_tiles) return;
+    const NnTile t = tiles[tile];
+    if (l >= t.n) return;
+    Best b = best_empty();
+    const uint32_t w0 = seg_start[tile], w1 = seg_start[tile + 1];
+    for (uint32_t w = w0; w < w1; ++w)
+        for (int cw = 0; cw < kConsumerWarps; ++cw)
+            b = best_merge(b, part[((size_t)w * kConsumerWarps + cw) * kTileLookups + l]);
+    const int li = t.lookup[l];
+    const imomd_nn_query nq = qs[li];
+    idx[li] = b.id1;
+    dist[li] = b.id1 == IMOMD_NONE ? INFINITY : haversine(P.g.lat[b.id1], P.g.lon[b.id1], nq.lat, nq.lon);
+    const double band = 2e-12 * b.v1 + 4e-15 * sqrt(b.v1);
+    ambiguous[li] = (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= band) ? 1u : 0u;
 }
 
 }  // namespace imomd

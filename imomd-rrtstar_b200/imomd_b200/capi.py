@@ -93,6 +93,8 @@ def cuda_lib():
         L.imomd_nearest.argtypes = [vp, C.c_int, C.c_void_p, u32p, f64p]
         L.imomd_nearest_batch.argtypes = [vp, C.c_int, C.c_void_p, u32p, f64p, C.POINTER(C.c_float),
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.imomd_nearest_batch_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                                      C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
         L.imomd_ctx_create.argtypes = [C.c_int, vpp]
         L.imomd_ctx_destroy.argtypes = [vp]
         L.imomd_ga_eval.argtypes = [vp, C.c_int, f64p, C.c_int, C.c_int, i32p, i32p, f64p]
@@ -316,14 +318,18 @@ class DevicePlanner:
 
 
 def nearest_batch(dp, lookups):
-    """imomd_nearest_batch: (idx, dist, dict(kernel_ms, bytes, refined))."""
+    """imomd_nearest_batch: (idx, dist, dict(kernel_ms, bytes, refined, prep_ms, merge_ms, segments))."""
     lk = np.ascontiguousarray(lookups, NN_DTYPE)
     n = lk.shape[0]
     idx = np.empty(n, np.uint32); dist = np.empty(n)
     ms, by, nr = C.c_float(), C.c_uint64(), C.c_uint32()
     _check(cuda_lib().imomd_nearest_batch(dp.h, n, lk.ctypes.data_as(C.c_void_p), idx, dist,
                                           C.byref(ms), C.byref(by), C.byref(nr)))
-    return idx, dist, dict(kernel_ms=ms.value, bytes=by.value, refined=nr.value)
+    prep, tiles, merge, nseg = C.c_float(), C.c_float(), C.c_float(), C.c_uint32()
+    _check(cuda_lib().imomd_nearest_batch_last_timing(dp.h, C.byref(prep), C.byref(tiles), C.byref(merge),
+                                                      C.byref(nseg)))
+    return idx, dist, dict(kernel_ms=ms.value, bytes=by.value, refined=nr.value, prep_ms=prep.value,
+                           merge_ms=merge.value, segments=nseg.value)
 
 
 class GaContext:

@@ -213,11 +213,16 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
 
 /* Same answers for LARGE batches: lookups are grouped into tiles of one frontier x 4 samples
  * and every frontier is streamed once per tile through a shared-memory ring filled by bulk
- * asynchronous copies (the bandwidth-shaped brute-force variant).  Optional outputs: device
- * time of the tile kernel, algorithmic bytes it streamed (32 B per frontier record per tile
- * + 36 B per lookup), number of lookups re-done on the exact path. */
+ * asynchronous copies of the occupied records (the bandwidth-shaped brute-force variant).
+ * Optional outputs: device time of the tile kernel, algorithmic bytes it streamed (32 B per
+ * occupied frontier record per tile + 8 B per chunk-list entry + 36 B per lookup), number of
+ * lookups re-done on the exact path. */
 int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* idx, double* dist,
                         float* kernel_ms, uint64_t* bytes_streamed, uint32_t* n_refined);
+/* Device times of the stages of the last imomd_nearest_batch call on this planner (chunk lists +
+ * seeds + segment scan, tile kernel, merge of the segment partials) and its number of segments. */
+int imomd_nearest_batch_last_timing(imomd_planner* p, float* prep_ms, float* tiles_ms, float* merge_ms,
+                                    uint32_t* n_segments);
 
 /* ---------------------------------------------------------------- ECI-Gen ---
  * EciGenSolver::calculatePathCost_ (src/eci_gen_tsp_solver.cpp:442-450) for a batch

@@ -222,6 +222,36 @@ def test_nearest_batch_tile_kernel_matches_exact_path():
     o.close(); dp.close(); dg.close()
 
 
+def test_nearest_batch_multi_segment_frontiers():
+    """frontiers of several hundred chunks: every tile is cut into several segments that different
+    CTAs rank; the merged answers equal the pruned exact path bit for bit and the oracle's indices"""
+    g = graphs.jittered_grid(400, seed=3)
+    K = 4
+    dests = [graphs.pick_destinations(g, K, seed=s) for s in (1, 2)]
+    dg = capi.DeviceGraph(g)
+    dp = capi.DevicePlanner(dg, dests)
+    dp.feed(capi.mt19937_words(0, 400000))
+    dp.expand(6000)
+    rng = np.random.default_rng(9)
+    n = 2 * K * 7                       # ragged: 7 lookups per frontier = tiles of 4 + 3
+    lk = np.empty(n, capi.NN_DTYPE)
+    lk["query"] = np.repeat(np.arange(2), K * 7); lk["tree"] = np.tile(np.repeat(np.arange(K), 7), 2)
+    lk["lat"] = rng.uniform(g.lat.min(), g.lat.max(), n); lk["lon"] = rng.uniform(g.lon.min(), g.lon.max(), n)
+    # a few samples that coincide with frontier vertices (distance 0) and with visited vertices
+    fr = dp.frontier(1, 0)
+    lk["lat"][:3] = g.lat[fr[:3].astype(np.int64)]; lk["lon"][:3] = g.lon[fr[:3].astype(np.int64)]
+    idx_a, dist_a = dp.nearest(lk)
+    idx_b, dist_b, info = capi.nearest_batch(dp, lk)
+    assert info["segments"] >= 2 * (2 * K * 2), info          # two or more segments per tile
+    assert np.array_equal(idx_a, idx_b)
+    assert np.array_equal(dist_a.view(np.uint64), dist_b.view(np.uint64))
+    o = ol.OraclePlanner(g, dests[0]); o.iterate(6000)
+    for i in range(0, K * 7):
+        ok, want, d, ties, _ = o.nearest(int(lk["tree"][i]), float(lk["lat"][i]), float(lk["lon"][i]))
+        assert int(idx_b[i]) == want
+    o.close(); dp.close(); dg.close()
+
+
 @pytest.mark.parametrize("width,hubs,spokes", [(40, 10, 3), (40, 14, 9)])
 def test_wide_adjacency_rows(width, hubs, spokes):
     """max degree 5..8 (8-slot kernels) and 9..13 (16-slot kernels)"""
