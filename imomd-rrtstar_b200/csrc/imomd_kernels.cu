@@ -490,7 +490,7 @@ cudaError_t dmalloc(T** p, size_t count)
 struct NnScratch
 {
     std::vector<void*> ptrs;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ~NnScratch()
     {
         for (void* x : ptrs) cudaFree(x);
@@ -1335,8 +1335,8 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaEventRecord(sc.ev[0], p->stream));
     k_tree_chunk_lists<<<QK, kListThreads, 0, p->stream>>>(p->d, lists, counts);
     CU(cudaGetLastError());
-    k_nn_seed<<<(n_tiles + 3) / 4, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, dq, lists, counts, seed,
-                                                        tile_valid, nseg);
+    k_nn_seed<<<n_tiles, kSeedThreads, 0, p->stream>>>(p->d, n_tiles, dtiles, dq, lists, counts, seed,
+                                                       tile_valid, nseg);
     CU(cudaGetLastError());
     k_nn_segments<<<1, 1024, 0, p->stream>>>(n_tiles, nseg, seg_start);
     CU(cudaGetLastError());
@@ -1346,6 +1346,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaStreamSynchronize(p->stream));
     CU(sc.get(&work, (size_t)n_work));
     CU(sc.get(&part, (size_t)n_work * kConsumerWarps * kTileLookups));
+    CU(cudaEventRecord(sc.ev[5], p->stream));
     k_nn_fill_work<<<(n_work + 127) / 128 + 1, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, lists, counts,
                                                                     seg_start, work);
     CU(cudaGetLastError());
@@ -1376,7 +1377,10 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaStreamSynchronize(p->stream));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, sc.ev[2], sc.ev[3]));
+    float fill_ms = 0.f;
     CU(cudaEventElapsedTime(&p->nn_prep_ms, sc.ev[0], sc.ev[1]));
+    CU(cudaEventElapsedTime(&fill_ms, sc.ev[5], sc.ev[2]));
+    p->nn_prep_ms += fill_ms;
     CU(cudaEventElapsedTime(&p->nn_merge_ms, sc.ev[3], sc.ev[4]));
     p->nn_tiles_ms = ms;
     p->nn_segments = n_work;

@@ -6,13 +6,19 @@
 // frontier lives in 1 KB chunks of 32 records (csrc/imomd_layout.h) of which only the first
 // `valid` are occupied.  The launch is cut into SEGMENTS of kSegChunks chunks of one tile
 // (k_nn_segments / k_nn_fill_work); persistent CTAs take segments from an atomic counter, so
-// the launch ends within one segment (~40 KB) of perfect balance whatever the frontier sizes.
-// Per CTA a producer warp streams the segment into a 3-stage shared-memory ring with bulk
-// asynchronous copies (cp.async.bulk ... mbarrier::complete_tx, the TMA engine): one copy per
-// chunk, of its VALID records only, packed back to back in the stage -- no padding crosses
-// the memory system and no consumer lane idles on an empty slot.  Four consumer warps rank the
-// staged records against the tile's samples and keep (best, lowest id on ties, runner-up) per
-// sample.  A record is first screened by its dot product with the sample (3 FP64 operations):
+// the launch ends within one segment (~40 KB) of perfect balance whatever the frontier sizes
+// (the counter's answer, the segment record and the first chunk ids of the next segment are
+// requested a segment / a stage ahead: no dependent global load sits between two stages).
+// Per CTA a producer warp streams the segment into a 3-stage shared-memory ring (8 KB = 256
+// records per stage) with bulk asynchronous copies (cp.async.bulk ... mbarrier::complete_tx,
+// the TMA engine): one copy per chunk, of its OCCUPIED records only, packed back to back in
+// the stage -- no padding crosses the memory system and no consumer lane idles on an empty
+// slot.  Two consumer warps rank the staged records against the tile's samples and keep (best,
+// lowest id on ties, runner-up) per sample.  The CTA is small on purpose (96 threads, 8 CTAs
+// per SM): a bulk copy is issued through the uniform datapath, one lane at a time (~10
+// instructions per copy), so the producer warp is the scarce resource -- one producer per two
+// consumer warps measured best (0.098 ms per launch against 0.120 ms with 1 : 4; ring depth
+// beyond 24 KB per CTA did not matter).  A record is first screened by its dot product with the sample (3 FP64 operations):
 // chord^2 = |v|^2 + |q|^2 - 2 v.q, so v.q < 1 - cap/2 - margin proves chord^2 > cap, where cap
 // is an upper bound of the runner-up (seeded by k_nn_seed from the first record of every
 // chunk, tightened by what the thread has seen); only survivors get the exact squared chord
@@ -34,12 +40,21 @@ namespace imomd {
 constexpr int kTileLookups = 4;        // samples per tile
 constexpr int kStageChunks = 16;       // at most this many chunks per pipeline stage (one producer lane each)
 constexpr int kStageRecs = 256;        // records per pipeline stage (8 KB)
-constexpr int kStages = 6;
+#ifndef IMOMD_NN_STAGES
+#define IMOMD_NN_STAGES 3
+#endif
+#ifndef IMOMD_NN_CW
+#define IMOMD_NN_CW 2
+#endif
+#ifndef IMOMD_NN_CTAS
+#define IMOMD_NN_CTAS 8
+#endif
+constexpr int kStages = IMOMD_NN_STAGES;
 constexpr int kSegChunks = 64;         // chunks per segment (work item)
 constexpr int kSegStagesMax = kSegChunks * IMOMD_CHUNK / kStageRecs;   // 8: a stage short of the end holds > 256 - 32 records or 16 chunks
-constexpr int kConsumerWarps = 4;
+constexpr int kConsumerWarps = IMOMD_NN_CW;
 constexpr int kTileThreads = 32 * (kConsumerWarps + 1);   // warp 0 = producer
-constexpr int kTileCtasPerSm = 4;
+constexpr int kTileCtasPerSm = IMOMD_NN_CTAS;
 constexpr double kDotMargin = 1e-14;   // >= 4x the rounding of |v|^2, |q|^2 and the dot product
 
 struct NnTile
@@ -191,87 +206,95 @@ __device__ __forceinline__ Best warp_best(Best x)
     return x;
 }
 
-// one warp per tile: unit vectors of the samples, runner-up bound from the first record of
-// every chunk (a spatially uniform subsample of the frontier: the chunks follow the hash
-// cells), occupied records and segments of the tile
-__global__ void k_nn_seed(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
-                          const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
-                          const uint32_t* __restrict__ counts, NnSeed* __restrict__ seed,
-                          uint32_t* __restrict__ tile_valid, uint32_t* __restrict__ nseg)
+// one CTA per tile: unit vectors of the samples, runner-up bound from the first record of every
+// chunk (a spatially uniform subsample of the frontier: the chunks follow the hash cells; the
+// tile kernel finds these sectors in L2 afterwards), occupied records and segments of the tile
+constexpr int kSeedThreads = 128;
+__global__ void __launch_bounds__(kSeedThreads)
+k_nn_seed(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
+          const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
+          const uint32_t* __restrict__ counts, NnSeed* __restrict__ seed, uint32_t* __restrict__ tile_valid,
+          uint32_t* __restrict__ nseg)
 {
-    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (tile >= n_tiles) return;
+    __shared__ double q[3][kTileLookups];
+    __shared__ Best part[kSeedThreads / 32][kTileLookups];
+    __shared__ uint32_t part_valid[kSeedThreads / 32];
+    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const NnTile t = tiles[tile];
-    double mx = 0, my = 0, mz = 0;
-    if (lane < t.n)
+    const uint32_t n_chunks = counts[t.qt];
+    const uint32_t* list = lists + (size_t)t.qt * 2 * P.chunks;
+    const VRec* rec = P.rec + (size_t)t.qt * (size_t)P.chunks * IMOMD_CHUNK;
+    // the first chunk of this thread is requested while the samples are being prepared
+    uint2 e = make_uint2(IMOMD_NONE, 0u);
+    VRec v;
+    if (threadIdx.x < n_chunks)
     {
-        imomd_nn_query nq = qs[t.lookup[lane]];
-        double la = nq.lat * kDeg2Rad, lo = nq.lon * kDeg2Rad;
-        double cl = cos(la);
-        mx = cl * cos(lo);
-        my = cl * sin(lo);
-        mz = sin(la);
+        e = *reinterpret_cast<const uint2*>(list + 2 * threadIdx.x);
+        v = rec[(size_t)e.x * IMOMD_CHUNK];
     }
+    if (threadIdx.x < kTileLookups)
+    {
+        double mx = 0, my = 0, mz = 0;
+        if ((int)threadIdx.x < t.n)
+        {
+            imomd_nn_query nq = qs[t.lookup[threadIdx.x]];
+            double la = nq.lat * kDeg2Rad, lo = nq.lon * kDeg2Rad;
+            double cl = cos(la);
+            mx = cl * cos(lo);
+            my = cl * sin(lo);
+            mz = sin(la);
+        }
+        q[0][threadIdx.x] = mx;
+        q[1][threadIdx.x] = my;
+        q[2][threadIdx.x] = mz;
+    }
+    __syncthreads();
     double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
     Best b[kTileLookups];
 #pragma unroll
     for (int l = 0; l < kTileLookups; ++l)
     {
-        qx[l] = __shfl_sync(0xFFFFFFFFu, mx, l);
-        qy[l] = __shfl_sync(0xFFFFFFFFu, my, l);
-        qz[l] = __shfl_sync(0xFFFFFFFFu, mz, l);
+        qx[l] = q[0][l];
+        qy[l] = q[1][l];
+        qz[l] = q[2][l];
         b[l] = best_empty();
     }
-    const uint32_t n_chunks = counts[t.qt];
-    const uint32_t* list = lists + (size_t)t.qt * 2 * P.chunks;
-    const VRec* rec = P.rec + (size_t)t.qt * (size_t)P.chunks * IMOMD_CHUNK;
     uint32_t valid = 0;
-    // four chunks per lane and round: the list entries, then the records, are requested together
-    for (uint32_t base = lane; base < n_chunks; base += 128)
+    for (uint32_t i = threadIdx.x; i < n_chunks; i += kSeedThreads)
     {
-        uint2 e[4];
-        VRec v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
+        if (i != threadIdx.x)
         {
-            const uint32_t i = base + 32 * j;
-            e[j] = i < n_chunks ? *reinterpret_cast<const uint2*>(list + 2 * i) : make_uint2(IMOMD_NONE, 0u);
+            e = *reinterpret_cast<const uint2*>(list + 2 * i);
+            v = rec[(size_t)e.x * IMOMD_CHUNK];
         }
+        valid += e.y;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (e[j].y) v[j] = rec[(size_t)e[j].x * IMOMD_CHUNK];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-            valid += e[j].y;
-            if (e[j].y)
-            {
-#pragma unroll
-                for (int l = 0; l < kTileLookups; ++l)
-                    best_add(b[l], chord2(v[j], qx[l], qy[l], qz[l]), v[j].id);
-            }
-        }
+        for (int l = 0; l < kTileLookups; ++l) best_add(b[l], chord2(v, qx[l], qy[l], qz[l]), v.id);
     }
     for (int off = 16; off > 0; off >>= 1) valid += __shfl_down_sync(0xFFFFFFFFu, valid, off);
-    double ub = INFINITY;
 #pragma unroll
     for (int l = 0; l < kTileLookups; ++l)
     {
         Best x = warp_best(b[l]);
-        double u = __shfl_sync(0xFFFFFFFFu, x.v2, 0);
-        if (lane == l) ub = u;
+        if (lane == 0) part[warp][l] = x;
     }
-    if (lane < kTileLookups)
+    if (lane == 0) part_valid[warp] = valid;
+    __syncthreads();
+    if (threadIdx.x < kTileLookups)
     {
-        seed[tile].qx[lane] = mx;
-        seed[tile].qy[lane] = my;
-        seed[tile].qz[lane] = mz;
-        seed[tile].ub[lane] = ub;
+        Best x = part[0][threadIdx.x];
+        for (int w = 1; w < kSeedThreads / 32; ++w) x = best_merge(x, part[w][threadIdx.x]);
+        seed[tile].qx[threadIdx.x] = q[0][threadIdx.x];
+        seed[tile].qy[threadIdx.x] = q[1][threadIdx.x];
+        seed[tile].qz[threadIdx.x] = q[2][threadIdx.x];
+        seed[tile].ub[threadIdx.x] = x.v2;
     }
-    if (lane == 0)
+    if (threadIdx.x == 0)
     {
-        tile_valid[tile] = valid;
+        uint32_t all = 0;
+        for (int w = 0; w < kSeedThreads / 32; ++w) all += part_valid[w];
+        tile_valid[tile] = all;
         nseg[tile] = (n_chunks + kSegChunks - 1) / kSegChunks;
     }
 }
@@ -396,7 +419,7 @@ struct NnStageMeta
 
 struct __align__(16) NnShared
 {
-    VRec stage[kStages][kStageRecs];                   // 6 x 8 KB
+    VRec stage[kStages][kStageRecs];                   // 3 x 8 KB
     NnSeed seed[kStages];                              // meaningful in a segment's first stage
     double cur[kConsumerWarps][3 * kTileLookups];      // samples of the segment a consumer warp is in
     NnStageMeta meta[kStages];

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_CUDA = os.path.join(PKG, "lib", "libimomd_b200.so")
+# IMOMD_B200_LIB: developer override (kernel variants built by tools/); the product path is lib/
+LIB_CUDA = os.environ.get("IMOMD_B200_LIB") or os.path.join(PKG, "lib", "libimomd_b200.so")
 LIB_HOST = os.path.join(PKG, "lib", "libimomd_host.so")
 
 NONE = 0xFFFFFFFF
