@@ -473,7 +473,7 @@ def b200_arm(args):
                                "note": "imomd_nearest_batch, 4 samples per frontier, best of 5 launches; "
                                        "frontier records total larger than L2; algorithmic bytes = 32 B per "
                                        "OCCUPIED frontier record + 8 B per chunk-list entry + 36 B per lookup; "
-                                       "prep_ms = chunk lists + seeds + segment scan + segment records, merge_ms = fold of the "
+                                       "prep_ms = chunk lists + seeds + segment records, merge_ms = fold of the "
                                        "segment partials (device times of the same call)"}
     except Exception as ex:  # the headline line must survive a failure of the side measurement
         line["roofline_nn"] = {"error": str(ex)}

@@ -1303,8 +1303,12 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     }
     NnScratch sc;
     const int n_tiles = (int)tiles.size();
+    // tiles are sorted by tree: [tile_begin[qt], tile_begin[qt + 1]) are the tiles of tree qt
+    std::vector<uint32_t> tile_begin((size_t)QK + 1, 0u);
+    for (const NnTile& t : tiles) ++tile_begin[(size_t)t.qt + 1];
+    for (int i = 0; i < QK; ++i) tile_begin[(size_t)i + 1] += tile_begin[i];
     uint32_t *lists = nullptr, *counts = nullptr, *didx = nullptr, *damb = nullptr, *tile_valid = nullptr,
-             *nseg = nullptr, *seg_start = nullptr, *next_work = nullptr;
+             *seg_start = nullptr, *next_work = nullptr, *n_work_dev = nullptr, *dbegin = nullptr;
     double* ddist = nullptr;
     imomd_nn_query* dq = nullptr;
     NnTile* dtiles = nullptr;
@@ -1320,35 +1324,34 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(sc.get(&ddist, (size_t)n));
     CU(sc.get(&dq, (size_t)n));
     CU(sc.get(&dtiles, (size_t)n_tiles));
+    CU(sc.get(&dbegin, (size_t)QK + 1));
     CU(sc.get(&seed, (size_t)n_tiles));
     CU(sc.get(&tile_valid, (size_t)n_tiles));
-    CU(sc.get(&nseg, (size_t)n_tiles));
-    CU(sc.get(&seg_start, (size_t)n_tiles + 1));
-    CU(sc.get(&next_work, 1));
+    CU(sc.get(&seg_start, (size_t)n_tiles));
+    CU(sc.get(&next_work, 2));
+    n_work_dev = next_work + 1;
     CU(sc.get(&derr, 1));
     CU(cudaMemsetAsync(derr, 0, sizeof(int), p->stream));
-    CU(cudaMemsetAsync(next_work, 0, sizeof(uint32_t), p->stream));
+    CU(cudaMemsetAsync(next_work, 0, 2 * sizeof(uint32_t), p->stream));
+    CU(cudaMemsetAsync(counts, 0, (size_t)QK * sizeof(uint32_t), p->stream));
     CU(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(imomd_nn_query), cudaMemcpyHostToDevice, p->stream));
     CU(cudaMemcpyAsync(dtiles, tiles.data(), tiles.size() * sizeof(NnTile), cudaMemcpyHostToDevice,
                        p->stream));
-    // preparation: chunk lists of the trees, seeds and segment counts of the tiles, segment scan
+    CU(cudaMemcpyAsync(dbegin, tile_begin.data(), tile_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                       p->stream));
+    // preparation: chunk lists of the trees, seeds and segment ranges of the tiles in one launch
     CU(cudaEventRecord(sc.ev[0], p->stream));
-    k_tree_chunk_lists<<<QK, kListThreads, 0, p->stream>>>(p->d, lists, counts);
-    CU(cudaGetLastError());
-    k_nn_seed<<<n_tiles, kSeedThreads, 0, p->stream>>>(p->d, n_tiles, dtiles, dq, lists, counts, seed,
-                                                       tile_valid, nseg);
-    CU(cudaGetLastError());
-    k_nn_segments<<<1, 1024, 0, p->stream>>>(n_tiles, nseg, seg_start);
+    k_nn_prepare<<<QK, kPrepThreads, 0, p->stream>>>(p->d, dbegin, dtiles, dq, lists, counts, seed, tile_valid,
+                                                     seg_start, n_work_dev);
     CU(cudaGetLastError());
     CU(cudaEventRecord(sc.ev[1], p->stream));
     uint32_t n_work = 0;
-    CU(cudaMemcpyAsync(&n_work, seg_start + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(&n_work, n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     CU(sc.get(&work, (size_t)n_work));
     CU(sc.get(&part, (size_t)n_work * kConsumerWarps * kTileLookups));
     CU(cudaEventRecord(sc.ev[5], p->stream));
-    k_nn_fill_work<<<(n_work + 127) / 128 + 1, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, lists, counts,
-                                                                    seg_start, work);
+    k_nn_fill_work<<<(n_tiles + 3) / 4, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, lists, counts, seg_start, work);
     CU(cudaGetLastError());
     // the tile kernel: persistent CTAs over the segments
     const size_t smem = sizeof(NnShared) + 128;
@@ -1357,13 +1360,13 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     if (n_work > 0)
     {
         const int grid = (int)std::min<size_t>(n_work, (size_t)148 * kTileCtasPerSm);
-        k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, dtiles, seed, work, seg_start + n_tiles,
-                                                                 next_work, lists, part, derr);
+        k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, dtiles, seed, work, n_work_dev, next_work,
+                                                                 lists, part, derr);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(sc.ev[3], p->stream));
     k_nn_merge<<<(n_tiles * kTileLookups + 255) / 256, 256, 0, p->stream>>>(p->d, n_tiles, dtiles, dq, seg_start,
-                                                                            part, didx, ddist, damb);
+                                                                            counts, part, didx, ddist, damb);
     CU(cudaGetLastError());
     CU(cudaEventRecord(sc.ev[4], p->stream));
     std::vector<uint32_t> amb(n), hcounts(QK), hvalid(n_tiles);

@@ -5,7 +5,7 @@
 // A tile = one (query, tree) frontier and up to kTileLookups (4) samples against it.  The
 // frontier lives in 1 KB chunks of 32 records (csrc/imomd_layout.h) of which only the first
 // `valid` are occupied.  The launch is cut into SEGMENTS of kSegChunks chunks of one tile
-// (k_nn_segments / k_nn_fill_work); persistent CTAs take segments from an atomic counter, so
+// (k_nn_prepare / k_nn_fill_work); persistent CTAs take segments from an atomic counter, so
 // the launch ends within one segment (~40 KB) of perfect balance whatever the frontier sizes
 // (the counter's answer, the segment record and the first chunk ids of the next segment are
 // requested a segment / a stage ahead: no dependent global load sits between two stages).
@@ -20,7 +20,7 @@
 // consumer warps measured best (0.098 ms per launch against 0.120 ms with 1 : 4; ring depth
 // beyond 24 KB per CTA did not matter).  A record is first screened by its dot product with the sample (3 FP64 operations):
 // chord^2 = |v|^2 + |q|^2 - 2 v.q, so v.q < 1 - cap/2 - margin proves chord^2 > cap, where cap
-// is an upper bound of the runner-up (seeded by k_nn_seed from the first record of every
+// is an upper bound of the runner-up (seeded by k_nn_prepare from the first record of every
 // chunk, tightened by what the thread has seen); only survivors get the exact squared chord
 // of the pruned path.  The screen never changes an answer: every record whose chord^2 does
 // not exceed the final runner-up passes it.  Full/empty mbarriers hand the stages back and
@@ -64,7 +64,7 @@ struct NnTile
     int32_t lookup[kTileLookups];
 };
 
-// per tile, written by k_nn_seed: unit vectors of the samples and an upper bound of each
+// per tile, written by k_nn_prepare: unit vectors of the samples and an upper bound of each
 // sample's runner-up chord^2 (unused sample slots: zero vector, bound 1 -> always screened out)
 struct __align__(16) NnSeed
 {
@@ -129,63 +129,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
-// flat (chunk id, occupied records) list of every tree: one CTA per tree, one thread per occupied
-// cell walks the cell's chunk chain (the dependent loads of 128 chains overlap)
-constexpr int kListThreads = 128;
-__global__ void __launch_bounds__(kListThreads)
-k_tree_chunk_lists(const __grid_constant__ PlannerDev P, uint32_t* lists, uint32_t* counts)
-{
-    __shared__ uint32_t warp_sum[kListThreads / 32];
-    const int qt = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = qt / P.K, k = qt % P.K;
-    TreeRef T = tree_ref(P, q, k);
-    const uint32_t n_occ = P.query[q].n_occ[k];
-    uint32_t* out = lists + (size_t)qt * 2 * P.chunks;
-    uint32_t total = 0;
-    for (uint32_t base = 0; base < n_occ; base += kListThreads)
-    {
-        const uint32_t i = base + threadIdx.x;
-        uint32_t cnt = 0, head = IMOMD_NONE, nch = 0;
-        if (i < n_occ)
-        {
-            const uint32_t c = T.occ[i];
-            cnt = T.cell_cnt[c];
-            head = T.cell_head[c];
-            nch = (cnt + IMOMD_CHUNK - 1) / IMOMD_CHUNK;
-        }
-        uint32_t inc = nch;
-        for (int off = 1; off < 32; off <<= 1)
-        {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
-            if (lane >= off) inc += t;
-        }
-        if (lane == 31) warp_sum[warp] = inc;
-        __syncthreads();
-        uint32_t before = 0, all = 0;
-#pragma unroll
-        for (int w = 0; w < kListThreads / 32; ++w)
-        {
-            const uint32_t x = warp_sum[w];
-            if (w < warp) before += x;
-            all += x;
-        }
-        __syncthreads();
-        const uint32_t at = total + before + inc - nch;
-        uint32_t n = cnt ? (cnt - 1) % IMOMD_CHUNK + 1 : 0;
-        uint32_t chunk = head;
-        for (uint32_t j = 0; j < nch; ++j)
-        {
-            out[2 * (at + j)] = chunk;
-            out[2 * (at + j) + 1] = n;
-            n = IMOMD_CHUNK;
-            chunk = T.chunk_next[chunk];
-        }
-        total += all;
-    }
-    if (threadIdx.x == 0) counts[qt] = total;
-}
-
 __device__ __forceinline__ double chord2(const VRec& v, double qx, double qy, double qz)
 {
     double dx = v.x - qx, dy = v.y - qy, dz = v.z - qz;
@@ -206,33 +149,28 @@ __device__ __forceinline__ Best warp_best(Best x)
     return x;
 }
 
-// one CTA per tile: unit vectors of the samples, runner-up bound from the first record of every
-// chunk (a spatially uniform subsample of the frontier: the chunks follow the hash cells; the
-// tile kernel finds these sectors in L2 afterwards), occupied records and segments of the tile
-constexpr int kSeedThreads = 128;
-__global__ void __launch_bounds__(kSeedThreads)
-k_nn_seed(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
-          const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ lists,
-          const uint32_t* __restrict__ counts, NnSeed* __restrict__ seed, uint32_t* __restrict__ tile_valid,
-          uint32_t* __restrict__ nseg)
+// ---- preparation, one CTA per tree that has lookups ------------------------------------------
+// (1) flat (chunk id, occupied records) list of the tree: one thread per occupied cell walks the
+//     cell's chunk chain (the dependent loads of 128 chains overlap);
+// (2) per tile of the tree: unit vectors of the samples and an upper bound of each sample's
+//     runner-up chord^2 from the FIRST record of every chunk (a spatially uniform subsample of
+//     the frontier: the chunks follow the hash cells; the tile kernel finds these sectors in L2
+//     afterwards).  For the tree's first tile the records are requested inside the chain walk,
+//     right when a chunk id is known; further tiles (more than 4 lookups on one frontier) re-read
+//     the heads through the list;
+// (3) the tile's segments are reserved with one atomicAdd (their order does not matter).
+constexpr int kPrepThreads = 128;
+
+struct NnPrepShared
 {
-    __shared__ double q[3][kTileLookups];
-    __shared__ Best part[kSeedThreads / 32][kTileLookups];
-    __shared__ uint32_t part_valid[kSeedThreads / 32];
-    const int tile = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const NnTile t = tiles[tile];
-    const uint32_t n_chunks = counts[t.qt];
-    const uint32_t* list = lists + (size_t)t.qt * 2 * P.chunks;
-    const VRec* rec = P.rec + (size_t)t.qt * (size_t)P.chunks * IMOMD_CHUNK;
-    // the first chunk of this thread is requested while the samples are being prepared
-    uint2 e = make_uint2(IMOMD_NONE, 0u);
-    VRec v;
-    if (threadIdx.x < n_chunks)
-    {
-        e = *reinterpret_cast<const uint2*>(list + 2 * threadIdx.x);
-        v = rec[(size_t)e.x * IMOMD_CHUNK];
-    }
+    double q[3][kTileLookups];
+    Best part[kPrepThreads / 32][kTileLookups];
+    uint32_t warp_sum[kPrepThreads / 32];
+};
+
+__device__ __forceinline__ void nn_prep_samples(NnPrepShared& sh, const NnTile& t,
+                                                const imomd_nn_query* __restrict__ qs)
+{
     if (threadIdx.x < kTileLookups)
     {
         double mx = 0, my = 0, mz = 0;
@@ -245,144 +183,196 @@ k_nn_seed(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __res
             my = cl * sin(lo);
             mz = sin(la);
         }
-        q[0][threadIdx.x] = mx;
-        q[1][threadIdx.x] = my;
-        q[2][threadIdx.x] = mz;
+        sh.q[0][threadIdx.x] = mx;
+        sh.q[1][threadIdx.x] = my;
+        sh.q[2][threadIdx.x] = mz;
     }
-    __syncthreads();
-    double qx[kTileLookups], qy[kTileLookups], qz[kTileLookups];
-    Best b[kTileLookups];
-#pragma unroll
-    for (int l = 0; l < kTileLookups; ++l)
-    {
-        qx[l] = q[0][l];
-        qy[l] = q[1][l];
-        qz[l] = q[2][l];
-        b[l] = best_empty();
-    }
-    uint32_t valid = 0;
-    for (uint32_t i = threadIdx.x; i < n_chunks; i += kSeedThreads)
-    {
-        if (i != threadIdx.x)
-        {
-            e = *reinterpret_cast<const uint2*>(list + 2 * i);
-            v = rec[(size_t)e.x * IMOMD_CHUNK];
-        }
-        valid += e.y;
-#pragma unroll
-        for (int l = 0; l < kTileLookups; ++l) best_add(b[l], chord2(v, qx[l], qy[l], qz[l]), v.id);
-    }
-    for (int off = 16; off > 0; off >>= 1) valid += __shfl_down_sync(0xFFFFFFFFu, valid, off);
+}
+
+// block reduction of the per-thread bounds, seed record and segment reservation of one tile
+__device__ __forceinline__ void nn_prep_finish(NnPrepShared& sh, int tile, Best* b, uint32_t n_chunks,
+                                               uint32_t n_valid, NnSeed* __restrict__ seed,
+                                               uint32_t* __restrict__ tile_valid, uint32_t* __restrict__ seg_start,
+                                               uint32_t* __restrict__ n_work)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int l = 0; l < kTileLookups; ++l)
     {
         Best x = warp_best(b[l]);
-        if (lane == 0) part[warp][l] = x;
+        if (lane == 0) sh.part[warp][l] = x;
     }
-    if (lane == 0) part_valid[warp] = valid;
     __syncthreads();
     if (threadIdx.x < kTileLookups)
     {
-        Best x = part[0][threadIdx.x];
-        for (int w = 1; w < kSeedThreads / 32; ++w) x = best_merge(x, part[w][threadIdx.x]);
-        seed[tile].qx[threadIdx.x] = q[0][threadIdx.x];
-        seed[tile].qy[threadIdx.x] = q[1][threadIdx.x];
-        seed[tile].qz[threadIdx.x] = q[2][threadIdx.x];
+        Best x = sh.part[0][threadIdx.x];
+        for (int w = 1; w < kPrepThreads / 32; ++w) x = best_merge(x, sh.part[w][threadIdx.x]);
+        seed[tile].qx[threadIdx.x] = sh.q[0][threadIdx.x];
+        seed[tile].qy[threadIdx.x] = sh.q[1][threadIdx.x];
+        seed[tile].qz[threadIdx.x] = sh.q[2][threadIdx.x];
         seed[tile].ub[threadIdx.x] = x.v2;
     }
     if (threadIdx.x == 0)
     {
-        uint32_t all = 0;
-        for (int w = 0; w < kSeedThreads / 32; ++w) all += part_valid[w];
-        tile_valid[tile] = all;
-        nseg[tile] = (n_chunks + kSegChunks - 1) / kSegChunks;
+        tile_valid[tile] = n_valid;
+        seg_start[tile] = atomicAdd(n_work, (n_chunks + kSegChunks - 1) / kSegChunks);
     }
+    __syncthreads();
 }
 
-// exclusive scan of the segment counts (one CTA): seg_start[0 .. n_tiles], total last
-__global__ void __launch_bounds__(1024) k_nn_segments(int n_tiles, const uint32_t* __restrict__ nseg,
-                                                      uint32_t* __restrict__ seg_start)
+__global__ void __launch_bounds__(kPrepThreads)
+k_nn_prepare(const __grid_constant__ PlannerDev P, const uint32_t* __restrict__ tile_begin,
+             const NnTile* __restrict__ tiles, const imomd_nn_query* __restrict__ qs, uint32_t* lists,
+             uint32_t* counts, NnSeed* __restrict__ seed, uint32_t* __restrict__ tile_valid,
+             uint32_t* __restrict__ seg_start, uint32_t* __restrict__ n_work)
 {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
+    __shared__ NnPrepShared sh;
+    const int qt = blockIdx.x;
+    const uint32_t t0 = tile_begin[qt], t1 = tile_begin[qt + 1];
+    if (t0 == t1) return;                               // no lookup on this tree
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n_tiles; base += 1024)
+    const int q = qt / P.K, k = qt % P.K;
+    TreeRef T = tree_ref(P, q, k);
+    const uint32_t n_occ = P.query[q].n_occ[k];
+    uint32_t* out = lists + (size_t)qt * 2 * P.chunks;
+    const VRec* rec = P.rec + (size_t)qt * (size_t)P.chunks * IMOMD_CHUNK;
+    // the first batch of cells is requested while the samples are being prepared
+    uint32_t cnt = 0, head = IMOMD_NONE;
+    if (threadIdx.x < n_occ)
     {
-        const int i = base + threadIdx.x;
-        const uint32_t x = i < n_tiles ? nseg[i] : 0u;
-        uint32_t inc = x;
+        const uint32_t c = T.occ[threadIdx.x];
+        cnt = T.cell_cnt[c];
+        head = T.cell_head[c];
+    }
+    nn_prep_samples(sh, tiles[t0], qs);
+    __syncthreads();
+    Best b[kTileLookups];
+#pragma unroll
+    for (int l = 0; l < kTileLookups; ++l) b[l] = best_empty();
+    uint32_t total = 0, n_valid = 0;
+    for (uint32_t base = 0; base < n_occ; base += kPrepThreads)
+    {
+        const uint32_t i = base + threadIdx.x;
+        if (base > 0)
+        {
+            cnt = 0;
+            head = IMOMD_NONE;
+            if (i < n_occ)
+            {
+                const uint32_t c = T.occ[i];
+                cnt = T.cell_cnt[c];
+                head = T.cell_head[c];
+            }
+        }
+        const uint32_t nch = (cnt + IMOMD_CHUNK - 1) / IMOMD_CHUNK;
+        uint32_t inc = nch, vinc = cnt;
         for (int off = 1; off < 32; off <<= 1)
         {
             uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
             if (lane >= off) inc += t;
         }
-        if (lane == 31) warp_sum[warp] = inc;
+        for (int off = 16; off > 0; off >>= 1) vinc += __shfl_down_sync(0xFFFFFFFFu, vinc, off);
+        if (lane == 31) sh.warp_sum[warp] = inc;
         __syncthreads();
-        if (warp == 0)
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < kPrepThreads / 32; ++w)
         {
-            uint32_t w = warp_sum[lane], winc = w;
-            for (int off = 1; off < 32; off <<= 1)
-            {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, off);
-                if (lane >= off) winc += t;
-            }
-            warp_sum[lane] = winc - w;
+            const uint32_t x = sh.warp_sum[w];
+            if (w < warp) before += x;
+            all += x;
         }
         __syncthreads();
-        const uint32_t excl = carry + warp_sum[warp] + inc - x;
-        if (i < n_tiles) seg_start[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + x;
-        __syncthreads();
+        if (lane == 0) n_valid += vinc;                 // per-warp partial, folded below
+        const uint32_t at = total + before + inc - nch;
+        uint32_t n = cnt ? (cnt - 1) % IMOMD_CHUNK + 1 : 0;
+        uint32_t chunk = head;
+        for (uint32_t j = 0; j < nch; ++j)
+        {
+            const VRec v = rec[(size_t)chunk * IMOMD_CHUNK];
+            const uint32_t nxt = j + 1 < nch ? T.chunk_next[chunk] : IMOMD_NONE;
+            out[2 * (at + j)] = chunk;
+            out[2 * (at + j) + 1] = n;
+#pragma unroll
+            for (int l = 0; l < kTileLookups; ++l)
+                best_add(b[l], chord2(v, sh.q[0][l], sh.q[1][l], sh.q[2][l]), v.id);
+            n = IMOMD_CHUNK;
+            chunk = nxt;
+        }
+        total += all;
     }
-    if (threadIdx.x == 0) seg_start[n_tiles] = carry;
+    // occupied records of the tree
+    if (lane == 0) sh.warp_sum[warp] = n_valid;
+    __syncthreads();
+    n_valid = 0;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) n_valid += sh.warp_sum[w];
+    if (threadIdx.x == 0) counts[qt] = total;
+    nn_prep_finish(sh, (int)t0, b, total, n_valid, seed, tile_valid, seg_start, n_work);
+    // further tiles of the same frontier: the heads again, through the list written above
+    for (uint32_t tile = t0 + 1; tile < t1; ++tile)
+    {
+        nn_prep_samples(sh, tiles[tile], qs);
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < kTileLookups; ++l) b[l] = best_empty();
+        for (uint32_t i = threadIdx.x; i < total; i += kPrepThreads)
+        {
+            const VRec v = rec[(size_t)out[2 * i] * IMOMD_CHUNK];
+#pragma unroll
+            for (int l = 0; l < kTileLookups; ++l)
+                best_add(b[l], chord2(v, sh.q[0][l], sh.q[1][l], sh.q[2][l]), v.id);
+        }
+        nn_prep_finish(sh, (int)tile, b, total, n_valid, seed, tile_valid, seg_start, n_work);
+    }
 }
 
-// one thread per segment slot of a tile: greedy packing of its chunks into stages
+// one warp per tile: the tile's segments, each packed greedily into stages of <= kStageRecs
+// occupied records and <= kStageChunks chunks (prefix sums + ballots)
 __global__ void k_nn_fill_work(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
                                const uint32_t* __restrict__ lists, const uint32_t* __restrict__ counts,
                                const uint32_t* __restrict__ seg_start, NnWork* __restrict__ work)
 {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_work = seg_start[n_tiles];
-    if (w >= n_work) return;
-    // tile of this segment: last tile whose first segment is <= w
-    int lo = 0, hi = n_tiles - 1;
-    while (lo < hi)
-    {
-        int mid = (lo + hi + 1) >> 1;
-        if (seg_start[mid] <= w)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    const int tile = lo;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
     const int32_t qt = tiles[tile].qt;
     const uint32_t n_chunks = counts[qt];
-    NnWork x;
-    x.tile = tile;
-    x.qt = qt;
-    x.chunk0 = (w - seg_start[tile]) * kSegChunks;
-    const uint32_t n = min((uint32_t)kSegChunks, n_chunks - x.chunk0);
-    const uint32_t* list = lists + (size_t)qt * 2 * P.chunks + 2 * (size_t)x.chunk0;
-    for (int j = 0; j < 12; ++j) x.stage[j] = 0;
-    uint32_t ns = 0, first = 0, recs = 0;
-    for (uint32_t i = 0; i < n; ++i)
+    const uint32_t w0 = seg_start[tile];
+    const uint32_t* list = lists + (size_t)qt * 2 * P.chunks;
+    for (uint32_t chunk0 = 0, w = w0; chunk0 < n_chunks; chunk0 += kSegChunks, ++w)
     {
-        const uint32_t v = list[2 * i + 1];
-        if (recs + v > (uint32_t)kStageRecs || i - first == (uint32_t)kStageChunks)
+        const uint32_t n = min((uint32_t)kSegChunks, n_chunks - chunk0);
+        uint32_t p0 = (uint32_t)lane < n ? list[2 * (chunk0 + lane) + 1] : 0u;
+        uint32_t p1 = (uint32_t)lane + 32 < n ? list[2 * (chunk0 + 32 + lane) + 1] : 0u;
+        for (int off = 1; off < 32; off <<= 1)
         {
-            x.stage[ns++] = first | ((i - first) << 7);
-            first = i;
-            recs = 0;
+            uint32_t a = __shfl_up_sync(0xFFFFFFFFu, p0, off), c = __shfl_up_sync(0xFFFFFFFFu, p1, off);
+            if (lane >= off)
+            {
+                p0 += a;
+                p1 += c;
+            }
         }
-        recs += v;
+        p1 += __shfl_sync(0xFFFFFFFFu, p0, 31);          // inclusive prefix over the 64 entries
+        uint32_t word = lane == 0 ? (uint32_t)tile : lane == 1 ? (uint32_t)qt : lane == 2 ? chunk0 : 0u;
+        uint32_t first = 0, base = 0, ns = 0;
+        while (first < n)
+        {
+            const uint32_t i0 = lane, i1 = lane + 32;
+            const bool in0 = i0 >= first && i0 < first + kStageChunks && i0 < n && p0 - base <= (uint32_t)kStageRecs;
+            const bool in1 = i1 >= first && i1 < first + kStageChunks && i1 < n && p1 - base <= (uint32_t)kStageRecs;
+            const uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, in0)) + __popc(__ballot_sync(0xFFFFFFFFu, in1));
+            if (lane == 4 + (int)ns) word = first | (cnt << 7);
+            const uint32_t last = first + cnt - 1;
+            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, p0, last & 31), b1 = __shfl_sync(0xFFFFFFFFu, p1, last & 31);
+            base = last < 32 ? b0 : b1;
+            first += cnt;
+            ++ns;
+        }
+        if (lane == 3) word = ns;
+        if (lane < 16) reinterpret_cast<uint32_t*>(work + w)[lane] = word;
     }
-    x.stage[ns++] = first | ((n - first) << 7);
-    x.n_stages = ns;
-    work[w] = x;
 }
 
 // Rare path of the consumers (a few percent of the records): exact squared chord of a record
@@ -642,7 +632,8 @@ k_nearest_tiles(const __grid_constant__ PlannerDev P, const NnTile* __restrict__
 // one thread per (tile, sample): fold the segment partials, write the answer
 __global__ void k_nn_merge(const __grid_constant__ PlannerDev P, int n_tiles, const NnTile* __restrict__ tiles,
                            const imomd_nn_query* __restrict__ qs, const uint32_t* __restrict__ seg_start,
-                           const Best* __restrict__ part, uint32_t* __restrict__ idx,
+                           const uint32_t* __restrict__ counts, const Best* __restrict__ part,
+                           uint32_t* __restrict__ idx,
                            double* __restrict__ dist, uint32_t* __restrict__ ambiguous)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -651,7 +642,7 @@ __global__ void k_nn_merge(const __grid_constant__ PlannerDev P, int n_tiles, co
     const NnTile t = tiles[tile];
     if (l >= t.n) return;
     Best b = best_empty();
-    const uint32_t w0 = seg_start[tile], w1 = seg_start[tile + 1];
+    const uint32_t w0 = seg_start[tile], w1 = w0 + (counts[t.qt] + kSegChunks - 1) / kSegChunks;
     for (uint32_t w = w0; w < w1; ++w)
         for (int cw = 0; cw < kConsumerWarps; ++cw)
             b = best_merge(b, part[((size_t)w * kConsumerWarps + cw) * kTileLookups + l]);

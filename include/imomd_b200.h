@@ -220,7 +220,7 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
 int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* idx, double* dist,
                         float* kernel_ms, uint64_t* bytes_streamed, uint32_t* n_refined);
 /* Device times of the stages of the last imomd_nearest_batch call on this planner (chunk lists +
- * seeds + segment scan + segment records, tile kernel, merge of the segment partials) and its number of segments. */
+ * seeds + segment records, tile kernel, merge of the segment partials) and its number of segments. */
 int imomd_nearest_batch_last_timing(imomd_planner* p, float* prep_ms, float* tiles_ms, float* merge_ms,
                                     uint32_t* n_segments);
 
