@@ -441,6 +441,57 @@ struct imomd_graph
     uint32_t max_degree;
 };
 
+// device scratch of imomd_nearest_batch: grow-only buffers and the events of its stage timers,
+// owned by the planner (a call allocates only when it needs more than any call before it)
+struct NnPool
+{
+    static constexpr int kSlots = 16;
+    void* ptr[kSlots] = {};
+    size_t bytes[kSlots] = {};
+    cudaEvent_t ev[6] = {};
+    bool have_events = false;
+    template <class T>
+    cudaError_t get(int slot, T** x, size_t count)
+    {
+        const size_t need = std::max<size_t>(count, 1) * sizeof(T);
+        if (need > bytes[slot])
+        {
+            cudaFree(ptr[slot]);
+            ptr[slot] = nullptr;
+            bytes[slot] = 0;
+            const size_t want = need + need / 4;
+            cudaError_t rc = cudaMalloc(&ptr[slot], want);
+            if (rc != cudaSuccess) return rc;
+            bytes[slot] = want;
+        }
+        *x = static_cast<T*>(ptr[slot]);
+        return cudaSuccess;
+    }
+    cudaError_t events()
+    {
+        if (have_events) return cudaSuccess;
+        for (cudaEvent_t& e : ev)
+        {
+            cudaError_t rc = cudaEventCreate(&e);
+            if (rc != cudaSuccess) return rc;
+        }
+        have_events = true;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        for (int i = 0; i < kSlots; ++i)
+        {
+            cudaFree(ptr[i]);
+            ptr[i] = nullptr;
+            bytes[i] = 0;
+        }
+        for (cudaEvent_t& e : ev)
+            if (e) cudaEventDestroy(e);
+        have_events = false;
+    }
+};
+
 struct imomd_planner
 {
     imomd_graph* g;
@@ -465,6 +516,7 @@ struct imomd_planner
     // device times of the last imomd_nearest_batch call
     float nn_prep_ms = 0.f, nn_tiles_ms = 0.f, nn_merge_ms = 0.f;
     uint32_t nn_segments = 0;
+    NnPool nn_pool;
 };
 
 struct imomd_ctx
@@ -485,26 +537,6 @@ cudaError_t dmalloc(T** p, size_t count)
 {
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
 }
-
-// device scratch of one imomd_nearest_batch call; released on every exit path
-struct NnScratch
-{
-    std::vector<void*> ptrs;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    ~NnScratch()
-    {
-        for (void* x : ptrs) cudaFree(x);
-        for (cudaEvent_t e : ev)
-            if (e) cudaEventDestroy(e);
-    }
-    template <class T>
-    cudaError_t get(T** x, size_t count)
-    {
-        cudaError_t rc = dmalloc(x, count);
-        if (rc == cudaSuccess) ptrs.push_back(*x);
-        return rc;
-    }
-};
 
 int planner_fill_initial(imomd_planner* p)
 {
@@ -752,6 +784,7 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(p->walk_buf);
     cudaFree(p->gather_u32);
     cudaFree(p->gather_f64);
+    p->nn_pool.release();
     cudaEventDestroy(p->ev0);
     cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->stream);
@@ -1286,22 +1319,29 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
             return fail(IMOMD_ERR_ARG, "lookup %d: query/tree out of range", i);
     }
     CU(cudaSetDevice(p->g->device));
-    // tiles: lookups grouped by (query, tree), at most kTileLookups per tile
+    // tiles: lookups grouped by (query, tree) in their order of appearance (counting sort by tree),
+    // at most kTileLookups per tile
+    std::vector<uint32_t> first((size_t)QK + 1, 0u);
+    for (int i = 0; i < n; ++i) ++first[(size_t)(q[i].query * p->d.K + q[i].tree) + 1];
+    for (int t = 0; t < QK; ++t) first[(size_t)t + 1] += first[t];
     std::vector<int> order(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return q[a].query * p->d.K + q[a].tree < q[b].query * p->d.K + q[b].tree;
-    });
-    std::vector<NnTile> tiles;
-    for (int i = 0; i < n;)
     {
-        NnTile t{};
-        t.qt = q[order[i]].query * p->d.K + q[order[i]].tree;
-        while (i < n && t.n < kTileLookups && q[order[i]].query * p->d.K + q[order[i]].tree == t.qt)
-            t.lookup[t.n++] = order[i++];
-        tiles.push_back(t);
+        std::vector<uint32_t> at(first.begin(), first.end() - 1);
+        for (int i = 0; i < n; ++i) order[at[(size_t)(q[i].query * p->d.K + q[i].tree)]++] = i;
     }
-    NnScratch sc;
+    std::vector<NnTile> tiles;
+    tiles.reserve((size_t)n / kTileLookups + (size_t)std::min(n, QK));
+    for (int t = 0; t < QK; ++t)
+    {
+        for (uint32_t i = first[t]; i < first[(size_t)t + 1];)
+        {
+            NnTile x{};
+            x.qt = t;
+            while (i < first[(size_t)t + 1] && x.n < kTileLookups) x.lookup[x.n++] = order[i++];
+            tiles.push_back(x);
+        }
+    }
+    NnPool& sc = p->nn_pool;
     const int n_tiles = (int)tiles.size();
     // tiles are sorted by tree: [tile_begin[qt], tile_begin[qt + 1]) are the tiles of tree qt
     std::vector<uint32_t> tile_begin((size_t)QK + 1, 0u);
@@ -1316,21 +1356,21 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     NnWork* work = nullptr;
     Best* part = nullptr;
     int* derr = nullptr;
-    for (cudaEvent_t& e : sc.ev) CU(cudaEventCreate(&e));
-    CU(sc.get(&lists, (size_t)QK * 2 * p->d.chunks));
-    CU(sc.get(&counts, (size_t)QK));
-    CU(sc.get(&didx, (size_t)n));
-    CU(sc.get(&damb, (size_t)n));
-    CU(sc.get(&ddist, (size_t)n));
-    CU(sc.get(&dq, (size_t)n));
-    CU(sc.get(&dtiles, (size_t)n_tiles));
-    CU(sc.get(&dbegin, (size_t)QK + 1));
-    CU(sc.get(&seed, (size_t)n_tiles));
-    CU(sc.get(&tile_valid, (size_t)n_tiles));
-    CU(sc.get(&seg_start, (size_t)n_tiles));
-    CU(sc.get(&next_work, 2));
+    CU(sc.events());
+    CU(sc.get(0, &lists, (size_t)QK * 2 * p->d.chunks));
+    CU(sc.get(1, &counts, (size_t)QK));
+    CU(sc.get(2, &didx, (size_t)n));
+    CU(sc.get(3, &damb, (size_t)n));
+    CU(sc.get(4, &ddist, (size_t)n));
+    CU(sc.get(5, &dq, (size_t)n));
+    CU(sc.get(6, &dtiles, (size_t)n_tiles));
+    CU(sc.get(7, &dbegin, (size_t)QK + 1));
+    CU(sc.get(8, &seed, (size_t)n_tiles));
+    CU(sc.get(9, &tile_valid, (size_t)n_tiles));
+    CU(sc.get(10, &seg_start, (size_t)n_tiles));
+    CU(sc.get(11, &next_work, 2));
     n_work_dev = next_work + 1;
-    CU(sc.get(&derr, 1));
+    CU(sc.get(12, &derr, 1));
     CU(cudaMemsetAsync(derr, 0, sizeof(int), p->stream));
     CU(cudaMemsetAsync(next_work, 0, 2 * sizeof(uint32_t), p->stream));
     CU(cudaMemsetAsync(counts, 0, (size_t)QK * sizeof(uint32_t), p->stream));
@@ -1348,8 +1388,8 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     uint32_t n_work = 0;
     CU(cudaMemcpyAsync(&n_work, n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
-    CU(sc.get(&work, (size_t)n_work));
-    CU(sc.get(&part, (size_t)n_work * kConsumerWarps * kTileLookups));
+    CU(sc.get(13, &work, (size_t)n_work));
+    CU(sc.get(14, &part, (size_t)n_work * kConsumerWarps * kTileLookups));
     CU(cudaEventRecord(sc.ev[5], p->stream));
     k_nn_fill_work<<<(n_tiles + 3) / 4, 128, 0, p->stream>>>(p->d, n_tiles, dtiles, lists, counts, seg_start, work);
     CU(cudaGetLastError());

@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+import time
 import numpy as np
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -319,18 +320,20 @@ class DevicePlanner:
 
 
 def nearest_batch(dp, lookups):
-    """imomd_nearest_batch: (idx, dist, dict(kernel_ms, bytes, refined, prep_ms, merge_ms, segments))."""
+    """imomd_nearest_batch: (idx, dist, dict(kernel_ms, bytes, refined, prep_ms, merge_ms, segments, call_ms))."""
     lk = np.ascontiguousarray(lookups, NN_DTYPE)
     n = lk.shape[0]
     idx = np.empty(n, np.uint32); dist = np.empty(n)
     ms, by, nr = C.c_float(), C.c_uint64(), C.c_uint32()
+    t0 = time.perf_counter()
     _check(cuda_lib().imomd_nearest_batch(dp.h, n, lk.ctypes.data_as(C.c_void_p), idx, dist,
                                           C.byref(ms), C.byref(by), C.byref(nr)))
+    call_ms = (time.perf_counter() - t0) * 1e3          # host buffers in, host buffers out
     prep, tiles, merge, nseg = C.c_float(), C.c_float(), C.c_float(), C.c_uint32()
     _check(cuda_lib().imomd_nearest_batch_last_timing(dp.h, C.byref(prep), C.byref(tiles), C.byref(merge),
                                                       C.byref(nseg)))
     return idx, dist, dict(kernel_ms=ms.value, bytes=by.value, refined=nr.value, prep_ms=prep.value,
-                           merge_ms=merge.value, segments=nseg.value)
+                           merge_ms=merge.value, segments=nseg.value, call_ms=call_ms)
 
 
 class GaContext:
