@@ -159,7 +159,10 @@ __device__ __forceinline__ Best warp_best(Best x)
 //     right when a chunk id is known; further tiles (more than 4 lookups on one frontier) re-read
 //     the heads through the list;
 // (3) the tile's segments are reserved with one atomicAdd (their order does not matter).
-constexpr int kPrepThreads = 128;
+#ifndef IMOMD_NN_PREP
+#define IMOMD_NN_PREP 64
+#endif
+constexpr int kPrepThreads = IMOMD_NN_PREP;
 
 struct NnPrepShared
 {
