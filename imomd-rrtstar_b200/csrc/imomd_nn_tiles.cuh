@@ -239,13 +239,20 @@ k_nn_prepare(const __grid_constant__ PlannerDev P, const uint32_t* __restrict__ 
     const uint32_t n_occ = P.query[q].n_occ[k];
     uint32_t* out = lists + (size_t)qt * 2 * P.chunks;
     const VRec* rec = P.rec + (size_t)qt * (size_t)P.chunks * IMOMD_CHUNK;
-    // the first batch of cells is requested while the samples are being prepared
-    uint32_t cnt = 0, head = IMOMD_NONE;
-    if (threadIdx.x < n_occ)
+    // Software pipeline over the batches of cells (three dependent loads per cell: occupied-cell
+    // id -> header -> first record): the ids are requested two batches ahead, the headers one
+    // batch ahead, so that a batch only waits for its records.  The first batch is requested
+    // while the samples are being prepared.
+    uint32_t cnt = 0, head = IMOMD_NONE, c_next = IMOMD_NONE;
     {
-        const uint32_t c = T.occ[threadIdx.x];
-        cnt = T.cell_cnt[c];
-        head = T.cell_head[c];
+        uint32_t c_first = IMOMD_NONE;
+        if (threadIdx.x < n_occ) c_first = T.occ[threadIdx.x];
+        if (threadIdx.x + kPrepThreads < n_occ) c_next = T.occ[threadIdx.x + kPrepThreads];
+        if (c_first != IMOMD_NONE)
+        {
+            cnt = T.cell_cnt[c_first];
+            head = T.cell_head[c_first];
+        }
     }
     nn_prep_samples(sh, tiles[t0], qs);
     __syncthreads();
@@ -255,17 +262,12 @@ k_nn_prepare(const __grid_constant__ PlannerDev P, const uint32_t* __restrict__ 
     uint32_t total = 0, n_valid = 0;
     for (uint32_t base = 0; base < n_occ; base += kPrepThreads)
     {
-        const uint32_t i = base + threadIdx.x;
-        if (base > 0)
+        uint32_t c_next2 = IMOMD_NONE, cnt_next = 0, head_next = IMOMD_NONE;
+        if (base + 2 * kPrepThreads + threadIdx.x < n_occ) c_next2 = T.occ[base + 2 * kPrepThreads + threadIdx.x];
+        if (c_next != IMOMD_NONE)
         {
-            cnt = 0;
-            head = IMOMD_NONE;
-            if (i < n_occ)
-            {
-                const uint32_t c = T.occ[i];
-                cnt = T.cell_cnt[c];
-                head = T.cell_head[c];
-            }
+            cnt_next = T.cell_cnt[c_next];
+            head_next = T.cell_head[c_next];
         }
         const uint32_t nch = (cnt + IMOMD_CHUNK - 1) / IMOMD_CHUNK;
         uint32_t inc = nch, vinc = cnt;
@@ -303,6 +305,9 @@ k_nn_prepare(const __grid_constant__ PlannerDev P, const uint32_t* __restrict__ 
             chunk = nxt;
         }
         total += all;
+        cnt = cnt_next;
+        head = head_next;
+        c_next = c_next2;
     }
     // occupied records of the tree
     if (lane == 0) sh.warp_sum[warp] = n_valid;
