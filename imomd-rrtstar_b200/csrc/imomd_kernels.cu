@@ -1400,7 +1400,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     if (n_work > 0)
     {
         const int grid = (int)std::min<size_t>(n_work, (size_t)148 * kTileCtasPerSm);
-        k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, dtiles, seed, work, n_work_dev, next_work,
+        k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, seed, work, n_work_dev, next_work,
                                                                  lists, part, derr);
         CU(cudaGetLastError());
     }

@@ -427,8 +427,8 @@ struct __align__(16) NnShared
 };
 
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm)
-k_nearest_tiles(const __grid_constant__ PlannerDev P, const NnTile* __restrict__ tiles,
-                const NnSeed* __restrict__ seed, const NnWork* __restrict__ work,
+k_nearest_tiles(const __grid_constant__ PlannerDev P, const NnSeed* __restrict__ seed,
+                const NnWork* __restrict__ work,
                 const uint32_t* __restrict__ n_work_ptr, uint32_t* __restrict__ next_work,
                 const uint32_t* __restrict__ lists, Best* __restrict__ part, int* __restrict__ error)
 {
