@@ -222,6 +222,37 @@ def test_nearest_batch_tile_kernel_matches_exact_path():
     o.close(); dp.close(); dg.close()
 
 
+def test_nearest_batch_tiny_frontiers():
+    """frontiers of one to four records (fresh planner: the roots' neighbours; fewer than two chunk
+    heads, so the screen has no bound and everything is ranked exactly), and an empty batch"""
+    g = graphs.jittered_grid(60, seed=2)
+    K = 4
+    dests = [graphs.pick_destinations(g, K, seed=s) for s in (3, 4, 5)]
+    dg = capi.DeviceGraph(g)
+    dp = capi.DevicePlanner(dg, dests)
+    dp.feed(capi.mt19937_words(0, 20000))
+    rng = np.random.default_rng(1)
+    for passes in (0, 1, 3):
+        if passes:
+            dp.expand(passes if passes == 1 else 2)
+        n = 3 * K * 5
+        lk = np.empty(n, capi.NN_DTYPE)
+        lk["query"] = np.repeat(np.arange(3), K * 5); lk["tree"] = np.tile(np.repeat(np.arange(K), 5), 3)
+        lk["lat"] = rng.uniform(g.lat.min(), g.lat.max(), n); lk["lon"] = rng.uniform(g.lon.min(), g.lon.max(), n)
+        idx_a, dist_a = dp.nearest(lk)
+        idx_b, dist_b, info = capi.nearest_batch(dp, lk)
+        assert (idx_a != capi.NONE).all()
+        assert np.array_equal(idx_a, idx_b)
+        assert np.array_equal(dist_a.view(np.uint64), dist_b.view(np.uint64))
+        # a batch that touches one tree only: the other trees are skipped by the preparation
+        one = lk[lk["tree"] == 2][:3]
+        idx_c, dist_c, _ = capi.nearest_batch(dp, one)
+        assert np.array_equal(idx_c, idx_a[lk["tree"] == 2][:3])
+    idx_e, dist_e, _ = capi.nearest_batch(dp, lk[:0])
+    assert len(idx_e) == 0 and len(dist_e) == 0
+    dp.close(); dg.close()
+
+
 def test_nearest_batch_multi_segment_frontiers():
     """frontiers of several hundred chunks: every tile is cut into several segments that different
     CTAs rank; the merged answers equal the pruned exact path bit for bit and the oracle's indices"""
