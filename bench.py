@@ -24,6 +24,17 @@ expandTree_ calls per second, whole job (all queries, all GPUs).
   cpu_baseline   the unmodified reference (oracle/_ref/ref_probe) on the box's host cores,
                  one process per core, a bounded sample of the same workload
 
+A step processes `--queries` (1184) queries per GPU through `--slots` (296 = two CTAs per SM)
+sets of per-query device state: the planner STREAMS -- CTAs take the next query from a device
+work queue as their slot falls free, so a step is four "waves" deep and ends with the slowest
+tail of the last ones instead of the slowest query of a single wave.
+
+  parity   the unmodified reference runs queries 0 .. cores-1 of the same batch at the same depth
+           (it is the cpu_baseline leg); its TREEHASH, expansion count and tree
+           sizes are compared with what the timed launch reported for those queries.  A mismatch
+           fails the run.
+  san_pablo_1024, ga   side legs (BASELINE configs[4], GA fitness path), see DESIGN.md section 7
+
 With N > 1 (torchrun) every rank drives its own GPU with its own `--queries` queries
 (independent queries shard with no data-path collective): weak scaling, value = all ranks'
 expansions / max-over-ranks device time.
@@ -56,7 +67,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries", type=int, default=296, help="independent queries per GPU")
+    ap.add_argument("--queries", type=int, default=1184, help="independent queries per GPU and step")
+    ap.add_argument("--slots", type=int, default=296,
+                    help="sets of per-query device state (queries stream through them); 0 = one per query")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the san_pablo_1024 / ga side measurements")
     ap.add_argument("--iters", type=int, default=3000, help="expandTreeLayers_ passes per query")
     ap.add_argument("--grid", type=int, default=1000, help="grid width (1000 = 1 M vertices)")
     ap.add_argument("--workload", default="grid", choices=["grid", "san_pablo"],
@@ -167,7 +181,7 @@ def run_reference_sample(g, dests, iters, cores, graph_file=None):
     secs = max(o["seconds"] for o in outs)          # loop time only (graph load excluded)
     return exp / secs, {"expansions": exp, "loop_seconds": secs, "wall_seconds": wall,
                         "per_process_exp_per_s": [round(o["expansions_per_s"], 1) for o in outs],
-                        "toolchain": outs[0]["toolchain"]}
+                        "toolchain": outs[0]["toolchain"], "runs": outs}
 
 
 class _stdout_to_stderr:
@@ -318,6 +332,151 @@ def algorithmic_bytes(counters, avg_degree, K):
     return nn + rewire + connect, {"nn_bytes": nn, "rewire_bytes": rewire, "connect_bytes": connect}
 
 
+def ga_leg(device):
+    """GA path (SURVEY 8a-10/11): EciGenSolver::solveRTSP through the facade's solver (host
+    insertion / crossover bookkeeping, every fitness batch on the GPU: k_ga_eval, one warp per
+    tour) on pseudo-complete K x K matrices, next to the unmodified reference's solver on the same
+    matrices (reference timings: cpu_baseline.ga_solve_ms).  Same mt19937 streams, so cost and
+    visiting sequence must be identical."""
+    import struct
+    from imomd_b200 import capi
+    out = {}
+    for K in (7, 12, 22):
+        rng = np.random.default_rng(100 + K)
+        D = rng.uniform(100.0, 5000.0, (K, K)); D = (D + D.T) / 2
+        np.fill_diagonal(D, 0.0)
+        D = np.ascontiguousarray(D)
+        fs = capi.FacadeSolver(device)
+        ms, costs, evaluated, seq = [], [], 0, None
+        for _ in range(5):
+            t0 = time.perf_counter()
+            cost, seq, ev = fs.solve(D, 0, K - 1)
+            ms.append((time.perf_counter() - t0) * 1e3)
+            costs.append(cost); evaluated = ev
+        fs.close()
+        # fitness kernel alone: the 15 000 tours a default solve evaluates, in one launch
+        ctx = capi.GaContext(device)
+        tours = np.stack([np.concatenate(([0], rng.permutation(np.arange(1, K - 1)), [K - 1])) for _ in range(15000)]).astype(np.int32)
+        lens = np.full(len(tours), K, np.int32)
+        ctx.eval(D, tours, lens)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ctx.eval(D, tours, lens)
+        call_ms = (time.perf_counter() - t0) * 1e3 / 10
+        ctx.close()
+        entry = {"solve_ms_b200": [round(x, 3) for x in ms], "cost": costs[-1], "tours_evaluated_per_solve": int(evaluated),
+                 "ga_eval_call_ms_15000_tours": round(call_ms, 3), "ga_eval_tours_per_s": round(15000 / (call_ms / 1e3))}
+        if os.path.exists(REF_PROBE):
+            fd, mf = tempfile.mkstemp(suffix=".bin", prefix="imomd_D_")
+            with os.fdopen(fd, "wb") as f:
+                f.write(struct.pack("<Q", K) + D.tobytes())
+            try:
+                ref = json.loads(subprocess.check_output([REF_PROBE, "--mode", "rtsp", "--matrix", mf, "--solves", "5"],
+                                                         text=True).strip().splitlines()[-1])
+            finally:
+                os.unlink(mf)
+            entry.update({"solve_ms_reference": [round(x, 3) for x in ref["ms"]],
+                          "identical_costs": [float(c) for c in ref["costs"]] == [float(c) for c in costs],
+                          "identical_sequence": ref["last_sequence"] == [int(v) for v in seq]})
+        out[f"K{K}"] = entry
+    return out
+
+
+def san_pablo_leg(device, rank, world, iters=3000, n_queries=1024):
+    """BASELINE configs[4]: 1024 source/target queries (K = 2) on san_pablo.osm, STRONG scaling:
+    the same 1024 queries over however many GPUs there are, ranks pulling chunks of 32 queries
+    from a shared counter (sharding.run_sharded, no data-path collective), every rank's planner
+    streaming its chunk; per-query TREEHASHes gathered and folded into one fingerprint that must
+    not depend on the number of GPUs (the driver's per-N lines carry it)."""
+    import hashlib
+    import torch
+    from imomd_b200 import graphs, sharding
+    src = graphs.RoadGraph.load(os.path.join(ROOT, "tests", "golden", "graphs", "san_pablo.npz"))
+    g = graphs.from_edges(src.lat, src.lon, *src.edge_list(), name="san_pablo")
+    lab = g.components()
+    big = np.nonzero(lab == np.bincount(lab).argmax())[0]
+    rng = np.random.default_rng(11)
+    dests = [[int(v) for v in rng.choice(big, size=2, replace=False)] for _ in range(n_queries)]
+    ex = sharding.CudaExecutor(device, max_resident=-1)
+    ex(g, dests[:8], 50)                      # warm-up: graph upload, kernel load
+    ex.kernel_ms = 0.0
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = sharding.run_sharded(g, dests, iters, ex, world=world, rank=rank, dynamic_chunk=32 if world > 1 else 0,
+                               tag="san_pablo_1024")
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    kernel_s = ex.kernel_ms / 1e3
+    ex.close()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([wall, kernel_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, kernel_s = float(t[0]), float(t[1])
+    exps = sum(r["expansions"] for r in res)
+    fp = hashlib.sha256(np.asarray([r["treehash"] for r in res], np.uint64).tobytes()).hexdigest()[:16]
+    return {"workload": f"san_pablo_osm_K2_iters{iters}_{n_queries}_queries", "scaling": "strong", "n_gpus": world,
+            "expansions": int(exps), "seconds": wall, "expansions_per_s": exps / wall,
+            "max_rank_kernel_seconds": kernel_s, "tree_vertices": int(sum(r["tree_vertices"] for r in res)),
+            "unresolved_ties": int(sum(r["unresolved_ties"] for r in res)),
+            "treehash_fingerprint": fp, "note": "fingerprint = sha256 over the 1024 per-query TREEHASHes in query "
+            "order: identical for every GPU count"}
+
+
+def ga_islands_leg(device, rank, world, generations=5):
+    """BASELINE configs[3]: GA islands, one per GPU, own population (mt19937{rank}), best-tour
+    migration after every generation = one NCCL all-gather of 528 bytes per rank.  K = 22
+    pseudo-complete matrix (half of the pairs unconnected, as after a partial exploration)."""
+    import torch
+    from imomd_b200 import sharding
+    K = 22
+    rng = np.random.default_rng(4)
+    D = rng.uniform(100.0, 5000.0, (K, K)); D = (D + D.T) / 2
+    miss = np.triu(rng.random((K, K)) < 0.5, 1); D[miss | miss.T] = np.inf
+    perm = rng.permutation(K)
+    for a, b in zip(perm[:-1], perm[1:]):
+        if np.isinf(D[a, b]):
+            D[a, b] = D[b, a] = rng.uniform(100.0, 5000.0)
+    np.fill_diagonal(D, 0.0)
+    D = np.ascontiguousarray(D)
+    # migration latency: the all-gather alone, device-timed
+    mig_us = None
+    if world > 1:
+        import torch.distributed as dist
+        rec = sharding.pack_best(1.0, [0, 1, 2]).to(torch.device("cuda", device))
+        bucket = [torch.empty_like(rec) for _ in range(world)]
+        for _ in range(5):
+            dist.all_gather(bucket, rec)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            dist.all_gather(bucket, rec)
+        e1.record(); torch.cuda.synchronize()
+        mig_us = e0.elapsed_time(e1) * 1e3 / 50
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cost, tour, hist, evaluated = sharding.run_islands(D, 0, K - 1, generations, device=device)
+    wall = time.perf_counter() - t0
+    total_eval, best = float(evaluated), cost
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([total_eval], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        w = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        b = torch.tensor([cost], dtype=torch.float64, device="cuda")
+        dist.all_reduce(b, op=dist.ReduceOp.MIN)
+        total_eval, wall, best = float(t[0]), float(w[0]), float(b[0])
+    return {"islands": world, "K": K, "generations": generations, "best_cost": best,
+            "best_by_generation": [h["best"] for h in hist], "island0_local_by_generation": [h["local"] for h in hist],
+            "tours_evaluated": int(total_eval), "seconds": wall, "tours_per_s": total_eval / wall,
+            "migration_allgather_us": mig_us}
+
+
 def b200_arm(args):
     import torch
     from imomd_b200 import capi
@@ -335,7 +494,9 @@ def b200_arm(args):
     Q, K = args.queries, len(dests[0])
     dg = capi.DeviceGraph(g, device=device)
     probs = np.stack([capi.selection_probabilities(g, d) for d in dests])
-    dp = capi.DevicePlanner(dg, dests, probs)
+    slots = min(args.slots, Q) if args.slots > 0 else 0
+    dp = capi.DevicePlanner(dg, dests, probs, max_resident=slots)
+    layout = dp.info()
     n_words = args.iters * K * 8 + 4096
     words_np = capi.mt19937_words(0, n_words)
 
@@ -347,7 +508,8 @@ def b200_arm(args):
     d_view = pin_dest.numpy().view(np.uint32); d_view[:] = np.asarray(dests, np.uint32).ravel()
     p_view = pin_prob.numpy(); p_view[:] = probs.ravel()
     h2d = w_view.nbytes + d_view.nbytes + p_view.nbytes
-    d2h = Q * (88 + capi.sizeof_query_state())
+    import ctypes
+    d2h = Q * (ctypes.sizeof(capi.Report) + capi.sizeof_query_state())
 
     def barrier():
         if world > 1:
@@ -355,36 +517,38 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(collect):
-        """reset -> kernel.  Returns (device ms of the kernel, expansions, e2e seconds)."""
+    def one_step():
+        """destinations + probabilities + sample stream in, kernel, reports + K x K state out.
+        Returns (device ms of the kernel, expansions, e2e seconds, reports, states)."""
         t0 = time.perf_counter()
         dp.clear_words()
         dp.set_queries(d_view, p_view)           # H2D destinations + probabilities, rebuild state
         dp.feed(w_view)                          # H2D sample stream
         reps = dp.expand(args.iters)             # kernel + D2H reports
-        if collect:
-            for q in range(Q):
-                dp.state(q)                      # D2H K x K matrices
+        st = dp.states()                         # D2H K x K matrices of every query, one copy
         e2e_s = time.perf_counter() - t0
         bad = [r.status for r in reps if r.status != 0]
         if bad:
             raise SystemExit(f"bench.py: device run status {bad[:4]}")
-        return dp.last_kernel_ms(), sum(r.expansions for r in reps), e2e_s, reps
+        return dp.last_kernel_ms(), sum(r.expansions for r in reps), e2e_s, reps, st
 
     for _ in range(max(args.warmup, 0)):
-        one_step(True)
+        one_step()
     barrier()
     sampler = ClockSampler(device)
     sampler.start()
     ker_ms, exps, e2e_secs = [], [], []
     reps = None
     for _ in range(args.steps):
-        ms, ex, es, reps = one_step(True)
+        ms, ex, es, reps, states = one_step()
         ker_ms.append(ms); exps.append(ex); e2e_secs.append(es)
     barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     counters = dp.counters()
+    n_check = min(os.cpu_count() or 1, Q)
+    tree_hashes = [int(r.tree_hash) for r in reps[:n_check]] if layout["streaming"] else \
+        [dp.treehash(q)[0] for q in range(n_check)]
     t_dev = sum(ker_ms) / 1e3
     t_e2e = sum(e2e_secs)
     exp_total = sum(exps)
@@ -396,6 +560,18 @@ def b200_arm(args):
         dist.all_reduce(e, op=dist.ReduceOp.SUM)
         t_dev, t_e2e = float(t[0]), float(t[1])
         exp_total = float(e[0])
+    side = {}
+    if not args.no_side_legs and getattr(args, "workload", "grid") == "grid":
+        # side legs run on every rank (they shard); rank 0 reports them
+        dp.close(); dp = None
+        try:
+            side["san_pablo_1024"] = san_pablo_leg(device, rank, world)
+        except Exception as ex:
+            side["san_pablo_1024"] = {"error": repr(ex)}
+        try:
+            side["ga_islands"] = ga_islands_leg(device, rank, world)
+        except Exception as ex:
+            side["ga_islands"] = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -412,6 +588,17 @@ def b200_arm(args):
     bytes_step, parts = algorithmic_bytes(counters, avg_deg, K)
     launch_s = ker_ms[-1] / 1e3
     achieved = bytes_step / launch_s / 1e9
+    busy = np.asarray([r.busy_cycles for r in reps], np.float64)
+    sm_hz = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
+    n_slots = layout["slots"]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_k_expand_traffic.json")) as f:
+            cap = json.load(f)
+        traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        traffic_note = cap.get("note")
+    except (OSError, KeyError, ValueError):
+        traffic_note = None
     line = {
         "metric": METRIC, "value": exp_total / t_dev, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -420,67 +607,36 @@ def b200_arm(args):
         "config": {"workload": workload_name(args, args.iters, K),
                    "graph": g.name, "vertices": g.n,
                    "trees_per_query": K, "iters_per_query": args.iters, "goal_bias": 1.0,
-                   "queries_per_gpu": Q, "l2": "inputs_larger_than_l2 (state rebuilt every step)",
+                   "queries_per_gpu": Q, "state_slots_per_gpu": n_slots, "streaming": layout["streaming"],
+                   "l2": "inputs_larger_than_l2 (state rebuilt every step)",
                    "hash_cells_per_axis": dg.info()["grid_dim"]},
         "e2e": {"value": exp_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(args.steps * (2 + 1)),   # k_init_trees + k_lower_bounds + k_expand per step
+        # k_fill_headers + k_expand per step (a streaming planner rebuilds its slots inside k_expand;
+        # a resident one adds k_init_trees + k_lower_bounds)
+        "gpu_launches": int(args.steps * (2 if layout["streaming"] else 4)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "k_expand",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "k_expand",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_step,
-                     "launch_ms": ker_ms[-1],
+                     "launch_ms": ker_ms[-1], "traffic_note": traffic_note,
                      "note": "latency-bound: one CTA per query walks dependent parent/child chains; "
                              "see DESIGN.md 'Roofline'", **{k: float(v) for k, v in parts.items()}},
         "clocks": sampler.summary(),
+        "batch": {"queries": Q, "slots": n_slots,
+                  "per_query_busy_ms": {"min": float(busy.min() / sm_hz * 1e3), "mean": float(busy.mean() / sm_hz * 1e3),
+                                        "max": float(busy.max() / sm_hz * 1e3)},
+                  "slot_utilisation": float(busy.sum() / sm_hz / (n_slots * launch_s)),
+                  "kernel_ms_per_step": {"min": min(ker_ms), "mean": float(np.mean(ker_ms)), "max": max(ker_ms)},
+                  "note": "busy = SM cycles a query held its CTA (incl. slot rebuild and tree hash); utilisation = "
+                          "sum of busy / (slots x launch time): what the tail of the launch leaves idle"},
         "tree_vertices_per_step": int(sum(r.tree_vertices for r in reps)),
+        "near_ties": int(sum(r.near_ties for r in reps)),
+        "certified_ties": int(sum(r.certified_ties for r in reps)),
         "unresolved_ties": int(sum(r.unresolved_ties for r in reps)),
     }
-    # secondary figure: the bandwidth-shaped nearest-vertex kernel (imomd_nearest_batch) on the
-    # frontiers the last step left in HBM: 4 samples per tree, every frontier streamed once
-    try:
-        rngl = np.random.default_rng(0)
-        n_lk = Q * K * 4
-        lk = np.empty(n_lk, capi.NN_DTYPE)
-        lk["query"] = np.repeat(np.arange(Q), K * 4)
-        lk["tree"] = np.tile(np.repeat(np.arange(K), 4), Q)
-        lk["lat"] = rngl.uniform(g.lat.min(), g.lat.max(), n_lk)
-        lk["lon"] = rngl.uniform(g.lon.min(), g.lon.max(), n_lk)
-        best = None
-        call_ms = float("inf")
-        for _ in range(5):
-            _, _, info = capi.nearest_batch(dp, lk)
-            call_ms = min(call_ms, info["call_ms"])
-            if best is None or info["kernel_ms"] < best["kernel_ms"]:
-                best = info
-        nn_gbs = best["bytes"] / (best["kernel_ms"] / 1e3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed
-        # `ncu --set full` capture (profiles/r01_nn_tiles_traffic.json), when the shape matches
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_nn_tiles_traffic.json")) as f:
-                cap = json.load(f)
-            if cap["lookups"] == n_lk and abs(cap["algorithmic_bytes"] - best["bytes"]) < 0.02 * best["bytes"]:
-                traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
-        except (OSError, KeyError, ValueError):
-            pass
-        line["roofline_nn"] = {"bound": "hbm", "achieved": nn_gbs, "peak": peak, "unit": "GB/s",
-                               "frac": nn_gbs / peak, "traffic": traffic, "kernel": "k_nearest_tiles",
-                               "algorithmic_bytes_per_launch": int(best["bytes"]),
-                               "launch_ms": best["kernel_ms"], "lookups": n_lk,
-                               "lookups_per_s": n_lk / (best["kernel_ms"] / 1e3),
-                               "segments": int(best["segments"]),
-                               "prep_ms": best["prep_ms"], "merge_ms": best["merge_ms"],
-                               "lookups_per_s_pipeline": n_lk / ((best["prep_ms"] + best["kernel_ms"] +
-                                                                  best["merge_ms"]) / 1e3),
-                               "call_ms": call_ms, "lookups_per_s_call": n_lk / (call_ms / 1e3),
-                               "note": "imomd_nearest_batch, 4 samples per frontier, best of 5 launches; "
-                                       "frontier records total larger than L2; algorithmic bytes = 32 B per "
-                                       "OCCUPIED frontier record + 8 B per chunk-list entry + 36 B per lookup; "
-                                       "prep_ms = chunk lists + seeds + segment records, merge_ms = fold of the "
-                                       "segment partials (device times of the same call); call_ms = the C-ABI call with "
-                                       "host buffers in and out (best of 5)"}
-    except Exception as ex:  # the headline line must survive a failure of the side measurement
-        line["roofline_nn"] = {"error": str(ex)}
+    line.update(side)
+    if dp is not None:
+        dp.close(); dp = None
     # time to first solution of ONE query through the drop-in C++ facade (planner construction ->
     # first accepted RTSP tour, same 100-pass cadence) next to the unmodified reference
     if not args.no_ttfs and not args.no_cpu_baseline and world == 1:
@@ -492,28 +648,56 @@ def b200_arm(args):
             line["ttfs_bugtrap"] = measure_ttfs_bugtrap(device)
         except Exception as ex:
             line["ttfs_bugtrap"] = {"error": str(ex)}
+    if not args.no_side_legs and world == 1:
+        try:
+            line["ga"] = ga_leg(device)
+        except Exception as ex:
+            line["ga"] = {"error": repr(ex)}
+    parity_failed = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cd = list(dests)
-        while len(cd) < cores:
-            rng = np.random.default_rng(5000 + len(cd))
-            cd.append([int(v) for v in rng.choice(g.n, size=K, replace=False)])
+        cores = min(os.cpu_count() or 1, Q)
         iters = args.cpu_sample_iters or args.iters
-        rate, info = run_reference_sample(g, cd, iters, cores)
+        rate, info = run_reference_sample(g, dests, iters, cores)
         if rate is None:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference",
                                     "sample": info}
         else:
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"{cores} queries x {iters} passes, one unmodified-reference process per core "
-                          f"({cpu_model()}); single-core mean "
+                "sample": f"queries 0..{cores - 1} of the timed batch x {iters} passes, one unmodified-reference "
+                          f"process per core ({cpu_model()}); single-core mean "
                           f"{np.mean(info['per_process_exp_per_s']):.0f} expansions/s"}
+            if "ga" in line and isinstance(line["ga"], dict):
+                line["cpu_baseline"]["ga_solve_ms"] = {k: v.get("solve_ms_reference") for k, v in line["ga"].items()
+                                                       if isinstance(v, dict)}
+            # parity of the TIMED batch: the reference's fingerprints of those very queries
+            if iters == args.iters:
+                same = 0
+                diffs = []
+                for q, o in enumerate(info["runs"]):
+                    ok = (int(o["treehash"], 16) == tree_hashes[q] and
+                          int(o["expansions"]) == int(reps[q].expansions) and
+                          int(o["tree_vertices"]) == int(reps[q].tree_vertices))
+                    same += bool(ok)
+                    if not ok:
+                        diffs.append({"query": q, "reference": [o["treehash"], o["expansions"], o["tree_vertices"]],
+                                      "b200": [f"{tree_hashes[q]:016x}", int(reps[q].expansions),
+                                               int(reps[q].tree_vertices)]})
+                line["parity"] = {"queries_checked": len(info["runs"]), "identical": same, "depth": iters,
+                                  "what": "TREEHASH (every vertex, parent and cost bit of the K trees), expansions, "
+                                          "tree vertices of the timed launch vs the unmodified reference",
+                                  "unresolved_ties_in_batch": line["unresolved_ties"]}
+                if diffs:
+                    line["parity"]["mismatches"] = diffs[:8]
+                    parity_failed = f"{len(diffs)} of {len(info['runs'])} checked queries differ from the reference"
     print(json.dumps(line))
-    dp.close(); dg.close()
+    dg.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    if parity_failed:
+        print("bench.py: PARITY FAILURE: " + parity_failed, file=sys.stderr)
+        return 3
     return 0
 
 

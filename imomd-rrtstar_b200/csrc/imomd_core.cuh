@@ -61,7 +61,7 @@ constexpr double kDeg2Rad = 3.14159265358979323846 / 180;
 constexpr double kEarthRadius = 6371000.0;   // `int EARTH_RADIUS = 6371e3` upstream
 constexpr double kCellPadDeg = 1e-9;         // cell rectangles are grown by this much
 constexpr double kPruneSlack = 1e-9;         // relative slack of every pruning test
-constexpr double kTieRel = 1e-12;            // "cannot be decided in device arithmetic"
+constexpr double kTieRel = 1e-12;            // default of PlannerDev::tie_rel: "cannot be decided in device arithmetic"
 
 enum ReqType
 {
@@ -239,17 +239,29 @@ IMOMD_HD inline VRec make_vrec(uint32_t v, double lat, double lon, int G, double
     return r;
 }
 
-// lbd[q][t][c]: lower bound (metres) of haversine(root of tree t, any point of cell c)
+// lower / upper bound (metres) of haversine(root, any point of cell c)
+IMOMD_HD inline double lbd_of(const GraphDev& g, uint32_t root, uint32_t c)
+{
+    double rlat = g.lat[root], rlon = g.lon[root];
+    double a = cell_lower_a(g, c, rlat, rlon, cos(rlat * kDeg2Rad));
+    return dist_of_a(a) * (1.0 - kPruneSlack);
+}
+
+IMOMD_HD inline double ubd_of(const GraphDev& g, uint32_t root, uint32_t c)
+{
+    double rlat = g.lat[root], rlon = g.lon[root];
+    double a = cell_upper_a(g, c, rlat, rlon, cos(rlat * kDeg2Rad));
+    return dist_of_a(a) * (1.0 + kPruneSlack);
+}
+
+// lbd[slot][t][c] of a RESIDENT planner (slot == query): entry i of the flat table
 IMOMD_HD inline double lbd_entry(const PlannerDev& P, size_t i)
 {
     uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
     uint32_t c = (uint32_t)(i % cells);
     int t = (int)((i / cells) % P.K);
     int q = (int)(i / ((size_t)cells * P.K));
-    uint32_t root = P.query[q].dest[t];
-    double rlat = P.g.lat[root], rlon = P.g.lon[root];
-    double a = cell_lower_a(P.g, c, rlat, rlon, cos(rlat * kDeg2Rad));
-    return dist_of_a(a) * (1.0 - kPruneSlack);
+    return lbd_of(P.g, P.query[q].dest[t], c);
 }
 
 IMOMD_HD inline double ubd_entry(const PlannerDev& P, size_t i)
@@ -258,10 +270,7 @@ IMOMD_HD inline double ubd_entry(const PlannerDev& P, size_t i)
     uint32_t c = (uint32_t)(i % cells);
     int t = (int)((i / cells) % P.K);
     int q = (int)(i / ((size_t)cells * P.K));
-    uint32_t root = P.query[q].dest[t];
-    double rlat = P.g.lat[root], rlon = P.g.lon[root];
-    double a = cell_upper_a(P.g, c, rlat, rlon, cos(rlat * kDeg2Rad));
-    return dist_of_a(a) * (1.0 + kPruneSlack);
+    return ubd_of(P.g, P.query[q].dest[t], c);
 }
 
 // --------------------------------------------------------- per-tree views ---
@@ -428,6 +437,9 @@ struct Shared
     int32_t phase;
     int32_t it;            // iterations completed in this launch
     int32_t k;             // tree being expanded
+    int32_t stop;          // the launch's time budget is spent: no further pass starts
+    int32_t pad_stop;
+    uint64_t t_start_ns;   // global timer at the start of the launch (time budget)
     // sample (selectRandomVertex_)
     uint64_t rand_id;
     int32_t sample_is_vertex;   // the sample's coordinates are exactly those of vertex rand_id
@@ -483,7 +495,61 @@ struct Shared
     // block reduction / scan scratch
     Best red[32];
     uint32_t scan[40];
+    // exact certification of a comparison the device arithmetic cannot decide (Cta::certify):
+    // candidate vertices, the coordinate pairs handed to the host, glibc's answers
+    uint32_t tie_n;
+    uint32_t mh_tie_mask;       // heuristic inserts: bit o = the comparison for tree o needs exact values
+    uint32_t tie_id[IMOMD_TIE_PAIRS];
+    double tie_in[IMOMD_TIE_PAIRS][4];
+    double tie_out[IMOMD_TIE_PAIRS];
 };
+
+// Thread 0: decide an arg-min among the n candidate vertices S.tie_id[0..n) with the REFERENCE's
+// arithmetic: the objective hav(v, a) (+ hav(v, b) when `two`) is evaluated by the host with glibc
+// (Cta::certify), the minimum is taken with the reference's strict `<` over ascending vertex ids
+// (lowest id among exact ties, north_star).  Returns the position of the winner, or -1 when no
+// host service is attached / the candidates do not fit (the caller keeps the device decision and
+// counts it as unresolved).  *exact_tie: the minimum is attained by two vertices bit for bit.
+template <class Cta>
+IMOMD_HD inline int certify_argmin(Cta& cta, const GraphDev& g, Shared& S, uint32_t n, bool two, double alat,
+                                   double alon, double blat, double blon, double* vals, bool* exact_tie)
+{
+    *exact_tie = false;
+    const uint32_t per = two ? 2u : 1u;
+    if (n == 0 || n * per > IMOMD_TIE_PAIRS) return -1;
+    for (uint32_t i = 1; i < n; ++i)     // ascending ids
+    {
+        uint32_t x = S.tie_id[i];
+        uint32_t j = i;
+        while (j > 0 && S.tie_id[j - 1] > x)
+        {
+            S.tie_id[j] = S.tie_id[j - 1];
+            --j;
+        }
+        S.tie_id[j] = x;
+    }
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t v = S.tie_id[i];
+        double* a = S.tie_in[per * i];
+        a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = alat; a[3] = alon;
+        if (two)
+        {
+            double* b = S.tie_in[per * i + 1];
+            b[0] = g.lat[v]; b[1] = g.lon[v]; b[2] = blat; b[3] = blon;
+        }
+    }
+    if (!cta.certify((int)(n * per), S.tie_in, S.tie_out)) return -1;
+    int best = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        vals[i] = two ? S.tie_out[2 * i] + S.tie_out[2 * i + 1] : S.tie_out[i];
+        if (i > 0 && vals[i] < vals[best]) best = (int)i;
+    }
+    for (uint32_t i = 0; i < n; ++i)
+        if ((int)i != best && vals[i] == vals[best]) *exact_tie = true;
+    return best;
+}
 
 // --------------------------------------------------- frontier hash (serial) ---
 
@@ -1285,7 +1351,8 @@ struct Seq
     }
 
     // updateSelectionProbability, src/imomd_rrt_star.cpp:602-643
-    IMOMD_HD void update_selection_probability(int k)
+    template <class Cta>
+    IMOMD_HD void update_selection_probability(Cta& cta, int k)
     {
         int K = Q->K;
         int other = K;
@@ -1298,7 +1365,32 @@ struct Seq
             }
         }
         if (other == K) return;
-        if (sm_MHv(S)[k * K + other] > sm_D(S)[k * K + other])
+        const double mh = sm_MHv(S)[k * K + other], dd = sm_D(S)[k * K + other];
+        bool prune = mh > dd;
+        if (sm_MHi(S)[k * K + other] != IMOMD_NONE && dd < INFINITY && fabs(mh - dd) <= P.tie_rel * dd)
+        {
+            // the heuristic value is CUDA libm's: this close to the distance the comparison is
+            // redone on glibc's value of the holder
+            const GraphDev& g = P.g;
+            const uint32_t v = sm_MHi(S)[k * K + other], rk = Q->view_root[k], ro = Q->view_root[other];
+            double* a = S.tie_in[0];
+            double* b = S.tie_in[1];
+            a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = g.lat[rk]; a[3] = g.lon[rk];
+            b[0] = g.lat[v]; b[1] = g.lon[v]; b[2] = g.lat[ro]; b[3] = g.lon[ro];
+            if (cta.certify(2, S.tie_in, S.tie_out))
+            {
+                prune = (S.tie_out[0] + S.tie_out[1]) > dd;
+                Q->certified_ties += 1;
+            }
+            else
+            {
+                Q->unresolved_ties += 1;
+                double* ti = Q->tie_info;
+                ti[0] = 4; ti[1] = k; ti[2] = other; ti[3] = mh; ti[4] = dd; ti[5] = v;
+                ti[6] = 0; ti[7] = 0;
+            }
+        }
+        if (prune)
         {
             double* Pm = sm_P(S);
             Pm[k * K + other] = 0.0;
@@ -1327,7 +1419,8 @@ struct Seq
 
     // Runs the serial part of expandTree_ (:337-356) until it needs the CTA or the
     // launch is over; S.req tells the CTA what to do next.
-    IMOMD_HD void step(int iters)
+    template <class Cta>
+    IMOMD_HD void step(Cta& cta, int iters)
     {
         int K = Q->K;
         for (;;)
@@ -1348,9 +1441,11 @@ struct Seq
                         S.it += 1;
                         S.k = 0;
                         Q->iterations += 1;
+                        // done_time is evaluated after every pass (:258-262)
+                        if (P.budget_ns && cta.now_ns() - S.t_start_ns > P.budget_ns) S.stop = 1;
                         continue;
                     }
-                    if (S.it >= iters)
+                    if (S.it >= iters || S.stop)
                     {
                         S.req = REQ_EXIT;
                         return;
@@ -1459,7 +1554,7 @@ struct Seq
                 {
                     if (!rewire_run(k, T)) return;   // REQ_BFS or REQ_CHECK posted
                     if (Q->status != 0) continue;
-                    if (!S.attach_mode) update_selection_probability(k);
+                    if (!S.attach_mode) update_selection_probability(cta, k);
                     S.conn_x = S.x_new;
                     S.req = REQ_CONN;
                     S.phase = PH_LAST_CONN;
@@ -1623,6 +1718,48 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
     if (acc == 0x9E3779B9u) S.scan[39] = acc;   // keeps the loads alive, practically never taken
 }
 
+// The same idea for imomd_attach_list (pseudo-tree merge): the vertices to attach are known in
+// advance, so while thread 0 works on entry i the other lanes of the (single-warp) CTA fetch what
+// entries i+1 .. i+8 will touch: the vertex's adjacency row, the tree records and child rows of its
+// neighbours, their hash cells.  Nothing is written; stale reads are harmless.
+template <class Cta>
+IMOMD_HD inline void warm_attach(Cta& cta, const PlannerDev& P, const TreeRef& T, uint32_t at, uint32_t n, Shared& S)
+{
+    const GraphDev& g = P.g;
+    // helpers: the second warp when there is one (no divergence with the serial lane), else the
+    // other lanes of the only warp
+    uint32_t t = (uint32_t)cta.tid();
+    if (cta.nt() >= 64)
+    {
+        if (t < 32 || t >= 64) return;
+        t -= 31;
+    }
+    if (t == 0 || t > 32) return;
+    const uint32_t ahead = 1 + (t - 1) / 4, slot = (t - 1) % 4;
+    if (at + ahead >= n) return;
+    const uint32_t x = P.attach_list[at + ahead];
+    if (x >= g.n) return;
+    uint32_t acc = 0;
+    const uint32_t e0 = row_begin(g, x), d = g.deg[x];
+    for (uint32_t j = slot; j < d; j += 4)
+    {
+        const uint32_t y = g.col[e0 + j];
+        const double w = g.w[e0 + j];
+        THead h = T.head(y);
+        acc += T.chl(y)[0] + h.parent + (w > 0.0 ? 1u : 0u);
+        VRec v = g.vrec[y];
+        acc += T.cell_cnt[v.cell] + T.cell_head[v.cell] + g.deg[y];
+    }
+    if (slot == 0)
+    {
+        THead h = T.head(x);
+        const uint32_t c = g.vrec[x].cell;
+        acc += h.fslot + T.chl(x)[0] + T.cell_cnt[c] + T.cell_head[c];
+        if (h.fslot != IMOMD_NONE) acc += T.rec[h.fslot].id;
+    }
+    if (acc == 0x9E3779B9u) S.scan[39] = acc;   // keeps the loads alive
+}
+
 // steerNewNode_ arg-min (src/imomd_rrt_star.cpp:406-418) for the sample in S.
 template <class Cta>
 IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, int k, Shared& S,
@@ -1668,7 +1805,10 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
     };
     // rounding band of a squared chord m: unit-vector components carry ~1e-16 each
     // (an upper bound of 2e-12 m + 4e-15 sqrt(m): single-precision root, rounded up)
-    auto band = [](double m) { return 2e-12 * m + 4.00001e-15 * (double)sqrtf((float)m) + 1e-33; };
+    // (a chord^2 differs relatively twice as much as the distance: a widened P.tie_rel -- tests --
+    // widens the band with it)
+    const double band_rel = 2e-12 + (P.tie_rel > kTieRel ? 4.0 * P.tie_rel : 0.0);
+    auto band = [band_rel](double m) { return band_rel * m + 4.00001e-15 * (double)sqrtf((float)m) + 1e-33; };
     auto bound = [&](double m) { return m * (1.0 + kPruneSlack) + 4.0 * band(m); };
     if (cta.tid() == 0)
     {
@@ -1691,15 +1831,43 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         Best e = scan_list(cta, T, clist, 0u, S.n_list, eval2);
         e = cta.reduce(e, S.red);
         b = e;
-        if (cta.tid() == 0)
+        if (cta.tid() == 0) *near_ties += 1;
+        if (e.v2 - e.v1 <= P.tie_rel * e.v1)
         {
-            *near_ties += 1;
-            if (e.v2 - e.v1 <= kTieRel * e.v1)
+            // CUDA's libm and glibc may order these differently: collect every vertex inside the
+            // band and let the host decide with the reference's own arithmetic
+            if (cta.tid() == 0) S.tie_n = 0;
+            cta.sync();
+            const double lim = e.v1 + 2.0 * P.tie_rel * e.v1;
+            auto collect = [&](const VRec& r) {
+                double v = eval2(r);
+                if (v <= lim)
+                {
+                    uint32_t at = cta.counter_add(&S.tie_n, 1u);
+                    if (at < IMOMD_TIE_PAIRS) S.tie_id[at] = r.id;
+                }
+                return v;
+            };
+            (void)scan_list(cta, T, clist, 0u, S.n_list, collect);
+            cta.sync();
+            if (cta.tid() == 0)
             {
-                *unresolved_ties += 1;
-                double* ti = S.Q->tie_info;
-                ti[0] = 1; ti[1] = k; ti[2] = -1; ti[3] = e.v1; ti[4] = e.v2; ti[5] = e.id1;
-                ti[6] = qlat; ti[7] = qlon;
+                double vals[IMOMD_TIE_PAIRS];
+                bool exact_tie = false;
+                int w = certify_argmin(cta, g, S, S.tie_n, false, qlat, qlon, 0.0, 0.0, vals, &exact_tie);
+                if (w >= 0)
+                {
+                    b.id1 = S.tie_id[w];
+                    b.v1 = vals[w];
+                    S.Q->certified_ties += 1;
+                }
+                if (w < 0 || exact_tie)
+                {
+                    *unresolved_ties += 1;
+                    double* ti = S.Q->tie_info;
+                    ti[0] = 1; ti[1] = k; ti[2] = -1; ti[3] = e.v1; ti[4] = e.v2; ti[5] = b.id1;
+                    ti[6] = qlat; ti[7] = qlon;
+                }
             }
         }
     }
@@ -1758,19 +1926,55 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
         }
         cta.sync();
         Best b = pruned_argmin(cta, P, T, S, Q->n_occ[k], lb, clist, bounds, eval, bound);
+        const bool undecided = b.id1 != IMOMD_NONE && b.v2 - b.v1 <= P.tie_rel * b.v1;
+        if (undecided)
+        {
+            if (cta.tid() == 0) S.tie_n = 0;
+            cta.sync();
+            const double lim = b.v1 + 2.0 * P.tie_rel * b.v1;
+            auto collect = [&](const VRec& r) {
+                double v = eval(r);
+                if (v <= lim)
+                {
+                    uint32_t at = cta.counter_add(&S.tie_n, 1u);
+                    if (at < IMOMD_TIE_PAIRS) S.tie_id[at] = r.id;
+                }
+                return v;
+            };
+            (void)scan_list(cta, T, clist, 0u, S.n_list, collect);
+            cta.sync();
+        }
         if (cta.tid() == 0)
         {
             Q->stat[0] += S.n_cells;
             Q->stat[7] += S.n_recs;
+            if (undecided)
+            {
+                double vals[IMOMD_TIE_PAIRS];
+                bool exact_tie = false;
+                int w = certify_argmin(cta, g, S, S.tie_n, true, klat, klon, olat, olon, vals, &exact_tie);
+                if (w >= 0)
+                {
+                    // the holder is glibc's; its value stays the device's (1e-12 relative)
+                    if (S.tie_id[w] != b.id1)
+                    {
+                        const uint32_t v = S.tie_id[w];
+                        b.id1 = v;
+                        b.v1 = haversine_pc(g.lat[v], g.lon[v], g.coslat[v], klat, klon, kcos) +
+                               haversine_pc(g.lat[v], g.lon[v], g.coslat[v], olat, olon, ocos);
+                    }
+                    Q->certified_ties += 1;
+                }
+                if (w < 0 || exact_tie)
+                {
+                    Q->unresolved_ties += 1;
+                    double* ti = Q->tie_info;
+                    ti[0] = 2; ti[1] = k; ti[2] = o; ti[3] = b.v1; ti[4] = b.v2; ti[5] = b.id1;
+                    ti[6] = 0; ti[7] = 0;
+                }
+            }
             sm_MHi(S)[k * K + o] = b.id1;
             sm_MHv(S)[k * K + o] = b.v1;
-            if (b.id1 != IMOMD_NONE && b.v2 - b.v1 <= kTieRel * b.v1)
-            {
-                Q->unresolved_ties += 1;
-                double* ti = Q->tie_info;
-                ti[0] = 2; ti[1] = k; ti[2] = o; ti[3] = b.v1; ti[4] = b.v2; ti[5] = b.id1;
-                ti[6] = 0; ti[7] = 0;
-            }
         }
         cta.sync();
     }
@@ -1794,23 +1998,101 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
         uint32_t r = Q->view_root[o];
         S.h[yi * IMOMD_KMAX + o] = haversine_pc(g.lat[y], g.lon[y], g.coslat[y], g.lat[r], g.lon[r], g.coslat[r]);
     }
+    if (cta.tid() == 0) S.mh_tie_mask = 0u;
     cta.sync();
     for (int o = cta.tid(); o < K; o += cta.nt())
     {
         if (o == k) continue;
         double best = sm_MHv(S)[k * K + o];
         uint32_t arg = sm_MHi(S)[k * K + o];
+        bool close = false;
         for (int yi = 0; yi < m; ++yi)
         {
             double h = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
+            // (an inserted vertex that already IS the holder compares equal in any arithmetic)
+            if (arg != IMOMD_NONE && S.ys[yi] != arg && fabs(h - best) <= P.tie_rel * best) close = true;
             if (h < best)
             {
                 best = h;
                 arg = S.ys[yi];
             }
         }
+        if (close)
+        {
+            cta.counter_or(&S.mh_tie_mask, 1u << o);   // redone below with the exact values
+            continue;
+        }
         sm_MHv(S)[k * K + o] = best;
         sm_MHi(S)[k * K + o] = arg;
+    }
+    cta.sync();
+    if (S.mh_tie_mask == 0u) return;
+    if (cta.tid() == 0)
+    {
+        // a candidate within 1e-12 of the holder (or of another candidate): the sequence of strict
+        // `<` comparisons of :541-556 is replayed on glibc's values (holder first, then the
+        // inserted vertices in adjacency order)
+        const uint32_t rk = Q->view_root[k];
+        for (int o = 0; o < K; ++o)
+        {
+            if (!((S.mh_tie_mask >> o) & 1u)) continue;
+            const uint32_t ro = Q->view_root[o];
+            const uint32_t holder = sm_MHi(S)[k * K + o];
+            uint32_t ids[IMOMD_MAXDEG + 1];
+            double dev[IMOMD_MAXDEG + 1];
+            int n = 0;
+            if (holder != IMOMD_NONE)
+            {
+                ids[n] = holder;
+                dev[n] = sm_MHv(S)[k * K + o];
+                ++n;
+            }
+            for (int yi = 0; yi < m; ++yi)
+            {
+                ids[n] = S.ys[yi];
+                dev[n] = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
+                ++n;
+            }
+            bool ok = 2 * n <= IMOMD_TIE_PAIRS;
+            if (ok)
+            {
+                for (int i = 0; i < n; ++i)
+                {
+                    const uint32_t v = ids[i];
+                    double* a = S.tie_in[2 * i];
+                    double* b = S.tie_in[2 * i + 1];
+                    a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = g.lat[rk]; a[3] = g.lon[rk];
+                    b[0] = g.lat[v]; b[1] = g.lon[v]; b[2] = g.lat[ro]; b[3] = g.lon[ro];
+                }
+                ok = cta.certify(2 * n, S.tie_in, S.tie_out);
+            }
+            int w = 0;
+            if (ok)
+            {
+                double best = S.tie_out[0] + S.tie_out[1];
+                for (int i = 1; i < n; ++i)
+                {
+                    double h = S.tie_out[2 * i] + S.tie_out[2 * i + 1];
+                    if (h < best)
+                    {
+                        best = h;
+                        w = i;
+                    }
+                }
+                Q->certified_ties += 1;
+            }
+            else
+            {
+                for (int i = 1; i < n; ++i)
+                    if (dev[i] < dev[w]) w = i;
+                Q->unresolved_ties += 1;
+                double* ti = Q->tie_info;
+                ti[0] = 3; ti[1] = k; ti[2] = o; ti[3] = dev[0]; ti[4] = dev[w]; ti[5] = ids[w];
+                ti[6] = 0; ti[7] = 0;
+            }
+            sm_MHv(S)[k * K + o] = dev[w];
+            sm_MHi(S)[k * K + o] = ids[w];
+        }
     }
 }
 
@@ -2139,10 +2421,11 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
 // Tree construction of the planner constructor (src/imomd_rrt_star.cpp:73-78):
 // tree i gets its root and updateExpandables(root, true) while trees j > i still
 // read as id 0 / root 0.  Serial; runs once per query.
-IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
+IMOMD_HD inline void construct_trees(const PlannerDev& P, int q, int hq)
 {
+    // q: the slot that holds the trees; hq: the query (header) they belong to
     const GraphDev& g = P.g;
-    QueryDev* Q = P.query + q;
+    QueryDev* Q = P.query + hq;
     int K = Q->K;
     for (int i = 0; i < K; ++i)
     {
@@ -2184,9 +2467,148 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q)
     }
 }
 
+// ------------------------------------------------ slot recycling (streaming planners) ---
+// A streaming planner has fewer sets of per-query device state ("slots") than queries: a CTA
+// takes the next query from a work queue, rebuilds its slot for it, runs the query to completion
+// and keeps only the header (K x K matrices, counters, tree hash).
+
+// All threads: the slot back to "nothing visited, empty frontier hashes, all chunks free".
+template <class Cta>
+IMOMD_HD inline void reset_slot(Cta& cta, const PlannerDev& P, int slot)
+{
+    const size_t K = (size_t)P.K;
+    const size_t cells = (size_t)P.g.G * P.g.G;
+    // all-ones = not visited / not in the frontier / no children; streaming 128-bit stores: the
+    // 12 n records of a slot must not evict the resident queries' working sets from L2
+    unsigned char* base = P.trec + (size_t)slot * K * (size_t)P.g.n * P.trec_stride;
+    const size_t vecs = K * (size_t)P.g.n * P.trec_stride / 16;
+    U4 ones;
+    ones.x = ones.y = ones.z = ones.w = IMOMD_NONE;
+    U4* dst = reinterpret_cast<U4*>(base);
+    for (size_t i = (size_t)cta.tid(); i < vecs; i += (size_t)cta.nt()) cta.store_streaming(dst + i, ones);
+    uint32_t* ch = P.cell_head + (size_t)slot * K * cells;
+    uint32_t* cc = P.cell_cnt + (size_t)slot * K * cells;
+    for (size_t i = (size_t)cta.tid(); i < K * cells; i += (size_t)cta.nt())
+    {
+        ch[i] = IMOMD_NONE;
+        cc[i] = 0u;
+    }
+    const size_t chunks = (size_t)P.chunks;
+    uint32_t* fs = P.free_stack + (size_t)slot * K * chunks;
+    for (size_t i = (size_t)cta.tid(); i < K * chunks; i += (size_t)cta.nt())
+        fs[i] = (uint32_t)(chunks - 1 - i % chunks);   // pop order 0, 1, 2, ...
+}
+
+// All threads: root -> cell distance bounds of the slot for the roots of query hq
+template <class Cta>
+IMOMD_HD inline void fill_bounds(Cta& cta, const PlannerDev& P, int slot, int hq)
+{
+    const size_t cells = (size_t)P.g.G * P.g.G;
+    const size_t total = (size_t)P.K * cells;
+    double* lbd = P.lbd + (size_t)slot * total;
+    double* ubd = P.ubd + (size_t)slot * total;
+    const QueryDev* Q = P.query + hq;
+    for (size_t i = (size_t)cta.tid(); i < total; i += (size_t)cta.nt())
+    {
+        const uint32_t root = Q->dest[i / cells];
+        const uint32_t c = (uint32_t)(i % cells);
+        lbd[i] = lbd_of(P.g, root, c);
+        ubd[i] = ubd_of(P.g, root, c);
+    }
+}
+
+IMOMD_HD inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+
+// one (tree, vertex, parent, cost bits) entry of the order-free tree checksum
+IMOMD_HD inline uint64_t tree_sum_term(int k, uint32_t v, uint32_t parent, uint64_t cost_bits)
+{
+    return mix64(mix64(((uint64_t)(uint32_t)k << 32 | v) + 0x9E3779B97F4A7C15ull) ^
+                 mix64(((uint64_t)parent << 1) + 1u) ^ mix64(cost_bits + 0xD6E8FEB86659FD93ull));
+}
+
+// TREEHASH of SURVEY.md Appendix A: FNV-1a-style fold over the trees in id order, each tree's
+// visited vertices in ascending id, of the three 64-bit values (vertex, parent, cost bits).
+// All threads compact a tile's visited records, in vertex order, into `buf` (u32 quadruples:
+// vertex, parent, cost bits lo / hi); thread 0 folds them.  Also returns the order-free checksum.
+// `buf` holds `cap` u32 (the slot's rewire arena).  Results are valid on thread 0.
+constexpr uint32_t kHashPerThread = 8;
+template <class Cta>
+IMOMD_HD inline void tree_hash(Cta& cta, const PlannerDev& P, int slot, Shared& S, uint32_t* buf, uint32_t cap,
+                               uint64_t* hash_out, uint64_t* sum_out)
+{
+    const uint32_t n = P.g.n;
+    uint64_t h = 1469598103934665603ull;
+    uint64_t sum = 0;
+    const uint32_t tile = (uint32_t)cta.nt() * kHashPerThread;
+    uint32_t filled = 0;          // entries waiting in buf (uniform across the CTA)
+    for (int k = 0; k < P.K; ++k)
+    {
+        const unsigned char* base = P.trec + ((size_t)slot * P.K + k) * (size_t)n * P.trec_stride;
+        for (uint32_t v0 = 0; v0 < n; v0 += tile)
+        {
+            U4 hd[kHashPerThread];
+            uint32_t cnt = 0, total = 0;
+            const uint32_t first = v0 + (uint32_t)cta.tid() * kHashPerThread;
+#pragma unroll
+            for (uint32_t j = 0; j < kHashPerThread; ++j)
+            {
+                hd[j].x = IMOMD_NONE;
+                if (first + j < n)
+                    hd[j] = cta.load_streaming(reinterpret_cast<const U4*>(base + (size_t)(first + j) * P.trec_stride));
+                if (hd[j].x != IMOMD_NONE) ++cnt;
+            }
+            uint32_t off = cta.scan_exclusive(cnt, &total, S.scan);
+#pragma unroll
+            for (uint32_t j = 0; j < kHashPerThread; ++j)
+            {
+                if (hd[j].x != IMOMD_NONE)
+                {
+                    uint32_t* e = buf + 4 * (size_t)(filled + off);
+                    e[0] = first + j;
+                    e[1] = hd[j].x;
+                    e[2] = hd[j].z;
+                    e[3] = hd[j].w;
+                    ++off;
+                    sum += tree_sum_term(k, first + j, hd[j].x, ((uint64_t)hd[j].w << 32) | hd[j].z);
+                }
+            }
+            filled += total;
+            // fold at the end of every tree and whenever the next tile might not fit
+            if (v0 + tile >= n || 4 * (size_t)(filled + tile) > cap)
+            {
+                cta.sync();
+                if (cta.tid() == 0)
+                {
+                    for (uint32_t i = 0; i < filled; ++i)
+                    {
+                        const uint32_t* e = buf + 4 * (size_t)i;
+                        h = (h ^ (uint64_t)e[0]) * 1099511628211ull;
+                        h = (h ^ (uint64_t)e[1]) * 1099511628211ull;
+                        h = (h ^ (((uint64_t)e[3] << 32) | e[2])) * 1099511628211ull;
+                    }
+                }
+                filled = 0;
+                cta.sync();
+            }
+        }
+    }
+    sum = cta.reduce_sum_u64(sum, S.red);
+    *hash_out = h;
+    *sum_out = sum;
+}
+
 // The per-query driver: the loop every CTA runs (device) / the host simulation runs.
+// q: the slot holding the query's trees and scratch; hq: the query (header / report index).
 template <int KW, class Cta>
-IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, Shared& S,
+IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int iters, Shared& S,
                                double* lb, uint32_t* lvl, double* mat, unsigned char* hot,
                                int attach_tree = -1, uint32_t attach_count = 0)
 {
@@ -2196,7 +2618,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     IMOMD_ASSUME_SHARED(lvl);
     IMOMD_ASSUME_SHARED(mat);
     IMOMD_ASSUME_SHARED(hot);
-    QueryDev* Qg = P.query + q;
+    QueryDev* Qg = P.query + hq;
     QueryDev* Q = reinterpret_cast<QueryDev*>(hot);
     const int KK = P.K * P.K;
     {
@@ -2229,6 +2651,8 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     {
         S.phase = PH_NEXT_TREE;
         S.it = 0;
+        S.stop = 0;
+        S.t_start_ns = P.budget_ns ? cta.now_ns() : 0;
         S.k = Q->resume_k;         // resume point inside an interrupted pass
         S.attach_mode = 0;
         if (attach_tree >= 0)
@@ -2249,17 +2673,26 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         Q->last_expansions = Q->expansions;
     }
     cta.sync();
+    const long long busy0 = cta.clock();
+    uint32_t attach_seen = IMOMD_NONE;
     int warm_k = -1;              // tree whose nearest search has just finished (helpers prefetch)
     uint32_t warm_x = IMOMD_NONE;
     for (;;)
     {
         long long t0 = cta.clock();
         if (warm_k >= 0) warm_x = S.result.id1;
+        // attach mode: warm the upcoming list entries once per entry (when the position moved)
+        uint32_t attach_at = IMOMD_NONE;
+        if (attach_tree >= 0 && S.attach_i != attach_seen)
+        {
+            attach_at = S.attach_i;
+            attach_seen = attach_at;
+        }
         if (cta.tid() == 0)
         {
             int ph0 = S.phase & 7;
             Seq<KW> seq(P, q, S);
-            seq.step(iters);
+            seq.step(cta, iters);
             Q->phase_cycles[ph0] += (uint64_t)(cta.clock() - t0);
             Q->phase_count[ph0] += 1;
         }
@@ -2267,6 +2700,10 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         {
             // a nearest search has just finished: fetch what the serial thread is about to touch
             warm_expansion(cta, P, tree_ref_of(P, q, warm_k, S), q, warm_k, warm_x, S);
+        }
+        else if (attach_tree >= 0 && attach_at != IMOMD_NONE)
+        {
+            warm_attach(cta, P, tree_ref_of(P, q, attach_tree, S), attach_at, attach_count, S);
         }
         cta.sync();
         int req = S.req;
@@ -2315,6 +2752,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
     if (cta.tid() == 0)
     {
         if (attach_tree < 0) Q->resume_k = S.k < Q->K ? S.k : 0;
+        Q->busy_cycles = (uint64_t)(cta.clock() - busy0);
         Q->last_iterations = Q->iterations - Q->last_iterations;
         Q->last_expansions = Q->expansions - Q->last_expansions;
         int active = 0;
@@ -2325,7 +2763,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
             tv += (int64_t)Q->tree_size[j];
         }
         Q->active_trees = active;
-        ReportDev* R = P.reports + q;
+        ReportDev* R = P.reports + hq;
         R->status = Q->status;
         R->active_trees = active;
         R->iterations = Q->last_iterations;
@@ -2337,12 +2775,53 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int iters, 
         R->near_ties = Q->near_ties;
         R->unresolved_ties = Q->unresolved_ties;
         R->log_entries = (int64_t)Q->log_count;
+        R->certified_ties = Q->certified_ties;
+        R->tree_hash = Q->tree_hash;
+        R->busy_cycles = Q->busy_cycles;
     }
     cta.sync();
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(hot);
         uint32_t* dst = reinterpret_cast<uint32_t*>(Qg);
         for (uint32_t i = cta.tid(); i < IMOMD_QUERY_HOT_BYTES / 4; i += cta.nt()) dst[i] = src[i];
+    }
+    cta.sync();
+}
+
+// One query of a streaming planner, start to finish, in slot `slot`: header from the freshly
+// constructed copy, slot rebuilt, trees constructed (ctor :73-78), `iters` passes, tree hash.
+template <int KW, class Cta>
+IMOMD_HD inline void run_streaming_query(Cta& cta, const PlannerDev& P, int slot, int hq, int iters, Shared& S,
+                                         double* lb, uint32_t* lvl, double* mat, unsigned char* hot)
+{
+    const long long t0 = cta.clock();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.query_init + hq);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(P.query + hq);
+        for (uint32_t i = cta.tid(); i < sizeof(QueryDev) / 4; i += cta.nt()) dst[i] = src[i];
+    }
+    reset_slot(cta, P, slot);
+    fill_bounds(cta, P, slot, hq);
+    cta.sync();
+    if (cta.tid() == 0)
+    {
+        QueryDev* Q = P.query + hq;
+        for (int k = 0; k < P.K; ++k) Q->free_top[k] = (uint32_t)P.chunks;
+        construct_trees(P, slot, hq);
+    }
+    cta.sync();
+    run_query<KW>(cta, P, slot, hq, iters, S, lb, lvl, mat, hot);
+    cta.sync();
+    uint64_t h = 0, sum = 0;
+    tree_hash(cta, P, slot, S, P.arena + (size_t)slot * P.arena_entries, P.arena_entries, &h, &sum);
+    if (cta.tid() == 0)
+    {
+        QueryDev* Q = P.query + hq;
+        Q->tree_hash = h;
+        Q->tree_sum = sum;
+        Q->busy_cycles = (uint64_t)(cta.clock() - t0);
+        P.reports[hq].tree_hash = h;
+        P.reports[hq].busy_cycles = Q->busy_cycles;
     }
     cta.sync();
 }

@@ -14,6 +14,7 @@
 // CUDA device and fails with IMOMD_ERR_CUDA otherwise.
 
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -49,12 +50,32 @@ int fail(int code, const char* fmt, ...)
     do                                                                                   \
     {                                                                                    \
         cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call, __FILE__, __LINE__);          \
+    } while (0)
+
+// a failed CUDA call: message, sticky error cleared, device OOM reported as IMOMD_ERR_NOMEM
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    (void)cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? IMOMD_ERR_NOMEM : IMOMD_ERR_CUDA, "%s failed: %s (%s:%d)", what,
+                cudaGetErrorString(e), file, line);
+}
+
+// like CU, but runs `cleanup` before returning (constructors: nothing half-built may leak)
+#define CU_OR(cleanup, call)                                                             \
+    do                                                                                   \
+    {                                                                                    \
+        cudaError_t e_ = (call);                                                         \
         if (e_ != cudaSuccess)                                                           \
-            return fail(IMOMD_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+        {                                                                                \
+            int rc_ = cuda_fail(e_, #call, __FILE__, __LINE__);                          \
+            cleanup;                                                                     \
+            return rc_;                                                                  \
+        }                                                                                \
     } while (0)
 
 constexpr int kThreads = 256;   // CTA size of the expansion kernel (8 warps)
+constexpr int kTieBoxes = 1024; // host mailboxes per planner (>= the largest grid that can ask)
 
 // ------------------------------------------------------------ Cta policy ---
 
@@ -102,6 +123,72 @@ struct CtaDev
     __device__ __forceinline__ uint32_t counter_add(uint32_t* p, uint32_t v) const
     {
         return atomicAdd(p, v);
+    }
+    __device__ __forceinline__ void counter_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
+    __device__ __forceinline__ uint64_t now_ns() const
+    {
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+    // 128-bit accesses that should not displace the resident working sets from L2 (evict-first)
+    __device__ __forceinline__ void store_streaming(U4* p, const U4& v) const
+    {
+        __stcs(reinterpret_cast<uint4*>(p), make_uint4(v.x, v.y, v.z, v.w));
+    }
+    __device__ __forceinline__ U4 load_streaming(const U4* p) const
+    {
+        uint4 t = __ldcs(reinterpret_cast<const uint4*>(p));
+        U4 r;
+        r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
+        return r;
+    }
+    // Exact values from the host (ONE thread calls): the n coordinate pairs go to this CTA's
+    // mailbox in mapped pinned host memory, the host thread waiting for the launch (wait_stream)
+    // answers with the reference's haversine evaluated by glibc.  System-scope release / acquire.
+    TieBox* box = nullptr;
+    __device__ __noinline__ bool certify(int n, double (*in)[4], double* out) const
+    {
+        if (box == nullptr) return false;
+        volatile TieBox* b = box;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < 4; ++j) b->in[i][j] = in[i][j];
+        b->n = (uint32_t)n;
+        __threadfence_system();
+        uint32_t* st = &box->state;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(st), "r"(1u) : "memory");
+        uint32_t v = 0;
+        for (;;)
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(st) : "memory");
+            if (v == 2u) break;
+            __nanosleep(2000);
+        }
+        for (int i = 0; i < n; ++i) out[i] = b->out[i];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(st), "r"(0u) : "memory");
+        return true;
+    }
+    __device__ __forceinline__ uint64_t reduce_sum_u64(uint64_t v, Best* red) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(full, v, off);
+        uint64_t* scr = reinterpret_cast<uint64_t*>(red);
+        if (lane == 0) scr[warp] = v;
+        __syncthreads();
+        if (warp == 0)
+        {
+            v = lane < nw ? scr[lane] : 0ull;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(full, v, off);
+            if (lane == 0) scr[32] = v;
+        }
+        __syncthreads();
+        v = scr[32];
+        __syncthreads();
+        return v;
     }
     // block-wide exclusive prefix sum (returns this thread's offset, *total to everyone)
     __device__ __forceinline__ uint32_t scan_exclusive(uint32_t v, uint32_t* total, uint32_t* scr) const
@@ -235,6 +322,28 @@ __global__ void k_lower_bounds(const __grid_constant__ PlannerDev P)
     P.ubd[i] = ubd_entry(P, i);
 }
 
+// Freshly constructed headers (src/imomd_rrt_star.cpp:57-71, :103-108) from the destinations and
+// the selection probabilities: one CTA per query; only 4 K + 8 K^2 bytes per query cross the bus.
+__global__ void k_fill_headers(const __grid_constant__ PlannerDev P, QueryDev* __restrict__ out,
+                               const uint32_t* __restrict__ dest, const double* __restrict__ prob)
+{
+    const int q = blockIdx.x, K = P.K;
+    QueryDev* h = out + q;
+    uint32_t* w = reinterpret_cast<uint32_t*>(h);
+    for (uint32_t i = threadIdx.x; i < sizeof(QueryDev) / 4; i += blockDim.x) w[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) h->K = K;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) h->dest[i] = dest[(size_t)q * K + i];
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    {
+        h->P[i] = prob[(size_t)q * K * K + i];
+        h->D[i] = (i / K == i % K) ? 0.0 : INFINITY;
+        h->MHv[i] = INFINITY;
+        h->MHi[i] = IMOMD_NONE;
+        h->CN[i] = IMOMD_NONE;
+    }
+}
+
 __global__ void k_init_trees(const __grid_constant__ PlannerDev P)
 {
     int q = blockIdx.x;
@@ -250,7 +359,7 @@ __global__ void k_init_trees(const __grid_constant__ PlannerDev P)
     {
         QueryDev* Q = P.query + q;
         for (int k = 0; k < K; ++k) Q->free_top[k] = (uint32_t)P.chunks;
-        construct_trees(P, q);
+        construct_trees(P, q, q);
     }
 }
 
@@ -271,10 +380,42 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand(const __grid_con
     double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev cta;
+    cta.box = P.tiebox ? P.tiebox + blockIdx.x : nullptr;
+    if (P.streaming)
+    {
+        // slot = this CTA; queries come from the work queue in submission order, so a slot that
+        // drew a short query simply takes the next one (no wave boundaries, no static tail)
+        __shared__ int next_q;
+        for (;;)
+        {
+            if (threadIdx.x == 0) next_q = (int)atomicAdd(P.queue, 1u);
+            __syncthreads();
+            const int hq = next_q;
+            __syncthreads();
+            if (hq >= P.Q) break;
+            run_streaming_query<KW>(cta, P, (int)blockIdx.x, hq, iters, S, lb, lvl, mat, hot);
+        }
+        return;
+    }
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
-        run_query<KW>(cta, P, q, iters, S, lb, lvl, mat, hot);
+        run_query<KW>(cta, P, q, q, iters, S, lb, lvl, mat, hot);
         __syncthreads();
+    }
+}
+
+// TREEHASH + checksum of one resident query (imomd_get_treehash)
+__global__ void __launch_bounds__(kThreads) k_tree_hash(const __grid_constant__ PlannerDev P, int q)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+    CtaDev cta;
+    uint64_t h = 0, sum = 0;
+    tree_hash(cta, P, q, S, P.arena + (size_t)q * P.arena_entries, P.arena_entries, &h, &sum);
+    if (threadIdx.x == 0)
+    {
+        P.query[q].tree_hash = h;
+        P.query[q].tree_sum = sum;
     }
 }
 
@@ -289,7 +430,8 @@ __global__ void __launch_bounds__(kThreads) k_attach(const __grid_constant__ Pla
     double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev cta;
-    run_query<KW>(cta, P, q, 0, S, lb, lvl, mat, hot, tree, count);
+    cta.box = P.tiebox ? P.tiebox + blockIdx.x : nullptr;
+    run_query<KW>(cta, P, q, q, 0, S, lb, lvl, mat, hot, tree, count);
 }
 
 // Sparse readback: parent and cost of the listed vertices of one tree (ids in, parents out, in place).
@@ -328,6 +470,7 @@ k_nearest(const __grid_constant__ PlannerDev P, int n, const imomd_nn_query* __r
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
     CtaDev cta;
+    cta.box = P.tiebox ? P.tiebox + blockIdx.x : nullptr;
     uint32_t* clist = scratch + (size_t)blockIdx.x * 2 * P.chunks;
     __shared__ int64_t near_ties, unresolved;
     if (threadIdx.x == 0)
@@ -388,7 +531,7 @@ constexpr int kGaMaxLen = 128;
 __global__ void __launch_bounds__(256)
 k_ga_eval(int K, const double* __restrict__ D, int n_tours, int stride,
           const int32_t* __restrict__ tours, const int32_t* __restrict__ lens,
-          double* __restrict__ cost)
+          double* __restrict__ cost, int* __restrict__ bad)
 {
     extern __shared__ double sD[];
     for (int i = threadIdx.x; i < K * K; i += blockDim.x) sD[i] = D[i];
@@ -400,13 +543,32 @@ k_ga_eval(int K, const double* __restrict__ D, int n_tours, int stride,
     for (int t = warp; t < n_tours; t += nwarps)
     {
         const int32_t* s = tours + (size_t)t * stride;
-        int legs = lens[t] - 1;
+        int len = lens[t];
+        bool ok = len >= 1 && len <= stride;
+        int legs = ok ? len - 1 : 0;
         double vals[kGaMaxLen / 32];
 #pragma unroll
         for (int j = 0; j < kGaMaxLen / 32; ++j)
         {
             int i = j * 32 + lane;
-            vals[j] = i < legs ? sD[s[i] * K + s[i + 1]] : 0.0;
+            vals[j] = 0.0;
+            if (i < legs)
+            {
+                // ids are validated here (the host no longer walks every tour before the launch)
+                unsigned a = (unsigned)s[i], b = (unsigned)s[i + 1];
+                if (a < (unsigned)K && b < (unsigned)K) vals[j] = sD[a * K + b];
+                else ok = false;
+            }
+        }
+        if (legs == 0 && ok && lane == 0 && (unsigned)s[0] >= (unsigned)K) ok = false;
+        if (!__all_sync(full, ok))
+        {
+            if (lane == 0)
+            {
+                atomicExch(bad, t + 1);
+                cost[t] = nan("");
+            }
+            continue;
         }
         double acc = 0.0;
 #pragma unroll
@@ -439,13 +601,14 @@ struct imomd_graph
     double* coslat;
     double* cosrow;
     uint32_t max_degree;
+    int sm_count;
 };
 
 // device scratch of imomd_nearest_batch: grow-only buffers and the events of its stage timers,
 // owned by the planner (a call allocates only when it needs more than any call before it)
 struct NnPool
 {
-    static constexpr int kSlots = 16;
+    static constexpr int kSlots = 20;
     void* ptr[kSlots] = {};
     size_t bytes[kSlots] = {};
     cudaEvent_t ev[6] = {};
@@ -498,7 +661,10 @@ struct imomd_planner
     PlannerDev d;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
-    std::vector<QueryDev> init;     // headers of the freshly constructed state
+    std::vector<uint32_t> dest_h;   // [Q][K] destinations and [Q][K][K] selection probabilities of the
+    std::vector<double> prob_h;     // freshly constructed state (host copies; imomd_planner_reset)
+    uint32_t* dest_d = nullptr;
+    double* prob_d = nullptr;
     uint32_t* words;
     size_t words_cap, words_fed;
     size_t smem_bytes;
@@ -517,17 +683,28 @@ struct imomd_planner
     float nn_prep_ms = 0.f, nn_tiles_ms = 0.f, nn_merge_ms = 0.f;
     uint32_t nn_segments = 0;
     NnPool nn_pool;
+    // streaming planners: device copy of the freshly constructed headers, the work queue
+    QueryDev* query_init = nullptr;
+    uint32_t* queue = nullptr;
+    // host mailboxes of the exact-value service (mapped pinned memory) and what they did
+    TieBox* box_host = nullptr;
+    uint64_t certified_requests = 0;
 };
 
 struct imomd_ctx
 {
     int device;
+    int sm_count;
     cudaStream_t stream;
     double* D;
     int32_t* tours;
     int32_t* lens;
     double* cost;
+    int* bad;                 // device flag: a tour held an id outside [0, K) or a bad length
     size_t cap_tours, cap_n;
+    // pinned staging: one stream-ordered H2D / kernel / D2H sequence per call
+    unsigned char* pin;
+    size_t pin_bytes;
 };
 
 namespace {
@@ -538,9 +715,58 @@ cudaError_t dmalloc(T** p, size_t count)
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
 }
 
+// Answers the mailboxes of the exact-value service: the reference's haversine
+// (include/osm_converter/compute_haversine.hpp:41-58) on the host, i.e. with glibc's sin / cos /
+// atan2 / sqrt -- imomd::haversine is the same expression, compiled for the host here.
+void service_boxes(imomd_planner* p)
+{
+    TieBox* boxes = p->box_host;
+    if (!boxes) return;
+    for (int i = 0; i < kTieBoxes; ++i)
+    {
+        TieBox& b = boxes[i];
+        if (__atomic_load_n(&b.state, __ATOMIC_ACQUIRE) != 1u) continue;
+        const uint32_t n = std::min<uint32_t>(b.n, IMOMD_TIE_PAIRS);
+        for (uint32_t j = 0; j < n; ++j) b.out[j] = haversine(b.in[j][0], b.in[j][1], b.in[j][2], b.in[j][3]);
+        p->certified_requests += 1;
+        __atomic_store_n(&b.state, 2u, __ATOMIC_RELEASE);
+    }
+}
+
+// cudaStreamSynchronize that keeps the exact-value service running: a kernel of this planner may
+// be waiting for an answer, so every wait on the planner's stream goes through here.
+cudaError_t wait_stream(imomd_planner* p)
+{
+    if (!p->box_host) return cudaStreamSynchronize(p->stream);
+    int spins = 0;
+    for (;;)
+    {
+        cudaError_t rc = cudaStreamQuery(p->stream);
+        if (rc != cudaErrorNotReady) return rc;
+        service_boxes(p);
+        if (++spins > 64)
+        {
+            struct timespec ts = {0, 20000};   // 20 us between polls once the wait is a long one
+            nanosleep(&ts, nullptr);
+        }
+    }
+}
+
 int planner_fill_initial(imomd_planner* p)
 {
     PlannerDev& d = p->d;
+    const size_t QK = (size_t)d.Q * d.K;
+    CU(cudaMemcpyAsync(p->dest_d, p->dest_h.data(), QK * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->prob_d, p->prob_h.data(), QK * d.K * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (d.streaming)
+    {
+        // slots are rebuilt by the kernel when a query takes them; headers are built on the device
+        k_fill_headers<<<d.Q, 256, 0, p->stream>>>(d, p->query_init, p->dest_d, p->prob_d);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(d.query, p->query_init, (size_t)d.Q * sizeof(QueryDev), cudaMemcpyDeviceToDevice,
+                           p->stream));
+        return IMOMD_OK;
+    }
     const size_t qk = (size_t)d.Q * d.K;
     const size_t n = d.g.n;
     const size_t cells = (size_t)d.g.G * d.g.G;
@@ -549,8 +775,8 @@ int planner_fill_initial(imomd_planner* p)
     CU(cudaMemsetAsync(d.trec, 0xFF, qk * n * d.trec_stride, p->stream));
     CU(cudaMemsetAsync(d.cell_cnt, 0, qk * cells * sizeof(uint32_t), p->stream));
     CU(cudaMemsetAsync(d.cell_head, 0xFF, qk * cells * sizeof(uint32_t), p->stream));
-    CU(cudaMemcpyAsync(d.query, p->init.data(), (size_t)d.Q * sizeof(QueryDev),
-                       cudaMemcpyHostToDevice, p->stream));
+    k_fill_headers<<<d.Q, 256, 0, p->stream>>>(d, d.query, p->dest_d, p->prob_d);
+    CU(cudaGetLastError());
     k_init_trees<<<d.Q, 128, 0, p->stream>>>(d);
     CU(cudaGetLastError());
     return IMOMD_OK;
@@ -588,6 +814,8 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     if (!g) return fail(IMOMD_ERR_NOMEM, "out of host memory");
     g->device = device;
     g->max_degree = max_deg;
+#define GCU(call) CU_OR(imomd_graph_destroy(g), call)
+    GCU(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device));
     GraphDev& d = g->d;
     d.n = n;
     d.arcs = arcs;
@@ -604,20 +832,20 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     std::vector<double> pw;
     std::vector<uint8_t> pdeg;
     build_padded_rows(n, row_ptr, col, w, d.width, &pcol, &pw, &pdeg);
-    CU(dmalloc(&g->deg, (size_t)n));
-    CU(dmalloc(&g->col, pcol.size()));
-    CU(dmalloc(&g->w, pw.size()));
-    CU(dmalloc(&g->lat, n));
-    CU(dmalloc(&g->lon, n));
-    CU(dmalloc(&g->vrec, n));
-    CU(dmalloc(&g->coslat, n));
-    CU(dmalloc(&g->cosrow, 2 * (size_t)G));
-    CU(cudaMemcpy(g->deg, pdeg.data(), (size_t)n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->col, pcol.data(), pcol.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->w, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->lat, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->lon, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(g->cosrow, cosrow.data(), 2 * (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
+    GCU(dmalloc(&g->deg, (size_t)n));
+    GCU(dmalloc(&g->col, pcol.size()));
+    GCU(dmalloc(&g->w, pw.size()));
+    GCU(dmalloc(&g->lat, n));
+    GCU(dmalloc(&g->lon, n));
+    GCU(dmalloc(&g->vrec, n));
+    GCU(dmalloc(&g->coslat, n));
+    GCU(dmalloc(&g->cosrow, 2 * (size_t)G));
+    GCU(cudaMemcpy(g->deg, pdeg.data(), (size_t)n, cudaMemcpyHostToDevice));
+    GCU(cudaMemcpy(g->col, pcol.data(), pcol.size() * 4, cudaMemcpyHostToDevice));
+    GCU(cudaMemcpy(g->w, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice));
+    GCU(cudaMemcpy(g->lat, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
+    GCU(cudaMemcpy(g->lon, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
+    GCU(cudaMemcpy(g->cosrow, cosrow.data(), 2 * (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
     d.deg = g->deg;
     d.col = g->col;
     d.w = g->w;
@@ -628,8 +856,9 @@ int imomd_graph_create_ex(int device, uint32_t n, const uint32_t* row_ptr, const
     d.cosrow = g->cosrow;
     k_build_vrec<<<(n + 255) / 256, 256>>>(n, g->lat, g->lon, g->vrec, g->coslat, G, d.lat0, d.lon0,
                                            d.hlat, d.hlon);
-    CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
+    GCU(cudaGetLastError());
+    GCU(cudaDeviceSynchronize());
+#undef GCU
     *out = g;
     return IMOMD_OK;
 }
@@ -672,10 +901,13 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     {
         if (dest[i] >= g->d.n) return fail(IMOMD_ERR_ARG, "destination %u out of range", dest[i]);
     }
+    if (params->pseudo_mode && params->max_resident_queries != 0 && params->max_resident_queries < n_queries)
+        return fail(IMOMD_ERR_ARG, "pseudo mode needs a resident planner (the merge reads the trees back)");
     *out = nullptr;
     CU(cudaSetDevice(g->device));
     imomd_planner* p = new (std::nothrow) imomd_planner();
     if (!p) return fail(IMOMD_ERR_NOMEM, "out of host memory");
+#define PCU(call) CU_OR(imomd_planner_destroy(p), call)
     p->g = g;
     p->words = nullptr;
     p->words_cap = p->words_fed = 0;
@@ -688,47 +920,85 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     p->gather_u32 = nullptr;
     p->gather_f64 = nullptr;
     p->walk_cap = 0;
+    p->stream = nullptr;
+    p->ev0 = p->ev1 = nullptr;
     PlannerDev& d = p->d;
+    std::memset(&d, 0, sizeof(d));
     d.g = g->d;
     d.Q = n_queries;
     d.K = K;
     d.goal_bias = params->goal_bias;
+    d.tie_rel = params->tie_band > 0.0 ? params->tie_band : kTieRel;
     d.pseudo = params->pseudo_mode ? 1 : 0;
     const size_t n = g->d.n;
     const size_t cells = (size_t)g->d.G * g->d.G;
     default_sizes(d, params->frontier_chunks, params->arena_entries, params->log_entries);
     const size_t chunks = (size_t)d.chunks;
-    const size_t qk = (size_t)n_queries * K;
-    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&p->ev0));
-    CU(cudaEventCreate(&p->ev1));
-    CU(dmalloc(&d.query, (size_t)n_queries));
     d.trec_stride = 16u + 4u * (uint32_t)g->d.width;
-    CU(dmalloc(&d.trec, qk * n * d.trec_stride));
-    CU(dmalloc(&d.cell_head, qk * cells));
-    CU(dmalloc(&d.cell_cnt, qk * cells));
-    CU(dmalloc(&d.rec, qk * chunks * IMOMD_CHUNK));
-    CU(dmalloc(&d.chunk_next, qk * chunks));
-    CU(dmalloc(&d.free_stack, qk * chunks));
-    CU(dmalloc(&d.lbd, qk * cells));
-    CU(dmalloc(&d.ubd, qk * cells));
-    CU(dmalloc(&d.occ, qk * 2 * cells));
-    CU(dmalloc(&d.arena, (size_t)n_queries * d.arena_entries));
-    CU(dmalloc(&d.clist, (size_t)n_queries * 2 * chunks));
-    CU(dmalloc(&d.log, (size_t)n_queries * 2 * d.log_entries));
-    CU(dmalloc(&d.reports, (size_t)n_queries));
+    // bytes of device state one resident query needs (trees, frontier hashes, scratch)
+    const size_t per_slot = (size_t)K * (n * d.trec_stride + cells * (4 + 4 + 8 + 8 + 8) +
+                                         chunks * (IMOMD_CHUNK * sizeof(VRec) + 8)) +
+                            (size_t)d.arena_entries * 4 + chunks * 8 + (size_t)d.log_entries * 8 +
+                            (d.pseudo ? (size_t)K * n * 4 : 0);
+    // resident planner: one slot per query.  Streaming planner (max_resident_queries < n_queries):
+    // queries share `slots` sets of state through a work queue.  -1 = as many as run concurrently
+    // (two CTAs per SM) and fit in 85 % of the free device memory.
+    int slots = n_queries;
+    if (params->max_resident_queries > 0) slots = std::min(n_queries, params->max_resident_queries);
+    else if (params->max_resident_queries < 0)
+    {
+        size_t free_b = 0, total_b = 0;
+        PCU(cudaMemGetInfo(&free_b, &total_b));
+        size_t fit = (size_t)((double)free_b * 0.85) / std::max<size_t>(per_slot, 1);
+        slots = (int)std::min<size_t>({(size_t)n_queries, (size_t)2 * g->sm_count, std::max<size_t>(fit, 1)});
+    }
+    d.slots = slots;
+    d.streaming = slots < n_queries ? 1 : 0;
+    const size_t sk = (size_t)slots * K;
+    PCU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PCU(cudaEventCreate(&p->ev0));
+    PCU(cudaEventCreate(&p->ev1));
+    PCU(dmalloc(&d.query, (size_t)n_queries));
+    PCU(dmalloc(&d.trec, sk * n * d.trec_stride));
+    PCU(dmalloc(&d.cell_head, sk * cells));
+    PCU(dmalloc(&d.cell_cnt, sk * cells));
+    PCU(dmalloc(&d.rec, sk * chunks * IMOMD_CHUNK));
+    PCU(dmalloc(&d.chunk_next, sk * chunks));
+    PCU(dmalloc(&d.free_stack, sk * chunks));
+    PCU(dmalloc(&d.lbd, sk * cells));
+    PCU(dmalloc(&d.ubd, sk * cells));
+    PCU(dmalloc(&d.occ, sk * 2 * cells));
+    PCU(dmalloc(&d.arena, (size_t)slots * d.arena_entries));
+    PCU(dmalloc(&d.clist, (size_t)slots * 2 * chunks));
+    PCU(dmalloc(&d.log, (size_t)slots * 2 * d.log_entries));
+    PCU(dmalloc(&d.reports, (size_t)n_queries));
+    PCU(cudaMemset(d.reports, 0, (size_t)n_queries * sizeof(ReportDev)));
     d.visit_log = nullptr;
     d.attach_list = nullptr;
-    if (d.pseudo) CU(dmalloc(&d.visit_log, qk * n));
-    if (d.pseudo) CU(dmalloc(&d.attach_list, n));
+    if (d.pseudo) PCU(dmalloc(&d.visit_log, sk * n));
+    if (d.pseudo) PCU(dmalloc(&d.attach_list, n));
+    if (d.streaming)
+    {
+        PCU(dmalloc(&p->query_init, (size_t)n_queries));
+        PCU(dmalloc(&p->queue, 2));
+        d.query_init = p->query_init;
+        d.queue = p->queue;
+    }
+    // exact-value service: mailboxes in mapped pinned host memory (IMOMD_NO_HOST_CERTIFY=1 runs
+    // without it: undecidable comparisons then keep the device's choice and are counted)
+    if (!getenv("IMOMD_NO_HOST_CERTIFY"))
+    {
+        PCU(cudaHostAlloc((void**)&p->box_host, sizeof(TieBox) * kTieBoxes, cudaHostAllocMapped));
+        std::memset(p->box_host, 0, sizeof(TieBox) * kTieBoxes);
+        PCU(cudaHostGetDevicePointer((void**)&d.tiebox, p->box_host, 0));
+    }
     d.words = nullptr;
     d.words_avail = 0;
     // initial headers
-    p->init.assign(n_queries, QueryDev());
-    for (int q = 0; q < n_queries; ++q)
-    {
-        fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
-    }
+    p->dest_h.assign(dest, dest + (size_t)n_queries * K);
+    p->prob_h.assign(prob, prob + (size_t)n_queries * K * K);
+    PCU(dmalloc(&p->dest_d, (size_t)n_queries * K));
+    PCU(dmalloc(&p->prob_d, (size_t)n_queries * K * K));
     p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
                     2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32 +
                     ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)K * sizeof(TreeRef);
@@ -742,16 +1012,24 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
 #define IMOMD_SET_ALL(W) set((const void*)k_expand<256, 1, W>); set((const void*)k_expand<256, 2, W>); set((const void*)k_attach<W>);
         IMOMD_SET_ALL(4) IMOMD_SET_ALL(8) IMOMD_SET_ALL(16)
 #undef IMOMD_SET_ALL
-        CU(e);
+        PCU(e);
     }
-    CU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)p->smem_bytes));
+    PCU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p->smem_bytes));
     int rc = planner_fill_initial(p);
-    if (rc != IMOMD_OK) return rc;
-    size_t total = qk * cells;
-    k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(d);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(p->stream));
+    if (rc != IMOMD_OK)
+    {
+        imomd_planner_destroy(p);
+        return rc;
+    }
+    if (!d.streaming)
+    {
+        size_t total = sk * cells;
+        k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(d);
+        PCU(cudaGetLastError());
+    }
+    PCU(wait_stream(p));
+#undef PCU
     *out = p;
     return IMOMD_OK;
 }
@@ -760,7 +1038,7 @@ int imomd_planner_destroy(imomd_planner* p)
 {
     if (!p) return IMOMD_OK;
     cudaSetDevice(p->g->device);
-    cudaStreamSynchronize(p->stream);
+    if (p->stream) wait_stream(p);
     PlannerDev& d = p->d;
     cudaFree(d.query);
     cudaFree(d.trec);
@@ -778,6 +1056,11 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(d.reports);
     cudaFree(d.visit_log);
     cudaFree(d.attach_list);
+    cudaFree(p->query_init);
+    cudaFree(p->queue);
+    cudaFree(p->dest_d);
+    cudaFree(p->prob_d);
+    if (p->box_host) cudaFreeHost(p->box_host);
     cudaFree(p->words);
     cudaFree(p->nn_scratch);
     cudaFree(p->nn_stats);
@@ -785,9 +1068,9 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(p->gather_u32);
     cudaFree(p->gather_f64);
     p->nn_pool.release();
-    cudaEventDestroy(p->ev0);
-    cudaEventDestroy(p->ev1);
-    cudaStreamDestroy(p->stream);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return IMOMD_OK;
 }
@@ -801,14 +1084,18 @@ int imomd_planner_set_queries(imomd_planner* p, const uint32_t* dest, const doub
         if (dest[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "destination %u out of range", dest[i]);
     }
     CU(cudaSetDevice(p->g->device));
-    for (int q = 0; q < Q; ++q)
-        fill_initial_header(p->init[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
+    CU(wait_stream(p));      // the previous upload may still be reading the host copies
+    p->dest_h.assign(dest, dest + (size_t)Q * K);
+    p->prob_h.assign(prob, prob + (size_t)Q * K * K);
     int rc = planner_fill_initial(p);
     if (rc != IMOMD_OK) return rc;
-    size_t total = (size_t)Q * K * p->d.g.G * p->d.g.G;
-    k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(p->d);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(p->stream));
+    if (!p->d.streaming)
+    {
+        size_t total = (size_t)Q * K * p->d.g.G * p->d.g.G;
+        k_lower_bounds<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(p->d);
+        CU(cudaGetLastError());
+    }
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -817,6 +1104,7 @@ int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* ver
 {
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !vertices)
         return fail(IMOMD_ERR_ARG, "bad planner/query/tree/list");
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     if (!p->d.attach_list) return fail(IMOMD_ERR_ARG, "imomd_attach needs a pseudo-mode planner");
     if (count == 0) return IMOMD_OK;
     if (count > p->d.g.n) return fail(IMOMD_ERR_ARG, "attach list longer than the graph");
@@ -824,10 +1112,19 @@ int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* ver
         if (vertices[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "attach list: vertex id out of range");
     CU(cudaSetDevice(p->g->device));
     CU(cudaMemcpyAsync(p->d.attach_list, vertices, (size_t)count * 4, cudaMemcpyHostToDevice, p->stream));
+    // One WARP per launch: an attach is a chain of small dependent steps (no frontier search), so
+    // the 256-thread CTA of the expansion kernel only added block barriers between them; with 32
+    // threads every barrier is a warp barrier and the idle lanes prefetch the list's next entries
+    // (warm_attach).  IMOMD_ATTACH_THREADS overrides (development aid).
+    static const int attach_threads = [] {
+        const char* e = getenv("IMOMD_ATTACH_THREADS");
+        int v = e ? atoi(e) : 32;
+        return (v >= 32 && v <= kThreads && v % 32 == 0) ? v : 32;
+    }();
     const int w = p->d.g.width;
-    if (w == 4) k_attach<4><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
-    else if (w == 8) k_attach<8><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
-    else k_attach<16><<<1, kThreads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
+    if (w == 4) k_attach<4><<<1, attach_threads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
+    else if (w == 8) k_attach<8><<<1, attach_threads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
+    else k_attach<16><<<1, attach_threads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
     CU(cudaGetLastError());
     if (report)
         CU(cudaMemcpyAsync(report, p->d.reports + query, sizeof(ReportDev), cudaMemcpyDeviceToHost,
@@ -835,7 +1132,7 @@ int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* ver
     if (parents_out)
         CU(cudaMemcpyAsync(parents_out, p->d.attach_list, (size_t)count * 4, cudaMemcpyDeviceToHost,
                            p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -850,9 +1147,10 @@ int imomd_get_visit_order(imomd_planner* p, int query, int tree, uint32_t* out, 
 {
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !count)
         return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     if (!p->d.visit_log) return fail(IMOMD_ERR_ARG, "the visit order is only recorded in pseudo mode");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     QueryDev h;
     CU(cudaMemcpy(&h, p->d.query + query, IMOMD_QUERY_HOT_BYTES, cudaMemcpyDeviceToHost));
     uint32_t n = (uint32_t)h.tree_size[tree];
@@ -871,7 +1169,7 @@ int imomd_set_distance(imomd_planner* p, int query, int i, int j, double d, uint
     if (!p || query < 0 || query >= p->d.Q || i < 0 || j < 0 || i >= p->d.K || j >= p->d.K)
         return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     QueryDev* qd = p->d.query + query;
     const int K = p->d.K;
     int32_t one = 1;
@@ -888,7 +1186,7 @@ int imomd_set_tree_done(imomd_planner* p, int query, int tree, int done)
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K)
         return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     int32_t v = done ? 1 : 0;
     CU(cudaMemcpy(&p->d.query[query].is_done[tree], &v, 4, cudaMemcpyHostToDevice));
     return IMOMD_OK;
@@ -899,7 +1197,7 @@ int imomd_set_contact(imomd_planner* p, int query, int set_idx)
     if (!p || query < 0 || query >= p->d.Q || set_idx < 0 || set_idx >= p->d.K * (p->d.K - 1) / 2)
         return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     uint8_t one = 1;
     CU(cudaMemcpy(&p->d.query[query].contact[set_idx], &one, 1, cudaMemcpyHostToDevice));
     return IMOMD_OK;
@@ -909,7 +1207,7 @@ int imomd_get_tie_info(imomd_planner* p, int query, double* out)
 {
     if (!p || query < 0 || query >= p->d.Q || !out) return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     CU(cudaMemcpy(out, p->d.query[query].tie_info, 8 * sizeof(double), cudaMemcpyDeviceToHost));
     return IMOMD_OK;
 }
@@ -918,7 +1216,7 @@ int imomd_get_counters(imomd_planner* p, uint64_t* out)
 {
     if (!p || !out) return fail(IMOMD_ERR_ARG, "null argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     CU(cudaMemcpy2D(out, 8 * sizeof(uint64_t), p->d.query[0].stat, sizeof(QueryDev),
                     8 * sizeof(uint64_t), (size_t)p->d.Q, cudaMemcpyDeviceToHost));
     return IMOMD_OK;
@@ -928,7 +1226,7 @@ int imomd_planner_clear_words(imomd_planner* p)
 {
     if (!p) return fail(IMOMD_ERR_ARG, "null planner");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     p->words_fed = 0;
     p->d.words_avail = 0;
     return IMOMD_OK;
@@ -940,7 +1238,7 @@ int imomd_planner_reset(imomd_planner* p)
     CU(cudaSetDevice(p->g->device));
     int rc = planner_fill_initial(p);
     if (rc != IMOMD_OK) return rc;
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -954,7 +1252,7 @@ int imomd_planner_feed_words(imomd_planner* p, const uint32_t* words, size_t n)
         cap = std::max<size_t>(cap, 1 << 16);
         uint32_t* nw = nullptr;
         CU(dmalloc(&nw, cap));
-        CU(cudaStreamSynchronize(p->stream));
+        CU(wait_stream(p));
         if (p->words_fed)
             CU(cudaMemcpy(nw, p->words, p->words_fed * 4, cudaMemcpyDeviceToDevice));
         cudaFree(p->words);
@@ -988,17 +1286,30 @@ int imomd_expand_async(imomd_planner* p, int iters)
         // (128 threads and/or 64 registers) are 5-20 % slower than two -- the CTA-wide
         // services lose more than the extra residency returns -- so larger query counts simply
         // run in waves.  Adjacency width by the graph.
-        const bool two_per_sm = p->d.Q > 148;
+        // A streaming planner launches one CTA per slot; its CTAs pull queries from the queue.
+        const int ctas = p->d.streaming ? p->d.slots : p->d.Q;
+        if (p->d.streaming) CU(cudaMemsetAsync(p->queue, 0, 2 * sizeof(uint32_t), p->stream));
+        const bool two_per_sm = ctas > p->g->sm_count;
         const int w = p->d.g.width;
         void (*kern)(PlannerDev, int) = nullptr;
         if (w == 4) kern = two_per_sm ? k_expand<256, 2, 4> : k_expand<256, 1, 4>;
         else if (w == 8) kern = two_per_sm ? k_expand<256, 2, 8> : k_expand<256, 1, 8>;
         else kern = two_per_sm ? k_expand<256, 2, 16> : k_expand<256, 1, 16>;
-        kern<<<p->d.Q, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
+        kern<<<ctas, kThreads, p->smem_bytes, p->stream>>>(p->d, iters);
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     p->pending = true;
+    return IMOMD_OK;
+}
+
+// max_time of the reference's loop (:258-262): the following imomd_expand calls stop after the
+// first pass that ends more than `seconds` after the launch started (reports say how many passes
+// ran); 0 = no budget
+int imomd_set_time_budget(imomd_planner* p, double seconds)
+{
+    if (!p || !(seconds >= 0.0)) return fail(IMOMD_ERR_ARG, "bad argument");
+    p->d.budget_ns = seconds > 0.0 ? std::max<uint64_t>(1, (uint64_t)(seconds * 1e9)) : 0;
     return IMOMD_OK;
 }
 
@@ -1010,7 +1321,7 @@ int imomd_sync(imomd_planner* p, imomd_query_report* reports)
     if (reports)
         CU(cudaMemcpyAsync(reports, p->d.reports, (size_t)p->d.Q * sizeof(ReportDev),
                            cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     if (p->pending)
     {
         CU(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
@@ -1038,7 +1349,7 @@ int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node,
 {
     if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     QueryDev h;
     CU(cudaMemcpy(&h, p->d.query + query, sizeof(h), cudaMemcpyDeviceToHost));
     int K = p->d.K;
@@ -1058,11 +1369,73 @@ int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node,
     return IMOMD_OK;
 }
 
+// K x K matrices of queries [first, first + count) in ONE device->host copy: each output holds
+// count * K * K entries (count * K for is_done), any of them may be NULL
+int imomd_get_states(imomd_planner* p, int first, int count, double* D, uint32_t* conn_node, double* prob,
+                     int32_t* is_done)
+{
+    if (!p || first < 0 || count < 0 || first + count > p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query range");
+    if (count == 0) return IMOMD_OK;
+    CU(cudaSetDevice(p->g->device));
+    CU(wait_stream(p));
+    std::vector<QueryDev> h((size_t)count);
+    CU(cudaMemcpy(h.data(), p->d.query + first, (size_t)count * sizeof(QueryDev), cudaMemcpyDeviceToHost));
+    const int K = p->d.K;
+    for (int q = 0; q < count; ++q)
+    {
+        const size_t o = (size_t)q * K * K;
+        for (int i = 0; i < K * K; ++i)
+        {
+            if (D) D[o + i] = h[q].D[i];
+            if (conn_node) conn_node[o + i] = h[q].CN[i];
+            if (prob) prob[o + i] = h[q].P[i];
+        }
+        if (is_done)
+            for (int k = 0; k < K; ++k) is_done[(size_t)q * K + k] = h[q].is_done[k];
+    }
+    return IMOMD_OK;
+}
+
+// TREEHASH of SURVEY.md Appendix A (trees in id order, visited vertices ascending, FNV fold of
+// vertex / parent / cost bits) and an order-free 64-bit checksum of the same entries, computed on
+// the device.  Streaming planners: the values the query left when it finished; resident planners:
+// computed now from the trees in HBM.
+int imomd_get_treehash(imomd_planner* p, int query, uint64_t* tree_hash, uint64_t* tree_sum)
+{
+    if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
+    CU(cudaSetDevice(p->g->device));
+    if (!p->d.streaming)
+    {
+        CU(cudaFuncSetAttribute(k_tree_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared) + 16));
+        k_tree_hash<<<1, kThreads, sizeof(Shared) + 16, p->stream>>>(p->d, query);
+        CU(cudaGetLastError());
+    }
+    CU(wait_stream(p));
+    uint64_t v[2];
+    CU(cudaMemcpy(v, &p->d.query[query].tree_hash, sizeof(v), cudaMemcpyDeviceToHost));   // tree_hash, tree_sum
+    if (tree_hash) *tree_hash = v[0];
+    if (tree_sum) *tree_sum = v[1];
+    return IMOMD_OK;
+}
+
+// how the planner is laid out: queries, sets of per-query device state, 1 when queries stream
+// through the slots, bytes of device memory per slot, requests the exact-value service answered
+int imomd_planner_info(imomd_planner* p, int32_t* n_queries, int32_t* slots, int32_t* streaming,
+                       uint64_t* certified_requests)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null planner");
+    if (n_queries) *n_queries = p->d.Q;
+    if (slots) *slots = p->d.slots;
+    if (streaming) *streaming = p->d.streaming;
+    if (certified_requests) *certified_requests = p->certified_requests;
+    return IMOMD_OK;
+}
+
 int imomd_get_flags(imomd_planner* p, int query, int32_t* connected, int32_t* dm_updated)
 {
     if (!p || query < 0 || query >= p->d.Q) return fail(IMOMD_ERR_ARG, "bad planner/query");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     int32_t v[2];
     QueryDev* qd = p->d.query + query;
     CU(cudaMemcpy(v, &qd->connected, sizeof(v), cudaMemcpyDeviceToHost));   // connected, dm_updated
@@ -1076,7 +1449,7 @@ int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* c
     if (!p || query < 0 || query >= p->d.Q || !cycles || !counts)
         return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     QueryDev* qd = p->d.query + query;
     CU(cudaMemcpy(cycles, qd->prof_cycles, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(counts, qd->prof_count, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -1099,7 +1472,7 @@ int imomd_clear_dm_updated(imomd_planner* p, int query)
     int32_t zero = 0;
     QueryDev* qd = p->d.query + query;
     CU(cudaMemcpyAsync(&qd->dm_updated, &zero, sizeof(zero), cudaMemcpyHostToDevice, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -1107,8 +1480,9 @@ int imomd_get_tree(imomd_planner* p, int query, int tree, uint32_t* parent, doub
 {
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !parent)
         return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     size_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
     const unsigned char* base = p->d.trec + qt * n * p->d.trec_stride;
@@ -1136,6 +1510,7 @@ int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uin
 {
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !count)
         return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     CU(cudaSetDevice(p->g->device));
     if (int rc = ensure_gather(p)) return rc;
     const uint32_t n = p->d.g.n;
@@ -1145,7 +1520,7 @@ int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uin
     CU(cudaGetLastError());
     uint32_t c = 0;
     CU(cudaMemcpyAsync(&c, p->gather_u32, 4, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     *count = c;
     uint32_t take = std::min(c, cap);
     if (take && out)
@@ -1165,6 +1540,7 @@ int imomd_gather_tree(imomd_planner* p, int query, int tree, const uint32_t* ver
     if (count == 0) return IMOMD_OK;
     for (uint32_t i = 0; i < count; ++i)
         if (vertices[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "gather list: vertex id out of range");
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     CU(cudaSetDevice(p->g->device));
     if (int rc = ensure_gather(p)) return rc;
     size_t qt = (size_t)query * p->d.K + tree;
@@ -1175,7 +1551,7 @@ int imomd_gather_tree(imomd_planner* p, int query, int tree, const uint32_t* ver
         CU(cudaMemcpyAsync(parent, p->gather_u32, (size_t)count * 4, cudaMemcpyDeviceToHost, p->stream));
     if (cost)
         CU(cudaMemcpyAsync(cost, p->gather_f64, (size_t)count * 8, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -1184,6 +1560,7 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
 {
     if (!p || query < 0 || query >= p->d.Q || tree < 0 || tree >= p->d.K || !out || !len)
         return fail(IMOMD_ERR_ARG, "bad planner/query/tree");
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     if (vertex >= p->d.g.n) return fail(IMOMD_ERR_ARG, "vertex out of range");
     CU(cudaSetDevice(p->g->device));
     if (p->walk_cap < cap + 1)
@@ -1195,13 +1572,13 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
     }
     size_t n = p->d.g.n;
     size_t qt = (size_t)query * p->d.K + tree;
-    uint32_t root = p->init[query].dest[tree];
+    uint32_t root = p->dest_h[(size_t)query * p->d.K + tree];
     k_walk<<<1, 32, 0, p->stream>>>(p->d.trec + qt * n * p->d.trec_stride, p->d.trec_stride, vertex,
                                     root, p->walk_buf + 1, cap, p->walk_buf);
     CU(cudaGetLastError());
     uint32_t l = 0;
     CU(cudaMemcpyAsync(&l, p->walk_buf, 4, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     *len = l;
     uint32_t take = std::min(l, cap);
     if (take) CU(cudaMemcpy(out, p->walk_buf + 1, (size_t)take * 4, cudaMemcpyDeviceToHost));
@@ -1213,7 +1590,7 @@ int imomd_get_connection_log_from(imomd_planner* p, int query, uint32_t first, u
 {
     if (!p || query < 0 || query >= p->d.Q || !count) return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     uint32_t total = 0;
     CU(cudaMemcpy(&total, &p->d.query[query].log_count, 4, cudaMemcpyDeviceToHost));
     *count = total;
@@ -1240,7 +1617,7 @@ int imomd_clear_connection_log(imomd_planner* p, int query)
     CU(cudaSetDevice(p->g->device));
     uint32_t zero = 0;
     CU(cudaMemcpyAsync(&p->d.query[query].log_count, &zero, 4, cudaMemcpyHostToDevice, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -1249,7 +1626,7 @@ int imomd_get_connection_log(imomd_planner* p, int query, uint32_t* set_idx, uin
 {
     if (!p || query < 0 || query >= p->d.Q || !count) return fail(IMOMD_ERR_ARG, "bad argument");
     CU(cudaSetDevice(p->g->device));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     QueryDev h;
     CU(cudaMemcpy(&h, p->d.query + query, sizeof(h), cudaMemcpyDeviceToHost));
     *count = h.log_count;
@@ -1277,8 +1654,9 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
         if (q[i].query < 0 || q[i].query >= p->d.Q || q[i].tree < 0 || q[i].tree >= p->d.K)
             return fail(IMOMD_ERR_ARG, "lookup %d: query/tree out of range", i);
     }
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     CU(cudaSetDevice(p->g->device));
-    int ctas = std::min(n, 148 * 4);
+    int ctas = std::min(n, p->g->sm_count * 4);
     if (p->nn_ctas < ctas)
     {
         cudaFree(p->nn_scratch);
@@ -1290,9 +1668,9 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
     imomd_nn_query* dq = nullptr;
     uint32_t* didx = nullptr;
     double* ddist = nullptr;
-    CU(dmalloc(&dq, (size_t)n));
-    CU(dmalloc(&didx, (size_t)n));
-    CU(dmalloc(&ddist, (size_t)n));
+    CU(p->nn_pool.get(16, &dq, (size_t)n));     // grow-only scratch owned by the planner
+    CU(p->nn_pool.get(17, &didx, (size_t)n));
+    CU(p->nn_pool.get(18, &ddist, (size_t)n));
     CU(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(imomd_nn_query), cudaMemcpyHostToDevice, p->stream));
     CU(cudaMemsetAsync(p->nn_stats, 0, 16, p->stream));
     k_nearest<<<ctas, kThreads, p->smem_bytes, p->stream>>>(p->d, n, dq, didx, ddist, p->nn_scratch,
@@ -1300,10 +1678,7 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(idx, didx, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
-    cudaFree(dq);
-    cudaFree(didx);
-    cudaFree(ddist);
+    CU(wait_stream(p));
     return IMOMD_OK;
 }
 
@@ -1318,6 +1693,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
         if (q[i].query < 0 || q[i].query >= p->d.Q || q[i].tree < 0 || q[i].tree >= p->d.K)
             return fail(IMOMD_ERR_ARG, "lookup %d: query/tree out of range", i);
     }
+    if (p->d.streaming) return fail(IMOMD_ERR_ARG, "%s: the per-query trees of a streaming planner are not resident", __func__);
     CU(cudaSetDevice(p->g->device));
     // tiles: lookups grouped by (query, tree) in their order of appearance (counting sort by tree),
     // at most kTileLookups per tile
@@ -1387,7 +1763,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaEventRecord(sc.ev[1], p->stream));
     uint32_t n_work = 0;
     CU(cudaMemcpyAsync(&n_work, n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     CU(sc.get(13, &work, (size_t)n_work));
     CU(sc.get(14, &part, (size_t)n_work * kConsumerWarps * kTileLookups));
     CU(cudaEventRecord(sc.ev[5], p->stream));
@@ -1399,7 +1775,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaEventRecord(sc.ev[2], p->stream));
     if (n_work > 0)
     {
-        const int grid = (int)std::min<size_t>(n_work, (size_t)148 * kTileCtasPerSm);
+        const int grid = (int)std::min<size_t>(n_work, (size_t)p->g->sm_count * kTileCtasPerSm);
         k_nearest_tiles<<<grid, kTileThreads, smem, p->stream>>>(p->d, seed, work, n_work_dev, next_work,
                                                                  lists, part, derr);
         CU(cudaGetLastError());
@@ -1417,7 +1793,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaMemcpyAsync(hcounts.data(), counts, (size_t)QK * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(hvalid.data(), tile_valid, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    CU(wait_stream(p));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, sc.ev[2], sc.ev[3]));
     float fill_ms = 0.f;
@@ -1478,13 +1854,12 @@ int imomd_ctx_create(int device, imomd_ctx** out)
     imomd_ctx* c = new (std::nothrow) imomd_ctx();
     if (!c) return fail(IMOMD_ERR_NOMEM, "out of host memory");
     c->device = device;
-    c->D = nullptr;
-    c->tours = nullptr;
-    c->lens = nullptr;
-    c->cost = nullptr;
-    c->cap_tours = c->cap_n = 0;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(dmalloc(&c->D, (size_t)IMOMD_KMAX * IMOMD_KMAX));
+#define XCU(call) CU_OR(imomd_ctx_destroy(c), call)
+    XCU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    XCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    XCU(dmalloc(&c->D, (size_t)IMOMD_KMAX * IMOMD_KMAX));
+    XCU(dmalloc(&c->bad, 1));
+#undef XCU
     *out = c;
     return IMOMD_OK;
 }
@@ -1497,7 +1872,9 @@ int imomd_ctx_destroy(imomd_ctx* c)
     cudaFree(c->tours);
     cudaFree(c->lens);
     cudaFree(c->cost);
-    cudaStreamDestroy(c->stream);
+    cudaFree(c->bad);
+    if (c->pin) cudaFreeHost(c->pin);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return IMOMD_OK;
 }
@@ -1509,23 +1886,15 @@ int imomd_ga_eval(imomd_ctx* c, int K, const double* D, int n_tours, int stride,
     if (K < 1 || K > (int)IMOMD_KMAX) return fail(IMOMD_ERR_ARG, "K out of range");
     if (stride < 1 || stride > kGaMaxLen) return fail(IMOMD_ERR_ARG, "stride must be in [1, %d]", kGaMaxLen);
     if (n_tours <= 0) return n_tours == 0 ? IMOMD_OK : fail(IMOMD_ERR_ARG, "negative tour count");
-    for (int t = 0; t < n_tours; ++t)
-    {
-        if (lens[t] < 1 || lens[t] > stride) return fail(IMOMD_ERR_ARG, "tour %d: bad length", t);
-        for (int i = 0; i < lens[t]; ++i)
-        {
-            int32_t v = tours[(size_t)t * stride + i];
-            if (v < 0 || v >= K) return fail(IMOMD_ERR_ARG, "tour %d: id out of range", t);
-        }
-    }
     CU(cudaSetDevice(c->device));
-    size_t need = (size_t)n_tours * stride;
+    const size_t need = (size_t)n_tours * stride;
     if (need > c->cap_tours)
     {
         cudaFree(c->tours);
         c->tours = nullptr;
-        CU(dmalloc(&c->tours, need));
-        c->cap_tours = need;
+        c->cap_tours = 0;
+        CU(dmalloc(&c->tours, need + need / 4));
+        c->cap_tours = need + need / 4;
     }
     if ((size_t)n_tours > c->cap_n)
     {
@@ -1533,20 +1902,43 @@ int imomd_ga_eval(imomd_ctx* c, int K, const double* D, int n_tours, int stride,
         cudaFree(c->cost);
         c->lens = nullptr;
         c->cost = nullptr;
-        CU(dmalloc(&c->lens, (size_t)n_tours));
-        CU(dmalloc(&c->cost, (size_t)n_tours));
-        c->cap_n = n_tours;
+        c->cap_n = 0;
+        const size_t cap = (size_t)n_tours + (size_t)n_tours / 4;
+        CU(dmalloc(&c->lens, cap));
+        CU(dmalloc(&c->cost, cap));
+        c->cap_n = cap;
     }
-    CU(cudaMemcpyAsync(c->D, D, (size_t)K * K * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->tours, tours, need * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->lens, lens, (size_t)n_tours * 4, cudaMemcpyHostToDevice, c->stream));
+    // pinned staging area: [D | tours | lens | cost out | bad flag]
+    const size_t bD = (size_t)K * K * 8, bT = need * 4, bL = (size_t)n_tours * 4, bC = (size_t)n_tours * 8;
+    const size_t oT = (bD + 15) / 16 * 16, oL = oT + (bT + 15) / 16 * 16, oC = oL + (bL + 15) / 16 * 16,
+                 oB = oC + (bC + 15) / 16 * 16, total = oB + 16;
+    if (total > c->pin_bytes)
+    {
+        if (c->pin) cudaFreeHost(c->pin);
+        c->pin = nullptr;
+        c->pin_bytes = 0;
+        CU(cudaHostAlloc((void**)&c->pin, total + total / 4, cudaHostAllocDefault));
+        c->pin_bytes = total + total / 4;
+    }
+    std::memcpy(c->pin, D, bD);
+    std::memcpy(c->pin + oT, tours, bT);
+    std::memcpy(c->pin + oL, lens, bL);
+    CU(cudaMemsetAsync(c->bad, 0, sizeof(int), c->stream));
+    CU(cudaMemcpyAsync(c->D, c->pin, bD, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->tours, c->pin + oT, bT, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->lens, c->pin + oL, bL, cudaMemcpyHostToDevice, c->stream));
     int warps_per_block = 8;
-    int blocks = std::min((n_tours + warps_per_block - 1) / warps_per_block, 148 * 8);
+    int blocks = std::min((n_tours + warps_per_block - 1) / warps_per_block, c->sm_count * 8);
     k_ga_eval<<<blocks, 256, (size_t)K * K * 8, c->stream>>>(K, c->D, n_tours, stride, c->tours,
-                                                             c->lens, c->cost);
+                                                             c->lens, c->cost, c->bad);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(cost_out, c->cost, (size_t)n_tours * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->pin + oC, c->cost, bC, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->pin + oB, c->bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    int bad = 0;
+    std::memcpy(&bad, c->pin + oB, sizeof(int));
+    if (bad) return fail(IMOMD_ERR_ARG, "tour %d: bad length or id out of range", bad - 1);
+    std::memcpy(cost_out, c->pin + oC, bC);
     return IMOMD_OK;
 }
 

@@ -110,6 +110,11 @@ struct QueryDev
                                 // other, best, runner-up, vertex, sample lat, sample lon
     uint64_t phase_cycles[8];   // serial-step cycles by the phase the step started in
     uint64_t phase_count[8];
+    int64_t certified_ties;     // near-ties decided with the host's glibc values (Cta::certify)
+    uint64_t tree_hash;         // SURVEY App. A TREEHASH of the K trees (streaming planners: written when
+                                // the query finishes; resident planners: by imomd_get_treehash)
+    uint64_t tree_sum;          // order-free companion: sum of mix64(tree, vertex, parent, cost bits)
+    uint64_t busy_cycles;       // SM-clock cycles this query kept its CTA busy (last launch)
     // ---- everything above is staged in shared memory while a launch runs (hot fields);
     // ---- the K x K matrices below are staged separately, compacted to stride K
     double P[IMOMD_KMAX * IMOMD_KMAX];    // probability_matrix_
@@ -134,6 +139,23 @@ struct ReportDev
     int64_t near_ties;
     int64_t unresolved_ties;
     int64_t log_entries;
+    int64_t certified_ties;
+    uint64_t tree_hash;
+    uint64_t busy_cycles;
+};
+
+// Mailbox between one CTA and the host thread that waits for the launch (mapped pinned host memory):
+// the device posts coordinate pairs of a comparison it cannot decide in its own arithmetic, the host
+// answers with the reference's haversine evaluated by glibc (include/osm_converter/
+// compute_haversine.hpp:41-58).  state: 0 idle, 1 request posted, 2 answer posted.
+#define IMOMD_TIE_PAIRS 16
+struct TieBox
+{
+    uint32_t state;
+    uint32_t n;
+    uint32_t pad_[2];
+    double in[IMOMD_TIE_PAIRS][4];   // lat1, lon1, lat2, lon2 (degrees)
+    double out[IMOMD_TIE_PAIRS];     // metres
 };
 
 struct PlannerDev
@@ -141,13 +163,24 @@ struct PlannerDev
     GraphDev g;
     int32_t Q;                 // queries
     int32_t K;
+    int32_t slots;             // sets of per-query device state (trees, frontier hashes, scratch):
+                               // == Q for a resident planner; < Q for a streaming planner, whose
+                               // queries take a slot from a work queue, run to completion and leave
+                               // only their header (matrices, counters, tree hash) behind
+    int32_t streaming;         // slots < Q
     double goal_bias;
+    double tie_rel;            // comparisons closer than this (relative) are decided on the host's values
+    uint64_t budget_ns;        // > 0: a launch stops after the first pass that ends later than this many
+                               // nanoseconds after its start (max_time, src/imomd_rrt_star.cpp:258-262)
     int32_t pseudo;
     int32_t chunks;            // chunks per tree
     uint32_t arena_entries;
     uint32_t log_entries;
     QueryDev* query;           // [Q]
-    // per (query, tree), index qt = q*K + k
+    const QueryDev* query_init;// [Q] freshly constructed headers (streaming planners restart from them)
+    uint32_t* queue;           // [2] streaming planners: next query to hand out, queries finished
+    TieBox* tiebox;            // [max grid] host mailboxes (device address of mapped pinned memory)
+    // per (slot, tree), index qt = slot*K + k.  A resident planner has slot == query.
     unsigned char* trec;       // [Q*K][n] vertex records of trec_stride bytes:
                                //   {u32 parent, u32 frontier slot, f64 cost, u32 child[width]}
     uint32_t trec_stride;      // 16 + 4 * width
@@ -158,7 +191,7 @@ struct PlannerDev
     VRec* rec;                 // [Q*K][chunks*32]
     uint32_t* chunk_next;      // [Q*K][chunks]
     uint32_t* free_stack;      // [Q*K][chunks]
-    // per query
+    // per slot
     double* lbd;               // [Q][K][G*G] lower bound root -> cell (metres)
     double* ubd;               // [Q][K][G*G] upper bound root -> cell (metres)
     uint32_t* arena;           // [Q][arena_entries]

@@ -68,7 +68,6 @@ public:
     const std::vector<LogRow>& getLog() const { return log_; }
     long long iterations() const { return iteration_count_; }
     long long expansions() const { return expansions_; }
-    void setDevice(int device) { device_ = device; }   // before the first expansion
     // findShortestPath runs on a pthread and cannot throw: a failure (device capacity status,
     // unmergeable pseudo tree) ends the run, is printed to stderr and kept here
     bool failed() const { return static_cast<bool>(failure_); }
@@ -78,6 +77,7 @@ public:
     void stepPasses(int passes) { expandBatch(passes); }
     void stepRTSP() { solveRTSP(); }
     imomd_planner* nativeHandle() { return planner_; }
+    // device of the planners constructed afterwards (graph, trees and solver live there)
     static void setDefaultDevice(int device);
 
 private:
@@ -104,6 +104,7 @@ private:
     imomd_planner* planner_ = nullptr;
     std::mt19937 rng_{0};
     size_t words_fed_ = 0;
+    size_t words_consumed_ = 0;
 
     long long iteration_count_ = 0;
     long long expansions_ = 0;

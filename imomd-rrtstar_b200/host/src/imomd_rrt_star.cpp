@@ -10,8 +10,7 @@
 //     exactly where the reference calls solveRTSP_ (every 100 passes), max_iter / max_time;
 //   * solveRTSP_ (:966-1003), updatePath_ (:918-964), logData_ (:1005-1029), printPath
 //     (:293-322).
-// One deliberate deviation: max_time is checked between batches (every 100 passes), not
-// after every pass.
+// max_time is enforced after every pass, as upstream, by a time budget the device kernel checks.
 #include "imomd_rrt_star/imomd_rrt_star.h"
 
 #include <algorithm>
@@ -123,6 +122,19 @@ ImomdRRT::ImomdRRT(size_t source, size_t target, std::vector<size_t> objectives,
     imomd_params params{};
     params.goal_bias = setting_.goal_bias;
     params.pseudo_mode = setting_.pseudo_mode ? 1 : 0;
+    // Device pools of the one query this planner drives.  The library's automatic sizes are meant
+    // for hundreds of queries per GPU (a frontier of ~N/8 vertices per tree); a single anytime run
+    // may grow tendril-like trees whose frontier is a multiple of that, and the reference has no
+    // capacity limit at all -- so be generous here (a frontier of up to N vertices per tree while
+    // that stays below ~4 GB, nested rewire lists of 4 N entries), and let the environment override:
+    // IMOMD_FRONTIER_CHUNKS (32-record chunks per tree), IMOMD_ARENA_ENTRIES (uint32 entries).
+    {
+        const double per_tree = static_cast<double>(n) / 32.0 + 8192.0;
+        if (per_tree * 1024.0 * K_ < 4e9) params.frontier_chunks = static_cast<uint32_t>(per_tree);
+        params.arena_entries = static_cast<uint32_t>(std::min<size_t>(std::max<size_t>(1u << 20, 4 * n), 1u << 28));
+        if (const char* e = std::getenv("IMOMD_FRONTIER_CHUNKS")) params.frontier_chunks = static_cast<uint32_t>(std::strtoul(e, nullptr, 10));
+        if (const char* e = std::getenv("IMOMD_ARENA_ENTRIES")) params.arena_entries = static_cast<uint32_t>(std::strtoul(e, nullptr, 10));
+    }
     if (setting_.pseudo_mode) connection_sets_.resize(static_cast<size_t>(K_) * (K_ - 1) / 2);
     check(imomd_planner_create(graph_, 1, K_, dest.data(), prob.data(), &params, &planner_),
           "planner creation");
@@ -176,8 +188,16 @@ bool ImomdRRT::expandBatch(int passes)
     int left = passes;
     while (left > 0)
     {
-        // every expansion draws 4 or 6 words (a few more for the rare Lemire rejection)
-        feedWords(static_cast<size_t>(left) * K_ * 8 + 256);
+        // every expansion draws 4 or 6 words (a few more for the rare Lemire rejection): top the
+        // injected stream up to what `left` passes can consume, counting what is still unread
+        const size_t want = static_cast<size_t>(left) * K_ * 8 + 256;
+        const size_t unread = words_fed_ - words_consumed_;
+        if (unread < want) feedWords(want - unread);
+        // max_time is tested after every pass upstream (:258-262): the launch gets what is left
+        // of the budget and stops by itself after the pass that crosses it
+        const double remaining = static_cast<double>(setting_.max_time) -
+                                 std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count();
+        check(imomd_set_time_budget(planner_, std::max(remaining, 1e-6)), "time budget");
         imomd_query_report rep{};
         check(imomd_expand(planner_, left, &rep), "expansion");
         left -= static_cast<int>(rep.iterations);
@@ -187,8 +207,14 @@ bool ImomdRRT::expandBatch(int passes)
         active_trees_ = rep.active_trees;
         connected_ = rep.connected != 0;
         dm_updated_ = rep.dm_updated != 0;
+        words_consumed_ = static_cast<size_t>(rep.words_consumed);
+        if (rep.status == IMOMD_RUN_FRONTIER_FULL || rep.status == IMOMD_RUN_ARENA_FULL)
+            throw std::runtime_error(std::string("ImomdRRT (B200): device ") +
+                                     (rep.status == IMOMD_RUN_FRONTIER_FULL ? "frontier pool" : "rewire scratch") +
+                                     " exhausted; raise IMOMD_FRONTIER_CHUNKS / IMOMD_ARENA_ENTRIES");
         if (rep.status != IMOMD_RUN_OK && rep.status != IMOMD_RUN_NEED_WORDS)
             throw std::runtime_error("ImomdRRT (B200): device run status " + std::to_string(rep.status));
+        if (rep.status == IMOMD_RUN_OK && left > 0) break;   // the time budget ended the launch
     }
     if (setting_.pseudo_mode) drainConnectionLog();
     return true;
@@ -451,7 +477,7 @@ void ImomdRRT::run()
             done_iter = true;
         else if (std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count() >
                  setting_.max_time)
-            done_time = true;
+            done_time = true;   // (the device stopped the batch after the pass that crossed max_time)
         if (iteration_count_ == before) break;   // defensive: the device made no progress
     }
     if (done_iter) std::cout << "[IMOMD] Reached Max Iteration" << std::endl;

@@ -30,16 +30,17 @@ class ImomdError(RuntimeError):
 
 
 class Params(C.Structure):
-    _fields_ = [("goal_bias", C.c_double), ("pseudo_mode", C.c_int32), ("reserved0", C.c_int32),
+    _fields_ = [("goal_bias", C.c_double), ("pseudo_mode", C.c_int32), ("max_resident_queries", C.c_int32),
                 ("frontier_chunks", C.c_uint32), ("arena_entries", C.c_uint32),
-                ("log_entries", C.c_uint32), ("reserved", C.c_uint32)]
+                ("log_entries", C.c_uint32), ("reserved", C.c_uint32), ("tie_band", C.c_double)]
 
 
 class Report(C.Structure):
     _fields_ = [("status", C.c_int32), ("active_trees", C.c_int32), ("iterations", C.c_int64),
                 ("expansions", C.c_int64), ("tree_vertices", C.c_int64),
                 ("words_consumed", C.c_int64), ("connected", C.c_int32), ("dm_updated", C.c_int32),
-                ("near_ties", C.c_int64), ("unresolved_ties", C.c_int64), ("log_entries", C.c_int64)]
+                ("near_ties", C.c_int64), ("unresolved_ties", C.c_int64), ("log_entries", C.c_int64),
+                ("certified_ties", C.c_int64), ("tree_hash", C.c_uint64), ("busy_cycles", C.c_uint64)]
 
 
 class NNQuery(C.Structure):
@@ -82,6 +83,10 @@ def cuda_lib():
         L.imomd_sync.argtypes = [vp, C.POINTER(Report)]
         L.imomd_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.imomd_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p]
+        L.imomd_get_states.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.imomd_get_treehash.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.imomd_planner_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_uint64)]
         L.imomd_clear_dm_updated.argtypes = [vp, C.c_int]
         L.imomd_get_visit_order.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.imomd_get_profile.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
@@ -204,7 +209,9 @@ class DevicePlanner:
     """Q independent queries (K trees each) on one device graph."""
 
     def __init__(self, dg: DeviceGraph, dests, probs=None, goal_bias=1.0, pseudo=False,
-                 frontier_chunks=0, arena_entries=0, log_entries=0):
+                 frontier_chunks=0, arena_entries=0, log_entries=0, max_resident=0, tie_band=0.0):
+        """max_resident: 0 = every query keeps its trees in HBM; n > 0 = at most n state slots (more
+        queries than that stream through them); -1 = automatic."""
         L = cuda_lib()
         self.dg, self.g = dg, dg.g
         self.Q, self.K = len(dests), len(dests[0])
@@ -212,7 +219,8 @@ class DevicePlanner:
             probs = [selection_probabilities(self.g, d) for d in dests]
         d = np.ascontiguousarray(np.asarray(dests, np.uint32).ravel())
         pr = np.ascontiguousarray(np.asarray(probs, np.float64).ravel())
-        par = Params(goal_bias, int(pseudo), 0, frontier_chunks, arena_entries, log_entries, 0)
+        par = Params(goal_bias, int(pseudo), int(max_resident), frontier_chunks, arena_entries, log_entries, 0,
+                     float(tie_band))
         self.h = C.c_void_p()
         _check(L.imomd_planner_create(dg.h, self.Q, self.K, d, pr, C.byref(par), C.byref(self.h)))
 
@@ -287,6 +295,28 @@ class DevicePlanner:
         return dict(D=D.reshape(K, K), conn=cn.reshape(K, K), P=P.reshape(K, K),
                     mh_id=mi.reshape(K, K), mh_val=mv.reshape(K, K), is_done=done, ds_parent=ds,
                     connected=c.value, dm_updated=u.value)
+
+    def states(self, first=0, count=None):
+        """K x K distance / connection-node / probability matrices and is_done flags of `count`
+        consecutive queries in one device->host copy."""
+        K = self.K
+        count = self.Q - first if count is None else count
+        D = np.empty((count, K, K)); cn = np.empty((count, K, K), np.uint32); P = np.empty((count, K, K))
+        done = np.empty((count, K), np.int32)
+        _check(cuda_lib().imomd_get_states(self.h, first, count, D.ctypes.data, cn.ctypes.data, P.ctypes.data,
+                                           done.ctypes.data))
+        return dict(D=D, conn=cn, P=P, is_done=done)
+
+    def treehash(self, q=0):
+        """(TREEHASH of SURVEY App. A, order-free checksum) of query q's trees, computed on the device."""
+        h, sm = C.c_uint64(), C.c_uint64()
+        _check(cuda_lib().imomd_get_treehash(self.h, q, C.byref(h), C.byref(sm)))
+        return h.value, sm.value
+
+    def info(self):
+        nq, sl, st, cr = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+        _check(cuda_lib().imomd_planner_info(self.h, C.byref(nq), C.byref(sl), C.byref(st), C.byref(cr)))
+        return dict(queries=nq.value, slots=sl.value, streaming=bool(st.value), certified_requests=cr.value)
 
     def frontier(self, k, q=0):
         out = np.empty(self.g.n, np.uint32); c = C.c_uint32()

@@ -20,42 +20,102 @@ def shard(n_queries: int, world: int, rank: int):
     return list(range(rank, n_queries, world))
 
 
-def run_sharded(graph, dests, iters, executor, world=None, rank=None):
-    """Run `executor(graph, my_dests, iters)` on this rank's queries and gather every rank's
-    per-query results in query order.  The executor returns one picklable result per query
-    (the CUDA executor: capi.DevicePlanner; the tests: the oracle)."""
-    if world is None:
-        world = dist.get_world_size() if dist.is_initialized() else 1
-        rank = dist.get_rank() if dist.is_initialized() else 0
-    mine = shard(len(dests), world, rank)
-    local = executor(graph, [dests[i] for i in mine], iters) if mine else []
-    assert len(local) == len(mine)
+def _gather(n_queries, mine, local, world):
     if world == 1:
-        return local
+        out = [None] * n_queries
+        for q, res in zip(mine, local):
+            out[q] = res
+        return out
     gathered = [None] * world
     dist.all_gather_object(gathered, list(zip(mine, local)))
-    out = [None] * len(dests)
+    out = [None] * n_queries
     for part in gathered:
         for q, res in part:
             out[q] = res
     return out
 
 
-def cuda_executor(device: int):
-    """Executor over the C ABI on one GPU: returns (expansions, tree_vertices, D matrix)."""
-    from . import capi
+def run_sharded(graph, dests, iters, executor, world=None, rank=None, dynamic_chunk=0, tag="imomd"):
+    """Run `executor(graph, my_dests, iters)` on this rank's queries and gather every rank's
+    per-query results in query order.  The executor returns one picklable result per query
+    (the CUDA executor: capi.DevicePlanner; the tests: the oracle).
 
-    def run(graph, my_dests, iters):
-        dg = capi.DeviceGraph(graph, device=device)
-        dp = capi.DevicePlanner(dg, my_dests)
+    dynamic_chunk = 0: query q runs on rank q mod world (static).  dynamic_chunk = c > 0: ranks
+    take chunks of c consecutive queries from a shared counter in the process group's store
+    (TCPStore `add`, no collective): a rank whose queries turn out cheap simply takes more, so a
+    job ends with the slowest CHUNK instead of the slowest static share.  Queries are independent:
+    the per-query results do not depend on who ran them."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    n = len(dests)
+    if dynamic_chunk <= 0 or world == 1:
+        mine = shard(n, world, rank)
+        local = executor(graph, [dests[i] for i in mine], iters) if mine else []
+        assert len(local) == len(mine)
+        return _gather(n, mine, local, world)
+    store = dist.distributed_c10d._get_default_store()
+    key = f"{tag}_next_query"
+    mine, local = [], []
+    while True:
+        start = store.add(key, dynamic_chunk) - dynamic_chunk
+        if start >= n:
+            break
+        ids = list(range(start, min(start + dynamic_chunk, n)))
+        res = executor(graph, [dests[i] for i in ids], iters)
+        assert len(res) == len(ids)
+        mine += ids
+        local += res
+    return _gather(n, mine, local, world)
+
+
+class CudaExecutor:
+    """Executor over the C ABI on one GPU.  The road graph is uploaded once and kept across
+    calls; every call builds a planner for its queries (streaming through `max_resident` state
+    slots when there are more queries than that), runs `iters` passes and returns, per query,
+    the report figures, the device-computed TREEHASH and the distance matrix."""
+
+    def __init__(self, device: int, max_resident: int = -1):
+        self.device, self.max_resident = device, max_resident
+        self._graph, self._dg = None, None
+        self.kernel_ms = 0.0
+
+    def _device_graph(self, graph):
+        from . import capi
+        if self._graph is not graph:
+            self.close()
+            self._dg, self._graph = capi.DeviceGraph(graph, device=self.device), graph
+        return self._dg
+
+    def __call__(self, graph, my_dests, iters):
+        from . import capi
+        dp = capi.DevicePlanner(self._device_graph(graph), my_dests, max_resident=self.max_resident)
+        # multi-query planners are fed up front: a query that starved (status 1) would need its
+        # own remainder on a re-call, so starvation is an error here, not a resume point
         dp.feed(capi.mt19937_words(0, iters * len(my_dests[0]) * 8 + 4096))
         reps = dp.expand(iters)
-        out = [dict(expansions=int(r.expansions), tree_vertices=int(r.tree_vertices),
-                    status=int(r.status), D=dp.state(q)["D"]) for q, r in enumerate(reps)]
-        dp.close(); dg.close()
+        self.kernel_ms += dp.last_kernel_ms()
+        bad = [(q, r.status) for q, r in enumerate(reps) if r.status != 0]
+        if bad:
+            dp.close()
+            raise capi.ImomdError(f"device run status {bad[:4]} (query, status)")
+        st = dp.states()
+        hashes = [int(r.tree_hash) for r in reps] if dp.info()["streaming"] else \
+            [dp.treehash(q)[0] for q in range(len(reps))]
+        out = [dict(expansions=int(r.expansions), tree_vertices=int(r.tree_vertices), status=int(r.status),
+                    treehash=hashes[q], unresolved_ties=int(r.unresolved_ties), D=st["D"][q].copy())
+               for q, r in enumerate(reps)]
+        dp.close()
         return out
 
-    return run
+    def close(self):
+        if self._dg is not None:
+            self._dg.close()
+            self._dg, self._graph = None, None
+
+
+def cuda_executor(device: int, max_resident: int = -1):
+    return CudaExecutor(device, max_resident)
 
 
 def pack_best(cost: float, tour) -> torch.Tensor:

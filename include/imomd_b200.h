@@ -58,11 +58,20 @@ typedef struct imomd_params
 {
     double goal_bias;           /* setting.goal_bias */
     int32_t pseudo_mode;        /* setting.pseudo_mode */
-    int32_t reserved0;
+    int32_t max_resident_queries; /* 0: every query keeps its trees in HBM (resident planner).
+                                   * n > 0: at most n sets of per-query state; with more queries than
+                                   * that the planner STREAMS: imomd_expand runs every query from its
+                                   * constructed state to `iters` passes, queries take a state slot from
+                                   * a device work queue as slots fall free, and only the K x K state,
+                                   * the report and the tree hash of a query outlive its run.
+                                   * -1: as many slots as run concurrently and fit in device memory. */
     uint32_t frontier_chunks;   /* 32-record chunks per tree, 0 = auto */
     uint32_t arena_entries;     /* rewire scratch (uint32 entries) per query, 0 = auto */
     uint32_t log_entries;       /* pseudo-mode connection log entries per query, 0 = auto */
     uint32_t reserved;
+    double tie_band;            /* relative band inside which a comparison of haversine values is
+                                 * decided with the host's libm instead of CUDA's; 0 = 1e-12 (tests
+                                 * widen it to exercise the service) */
 } imomd_params;
 
 /* what one imomd_expand call did for one query */
@@ -77,8 +86,12 @@ typedef struct imomd_query_report
     int32_t connected;          /* is_connected_graph_ */
     int32_t dm_updated;         /* is_distance_matrix_updated_ */
     int64_t near_ties;          /* arg-min decisions certified on the slow exact path */
-    int64_t unresolved_ties;    /* decisions closer than 1e-12 relative (lowest id taken) */
+    int64_t unresolved_ties;    /* exact ties on the reference's own values, or near-ties the host
+                                 * could not be asked about (lowest id / device choice taken) */
     int64_t log_entries;        /* pseudo-mode connection log length */
+    int64_t certified_ties;     /* near-ties decided on the host's glibc values (cumulative) */
+    uint64_t tree_hash;         /* streaming planners: TREEHASH of the finished query (imomd_get_treehash) */
+    uint64_t busy_cycles;       /* SM-clock cycles the query occupied its CTA in this call */
 } imomd_query_report;
 
 typedef struct imomd_nn_query
@@ -136,6 +149,10 @@ int imomd_planner_clear_words(imomd_planner* p);
 int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports);
 int imomd_expand_async(imomd_planner* p, int iters);
 int imomd_sync(imomd_planner* p, imomd_query_report* reports);
+/* ImomdRRT::findShortestPath's max_time test runs after EVERY pass (:258-262): with a budget
+ * set, an imomd_expand launch stops after the first pass that ends more than `seconds` after
+ * the launch began (imomd_query_report.iterations tells how many ran).  0 = none. */
+int imomd_set_time_budget(imomd_planner* p, double seconds);
 /* cumulative SM-clock cycles and call counts per kind of work of one query: index 1..6 =
  * nearest search, heuristic rescan, heuristic insert, connection gather, cost propagation,
  * rewire batch check; index 7 = the serial steps in between (development / profiling aid) */
@@ -158,6 +175,19 @@ int imomd_last_kernel_ms(imomd_planner* p, float* ms);
  * disjoint_set_parent_ (include/imomd_rrt_star/imomd_rrt_star.h:159-178) */
 int imomd_get_state(imomd_planner* p, int query, double* D, uint32_t* conn_node, double* prob,
                     uint32_t* mh_id, double* mh_val, int32_t* is_done, int32_t* ds_parent);
+/* the K x K matrices (and is_done flags) of queries [first, first + count) in one device->host
+ * copy; every output holds `count` consecutive blocks, any of them may be NULL */
+int imomd_get_states(imomd_planner* p, int first, int count, double* D, uint32_t* conn_node, double* prob,
+                     int32_t* is_done);
+/* Fingerprint of a query's K trees, computed on the device: tree_hash = FNV-style fold over the
+ * trees in id order, each tree's visited vertices in ascending id, of (vertex, parent, bits of
+ * cost) -- what a walk over the reference's tree.parent / tree.cost maps (imomd_rrt_star.h:66-76)
+ * in sorted order produces; tree_sum = order-free 64-bit checksum of the same entries. */
+int imomd_get_treehash(imomd_planner* p, int query, uint64_t* tree_hash, uint64_t* tree_sum);
+/* layout of the planner: queries, state slots, 1 when it streams, requests answered by the
+ * exact-value service (near-ties decided with the host's libm, see DESIGN.md "Exactness") */
+int imomd_planner_info(imomd_planner* p, int32_t* n_queries, int32_t* slots, int32_t* streaming,
+                       uint64_t* certified_requests);
 /* is_connected_graph_ / is_distance_matrix_updated_ (imomd_rrt_star.h:178, :190) */
 int imomd_get_flags(imomd_planner* p, int query, int32_t* connected, int32_t* dm_updated);
 /* the facade clears is_distance_matrix_updated_ after updatePath_ (:960) */

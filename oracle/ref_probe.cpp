@@ -10,6 +10,7 @@
 //             (--dest s,o1,..,t | --pick seed:count)
 //             [--iters N] [--goal-bias g] [--pseudo] [--mode expand|run]
 //             [--max-time s] [--max-iter n] [--dump out.bin]
+//   ref_probe --mode rtsp --matrix D.bin [--solves n] [--ga mut,pop,gen]
 //
 // Prints one JSON line.  `--mode expand` times `iters` calls of
 // expandTreeLayers_() (the expansion hot path, RTSP excluded); `--mode run`
@@ -56,6 +57,58 @@ int ref_planner_run(void* p, ref_log_row_t* rows, int cap, int64_t* iterations,
 double ref_planner_path_cost(void* p);
 uint64_t ref_planner_path(void* p, uint64_t* out, uint64_t cap);
 const char* ref_toolchain(void);
+void* ref_solver_create(int swapping, int genetic, int ga_mutation_iter, int ga_population,
+                        int ga_generation);
+int ref_solver_solve(void* sp, int K, const double* D, int source, int target, double* cost,
+                     int32_t* seq, int cap);
+}
+
+// --mode rtsp: times EciGenSolver::solveRTSP (src/eci_gen_tsp_solver.cpp:76-101) of the unmodified
+// reference on a K x K matrix read from a file {u64 K, f64 D[K*K]}: `solves` consecutive calls on
+// one solver (its mt19937 persists across calls, as in the planner).
+static int rtsp_mode(const char* matrix_file, int solves, int ga_mut, int ga_pop, int ga_gen)
+{
+    FILE* f = std::fopen(matrix_file, "rb");
+    if (!f)
+    {
+        std::perror(matrix_file);
+        return 2;
+    }
+    uint64_t K = 0;
+    if (std::fread(&K, 8, 1, f) != 1 || K < 2 || K > 64)
+    {
+        std::fprintf(stderr, "bad matrix file\n");
+        return 2;
+    }
+    std::vector<double> D(K * K);
+    if (std::fread(D.data(), 8, K * K, f) != K * K)
+    {
+        std::fprintf(stderr, "short matrix file\n");
+        return 2;
+    }
+    std::fclose(f);
+    void* s = ref_solver_create(1, 1, ga_mut, ga_pop, ga_gen);
+    std::vector<int32_t> seq(4096);
+    std::vector<double> costs, ms;
+    int len = 0;
+    for (int i = 0; i < solves; ++i)
+    {
+        double cost = 0;
+        auto t0 = std::chrono::steady_clock::now();
+        len = ref_solver_solve(s, (int)K, D.data(), 0, (int)K - 1, &cost, seq.data(), (int)seq.size());
+        ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        costs.push_back(cost);
+    }
+    std::printf("{\"toolchain\": \"%s\", \"mode\": \"rtsp\", \"K\": %llu, \"solves\": %d, \"ms\": [", ref_toolchain(),
+                (unsigned long long)K, solves);
+    for (size_t i = 0; i < ms.size(); ++i) std::printf("%s%.4f", i ? ", " : "", ms[i]);
+    std::printf("], \"costs\": [");
+    for (size_t i = 0; i < costs.size(); ++i) std::printf("%s%.17g", i ? ", " : "", costs[i]);
+    std::printf("], \"last_sequence\": [");
+    for (int i = 0; i < len; ++i) std::printf("%s%d", i ? ", " : "", seq[i]);
+    std::printf("]}\n");
+    std::fflush(stdout);
+    _exit(0);
 }
 
 static void* load_graph_file(const char* path)
@@ -94,7 +147,8 @@ int main(int argc, char** argv)
     std::vector<uint64_t> dest;
     int iters = 1000, pseudo = 0, max_time = 60, max_iter = 1000000;
     double goal_bias = 1.0;
-    std::string mode = "expand", dump;
+    std::string mode = "expand", dump, matrix;
+    int solves = 5;
     int ga_mut = 10000, ga_pop = 1000, ga_gen = 5;
     uint32_t pick_seed = 0;
     int pick_count = 0;
@@ -144,12 +198,15 @@ int main(int argc, char** argv)
             std::sscanf(s.c_str(), "%d,%d,%d", &ga_mut, &ga_pop, &ga_gen);
         }
         else if (a == "--dump") dump = next();
+        else if (a == "--matrix") matrix = next();
+        else if (a == "--solves") solves = std::atoi(next());
         else
         {
             std::fprintf(stderr, "unknown argument %s\n", a.c_str());
             return 2;
         }
     }
+    if (mode == "rtsp") return rtsp_mode(matrix.c_str(), solves, ga_mut, ga_pop, ga_gen);
     if (!g)
     {
         std::fprintf(stderr, "no graph\n");

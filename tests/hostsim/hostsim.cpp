@@ -57,6 +57,22 @@ struct CtaHost
         return 0;
     }
     uint32_t reduce_min_u32(uint32_t v, uint32_t*) const { return v; }
+    void counter_or(uint32_t* p, uint32_t v) const { *p |= v; }
+    mutable uint64_t fake_ns = 0;
+    uint64_t now_ns() const { return fake_ns += 1000; }   // every reading is 1 us later
+    void store_streaming(U4* p, const U4& v) const { *p = v; }
+    U4 load_streaming(const U4* p) const { return *p; }
+    uint64_t reduce_sum_u64(uint64_t v, Best*) const { return v; }
+    // the exact-value service: here the caller already IS the host (glibc)
+    mutable uint64_t certified = 0;
+    bool enabled = true;
+    bool certify(int n, double (*in)[4], double* out) const
+    {
+        if (!enabled) return false;
+        for (int i = 0; i < n; ++i) out[i] = haversine(in[i][0], in[i][1], in[i][2], in[i][3]);
+        ++certified;
+        return true;
+    }
 };
 
 struct HsPlanner
@@ -79,7 +95,9 @@ struct HsPlanner
     std::vector<uint32_t> lvl;
     std::vector<double> mat;
     std::vector<unsigned char> hot;
+    std::vector<QueryDev> query_init;
     Shared S;
+    CtaHost cta;
 };
 
 }  // namespace
@@ -88,8 +106,8 @@ extern "C" {
 
 void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const double* w,
                 const double* lat, const double* lon, int Q, int K, const uint32_t* dest,
-                const double* prob, double goal_bias, int pseudo, int grid_dim, char* err,
-                int errlen)
+                const double* prob, double goal_bias, int pseudo, int grid_dim, int slots, double tie_band,
+                char* err, int errlen)
 {
     uint32_t md = 0;
     std::string verr;
@@ -127,9 +145,14 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     d.Q = Q;
     d.K = K;
     d.goal_bias = goal_bias;
+    d.tie_rel = tie_band > 0.0 ? tie_band : kTieRel;
     d.pseudo = pseudo;
     default_sizes(d, 0, 0, 0);
-    size_t qk = (size_t)Q * K, cells = (size_t)d.g.G * d.g.G, chunks = d.chunks;
+    if (slots <= 0 || slots > Q) slots = Q;
+    d.slots = slots;
+    d.streaming = slots < Q ? 1 : 0;
+    // heavy state is per SLOT (resident planner: slot == query)
+    size_t qk = (size_t)slots * K, cells = (size_t)d.g.G * d.g.G, chunks = d.chunks;
     p->query.resize(Q);
     for (int q = 0; q < Q; ++q)
         fill_initial_header(p->query[q], K, dest + (size_t)q * K, prob + (size_t)q * K * K);
@@ -143,9 +166,9 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->lbd.resize(qk * cells);
     p->ubd.resize(qk * cells);
     p->occ.assign(qk * 2 * cells, 0);
-    p->arena.resize((size_t)Q * d.arena_entries);
-    p->clist.resize((size_t)Q * 2 * chunks);
-    p->log.resize((size_t)Q * 2 * d.log_entries);
+    p->arena.resize((size_t)slots * d.arena_entries);
+    p->clist.resize((size_t)slots * 2 * chunks);
+    p->log.resize((size_t)slots * 2 * d.log_entries);
     p->reports.resize(Q);
     p->lb.resize(cells);
     p->lvl.resize(2 * kLevelCap);
@@ -172,12 +195,15 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     d.clist = p->clist.data();
     d.log = p->log.data();
     d.reports = p->reports.data();
+    p->query_init = p->query;
+    d.query_init = p->query_init.data();
+    if (d.streaming) return p;     // slots are rebuilt when a query takes them (run_streaming_query)
     for (size_t i = 0; i < qk; ++i)
         for (size_t c = 0; c < chunks; ++c) p->free_stack[i * chunks + c] = (uint32_t)(chunks - 1 - c);
     for (int q = 0; q < Q; ++q)
     {
         for (int k = 0; k < K; ++k) p->query[q].free_top[k] = (uint32_t)chunks;
-        construct_trees(d, q);
+        construct_trees(d, q, q);
     }
     for (size_t i = 0; i < qk * cells; ++i)
     {
@@ -202,16 +228,33 @@ void hs_feed_words(void* hp, const uint32_t* words, size_t n)
 void hs_expand(void* hp, int iters, ReportDev* reports)
 {
     HsPlanner* p = (HsPlanner*)hp;
-    CtaHost cta;
+    CtaHost& cta = p->cta;
     unsigned char* hot = reinterpret_cast<unsigned char*>(((uintptr_t)p->hot.data() + 15) & ~(uintptr_t)15);
+    if (p->d.streaming)
+    {
+        // the device hands queries to whichever slot falls free; queries are independent, so any
+        // assignment gives the same per-query results -- here query hq reuses slot hq % slots
+        for (int hq = 0; hq < p->d.Q; ++hq)
+        {
+            const int slot = hq % p->d.slots;
+            if (p->d.g.width == 4)
+                run_streaming_query<4>(cta, p->d, slot, hq, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+            else if (p->d.g.width == 8)
+                run_streaming_query<8>(cta, p->d, slot, hq, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+            else
+                run_streaming_query<16>(cta, p->d, slot, hq, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+        }
+        if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
+        return;
+    }
     for (int q = 0; q < p->d.Q; ++q)
     {
         if (p->d.g.width == 4)
-            run_query<4>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+            run_query<4>(cta, p->d, q, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
         else if (p->d.g.width == 8)
-            run_query<8>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+            run_query<8>(cta, p->d, q, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
         else
-            run_query<16>(cta, p->d, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+            run_query<16>(cta, p->d, q, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
     }
     if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
 }
@@ -222,14 +265,14 @@ void hs_attach_list(void* hp, int q, int k, const uint32_t* vertices, uint32_t c
     HsPlanner* p = (HsPlanner*)hp;
     if (!p->d.attach_list || count == 0) return;
     std::memcpy(p->d.attach_list, vertices, (size_t)count * 4);
-    CtaHost cta;
+    CtaHost& cta = p->cta;
     unsigned char* hot = reinterpret_cast<unsigned char*>(((uintptr_t)p->hot.data() + 15) & ~(uintptr_t)15);
     if (p->d.g.width == 4)
-        run_query<4>(cta, p->d, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
+        run_query<4>(cta, p->d, q, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
     else if (p->d.g.width == 8)
-        run_query<8>(cta, p->d, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
+        run_query<8>(cta, p->d, q, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
     else
-        run_query<16>(cta, p->d, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
+        run_query<16>(cta, p->d, q, q, 0, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot, k, count);
     if (parents_out) std::memcpy(parents_out, p->d.attach_list, (size_t)count * 4);
 }
 
@@ -326,7 +369,7 @@ void hs_nearest(void* hp, int q, int k, double lat, double lon, uint32_t* idx, d
                 int64_t* stats)
 {
     HsPlanner* p = (HsPlanner*)hp;
-    CtaHost cta;
+    CtaHost& cta = p->cta;
     p->S.Q = &p->query[q];
     p->S.tref = nullptr;
     p->S.qlat = lat;
@@ -338,6 +381,23 @@ void hs_nearest(void* hp, int q, int k, double lat, double lon, uint32_t* idx, d
     *dist = v == IMOMD_NONE ? INFINITY : haversine(p->lat[v], p->lon[v], lat, lon);
     stats[2] = p->S.n_list;   // chunks examined by the pruned search
 }
+
+// TREEHASH / checksum of a resident query's trees through the device routine
+void hs_treehash(void* hp, int q, uint64_t* hash, uint64_t* sum)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    if (p->d.streaming)
+    {
+        *hash = p->query[q].tree_hash;
+        *sum = p->query[q].tree_sum;
+        return;
+    }
+    tree_hash(p->cta, p->d, q, p->S, p->d.arena + (size_t)q * p->d.arena_entries, p->d.arena_entries, hash, sum);
+}
+
+// exact-value service: requests answered so far; enable = 0 detaches it (device decisions kept)
+uint64_t hs_certified(void* hp) { return ((HsPlanner*)hp)->cta.certified; }
+void hs_set_certify(void* hp, int enable) { ((HsPlanner*)hp)->cta.enabled = enable != 0; }
 
 uint32_t hs_connection_log(void* hp, int q, uint32_t* set_idx, uint32_t* vertex, uint32_t cap)
 {

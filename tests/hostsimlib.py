@@ -23,7 +23,8 @@ class Report(C.Structure):
     _fields_ = [("status", C.c_int32), ("active_trees", C.c_int32), ("iterations", C.c_int64),
                 ("expansions", C.c_int64), ("tree_vertices", C.c_int64),
                 ("words_consumed", C.c_int64), ("connected", C.c_int32), ("dm_updated", C.c_int32),
-                ("near_ties", C.c_int64), ("unresolved_ties", C.c_int64), ("log_entries", C.c_int64)]
+                ("near_ties", C.c_int64), ("unresolved_ties", C.c_int64), ("log_entries", C.c_int64),
+                ("certified_ties", C.c_int64), ("tree_hash", C.c_uint64), ("busy_cycles", C.c_uint64)]
 
 
 def _stale():
@@ -47,7 +48,7 @@ def lib():
         vp = C.c_void_p
         L.hs_create.restype = vp
         L.hs_create.argtypes = [C.c_uint32, u32p, u32p, f64p, f64p, f64p, C.c_int, C.c_int, u32p, f64p,
-                                C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_int]
+                                C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
         L.hs_destroy.argtypes = [vp]
         L.hs_grid_dim.argtypes = [vp]
         L.hs_feed_words.argtypes = [vp, u32p, C.c_size_t]
@@ -62,6 +63,10 @@ def lib():
         L.hs_attach_list.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, u32p]
         L.hs_visit_order.restype = C.c_uint32
         L.hs_visit_order.argtypes = [vp, C.c_int, C.c_int, u32p]
+        L.hs_treehash.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.hs_certified.restype = C.c_uint64
+        L.hs_certified.argtypes = [vp]
+        L.hs_set_certify.argtypes = [vp, C.c_int]
         L.hs_connection_log.restype = C.c_uint32
         L.hs_connection_log.argtypes = [vp, C.c_int, u32p, u32p, C.c_uint32]
         _lib = L
@@ -69,7 +74,7 @@ def lib():
 
 
 class HostSimPlanner:
-    def __init__(self, g, dests, probs, goal_bias=1.0, pseudo=False, grid_dim=0):
+    def __init__(self, g, dests, probs, goal_bias=1.0, pseudo=False, grid_dim=0, slots=0, tie_band=0.0):
         """dests: list of per-query destination lists; probs: list of KxK matrices."""
         L = lib()
         self.L, self.g = L, g
@@ -78,7 +83,7 @@ class HostSimPlanner:
         pr = np.ascontiguousarray(np.asarray(probs, np.float64).ravel())
         err = C.create_string_buffer(256)
         self.h = L.hs_create(g.n, g.row_ptr, g.col, g.w, g.lat, g.lon, self.Q, self.K, d, pr,
-                             goal_bias, int(pseudo), grid_dim, err, 256)
+                             goal_bias, int(pseudo), grid_dim, slots, tie_band, err, 256)
         if not self.h:
             raise ValueError(err.value.decode())
 
@@ -113,6 +118,17 @@ class HostSimPlanner:
         out = np.empty(self.g.n, np.uint32)
         c = self.L.hs_get_frontier(self.h, q, k, out)
         return np.sort(out[:c]).astype(np.uint64)
+
+    def treehash(self, q=0):
+        h, sm = C.c_uint64(), C.c_uint64()
+        self.L.hs_treehash(self.h, q, C.byref(h), C.byref(sm))
+        return h.value, sm.value
+
+    def certified(self):
+        return int(self.L.hs_certified(self.h))
+
+    def set_certify(self, enable):
+        self.L.hs_set_certify(self.h, int(enable))
 
     def check_hash(self, k, q=0):
         return self.L.hs_check_hash(self.h, q, k)

@@ -180,3 +180,70 @@ def test_attach_list_matches_reference_merge_step(kind, K, warm):
     for k in range(K):
         assert sorted(int(v) for v in hp.visit_order(k)) == sorted(int(v) for v in rp.parent_order(k))
     hp.close()
+
+
+def test_device_treehash_matches_oracle():
+    """tree_hash (the routine behind imomd_get_treehash and the streaming planners' reports) ==
+    the SURVEY Appendix A TREEHASH of the oracle's trees."""
+    g = graphs.road_like(5000, seed=4)
+    dest = graphs.pick_destinations(g, 5, seed=3)
+    op, hp = _pair(g, dest)
+    hp.feed(_words(200000))
+    seen = set()
+    for chunk in (0, 3, 200, 700):
+        if chunk:
+            hp.expand(chunk); op.iterate(chunk)
+        h, sm = hp.treehash()
+        assert h == op.treehash()
+        seen.add((h, sm))
+    assert len(seen) == 4          # the fingerprints move with the trees
+    op.close(); hp.close()
+
+
+@pytest.mark.parametrize("slots", [1, 2, 3])
+def test_streaming_slots_reproduce_every_query(slots):
+    """A streaming planner (fewer state slots than queries) rebuilds a slot for every query it
+    takes: per-query results equal the oracle's, whatever ran in the slot before."""
+    g = graphs.jittered_grid(48, seed=9)
+    dests = [graphs.pick_destinations(g, 4, seed=20 + q) for q in range(5)]
+    ops = [ol.OraclePlanner(g, d) for d in dests]
+    probs = [o.matrices()["P"] for o in ops]
+    hp = hs.HostSimPlanner(g, dests, probs, slots=slots)
+    hp.feed(_words(200000))
+    for rounds in range(2):          # a second expand() starts every query afresh
+        reps = hp.expand(250)
+        for q, o in enumerate(ops):
+            if rounds == 0:
+                e = o.iterate(250)
+                assert reps[q].expansions == e
+            assert reps[q].status == 0 and reps[q].iterations == 250
+            assert reps[q].tree_hash == o.treehash() == hp.treehash(q)[0]
+            s = hp.state(q)
+            assert np.array_equal(s["D"].view(np.uint64), o.matrices()["D"].view(np.uint64))
+            assert np.array_equal(s["P"].view(np.uint64), o.matrices()["P"].view(np.uint64))
+    for o in ops:
+        o.close()
+    hp.close()
+
+
+def test_widened_tie_band_is_certified_exactly():
+    """With the tie band widened to 1e-5 a visible share of the arg-min / heuristic decisions goes
+    through the exact-value service (Cta::certify: the reference's haversine on glibc); the trees
+    must still equal the oracle's bit for bit, with nothing left unresolved."""
+    g = graphs.jittered_grid(60, seed=11)
+    dest = graphs.pick_destinations(g, 6, seed=5)
+    op = ol.OraclePlanner(g, dest, 0.7)
+    hp = hs.HostSimPlanner(g, [dest], [op.matrices()["P"]], 0.7, tie_band=1e-5)
+    hp.feed(_words(300000))
+    rep = hp.expand(600)[0]
+    assert rep.expansions == op.iterate(600)
+    compare_with_oracle(hp, op, 6, True)
+    assert rep.certified_ties > 20 and hp.certified() >= rep.certified_ties
+    assert rep.unresolved_ties == 0
+    # detached service: the same decisions are counted as unresolved instead
+    hp2 = hs.HostSimPlanner(g, [dest], [op.matrices()["P"]], 0.7, tie_band=1e-5)
+    hp2.set_certify(False)
+    hp2.feed(_words(300000))
+    rep2 = hp2.expand(600)[0]
+    assert rep2.certified_ties == 0 and rep2.unresolved_ties > 20 and hp2.certified() == 0
+    op.close(); hp.close(); hp2.close()

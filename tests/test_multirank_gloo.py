@@ -36,11 +36,14 @@ def _worker(rank, world, port, q):
     rng = np.random.default_rng(1)
     dests = [graphs.pick_destinations(g, 2, seed=int(s)) for s in rng.integers(0, 10**6, 7)]
     res = sharding.run_sharded(g, dests, 150, _oracle_executor)
+    # the same job with ranks pulling chunks of two queries from the shared counter
+    dyn = sharding.run_sharded(g, dests, 150, _oracle_executor, dynamic_chunk=2, tag="gloo_test")
     # island migration: rank r offers cost 100 - r (so the last rank wins), ties -> lowest rank
     cost, tour, winner, costs = sharding.migrate_best(100.0 - rank, [0, rank + 1, 9])
     tie = sharding.migrate_best(5.0, [0, 7 + rank, 9])
     if rank == 0:
         q.put(dict(hashes=[r["treehash"] for r in res], exps=[r["expansions"] for r in res],
+                   dyn_hashes=[r["treehash"] for r in dyn],
                    mine=sharding.shard(len(dests), world, rank), best=(cost, tour, winner, costs), tie=tie))
     dist.barrier()
     dist.destroy_process_group()
@@ -66,6 +69,7 @@ def test_sharding_and_migration_world2():
     solo = sharding.run_sharded(g, dests, 150, _oracle_executor, world=1, rank=0)
     assert got["hashes"] == [r["treehash"] for r in solo]
     assert got["exps"] == [r["expansions"] for r in solo]
+    assert got["dyn_hashes"] == got["hashes"]          # who ran a query does not matter
     assert got["mine"] == [0, 2, 4, 6]
     cost, tour, winner, costs = got["best"]
     assert (cost, tour, winner, costs) == (99.0, [0, 2, 9], 1, [100.0, 99.0])
