@@ -495,6 +495,19 @@ struct Shared
     // block reduction / scan scratch
     Best red[32];
     uint32_t scan[40];
+    // scratch of the cooperating group in HBM: rewire arena (frames + update lists), chunk work
+    // list of the pruned searches.  One group (the CTA) per query in the exact mode; one group (a
+    // warp) per TREE in the batched mode, each with its own share.
+    uint32_t* arena;
+    uint32_t arena_cap;
+    int32_t batch;              // 1: batched mode (cross-tree effects are logged, not applied)
+    uint32_t* clist;
+    BEvent* ev;                 // batched mode: event log of the tree being expanded
+    uint32_t ev_n;              //   entries written
+    uint32_t exp_n;             //   expansions performed in this batch
+    // counters of this group, folded into the query header when the launch ends
+    uint64_t stat[8];
+    int64_t near_ties, unresolved_ties, certified_ties;
     // exact certification of a comparison the device arithmetic cannot decide (Cta::certify):
     // candidate vertices, the coordinate pairs handed to the host, glibc's answers
     uint32_t tie_n;
@@ -872,7 +885,7 @@ struct Seq
     uint32_t* arena;
 
     IMOMD_HD Seq(const PlannerDev& P_, int q_, Shared& S_)
-        : P(P_), Q(S_.Q), q(q_), S(S_), arena(P_.arena + (size_t)q_ * P_.arena_entries)
+        : P(P_), Q(S_.Q), q(q_), S(S_), arena(S_.arena)
     {
         assume_planner(P);
         IMOMD_ASSUME_SHARED(&S);
@@ -890,11 +903,17 @@ struct Seq
     // selectRandomVertex_, src/imomd_rrt_star.cpp:358-400
     IMOMD_HD void sample(int k, const TreeRef& T)
     {
+        Q->word_cursor = sample_at(k, T, Q->word_cursor);
+    }
+
+    // the same, reading the injected stream from `cursor`; returns the cursor behind the sample
+    IMOMD_HD uint64_t sample_at(int k, const TreeRef& T, uint64_t cursor)
+    {
         const GraphDev& g = P.g;
         int K = Q->K;
         WordStream ws;
         ws.words = P.words;
-        ws.cursor = Q->word_cursor;
+        ws.cursor = cursor;
         if (ws_uniform_real(ws, 0, 1) < P.goal_bias)
         {
             double rnd = ws_uniform_real(ws, 0, 1);
@@ -934,7 +953,28 @@ struct Seq
             S.qlat = g.lat[v];
             S.qlon = g.lon[v];
         }
-        Q->word_cursor = ws.cursor;
+        return ws.cursor;
+    }
+
+    // ---- batched mode: what an expansion does to the OTHER trees' shared state is logged ------
+    // updateConnectionTree_(tree, x) with the cost x had at that moment, and
+    // updateSelectionProbability with the heuristic entry of that moment, in program order; the
+    // block applies the logs of all trees, in tree order, when every tree has finished its batch.
+    IMOMD_HD void log_event(int k, uint32_t kind, uint32_t x, uint32_t aux, double val, uint32_t extra)
+    {
+        uint32_t i = S.ev_n;
+        if (i >= P.ev_cap)
+        {
+            Q->status = 3;   // IMOMD_RUN_ARENA_FULL: event log of the batch exhausted
+            return;
+        }
+        BEvent* e = S.ev + i;
+        e->x = x;
+        e->aux = aux;
+        e->val = val;
+        e->extra = extra;
+        e->kind = kind;
+        S.ev_n = i + 1;
     }
 
     // which (k, o) min-heuristic holders equal x  (updateExpandables :503-512)
@@ -955,7 +995,7 @@ struct Seq
     IMOMD_HD void apply_connection(int k, const TreeRef& T, uint32_t x, double cx)
     {
         int K = Q->K;
-        Q->stat[6] += 1;
+        S.stat[6] += 1;
         for (int o = 0; o < K; ++o)
         {
             if (o == k) continue;
@@ -1181,12 +1221,12 @@ struct Seq
     IMOMD_HD bool push_frame(uint32_t x, uint32_t e, uint32_t e_end)
     {
         uint32_t top = S.rw_top;
-        if (top + FR > P.arena_entries)
+        if (top + FR > S.arena_cap)
         {
             Q->status = 3;   // IMOMD_RUN_ARENA_FULL
             return false;
         }
-        Q->stat[2] += 1;
+        S.stat[2] += 1;
         uint32_t* f = arena + top;
         f[0] = S.rw_fp;
         f[1] = x;
@@ -1224,7 +1264,7 @@ struct Seq
         {
             if (e0 + i < e1) hs[i] = T.head(ys[i]);
         }
-        Q->stat[3] += e1 - e0;
+        S.stat[3] += e1 - e0;
 #pragma unroll
         for (int i = 0; i < W; ++i)
         {
@@ -1262,7 +1302,7 @@ struct Seq
 
     IMOMD_HD void reparent(const TreeRef& T, uint32_t y, uint32_t py, uint32_t x, double nc)
     {
-        Q->stat[4] += 1;
+        S.stat[4] += 1;
         move_child_w<KW>(T, y, py, x);
         T.set_parent(y, x);
         S.bfs_node = y;
@@ -1285,7 +1325,7 @@ struct Seq
                 if (S.chk_valid)
                 {
                     S.chk_valid = 0;
-                    Q->stat[2] += S.chk_noop;
+                    S.stat[2] += S.chk_noop;
                     f[6] -= S.chk_noop;          // calls that would have changed nothing
                     if (S.chk_slot != IMOMD_NONE)
                     {
@@ -1320,7 +1360,8 @@ struct Seq
                     Q->status = 3;
                     return true;
                 }
-                apply_connection(k, T, S.bfs_node, S.bfs_cost);      // :586
+                if (S.batch) log_event(k, 0u, S.bfs_node, 0u, S.bfs_cost, 0u);
+                else apply_connection(k, T, S.bfs_node, S.bfs_cost);      // :586
                 f[4] = S.bfs_node;
                 f[5] = S.rw_top;
                 f[6] = S.bfs_hi;
@@ -1365,14 +1406,22 @@ struct Seq
             }
         }
         if (other == K) return;
-        const double mh = sm_MHv(S)[k * K + other], dd = sm_D(S)[k * K + other];
+        selection_probability_apply(cta, k, other, sm_MHv(S)[k * K + other], sm_MHi(S)[k * K + other]);
+    }
+
+    // the test and the pruning of :617-642 for the pair (k, other), given the min-heuristic entry
+    template <class Cta>
+    IMOMD_HD void selection_probability_apply(Cta& cta, int k, int other, double mh, uint32_t mh_holder)
+    {
+        int K = Q->K;
+        const double dd = sm_D(S)[k * K + other];
         bool prune = mh > dd;
-        if (sm_MHi(S)[k * K + other] != IMOMD_NONE && dd < INFINITY && fabs(mh - dd) <= P.tie_rel * dd)
+        if (mh_holder != IMOMD_NONE && dd < INFINITY && fabs(mh - dd) <= P.tie_rel * dd)
         {
             // the heuristic value is CUDA libm's: this close to the distance the comparison is
             // redone on glibc's value of the holder
             const GraphDev& g = P.g;
-            const uint32_t v = sm_MHi(S)[k * K + other], rk = Q->view_root[k], ro = Q->view_root[other];
+            const uint32_t v = mh_holder, rk = Q->view_root[k], ro = Q->view_root[other];
             double* a = S.tie_in[0];
             double* b = S.tie_in[1];
             a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = g.lat[rk]; a[3] = g.lon[rk];
@@ -1380,11 +1429,11 @@ struct Seq
             if (cta.certify(2, S.tie_in, S.tie_out))
             {
                 prune = (S.tie_out[0] + S.tie_out[1]) > dd;
-                Q->certified_ties += 1;
+                S.certified_ties += 1;
             }
             else
             {
-                Q->unresolved_ties += 1;
+                S.unresolved_ties += 1;
                 double* ti = Q->tie_info;
                 ti[0] = 4; ti[1] = k; ti[2] = other; ti[3] = mh; ti[4] = dd; ti[5] = v;
                 ti[6] = 0; ti[7] = 0;
@@ -1510,7 +1559,16 @@ struct Seq
                         S.conn_pending = 0;
                         S.x_new = S.jps_next;
                     }
-                    if (!S.attach_mode && jps_hop(k, T))
+                    if (S.batch)
+                    {
+                        // hops need no service here: their connection checks are only logged
+                        while (Q->status == 0 && jps_hop(k, T))
+                        {
+                            log_event(k, 0u, S.conn_x, 0u, S.conn_cx, 0u);
+                            S.x_new = S.jps_next;
+                        }
+                    }
+                    else if (!S.attach_mode && jps_hop(k, T))
                     {
                         S.conn_pending = 1;
                         S.req = REQ_CONN;
@@ -1554,6 +1612,28 @@ struct Seq
                 {
                     if (!rewire_run(k, T)) return;   // REQ_BFS or REQ_CHECK posted
                     if (Q->status != 0) continue;
+                    if (S.batch)
+                    {
+                        // :354-355 deferred: the selection-probability test with the heuristic
+                        // entry as it is NOW, then the connection check of x_new
+                        int other = Q->K;
+                        for (int i = 0; i < Q->K; ++i)
+                        {
+                            if ((uint64_t)Q->dest[i] == S.rand_id)
+                            {
+                                other = i;
+                                break;
+                            }
+                        }
+                        if (other < Q->K)
+                            log_event(k, 1u, IMOMD_NONE, (uint32_t)other, sm_MHv(S)[k * Q->K + other],
+                                      sm_MHi(S)[k * Q->K + other]);
+                        log_event(k, 0u, S.x_new, 0u, T.cost(S.x_new), 0u);
+                        S.exp_n += 1;
+                        S.req = REQ_EXIT;
+                        S.phase = PH_NEXT_TREE;
+                        return;
+                    }
                     if (!S.attach_mode) update_selection_probability(cta, k);
                     S.conn_x = S.x_new;
                     S.req = REQ_CONN;
@@ -1652,7 +1732,7 @@ IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef&
         uint32_t c = T.occ[i];
         double l, u;
         bounds(c, l, u);
-        lb[i] = l;
+        if (lb) lb[i] = l;      // (no table in the batched mode: a warp recomputes the bound below)
         if (u < mub) mub = u;
     }
     if (cta.tid() == 0)
@@ -1664,11 +1744,15 @@ IMOMD_HD inline Best pruned_argmin(Cta& cta, const PlannerDev& P, const TreeRef&
     const double limit = bound(mub);
     for (uint32_t i = cta.tid(); i < n_occ; i += cta.nt())
     {
-        if (lb[i] <= limit)
+        uint32_t c = T.occ[i];
+        double l;
+        if (lb) l = lb[i];
+        else
         {
-            uint32_t c = T.occ[i];
-            list_cell(cta, T, clist, &S.n_list, c, T.cell_cnt[c]);
+            double u;
+            bounds(c, l, u);
         }
+        if (l <= limit) list_cell(cta, T, clist, &S.n_list, c, T.cell_cnt[c]);
     }
     cta.sync();
     Best b = scan_list(cta, T, clist, 0u, S.n_list, eval);
@@ -1768,7 +1852,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
 {
     assume_planner(P);
     IMOMD_ASSUME_SHARED(&S);
-    IMOMD_ASSUME_SHARED(lb);
+    if (lb) IMOMD_ASSUME_SHARED(lb);
     const GraphDev& g = P.g;
     TreeRef T = tree_ref_of(P, q, k, S);
     double qlat = S.qlat, qlon = S.qlon;
@@ -1859,7 +1943,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
                 {
                     b.id1 = S.tie_id[w];
                     b.v1 = vals[w];
-                    S.Q->certified_ties += 1;
+                    S.certified_ties += 1;
                 }
                 if (w < 0 || exact_tie)
                 {
@@ -1876,8 +1960,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
         S.result = b;
         S.ambiguous = ambiguous;
         QueryDev* Qs = S.Q;
-        Qs->stat[0] += S.n_cells;
-        Qs->stat[1] += S.n_recs;
+        S.stat[0] += S.n_cells;
+        S.stat[1] += S.n_recs;
     }
 }
 
@@ -1888,13 +1972,14 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
 {
     assume_planner(P);
     IMOMD_ASSUME_SHARED(&S);
-    IMOMD_ASSUME_SHARED(lb);
+    if (lb) IMOMD_ASSUME_SHARED(lb);
     const GraphDev& g = P.g;
     QueryDev* Q = S.Q;
     TreeRef T = tree_ref_of(P, q, k, S);
     int K = Q->K;
     uint32_t cells = (uint32_t)g.G * (uint32_t)g.G;
-    uint32_t* clist = P.clist + (size_t)q * 2 * P.chunks;
+    uint32_t* clist = S.clist;
+    IMOMD_ASSUME_GLOBAL(clist);
     const double* lbd = P.lbd + (size_t)q * K * cells;
     const double* ubd = P.ubd + (size_t)q * K * cells;
     uint32_t rk = Q->view_root[k];
@@ -1946,8 +2031,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
         }
         if (cta.tid() == 0)
         {
-            Q->stat[0] += S.n_cells;
-            Q->stat[7] += S.n_recs;
+            S.stat[0] += S.n_cells;
+            S.stat[7] += S.n_recs;
             if (undecided)
             {
                 double vals[IMOMD_TIE_PAIRS];
@@ -1963,11 +2048,11 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
                         b.v1 = haversine_pc(g.lat[v], g.lon[v], g.coslat[v], klat, klon, kcos) +
                                haversine_pc(g.lat[v], g.lon[v], g.coslat[v], olat, olon, ocos);
                     }
-                    Q->certified_ties += 1;
+                    S.certified_ties += 1;
                 }
                 if (w < 0 || exact_tie)
                 {
-                    Q->unresolved_ties += 1;
+                    S.unresolved_ties += 1;
                     double* ti = Q->tie_info;
                     ti[0] = 2; ti[1] = k; ti[2] = o; ti[3] = b.v1; ti[4] = b.v2; ti[5] = b.id1;
                     ti[6] = 0; ti[7] = 0;
@@ -2079,13 +2164,13 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
                         w = i;
                     }
                 }
-                Q->certified_ties += 1;
+                S.certified_ties += 1;
             }
             else
             {
                 for (int i = 1; i < n; ++i)
                     if (dev[i] < dev[w]) w = i;
-                Q->unresolved_ties += 1;
+                S.unresolved_ties += 1;
                 double* ti = Q->tie_info;
                 ti[0] = 3; ti[1] = k; ti[2] = o; ti[3] = dev[0]; ti[4] = dev[w]; ti[5] = ids[w];
                 ti[6] = 0; ti[7] = 0;
@@ -2170,8 +2255,9 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     IMOMD_ASSUME_SHARED(&S);
     IMOMD_ASSUME_SHARED(lvl);
     TreeRef T = tree_ref_of(P, q, k, S);
-    uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
-    const uint32_t cap = P.arena_entries;
+    uint32_t* arena = S.arena;
+    IMOMD_ASSUME_GLOBAL(arena);
+    const uint32_t cap = S.arena_cap;
     const uint32_t rewired = S.bfs_node;
     const double new_cost = S.bfs_cost;
     const uint32_t lo = S.bfs_lo;
@@ -2180,7 +2266,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
     pd.n = 0;
     // The connection check that follows the propagation needs the OTHER trees' records of
     // `rewired` (untouched by this walk): the second warp fetches them while the first one walks.
-    const bool early_gather = cta.nt() >= 64;
+    const bool early_gather = cta.nt() >= 64 && !S.batch;
     if (early_gather)
     {
         const int o = cta.tid() - 32;
@@ -2338,12 +2424,12 @@ IMOMD_HD IMOMD_NOINLINE void svc_bfs_w(Cta& cta, const PlannerDev& P, int q, int
         }
     }
     bfs_flush<W>(T, pd, new_cost, old);
-    if (!early_gather) svc_conn_gather(cta, P, q, rewired, S);
+    if (!early_gather && !S.batch) svc_conn_gather(cta, P, q, rewired, S);
     if (cta.tid() == 0)
     {
         // statistics: [0] = subtree vertices (cycles slot) and levels... see imomd_get_profile
         S.Q->prof_cycles[0] += (uint64_t)(S.lv_tail - lo);
-        S.Q->stat[5] += (uint64_t)(S.lv_tail - lo - 1);
+        S.stat[5] += (uint64_t)(S.lv_tail - lo - 1);
         bool overflow = S.lv_overflow != 0;
         if (!overflow) T.set_cost(rewired, new_cost);
         S.bfs_hi = overflow ? IMOMD_NONE : S.lv_tail;
@@ -2366,7 +2452,8 @@ IMOMD_HD IMOMD_NOINLINE void svc_check(Cta& cta, const PlannerDev& P, int q, int
     IMOMD_ASSUME_SHARED(&S);
     const GraphDev& g = P.g;
     TreeRef T = tree_ref_of(P, q, k, S);
-    const uint32_t* arena = P.arena + (size_t)q * P.arena_entries;
+    const uint32_t* arena = S.arena;
+    IMOMD_ASSUME_GLOBAL(arena);
     const uint32_t W = (uint32_t)KW;
     uint32_t n = S.chk_hi - S.chk_lo;
     if (n > kCheckBatch) n = kCheckBatch;
@@ -2631,6 +2718,12 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
     if (cta.tid() == 0)
     {
         S.Q = Q;
+        S.arena = P.arena + (size_t)q * P.arena_entries;
+        S.arena_cap = P.arena_entries;
+        S.clist = P.clist + (size_t)q * 2 * P.chunks;
+        S.batch = 0;
+        for (int i = 0; i < 8; ++i) S.stat[i] = 0;
+        S.near_ties = S.unresolved_ties = S.certified_ties = 0;
         S.tref = tref;
         S.mP = mat;
         S.mD = mat + KK;
@@ -2718,8 +2811,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
         if (req == REQ_EXIT) break;
         if (req == REQ_NN)
         {
-            svc_nearest(cta, P, q, k, S, lb, P.clist + (size_t)q * 2 * P.chunks, &Q->near_ties,
-                        &Q->unresolved_ties, true);
+            svc_nearest(cta, P, q, k, S, lb, S.clist, &S.near_ties, &S.unresolved_ties, true);
             warm_k = k;
         }
         else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
@@ -2752,6 +2844,10 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
     if (cta.tid() == 0)
     {
         if (attach_tree < 0) Q->resume_k = S.k < Q->K ? S.k : 0;
+        for (int i = 0; i < 8; ++i) Q->stat[i] += S.stat[i];
+        Q->near_ties += S.near_ties;
+        Q->unresolved_ties += S.unresolved_ties;
+        Q->certified_ties += S.certified_ties;
         Q->busy_cycles = (uint64_t)(cta.clock() - busy0);
         Q->last_iterations = Q->iterations - Q->last_iterations;
         Q->last_expansions = Q->expansions - Q->last_expansions;
@@ -2824,6 +2920,359 @@ IMOMD_HD inline void run_streaming_query(Cta& cta, const PlannerDev& P, int slot
         P.reports[hq].busy_cycles = Q->busy_cycles;
     }
     cta.sync();
+}
+
+// ====================================================== batched expansion ====
+// imomd_expand_batch: B expansions per tree per STEP.  The K trees of a query are expanded
+// CONCURRENTLY, one cooperating group (a warp on the device) per tree: everything an expansion
+// does to its own tree -- sample, nearest frontier vertex, jump-point hops, choose-parent,
+// frontier / min-heuristic maintenance, the rewire cascade -- is exactly the sequential code of
+// the exact mode and touches only that tree's records and its row of the heuristic matrix.  What
+// an expansion does to state the trees SHARE (updateConnectionTree_: contacts, union-find,
+// distance / connection-node matrices; updateSelectionProbability: probability rows, is_done) is
+// logged with the values of that moment and applied by the whole CTA after the step, in tree
+// order and program order.  So a step differs from B reference passes only in WHEN the other
+// trees' state is looked at (end of the step), and in how the injected stream is read: every
+// (pass, tree) owns a fixed slot of kBatchWords words, so that trees can draw independently.
+// Deterministic: the result depends on neither the number of groups nor their timing.
+constexpr uint32_t kBatchWords = 8;
+constexpr uint32_t kEvChunk = 32;
+
+struct BatchShared
+{
+    uint32_t ev_count[IMOMD_KMAX];
+    uint32_t exp_count[IMOMD_KMAX];
+    int32_t active[IMOMD_KMAX];
+    int32_t n_active;
+    int32_t stop;
+    // the other trees' (parent, cost) at the vertices of a chunk of logged connection checks
+    uint32_t gpar[kEvChunk][IMOMD_KMAX];
+    double gcost[kEvChunk][IMOMD_KMAX];
+};
+
+// One group: up to B expansions of tree k (fewer when its frontier runs empty).
+template <int KW, class Grp>
+IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, int k, Shared& S, uint32_t* lvl,
+                                       int B, uint64_t pass0)
+{
+    const int K = P.K;
+    if (grp.tid() == 0)
+    {
+        const uint32_t share = P.arena_entries / (uint32_t)K;
+        S.arena = P.arena + (size_t)slot * P.arena_entries + (size_t)k * share;
+        S.arena_cap = share;
+        S.clist = P.clist_tree + ((size_t)slot * K + k) * 2 * (size_t)P.chunks;
+        S.ev = P.events + ((size_t)slot * K + k) * (size_t)P.ev_cap;
+        S.ev_n = 0;
+        S.exp_n = 0;
+        S.batch = 1;
+        S.attach_mode = 0;
+        S.k = k;
+    }
+    grp.sync();
+    for (int b = 0; b < B; ++b)
+    {
+        if (grp.tid() == 0)
+        {
+            QueryDev* Q = S.Q;
+            if (Q->frontier_count[k] == 0 || Q->status != 0) S.req = REQ_EXIT;
+            else
+            {
+                Seq<KW> seq(P, slot, S);
+                TreeRef T = tree_ref_of(P, slot, k, S);
+                seq.sample_at(k, T, ((pass0 + (uint64_t)b) * (uint64_t)K + (uint64_t)k) * kBatchWords);
+                S.req = Q->status == 0 ? REQ_NN : REQ_EXIT;
+                S.phase = PH_AFTER_NN;
+                S.conn_pending = 0;
+            }
+        }
+        grp.sync();
+        if (S.req == REQ_EXIT) break;
+        for (;;)
+        {
+            const int req = S.req;
+            if (req == REQ_EXIT) break;
+            if (req == REQ_NN) svc_nearest(grp, P, slot, k, S, (double*)nullptr, S.clist, &S.near_ties, &S.unresolved_ties, true);
+            else if (req == REQ_RESCAN) svc_rescan(grp, P, slot, k, S, (double*)nullptr);
+            else if (req == REQ_MHINS) svc_mhins(grp, P, slot, k, S);
+            else if (req == REQ_BFS)
+            {
+                svc_bfs_w<KW>(grp, P, slot, k, S, lvl);
+                grp.sync();
+                if (S.bfs_hi != IMOMD_NONE) svc_check<KW>(grp, P, slot, k, S);
+            }
+            else if (req == REQ_CHECK) svc_check<KW>(grp, P, slot, k, S);
+            grp.sync();
+            if (grp.tid() == 0)
+            {
+                Seq<KW> seq(P, slot, S);
+                seq.step(grp, 1);
+            }
+            grp.sync();
+        }
+    }
+    grp.sync();
+}
+
+// The whole CTA: the logged cross-tree effects of one step, trees in id order, each tree's
+// events in the order its expansions produced them.
+template <int KW, class Blk>
+IMOMD_HD inline void batch_apply_events(Blk& blk, const PlannerDev& P, int slot, Shared& S0, BatchShared& BS)
+{
+    QueryDev* Q = S0.Q;
+    const int K = P.K;
+    for (int k = 0; k < K; ++k)
+    {
+        const uint32_t n = BS.ev_count[k];
+        const BEvent* ev = P.events + ((size_t)slot * K + k) * (size_t)P.ev_cap;
+        for (uint32_t e0 = 0; e0 < n; e0 += kEvChunk)
+        {
+            const uint32_t cnt = n - e0 < kEvChunk ? n - e0 : kEvChunk;
+            for (uint32_t i = (uint32_t)blk.tid(); i < cnt * (uint32_t)K; i += (uint32_t)blk.nt())
+            {
+                const uint32_t e = i / (uint32_t)K, o = i % (uint32_t)K;
+                const BEvent E = ev[e0 + e];
+                if (E.kind == 0u && (int)o != k)
+                {
+                    const size_t qt = (size_t)slot * K + o;
+                    const U4 t = *reinterpret_cast<const U4*>(P.trec + (qt * (size_t)P.g.n + E.x) * (size_t)P.trec_stride);
+                    unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
+                    double c;
+                    memcpy(&c, &bits, 8);
+                    BS.gpar[e][o] = t.x;
+                    BS.gcost[e][o] = c;
+                }
+            }
+            blk.sync();
+            if (blk.tid() == 0)
+            {
+                Seq<KW> seq(P, slot, S0);
+                TreeRef T = tree_ref_of(P, slot, k, S0);
+                for (uint32_t e = 0; e < cnt; ++e)
+                {
+                    const BEvent E = ev[e0 + e];
+                    if (E.kind == 0u)
+                    {
+                        for (int o = 0; o < K; ++o)
+                        {
+                            S0.conn_par[o] = BS.gpar[e][o];
+                            S0.conn_cost[o] = BS.gcost[e][o];
+                        }
+                        seq.apply_connection(k, T, E.x, E.val);
+                    }
+                    else
+                    {
+                        seq.selection_probability_apply(blk, k, (int)E.aux, E.val, E.extra);
+                    }
+                }
+            }
+            blk.sync();
+        }
+        if (blk.tid() == 0) Q->expansions += (int64_t)BS.exp_count[k];
+    }
+}
+
+// `steps` steps of B expansions per tree for query hq in slot `slot`.  SG: one Shared per group;
+// lvl_all: one level buffer (2 * kLevelCap words) per group.
+template <int KW, class Blk, class Grp>
+IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, int slot, int hq, int steps, int B,
+                                       Shared* SG, BatchShared& BS, uint32_t* lvl_all, double* mat,
+                                       unsigned char* hot)
+{
+    assume_planner(P);
+    QueryDev* Qg = P.query + hq;
+    QueryDev* Q = reinterpret_cast<QueryDev*>(hot);
+    const int K = P.K, KK = K * K;
+    const int G = grp.n_groups();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Qg);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(hot);
+        for (uint32_t i = blk.tid(); i < IMOMD_QUERY_HOT_BYTES / 4; i += blk.nt()) dst[i] = src[i];
+    }
+    TreeRef* tref = reinterpret_cast<TreeRef*>(hot + ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16);
+    for (int k = blk.tid(); k < K; k += blk.nt()) tref[k] = tree_ref(P, slot, k);
+    for (int g = blk.tid(); g < G; g += blk.nt())
+    {
+        Shared& S = SG[g];
+        S.Q = Q;
+        S.tref = tref;
+        S.mP = mat;
+        S.mD = mat + KK;
+        S.mMHv = mat + 2 * KK;
+        S.mMHi = reinterpret_cast<uint32_t*>(mat + 3 * KK);
+        S.mCN = S.mMHi + KK;
+        S.batch = 1;
+        S.attach_mode = 0;
+        S.stop = 0;
+        S.it = 0;
+        for (int i = 0; i < 8; ++i) S.stat[i] = 0;
+        S.near_ties = S.unresolved_ties = S.certified_ties = 0;
+        S.arena = P.arena + (size_t)slot * P.arena_entries;
+        S.arena_cap = 0;
+        S.clist = nullptr;
+        S.ev = nullptr;
+        S.ev_n = S.exp_n = 0;
+    }
+    blk.sync();
+    Shared& S0 = SG[0];
+    for (int i = blk.tid(); i < KK; i += blk.nt())
+    {
+        sm_P(S0)[i] = Qg->P[i];
+        sm_D(S0)[i] = Qg->D[i];
+        sm_MHv(S0)[i] = Qg->MHv[i];
+        sm_MHi(S0)[i] = Qg->MHi[i];
+        sm_CN(S0)[i] = Qg->CN[i];
+    }
+    if (blk.tid() == 0)
+    {
+        if (Q->status == 1) Q->status = 0;
+        Q->last_iterations = Q->iterations;
+        Q->last_expansions = Q->expansions;
+    }
+    blk.sync();
+    const long long busy0 = blk.clock();
+    const uint64_t t_start = P.budget_ns ? blk.now_ns() : 0;
+    for (int step = 0; step < steps; ++step)
+    {
+        if (blk.tid() == 0)
+        {
+            int active = 0;
+            for (int k = 0; k < K; ++k)
+            {
+                BS.active[k] = (Q->frontier_count[k] != 0 && !Q->is_done[k]) ? 1 : 0;
+                BS.ev_count[k] = 0;
+                BS.exp_count[k] = 0;
+                active += BS.active[k];
+            }
+            BS.n_active = active;
+            BS.stop = 0;
+            if (Q->status != 0) BS.stop = 1;
+            else if (active == 0)
+            {
+                Q->iterations += (int64_t)(steps - step) * B;   // nothing can expand any more
+                BS.stop = 1;
+            }
+            else if (((uint64_t)Q->iterations + (uint64_t)B) * (uint64_t)K * kBatchWords + IMOMD_WORD_MARGIN > P.words_avail)
+            {
+                Q->status = 1;   // IMOMD_RUN_NEED_WORDS
+                BS.stop = 1;
+            }
+            else if (P.budget_ns && step > 0 && blk.now_ns() - t_start > P.budget_ns) BS.stop = 1;
+        }
+        blk.sync();
+        if (BS.stop) break;
+        const uint64_t pass0 = (uint64_t)Q->iterations;
+        blk.sync();
+        Shared& S = SG[grp.group()];
+        for (int k = grp.group(); k < K; k += G)
+        {
+            if (!BS.active[k]) continue;
+            batch_expand_tree<KW>(grp, P, slot, k, S, lvl_all + (size_t)grp.group() * 2 * kLevelCap, B, pass0);
+            if (grp.tid() == 0)
+            {
+                BS.ev_count[k] = S.ev_n;
+                BS.exp_count[k] = S.exp_n;
+            }
+        }
+        blk.sync();
+        batch_apply_events<KW>(blk, P, slot, S0, BS);
+        if (blk.tid() == 0)
+        {
+            Q->iterations += B;
+            Q->word_cursor = (uint64_t)Q->iterations * (uint64_t)K * kBatchWords;
+        }
+        blk.sync();
+    }
+    for (int i = blk.tid(); i < KK; i += blk.nt())
+    {
+        Qg->P[i] = sm_P(S0)[i];
+        Qg->D[i] = sm_D(S0)[i];
+        Qg->MHv[i] = sm_MHv(S0)[i];
+        Qg->MHi[i] = sm_MHi(S0)[i];
+        Qg->CN[i] = sm_CN(S0)[i];
+    }
+    if (blk.tid() == 0)
+    {
+        for (int g = 0; g < G; ++g)
+        {
+            for (int i = 0; i < 8; ++i) Q->stat[i] += SG[g].stat[i];
+            Q->near_ties += SG[g].near_ties;
+            Q->unresolved_ties += SG[g].unresolved_ties;
+            Q->certified_ties += SG[g].certified_ties;
+        }
+        Q->resume_k = 0;
+        Q->busy_cycles = (uint64_t)(blk.clock() - busy0);
+        Q->last_iterations = Q->iterations - Q->last_iterations;
+        Q->last_expansions = Q->expansions - Q->last_expansions;
+        int active = 0;
+        int64_t tv = 0;
+        for (int j = 0; j < K; ++j)
+        {
+            if (Q->frontier_count[j] != 0 && !Q->is_done[j]) ++active;
+            tv += (int64_t)Q->tree_size[j];
+        }
+        Q->active_trees = active;
+        ReportDev* R = P.reports + hq;
+        R->status = Q->status;
+        R->active_trees = active;
+        R->iterations = Q->last_iterations;
+        R->expansions = Q->last_expansions;
+        R->tree_vertices = tv;
+        R->words_consumed = (int64_t)Q->word_cursor;
+        R->connected = Q->connected;
+        R->dm_updated = Q->dm_updated;
+        R->near_ties = Q->near_ties;
+        R->unresolved_ties = Q->unresolved_ties;
+        R->log_entries = (int64_t)Q->log_count;
+        R->certified_ties = Q->certified_ties;
+        R->tree_hash = Q->tree_hash;
+        R->busy_cycles = Q->busy_cycles;
+    }
+    blk.sync();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(hot);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(Qg);
+        for (uint32_t i = blk.tid(); i < IMOMD_QUERY_HOT_BYTES / 4; i += blk.nt()) dst[i] = src[i];
+    }
+    blk.sync();
+}
+
+// a streaming planner's query in the batched mode (cf. run_streaming_query)
+template <int KW, class Blk, class Grp>
+IMOMD_HD inline void run_streaming_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, int slot, int hq, int steps,
+                                                 int B, Shared* SG, BatchShared& BS, uint32_t* lvl_all, double* mat,
+                                                 unsigned char* hot)
+{
+    const long long t0 = blk.clock();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.query_init + hq);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(P.query + hq);
+        for (uint32_t i = blk.tid(); i < sizeof(QueryDev) / 4; i += blk.nt()) dst[i] = src[i];
+    }
+    reset_slot(blk, P, slot);
+    fill_bounds(blk, P, slot, hq);
+    blk.sync();
+    if (blk.tid() == 0)
+    {
+        QueryDev* Q = P.query + hq;
+        for (int k = 0; k < P.K; ++k) Q->free_top[k] = (uint32_t)P.chunks;
+        construct_trees(P, slot, hq);
+    }
+    blk.sync();
+    run_query_batched<KW>(blk, grp, P, slot, hq, steps, B, SG, BS, lvl_all, mat, hot);
+    blk.sync();
+    uint64_t h = 0, sum = 0;
+    tree_hash(blk, P, slot, SG[0], P.arena + (size_t)slot * P.arena_entries, P.arena_entries, &h, &sum);
+    if (blk.tid() == 0)
+    {
+        QueryDev* Q = P.query + hq;
+        Q->tree_hash = h;
+        Q->tree_sum = sum;
+        Q->busy_cycles = (uint64_t)(blk.clock() - t0);
+        P.reports[hq].tree_hash = h;
+        P.reports[hq].busy_cycles = Q->busy_cycles;
+    }
+    blk.sync();
 }
 
 }  // namespace imomd

@@ -75,7 +75,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
     } while (0)
 
 constexpr int kThreads = 256;   // CTA size of the expansion kernel (8 warps)
-constexpr int kTieBoxes = 1024; // host mailboxes per planner (>= the largest grid that can ask)
+constexpr int kTieBoxes = 4096; // host mailboxes per planner (>= 8 x the largest grid of the batched kernel)
 
 // ------------------------------------------------------------ Cta policy ---
 
@@ -125,6 +125,8 @@ struct CtaDev
         return atomicAdd(p, v);
     }
     __device__ __forceinline__ void counter_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
+    __device__ __forceinline__ int group() const { return 0; }
+    __device__ __forceinline__ int n_groups() const { return 1; }
     __device__ __forceinline__ uint64_t now_ns() const
     {
         uint64_t t;
@@ -299,6 +301,109 @@ struct CtaDev
     }
 };
 
+// The cooperating group of the BATCHED mode: one warp (one tree).  Same interface as CtaDev; every
+// barrier is a warp barrier, every reduction a shuffle tree, scratch is the warp's own Shared.
+struct WarpDev
+{
+    TieBox* box = nullptr;
+    __device__ __forceinline__ int tid() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ int nt() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ long long clock() const { return clock64(); }
+    __device__ __forceinline__ int warp() const { return 0; }
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ int warp_width() const { return 32; }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    __device__ __forceinline__ int group() const { return (int)(threadIdx.x >> 5); }
+    __device__ __forceinline__ int n_groups() const { return (int)(blockDim.x >> 5); }
+    __device__ __forceinline__ bool warp_all(bool p) const { return __all_sync(0xFFFFFFFFu, p) != 0; }
+    __device__ __forceinline__ uint32_t warp_scan_small(uint32_t v, int maxv, uint32_t* total) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+        uint32_t off = 0, tot = 0;
+        for (int j = 1; j <= maxv; ++j)
+        {
+            unsigned b = __ballot_sync(full, v >= (uint32_t)j);
+            off += __popc(b & lt);
+            tot += __popc(b);
+        }
+        *total = tot;
+        return off;
+    }
+    __device__ __forceinline__ uint32_t counter_add(uint32_t* p, uint32_t v) const { return atomicAdd(p, v); }
+    __device__ __forceinline__ void counter_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
+    __device__ __forceinline__ uint64_t now_ns() const
+    {
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ __forceinline__ void store_streaming(U4* p, const U4& v) const
+    {
+        __stcs(reinterpret_cast<uint4*>(p), make_uint4(v.x, v.y, v.z, v.w));
+    }
+    __device__ __forceinline__ U4 load_streaming(const U4* p) const
+    {
+        uint4 t = __ldcs(reinterpret_cast<const uint4*>(p));
+        U4 r;
+        r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
+        return r;
+    }
+    __device__ __noinline__ bool certify(int n, double (*in)[4], double* out) const
+    {
+        CtaDev c;
+        c.box = box;
+        return c.certify(n, in, out);
+    }
+    __device__ __forceinline__ uint32_t scan_exclusive(uint32_t v, uint32_t* total, uint32_t*) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+        int ln = threadIdx.x & 31;
+        uint32_t inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(full, inc, off);
+            if (ln >= off) inc += t;
+        }
+        *total = __shfl_sync(full, inc, 31);
+        return inc - v;
+    }
+    __device__ __forceinline__ uint32_t reduce_min_u32(uint32_t v, uint32_t*) const
+    {
+        return __reduce_min_sync(0xFFFFFFFFu, v);
+    }
+    __device__ __forceinline__ double reduce_min_f64(double v, Best*) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(full, v, off));
+        return v;
+    }
+    __device__ __forceinline__ uint64_t reduce_sum_u64(uint64_t v, Best*) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(full, v, off);
+        return v;
+    }
+    __device__ __forceinline__ Best reduce(Best b, Best*) const
+    {
+        const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            Best o;
+            o.v1 = __shfl_xor_sync(full, b.v1, off);
+            o.id1 = __shfl_xor_sync(full, b.id1, off);
+            o.v2 = __shfl_xor_sync(full, b.v2, off);
+            b = best_merge(b, o);
+        }
+        return b;
+    }
+};
+
 // ---------------------------------------------------------------- kernels ---
 
 __global__ void k_build_vrec(uint32_t n, const double* __restrict__ lat,
@@ -400,6 +505,46 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand(const __grid_con
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
         run_query<KW>(cta, P, q, q, iters, S, lb, lvl, mat, hot);
+        __syncthreads();
+    }
+}
+
+// imomd_expand_batch: one CTA per query (resident) or per state slot (streaming), one WARP per
+// tree inside it; `steps` steps of B expansions per tree (run_query_batched, imomd_core.cuh).
+// Shared memory: [Shared x warps | BatchShared | level buffers x warps | K x K matrices | hot header]
+template <int THREADS, int MIN_BLOCKS, int KW>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand_batch(const __grid_constant__ PlannerDev P, int steps, int B)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = THREADS / 32;
+    constexpr size_t kShared = ((sizeof(Shared) + 15) / 16) * 16;
+    Shared* SG = reinterpret_cast<Shared*>(smem_raw);
+    BatchShared& BS = *reinterpret_cast<BatchShared*>(smem_raw + NW * kShared);
+    uint32_t* lvl_all = reinterpret_cast<uint32_t*>(smem_raw + NW * kShared + ((sizeof(BatchShared) + 15) / 16) * 16);
+    double* mat = reinterpret_cast<double*>(lvl_all + (size_t)NW * 2 * kLevelCap);
+    unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
+    CtaDev blk;
+    WarpDev grp;
+    // mailboxes of the exact-value service: eight per CTA (the block's = its first warp's)
+    blk.box = P.tiebox ? P.tiebox + (size_t)blockIdx.x * 8 : nullptr;
+    grp.box = P.tiebox ? P.tiebox + (size_t)blockIdx.x * 8 + (threadIdx.x >> 5) % 8 : nullptr;
+    if (P.streaming)
+    {
+        __shared__ int next_q;
+        for (;;)
+        {
+            if (threadIdx.x == 0) next_q = (int)atomicAdd(P.queue, 1u);
+            __syncthreads();
+            const int hq = next_q;
+            __syncthreads();
+            if (hq >= P.Q) break;
+            run_streaming_query_batched<KW>(blk, grp, P, (int)blockIdx.x, hq, steps, B, SG, BS, lvl_all, mat, hot);
+        }
+        return;
+    }
+    for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
+    {
+        run_query_batched<KW>(blk, grp, P, q, q, steps, B, SG, BS, lvl_all, mat, hot);
         __syncthreads();
     }
 }
@@ -689,6 +834,8 @@ struct imomd_planner
     // host mailboxes of the exact-value service (mapped pinned memory) and what they did
     TieBox* box_host = nullptr;
     uint64_t certified_requests = 0;
+    size_t smem_batch = 0;          // dynamic shared memory of k_expand_batch
+    bool batch_ready = false;       // event logs / per-tree chunk lists allocated
 };
 
 struct imomd_ctx
@@ -1060,6 +1207,8 @@ int imomd_planner_destroy(imomd_planner* p)
     cudaFree(p->queue);
     cudaFree(p->dest_d);
     cudaFree(p->prob_d);
+    cudaFree(d.events);
+    cudaFree(d.clist_tree);
     if (p->box_host) cudaFreeHost(p->box_host);
     cudaFree(p->words);
     cudaFree(p->nn_scratch);
@@ -1126,6 +1275,10 @@ int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* ver
     else if (w == 8) k_attach<8><<<1, attach_threads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
     else k_attach<16><<<1, attach_threads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);
     CU(cudaGetLastError());
+    // (a device->host copy into pageable memory blocks the host until the stream reaches it: the
+    // kernel may be waiting for the exact-value service, so the wait -- which runs the service --
+    // always comes BEFORE the copies)
+    CU(wait_stream(p));
     if (report)
         CU(cudaMemcpyAsync(report, p->d.reports + query, sizeof(ReportDev), cudaMemcpyDeviceToHost,
                            p->stream));
@@ -1303,6 +1456,59 @@ int imomd_expand_async(imomd_planner* p, int iters)
     return IMOMD_OK;
 }
 
+// Batched mode: `steps` steps of B expansions per tree, the K trees of a query expanded
+// concurrently (one warp each), cross-tree effects applied after every step.
+int imomd_expand_batch_async(imomd_planner* p, int steps, int B)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "null planner");
+    if (steps < 0 || B < 1 || B > 4096) return fail(IMOMD_ERR_ARG, "steps must be >= 0 and B in [1, 4096]");
+    if (p->d.pseudo) return fail(IMOMD_ERR_ARG, "the batched mode does not cover pseudo mode (the merge needs the exact visit order)");
+    CU(cudaSetDevice(p->g->device));
+    PlannerDev& d = p->d;
+    constexpr int kBatchThreads = 256;
+    if (!p->batch_ready)
+    {
+        CU(wait_stream(p));
+        const size_t sk = (size_t)d.slots * d.K;
+        d.ev_cap = 2048;
+        CU(dmalloc(&d.events, sk * d.ev_cap));
+        CU(dmalloc(&d.clist_tree, sk * 2 * (size_t)d.chunks));
+        const size_t cells_unused = 0;
+        (void)cells_unused;
+        p->smem_batch = (kBatchThreads / 32) * (((sizeof(Shared) + 15) / 16) * 16) + ((sizeof(BatchShared) + 15) / 16) * 16 +
+                        (size_t)(kBatchThreads / 32) * 2 * kLevelCap * sizeof(uint32_t) + (size_t)d.K * d.K * 32 +
+                        ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)d.K * sizeof(TreeRef) + 64;
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* f) {
+            cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_batch);
+            if (r != cudaSuccess) e = r;
+        };
+        set((const void*)k_expand_batch<kBatchThreads, 2, 4>);
+        set((const void*)k_expand_batch<kBatchThreads, 2, 8>);
+        set((const void*)k_expand_batch<kBatchThreads, 2, 16>);
+        CU(e);
+        p->batch_ready = true;
+    }
+    CU(cudaEventRecord(p->ev0, p->stream));
+    const int ctas = d.streaming ? d.slots : d.Q;
+    if (d.streaming) CU(cudaMemsetAsync(p->queue, 0, 2 * sizeof(uint32_t), p->stream));
+    const int w = d.g.width;
+    if (w == 4) k_expand_batch<kBatchThreads, 2, 4><<<ctas, kBatchThreads, p->smem_batch, p->stream>>>(d, steps, B);
+    else if (w == 8) k_expand_batch<kBatchThreads, 2, 8><<<ctas, kBatchThreads, p->smem_batch, p->stream>>>(d, steps, B);
+    else k_expand_batch<kBatchThreads, 2, 16><<<ctas, kBatchThreads, p->smem_batch, p->stream>>>(d, steps, B);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev1, p->stream));
+    p->pending = true;
+    return IMOMD_OK;
+}
+
+int imomd_expand_batch(imomd_planner* p, int steps, int B, imomd_query_report* reports)
+{
+    int rc = imomd_expand_batch_async(p, steps, B);
+    if (rc != IMOMD_OK) return rc;
+    return imomd_sync(p, reports);
+}
+
 // max_time of the reference's loop (:258-262): the following imomd_expand calls stop after the
 // first pass that ends more than `seconds` after the launch started (reports say how many passes
 // ran); 0 = no budget
@@ -1318,10 +1524,9 @@ int imomd_sync(imomd_planner* p, imomd_query_report* reports)
     if (!p) return fail(IMOMD_ERR_ARG, "null planner");
     CU(cudaSetDevice(p->g->device));
     static_assert(sizeof(imomd_query_report) == sizeof(ReportDev), "report layouts must agree");
+    CU(wait_stream(p));      // first: the kernel may be asking the exact-value service
     if (reports)
-        CU(cudaMemcpyAsync(reports, p->d.reports, (size_t)p->d.Q * sizeof(ReportDev),
-                           cudaMemcpyDeviceToHost, p->stream));
-    CU(wait_stream(p));
+        CU(cudaMemcpy(reports, p->d.reports, (size_t)p->d.Q * sizeof(ReportDev), cudaMemcpyDeviceToHost));
     if (p->pending)
     {
         CU(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
@@ -1519,6 +1724,7 @@ int imomd_get_frontier(imomd_planner* p, int query, int tree, uint32_t* out, uin
     k_frontier_list<<<(n + 255) / 256, 256, 0, p->stream>>>(p->d, qt, p->gather_u32);
     CU(cudaGetLastError());
     uint32_t c = 0;
+    CU(wait_stream(p));
     CU(cudaMemcpyAsync(&c, p->gather_u32, 4, cudaMemcpyDeviceToHost, p->stream));
     CU(wait_stream(p));
     *count = c;
@@ -1547,6 +1753,7 @@ int imomd_gather_tree(imomd_planner* p, int query, int tree, const uint32_t* ver
     CU(cudaMemcpyAsync(p->gather_u32, vertices, (size_t)count * 4, cudaMemcpyHostToDevice, p->stream));
     k_gather_tree<<<(count + 255) / 256, 256, 0, p->stream>>>(p->d, qt, p->gather_u32, p->gather_f64, count);
     CU(cudaGetLastError());
+    CU(wait_stream(p));
     if (parent)
         CU(cudaMemcpyAsync(parent, p->gather_u32, (size_t)count * 4, cudaMemcpyDeviceToHost, p->stream));
     if (cost)
@@ -1577,6 +1784,7 @@ int imomd_walk_to_root(imomd_planner* p, int query, int tree, uint32_t vertex, u
                                     root, p->walk_buf + 1, cap, p->walk_buf);
     CU(cudaGetLastError());
     uint32_t l = 0;
+    CU(wait_stream(p));
     CU(cudaMemcpyAsync(&l, p->walk_buf, 4, cudaMemcpyDeviceToHost, p->stream));
     CU(wait_stream(p));
     *len = l;
@@ -1676,6 +1884,7 @@ int imomd_nearest(imomd_planner* p, int n, const imomd_nn_query* q, uint32_t* id
     k_nearest<<<ctas, kThreads, p->smem_bytes, p->stream>>>(p->d, n, dq, didx, ddist, p->nn_scratch,
                                                             p->nn_stats);
     CU(cudaGetLastError());
+    CU(wait_stream(p));      // runs the exact-value service while k_nearest may be asking
     CU(cudaMemcpyAsync(idx, didx, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
     CU(wait_stream(p));
@@ -1762,6 +1971,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaGetLastError());
     CU(cudaEventRecord(sc.ev[1], p->stream));
     uint32_t n_work = 0;
+    CU(wait_stream(p));
     CU(cudaMemcpyAsync(&n_work, n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
     CU(wait_stream(p));
     CU(sc.get(13, &work, (size_t)n_work));
@@ -1787,6 +1997,7 @@ int imomd_nearest_batch(imomd_planner* p, int n, const imomd_nn_query* q, uint32
     CU(cudaEventRecord(sc.ev[4], p->stream));
     std::vector<uint32_t> amb(n), hcounts(QK), hvalid(n_tiles);
     int herr = 0;
+    CU(wait_stream(p));
     CU(cudaMemcpyAsync(idx, didx, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(amb.data(), damb, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));

@@ -158,6 +158,19 @@ struct TieBox
     double out[IMOMD_TIE_PAIRS];     // metres
 };
 
+// Batched mode: one deferred cross-tree effect of an expansion.
+//   kind 0: updateConnectionTree_(tree, x) -- val = cost of x in the tree at that moment
+//   kind 1: updateSelectionProbability for the pair (tree, aux) -- val / extra = the
+//           min-heuristic value / holder of that pair at that moment
+struct BEvent
+{
+    uint32_t x;
+    uint32_t aux;
+    double val;
+    uint32_t extra;
+    uint32_t kind;
+};
+
 struct PlannerDev
 {
     GraphDev g;
@@ -201,6 +214,11 @@ struct PlannerDev
     uint32_t* attach_list;     // pseudo mode: [n] vertices imomd_attach_list works through; each entry is
                                // overwritten with the parent the vertex received
     struct ReportDev* reports; // [Q] compact per-launch report (copied back to the host)
+    // batched mode (imomd_expand_batch): per (slot, tree) event logs and chunk work lists
+    BEvent* events;            // [slots*K][ev_cap]
+    uint32_t ev_cap;
+    uint32_t pad2_;
+    uint32_t* clist_tree;      // [slots*K][2*chunks]
     // injected random words
     const uint32_t* words;
     uint64_t words_avail;

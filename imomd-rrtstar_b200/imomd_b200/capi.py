@@ -80,6 +80,9 @@ def cuda_lib():
         L.imomd_planner_words_available.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.imomd_expand.argtypes = [vp, C.c_int, C.POINTER(Report)]
         L.imomd_expand_async.argtypes = [vp, C.c_int]
+        L.imomd_expand_batch.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Report)]
+        L.imomd_expand_batch_async.argtypes = [vp, C.c_int, C.c_int]
+        L.imomd_set_time_budget.argtypes = [vp, C.c_double]
         L.imomd_sync.argtypes = [vp, C.POINTER(Report)]
         L.imomd_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.imomd_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p]
@@ -257,6 +260,15 @@ class DevicePlanner:
         rep = (Report * self.Q)()
         _check(cuda_lib().imomd_expand(self.h, iters, rep))
         return list(rep)
+
+    def expand_batch(self, steps, B):
+        """batched mode: `steps` steps of B expansions per tree, trees expanded concurrently"""
+        rep = (Report * self.Q)()
+        _check(cuda_lib().imomd_expand_batch(self.h, steps, B, rep))
+        return list(rep)
+
+    def set_time_budget(self, seconds):
+        _check(cuda_lib().imomd_set_time_budget(self.h, seconds))
 
     def expand_async(self, iters):
         _check(cuda_lib().imomd_expand_async(self.h, iters))

@@ -149,6 +149,18 @@ int imomd_planner_clear_words(imomd_planner* p);
 int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports);
 int imomd_expand_async(imomd_planner* p, int iters);
 int imomd_sync(imomd_planner* p, imomd_query_report* reports);
+/* BATCHED expansion (north_star (2), (4)): `steps` steps, each of them B expansions of EVERY tree of
+ * every query.  The K trees of a query are expanded concurrently -- one warp per tree runs the very
+ * code of the exact mode on its own tree: sample, nearest frontier vertex, jump-point hops,
+ * choose-parent, frontier / heuristic maintenance, rewire cascade -- while what an expansion does
+ * to state the trees share (updateConnectionTree_ :645-706, updateSelectionProbability :602-643)
+ * is logged with the values of that moment and applied after the step, in tree order and program
+ * order.  Samples come from the injected stream in fixed slots of 8 words per (pass, tree).
+ * Deterministic; differs from B reference passes only in when the other trees are looked at.
+ * imomd_expand (one sample per tree per pass, sequential) remains the exact, batch-size-1 mode.
+ * A report's `iterations` counts passes (steps * B).  Not available in pseudo mode. */
+int imomd_expand_batch(imomd_planner* p, int steps, int B, imomd_query_report* reports);
+int imomd_expand_batch_async(imomd_planner* p, int steps, int B);
 /* ImomdRRT::findShortestPath's max_time test runs after EVERY pass (:258-262): with a budget
  * set, an imomd_expand launch stops after the first pass that ends more than `seconds` after
  * the launch began (imomd_query_report.iterations tells how many ran).  0 = none. */

@@ -248,6 +248,29 @@ struct orc_planner
     uint64_t ties = 0;
     uint64_t cdf_overrun = 0;
 
+    // ---- batched mode (restatement of imomd_expand_batch's semantics, DESIGN.md "Batched mode"):
+    // the trees of a step are expanded independently; updateConnectionTree_ / the selection-
+    // probability test are logged with the values of the moment and applied after the step in
+    // tree order.  Samples come from fixed 8-word slots of the mt19937{0} stream.
+    struct Event
+    {
+        int kind;          // 0 connection check, 1 selection-probability test
+        uint32_t x;
+        int other;
+        double val;        // cost of x / min-heuristic value
+    };
+    bool defer = false;
+    std::vector<Event> events;          // of the tree being expanded
+    std::vector<uint32_t> word_cache;   // outputs 0, 1, 2, ... of mt19937{0}
+    Mt19937 word_gen{0};
+    uint64_t batch_passes = 0;          // passes performed in batched mode so far
+
+    uint32_t word(uint64_t i)
+    {
+        while (word_cache.size() <= i) word_cache.push_back(word_gen.next());
+        return word_cache[(size_t)i];
+    }
+
     // ---- children container order: SURVEY.md 8a-7 (unordered_set<size_t>, <= 13) ----
     void chl_insert(Tree& t, uint32_t p, uint32_t x)
     {
@@ -587,7 +610,17 @@ struct orc_planner
             }
         }
         if (other_id == K) return;
-        if (MH[(size_t)t.id * K + other_id].val > D[(size_t)t.id * K + other_id])
+        if (defer)
+        {
+            events.push_back(Event{1, NONE, other_id, MH[(size_t)t.id * K + other_id].val});
+            return;
+        }
+        apply_selection_probability(t, other_id, MH[(size_t)t.id * K + other_id].val);
+    }
+
+    void apply_selection_probability(Tree& t, int other_id, double mh_val)
+    {
+        if (mh_val > D[(size_t)t.id * K + other_id])
         {
             Tree& other = trees[other_id];
             P[(size_t)t.id * K + other.id] = 0.0;
@@ -615,6 +648,17 @@ struct orc_planner
     // src/imomd_rrt_star.cpp:645-706
     void update_connection(Tree& t, uint32_t x_new)
     {
+        if (defer)
+        {
+            events.push_back(Event{0, x_new, 0, t.cost[x_new]});
+            return;
+        }
+        apply_connection(t, x_new, t.cost[x_new]);
+    }
+
+    // the body of updateConnectionTree_ with the tree's cost at x_new given
+    void apply_connection(Tree& t, uint32_t x_new, double cost_here)
+    {
         for (int o = 0; o < K; ++o)
         {
             Tree& other = trees[o];
@@ -628,7 +672,7 @@ struct orc_planner
                 if (pseudo) conn_log.push_back({(uint32_t)set_idx, x_new});
                 connect_two_trees(t.id, other.id);
             }
-            double distance = t.cost[x_new] + other.cost[x_new];
+            double distance = cost_here + other.cost[x_new];
             if (distance < D[(size_t)t.id * K + other.id] - 0.1)
             {
                 D[(size_t)t.id * K + other.id] = distance;
@@ -665,6 +709,132 @@ struct orc_planner
         {
             if (ds_parent[i] != ds_parent[0]) connected = false;
         }
+    }
+
+    // selectRandomVertex_ reading the stream from a fixed position (batched mode)
+    struct SlotWords
+    {
+        orc_planner* p;
+        uint64_t cursor;
+        uint32_t next() { return p->word(cursor++); }
+    };
+    static double canonical_w(SlotWords& w)
+    {
+        double sum = 0.0, tmp = 1.0;
+        for (int k = 0; k < 2; ++k)
+        {
+            sum += (double)w.next() * tmp;
+            tmp *= 4294967296.0;
+        }
+        double ret = sum / tmp;
+        if (ret >= 1.0) ret = std::nextafter(1.0, 0.0);
+        return ret;
+    }
+    static uint32_t uniform_u32_w(SlotWords& w, uint32_t urange)
+    {
+        if (urange == 0xFFFFFFFFu) return w.next();
+        uint32_t range = urange + 1u;
+        uint64_t product = (uint64_t)w.next() * (uint64_t)range;
+        uint32_t low = (uint32_t)product;
+        if (low < range)
+        {
+            uint32_t threshold = (0u - range) % range;
+            while (low < threshold)
+            {
+                product = (uint64_t)w.next() * (uint64_t)range;
+                low = (uint32_t)product;
+            }
+        }
+        return (uint32_t)(product >> 32);
+    }
+    void select_random_vertex_at(Tree& t, uint64_t cursor, uint64_t& rid, double& rlat, double& rlon)
+    {
+        SlotWords w{this, cursor};
+        if (canonical_w(w) * (1.0 - 0.0) + 0.0 < goal_bias)
+        {
+            double rand = canonical_w(w) * (1.0 - 0.0) + 0.0;
+            int i = 0;
+            while (rand >= 0)
+            {
+                if (i >= K)
+                {
+                    ++cdf_overrun;
+                    break;
+                }
+                rand -= P[(size_t)t.id * K + i++];
+            }
+            uint32_t random_dest = trees[i - 1].root;
+            rid = random_dest;
+            rlat = g->lat[random_dest];
+            rlon = g->lon[random_dest];
+            if (t.visited(random_dest))
+            {
+                double ratio = canonical_w(w) * (0.5 - 0.0) + 0.0;
+                rlat *= ratio;
+                rlon *= ratio;
+                rlat += (1.0 - ratio) * g->lat[t.root];
+                rlon += (1.0 - ratio) * g->lon[t.root];
+            }
+        }
+        else
+        {
+            uint32_t v = uniform_u32_w(w, g->n - 1);
+            rid = v;
+            rlat = g->lat[v];
+            rlon = g->lon[v];
+        }
+    }
+
+    // one step of the batched mode: B expansions per tree, cross-tree effects afterwards
+    uint64_t batched_step(int B)
+    {
+        uint64_t expansions = 0;
+        std::vector<std::vector<Event>> logs(K);
+        std::vector<char> active(K);
+        int n_active = 0;
+        for (int k = 0; k < K; ++k)
+        {
+            active[k] = !trees[k].fr_items.empty() && !trees[k].is_done;
+            n_active += active[k];
+        }
+        if (n_active == 0)
+        {
+            batch_passes += (uint64_t)B;
+            return 0;
+        }
+        defer = true;
+        for (int k = 0; k < K; ++k)
+        {
+            if (!active[k]) continue;
+            Tree& t = trees[k];
+            events.clear();
+            for (int b = 0; b < B; ++b)
+            {
+                if (t.fr_items.empty()) break;
+                uint64_t rid;
+                double rlat, rlon;
+                select_random_vertex_at(t, ((batch_passes + (uint64_t)b) * (uint64_t)K + (uint64_t)k) * 8u, rid, rlat, rlon);
+                uint32_t x_new = steer(t, rlat, rlon, nullptr, nullptr);
+                connect_new_node(t, x_new);
+                update_expandables(t, x_new, true);
+                rewire(t, x_new);
+                update_selection_probability(t, rid);
+                update_connection(t, x_new);
+                ++expansions;
+            }
+            logs[k] = events;
+        }
+        defer = false;
+        for (int k = 0; k < K; ++k)
+        {
+            for (const Event& e : logs[k])
+            {
+                if (e.kind == 0) apply_connection(trees[k], e.x, e.val);
+                else apply_selection_probability(trees[k], e.other, e.val);
+            }
+        }
+        batch_passes += (uint64_t)B;
+        return expansions;
     }
 
     // src/imomd_rrt_star.cpp:337-356
@@ -908,6 +1078,14 @@ uint64_t orc_planner_iterate(orc_planner* p, int iters)
             if (p->expand_tree(p->trees[k], nullptr)) ++expansions;
         }
     }
+    return expansions;
+}
+
+// `steps` steps of the batched mode (B expansions per tree per step); returns the expansions
+uint64_t orc_planner_iterate_batched(orc_planner* p, int steps, int B)
+{
+    uint64_t expansions = 0;
+    for (int s = 0; s < steps; ++s) expansions += p->batched_step(B);
     return expansions;
 }
 

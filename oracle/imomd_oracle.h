@@ -63,6 +63,8 @@ orc_planner* orc_planner_create(orc_graph* g, int K, const uint64_t* dest, doubl
                                 int pseudo_mode);
 void orc_planner_destroy(orc_planner* p);
 uint64_t orc_planner_iterate(orc_planner* p, int iters);
+/* batched mode (imomd_expand_batch): `steps` steps of B expansions per tree */
+uint64_t orc_planner_iterate_batched(orc_planner* p, int steps, int B);
 int orc_planner_expand_traced(orc_planner* p, int k, orc_trace* tr);
 void orc_planner_get_tree(orc_planner* p, int k, uint32_t* parent, double* cost);
 uint64_t orc_planner_tree_size(orc_planner* p, int k);

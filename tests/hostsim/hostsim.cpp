@@ -58,6 +58,8 @@ struct CtaHost
     }
     uint32_t reduce_min_u32(uint32_t v, uint32_t*) const { return v; }
     void counter_or(uint32_t* p, uint32_t v) const { *p |= v; }
+    int group() const { return 0; }       // batched mode: one group walks the trees one by one
+    int n_groups() const { return 1; }
     mutable uint64_t fake_ns = 0;
     uint64_t now_ns() const { return fake_ns += 1000; }   // every reading is 1 us later
     void store_streaming(U4* p, const U4& v) const { *p = v; }
@@ -96,6 +98,9 @@ struct HsPlanner
     std::vector<double> mat;
     std::vector<unsigned char> hot;
     std::vector<QueryDev> query_init;
+    std::vector<BEvent> events;
+    std::vector<uint32_t> clist_tree;
+    BatchShared BS;
     Shared S;
     CtaHost cta;
 };
@@ -197,6 +202,11 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     d.reports = p->reports.data();
     p->query_init = p->query;
     d.query_init = p->query_init.data();
+    d.ev_cap = 4096;
+    p->events.resize(qk * d.ev_cap);
+    d.events = p->events.data();
+    p->clist_tree.resize(qk * 2 * chunks);
+    d.clist_tree = p->clist_tree.data();
     if (d.streaming) return p;     // slots are rebuilt when a query takes them (run_streaming_query)
     for (size_t i = 0; i < qk; ++i)
         for (size_t c = 0; c < chunks; ++c) p->free_stack[i * chunks + c] = (uint32_t)(chunks - 1 - c);
@@ -255,6 +265,29 @@ void hs_expand(void* hp, int iters, ReportDev* reports)
             run_query<8>(cta, p->d, q, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
         else
             run_query<16>(cta, p->d, q, q, iters, p->S, p->lb.data(), p->lvl.data(), p->mat.data(), hot);
+    }
+    if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
+}
+
+// imomd_expand_batch on the host simulation: `steps` steps of B expansions per tree
+void hs_expand_batch(void* hp, int steps, int B, ReportDev* reports)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    CtaHost& cta = p->cta;
+    unsigned char* hot = reinterpret_cast<unsigned char*>(((uintptr_t)p->hot.data() + 15) & ~(uintptr_t)15);
+    for (int hq = 0; hq < p->d.Q; ++hq)
+    {
+        const int slot = p->d.streaming ? hq % p->d.slots : hq;
+#define HS_BATCH(W)                                                                                              \
+    if (p->d.streaming)                                                                                          \
+        run_streaming_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->lvl.data(),           \
+                                       p->mat.data(), hot);                                                      \
+    else                                                                                                         \
+        run_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->lvl.data(), p->mat.data(), hot);
+        if (p->d.g.width == 4) { HS_BATCH(4) }
+        else if (p->d.g.width == 8) { HS_BATCH(8) }
+        else { HS_BATCH(16) }
+#undef HS_BATCH
     }
     if (reports) std::memcpy(reports, p->reports.data(), p->reports.size() * sizeof(ReportDev));
 }

@@ -53,6 +53,7 @@ def lib():
         L.hs_grid_dim.argtypes = [vp]
         L.hs_feed_words.argtypes = [vp, u32p, C.c_size_t]
         L.hs_expand.argtypes = [vp, C.c_int, C.POINTER(Report)]
+        L.hs_expand_batch.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Report)]
         L.hs_get_tree.argtypes = [vp, C.c_int, C.c_int, u32p, f64p]
         L.hs_get_state.argtypes = [vp, C.c_int, f64p, u32p, f64p, u32p, f64p, i32p, i32p, i32p]
         L.hs_get_frontier.restype = C.c_uint32
@@ -97,6 +98,11 @@ class HostSimPlanner:
     def expand(self, iters):
         rep = (Report * self.Q)()
         self.L.hs_expand(self.h, iters, rep)
+        return list(rep)
+
+    def expand_batch(self, steps, B):
+        rep = (Report * self.Q)()
+        self.L.hs_expand_batch(self.h, steps, B, rep)
         return list(rep)
 
     def tree(self, k, q=0):

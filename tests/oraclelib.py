@@ -78,6 +78,7 @@ def oracle():
         _sig(L.orc_planner_create, vp, [vp, C.c_int, u64p, C.c_double, C.c_int])
         _sig(L.orc_planner_destroy, None, [vp])
         _sig(L.orc_planner_iterate, C.c_uint64, [vp, C.c_int])
+        _sig(L.orc_planner_iterate_batched, C.c_uint64, [vp, C.c_int, C.c_int])
         _sig(L.orc_planner_expand_traced, C.c_int, [vp, C.c_int, C.POINTER(Trace)])
         _sig(L.orc_planner_get_tree, None, [vp, C.c_int, u32p, f64p])
         _sig(L.orc_planner_tree_size, C.c_uint64, [vp, C.c_int])
@@ -184,6 +185,10 @@ class OraclePlanner:
 
     def iterate(self, iters):
         return self.L.orc_planner_iterate(self.ph, iters)
+
+    def iterate_batched(self, steps, B):
+        """the batched mode's semantics (imomd_expand_batch): steps x (B expansions per tree)"""
+        return self.L.orc_planner_iterate_batched(self.ph, steps, B)
 
     def expand_traced(self, k):
         t = Trace()

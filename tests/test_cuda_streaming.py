@@ -38,7 +38,8 @@ def test_resident_treehash_and_batched_states():
             assert h == o.treehash()
             one = dp.state(q)
             assert np.array_equal(st["D"][q].view(np.uint64), one["D"].view(np.uint64))
-            assert np.array_equal(st["conn"][q], one["conn"]) and np.array_equal(st["P"][q], one["P"])
+            assert np.array_equal(st["conn"][q], one["conn"])
+            assert np.array_equal(st["P"][q].view(np.uint64), one["P"].view(np.uint64))
             assert np.array_equal(st["is_done"][q], one["is_done"])
             assert np.array_equal(st["D"][q].view(np.uint64), o.matrices()["D"].view(np.uint64))
     for o in ops:
