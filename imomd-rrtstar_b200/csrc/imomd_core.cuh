@@ -512,7 +512,7 @@ struct Shared
     // candidate vertices, the coordinate pairs handed to the host, glibc's answers
     uint32_t tie_n;
     uint32_t mh_tie_mask;       // heuristic inserts: bit o = the comparison for tree o needs exact values
-    uint32_t tie_id[IMOMD_TIE_PAIRS];
+    uint32_t tie_id[IMOMD_TIE_IDS];
     double tie_in[IMOMD_TIE_PAIRS][4];
     double tie_out[IMOMD_TIE_PAIRS];
 };
@@ -529,7 +529,7 @@ IMOMD_HD inline int certify_argmin(Cta& cta, const GraphDev& g, Shared& S, uint3
 {
     *exact_tie = false;
     const uint32_t per = two ? 2u : 1u;
-    if (n == 0 || n * per > IMOMD_TIE_PAIRS) return -1;
+    if (n == 0 || n > IMOMD_TIE_IDS) return -1;
     for (uint32_t i = 1; i < n; ++i)     // ascending ids
     {
         uint32_t x = S.tie_id[i];
@@ -541,24 +541,30 @@ IMOMD_HD inline int certify_argmin(Cta& cta, const GraphDev& g, Shared& S, uint3
         }
         S.tie_id[j] = x;
     }
-    for (uint32_t i = 0; i < n; ++i)
+    // the mailbox takes IMOMD_TIE_PAIRS coordinate pairs per request: long candidate lists (vertices
+    // along the segment between two roots all have the same two-root heuristic) go in rounds
+    const uint32_t round = IMOMD_TIE_PAIRS / per;
+    for (uint32_t i0 = 0; i0 < n; i0 += round)
     {
-        const uint32_t v = S.tie_id[i];
-        double* a = S.tie_in[per * i];
-        a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = alat; a[3] = alon;
-        if (two)
+        const uint32_t m = n - i0 < round ? n - i0 : round;
+        for (uint32_t i = 0; i < m; ++i)
         {
-            double* b = S.tie_in[per * i + 1];
-            b[0] = g.lat[v]; b[1] = g.lon[v]; b[2] = blat; b[3] = blon;
+            const uint32_t v = S.tie_id[i0 + i];
+            double* a = S.tie_in[per * i];
+            a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = alat; a[3] = alon;
+            if (two)
+            {
+                double* b = S.tie_in[per * i + 1];
+                b[0] = g.lat[v]; b[1] = g.lon[v]; b[2] = blat; b[3] = blon;
+            }
         }
+        if (!cta.certify((int)(m * per), S.tie_in, S.tie_out)) return -1;
+        for (uint32_t i = 0; i < m; ++i)
+            vals[i0 + i] = two ? S.tie_out[2 * i] + S.tie_out[2 * i + 1] : S.tie_out[i];
     }
-    if (!cta.certify((int)(n * per), S.tie_in, S.tie_out)) return -1;
     int best = 0;
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        vals[i] = two ? S.tie_out[2 * i] + S.tie_out[2 * i + 1] : S.tie_out[i];
-        if (i > 0 && vals[i] < vals[best]) best = (int)i;
-    }
+    for (uint32_t i = 1; i < n; ++i)
+        if (vals[i] < vals[best]) best = (int)i;
     for (uint32_t i = 0; i < n; ++i)
         if ((int)i != best && vals[i] == vals[best]) *exact_tie = true;
     return best;
@@ -1928,7 +1934,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
                 if (v <= lim)
                 {
                     uint32_t at = cta.counter_add(&S.tie_n, 1u);
-                    if (at < IMOMD_TIE_PAIRS) S.tie_id[at] = r.id;
+                    if (at < IMOMD_TIE_IDS) S.tie_id[at] = r.id;
                 }
                 return v;
             };
@@ -1936,7 +1942,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_nearest(Cta& cta, const PlannerDev& P, int q, i
             cta.sync();
             if (cta.tid() == 0)
             {
-                double vals[IMOMD_TIE_PAIRS];
+                double vals[IMOMD_TIE_IDS];
                 bool exact_tie = false;
                 int w = certify_argmin(cta, g, S, S.tie_n, false, qlat, qlon, 0.0, 0.0, vals, &exact_tie);
                 if (w >= 0)
@@ -2022,7 +2028,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
                 if (v <= lim)
                 {
                     uint32_t at = cta.counter_add(&S.tie_n, 1u);
-                    if (at < IMOMD_TIE_PAIRS) S.tie_id[at] = r.id;
+                    if (at < IMOMD_TIE_IDS) S.tie_id[at] = r.id;
                 }
                 return v;
             };
@@ -2035,7 +2041,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_rescan(Cta& cta, const PlannerDev& P, int q, in
             S.stat[7] += S.n_recs;
             if (undecided)
             {
-                double vals[IMOMD_TIE_PAIRS];
+                double vals[IMOMD_TIE_IDS];
                 bool exact_tie = false;
                 int w = certify_argmin(cta, g, S, S.tie_n, true, klat, klon, olat, olon, vals, &exact_tie);
                 if (w >= 0)
@@ -2138,26 +2144,30 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
                 dev[n] = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
                 ++n;
             }
-            bool ok = 2 * n <= IMOMD_TIE_PAIRS;
-            if (ok)
+            // (rounds of IMOMD_TIE_PAIRS / 2 candidates per mailbox request)
+            double exact[IMOMD_MAXDEG + 1];
+            bool ok = true;
+            for (int i0 = 0; ok && i0 < n; i0 += IMOMD_TIE_PAIRS / 2)
             {
-                for (int i = 0; i < n; ++i)
+                const int mm = n - i0 < IMOMD_TIE_PAIRS / 2 ? n - i0 : IMOMD_TIE_PAIRS / 2;
+                for (int i = 0; i < mm; ++i)
                 {
-                    const uint32_t v = ids[i];
+                    const uint32_t v = ids[i0 + i];
                     double* a = S.tie_in[2 * i];
                     double* b = S.tie_in[2 * i + 1];
                     a[0] = g.lat[v]; a[1] = g.lon[v]; a[2] = g.lat[rk]; a[3] = g.lon[rk];
                     b[0] = g.lat[v]; b[1] = g.lon[v]; b[2] = g.lat[ro]; b[3] = g.lon[ro];
                 }
-                ok = cta.certify(2 * n, S.tie_in, S.tie_out);
+                ok = cta.certify(2 * mm, S.tie_in, S.tie_out);
+                for (int i = 0; ok && i < mm; ++i) exact[i0 + i] = S.tie_out[2 * i] + S.tie_out[2 * i + 1];
             }
             int w = 0;
             if (ok)
             {
-                double best = S.tie_out[0] + S.tie_out[1];
+                double best = exact[0];
                 for (int i = 1; i < n; ++i)
                 {
-                    double h = S.tie_out[2 * i] + S.tie_out[2 * i + 1];
+                    double h = exact[i];
                     if (h < best)
                     {
                         best = h;

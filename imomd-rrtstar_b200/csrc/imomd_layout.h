@@ -149,6 +149,7 @@ struct ReportDev
 // answers with the reference's haversine evaluated by glibc (include/osm_converter/
 // compute_haversine.hpp:41-58).  state: 0 idle, 1 request posted, 2 answer posted.
 #define IMOMD_TIE_PAIRS 16
+#define IMOMD_TIE_IDS 64     /* candidates of one certified arg-min (asked in rounds of IMOMD_TIE_PAIRS) */
 struct TieBox
 {
     uint32_t state;

@@ -353,6 +353,12 @@ void hs_get_state(void* hp, int q, double* D, uint32_t* cn, double* prob, uint32
     flags[1] = h.dm_updated;
 }
 
+void hs_tie_info(void* hp, int q, double* out)
+{
+    HsPlanner* p = (HsPlanner*)hp;
+    for (int i = 0; i < 8; ++i) out[i] = p->query[q].tie_info[i];
+}
+
 uint32_t hs_get_frontier(void* hp, int q, int k, uint32_t* out)
 {
     HsPlanner* p = (HsPlanner*)hp;
