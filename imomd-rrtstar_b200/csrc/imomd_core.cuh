@@ -289,6 +289,16 @@ struct THead
     double cost;
 };
 
+IMOMD_HD inline THead head_from(const U4& t)
+{
+    THead h;
+    h.parent = t.x;
+    h.fslot = t.y;
+    unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
+    memcpy(&h.cost, &bits, 8);
+    return h;
+}
+
 // padded adjacency rows (see GraphDev)
 IMOMD_HD inline uint32_t row_begin(const GraphDev& g, uint32_t v) { return v * (uint32_t)g.width; }
 IMOMD_HD inline uint32_t row_end(const GraphDev& g, uint32_t v) { return v * (uint32_t)g.width + g.deg[v]; }
@@ -502,11 +512,16 @@ struct Shared
     uint32_t arena_cap;
     int32_t batch;              // 1: batched mode (cross-tree effects are logged, not applied)
     uint32_t* clist;
-    BEvent* ev;                 // batched mode: event log of the tree being expanded
+    BEvent* ev;                 // batched mode: selection-probability tests of the tree being expanded
     uint32_t ev_n;              //   entries written
     uint32_t exp_n;             //   expansions performed in this batch
+    uint32_t* dirty;            // batched mode: vertices queued for the rewiring relaxation of the step
+    uint32_t dirty_n, dirty_cap;
+    uint32_t* chk;              // batched mode: vertices whose connection check is due after the step
+    uint32_t chk_n, chk_cap;
     // counters of this group, folded into the query header when the launch ends
     uint64_t stat[8];
+    uint64_t gprof[8];          // batched mode: cycles of this group by request type (7 = serial steps)
     int64_t near_ties, unresolved_ties, certified_ties;
     // exact certification of a comparison the device arithmetic cannot decide (Cta::certify):
     // candidate vertices, the coordinate pairs handed to the host, glibc's answers
@@ -962,10 +977,28 @@ struct Seq
         return ws.cursor;
     }
 
-    // ---- batched mode: what an expansion does to the OTHER trees' shared state is logged ------
-    // updateConnectionTree_(tree, x) with the cost x had at that moment, and
-    // updateSelectionProbability with the heuristic entry of that moment, in program order; the
-    // block applies the logs of all trees, in tree order, when every tree has finished its batch.
+    // ---- batched mode: what an expansion does beyond its own attach is queued ------------------
+    // the rewiring of x_new (relaxation after the step), the connection checks of the attached
+    // vertices (after the relaxation, with the final costs), and updateSelectionProbability with
+    // the heuristic entry of that moment, in program order.
+    IMOMD_HD void queue_rewire(uint32_t x)
+    {
+        if (S.dirty_n >= S.dirty_cap)
+        {
+            Q->status = 3;   // IMOMD_RUN_ARENA_FULL
+            return;
+        }
+        S.dirty[S.dirty_n++] = x;
+    }
+    IMOMD_HD void queue_check(uint32_t x)
+    {
+        if (S.chk_n >= S.chk_cap)
+        {
+            Q->status = 3;
+            return;
+        }
+        S.chk[S.chk_n++] = x;
+    }
     IMOMD_HD void log_event(int k, uint32_t kind, uint32_t x, uint32_t aux, double val, uint32_t extra)
     {
         uint32_t i = S.ev_n;
@@ -1110,7 +1143,7 @@ struct Seq
             log_visit(k, x_new);
         }
         T.set_parent(x_new, via);
-        chl_assign_single_w<KW>(T.chl(via), x_new);
+        if (!S.batch) chl_assign_single_w<KW>(T.chl(via), x_new);
         double cnew = T.cost(via) + edge_weight(g, via, x_new);
         T.set_cost(x_new, cnew);
         S.conn_x = x_new;
@@ -1167,7 +1200,7 @@ struct Seq
                 log_visit(k, x_new);
             }
             T.set_parent(x_new, x_parent);
-            chl_insert_w<KW>(T.chl(x_parent), x_new);
+            if (!S.batch) chl_insert_w<KW>(T.chl(x_parent), x_new);
             T.set_cost(x_new, min_cost);
         }
     }
@@ -1366,8 +1399,7 @@ struct Seq
                     Q->status = 3;
                     return true;
                 }
-                if (S.batch) log_event(k, 0u, S.bfs_node, 0u, S.bfs_cost, 0u);
-                else apply_connection(k, T, S.bfs_node, S.bfs_cost);      // :586
+                apply_connection(k, T, S.bfs_node, S.bfs_cost);      // :586
                 f[4] = S.bfs_node;
                 f[5] = S.rw_top;
                 f[6] = S.bfs_hi;
@@ -1570,7 +1602,7 @@ struct Seq
                         // hops need no service here: their connection checks are only logged
                         while (Q->status == 0 && jps_hop(k, T))
                         {
-                            log_event(k, 0u, S.conn_x, 0u, S.conn_cx, 0u);
+                            queue_check(S.conn_x);
                             S.x_new = S.jps_next;
                         }
                     }
@@ -1606,22 +1638,11 @@ struct Seq
                 }
                 case PH_FINISH:
                 {
-                    S.rw_fp = IMOMD_NONE;
-                    S.rw_top = 0;
-                    S.bfs_valid = 0;
-                    S.chk_valid = 0;
-                    push_frame(S.x_new, row_begin(P.g, S.x_new));
-                    S.phase = PH_REWIRE;
-                    continue;
-                }
-                case PH_REWIRE:
-                {
-                    if (!rewire_run(k, T)) return;   // REQ_BFS or REQ_CHECK posted
-                    if (Q->status != 0) continue;
                     if (S.batch)
                     {
-                        // :354-355 deferred: the selection-probability test with the heuristic
-                        // entry as it is NOW, then the connection check of x_new
+                        // rewireTree_(x_new) is the relaxation after the step; :354-355 deferred: the
+                        // selection-probability test with the heuristic entry as it is NOW, the
+                        // connection check of x_new with the costs the relaxation leaves
                         int other = Q->K;
                         for (int i = 0; i < Q->K; ++i)
                         {
@@ -1634,12 +1655,28 @@ struct Seq
                         if (other < Q->K)
                             log_event(k, 1u, IMOMD_NONE, (uint32_t)other, sm_MHv(S)[k * Q->K + other],
                                       sm_MHi(S)[k * Q->K + other]);
-                        log_event(k, 0u, S.x_new, 0u, T.cost(S.x_new), 0u);
+                        if (T.parent(S.x_new) != IMOMD_NONE)
+                        {
+                            queue_rewire(S.x_new);
+                            queue_check(S.x_new);
+                        }
                         S.exp_n += 1;
                         S.req = REQ_EXIT;
                         S.phase = PH_NEXT_TREE;
                         return;
                     }
+                    S.rw_fp = IMOMD_NONE;
+                    S.rw_top = 0;
+                    S.bfs_valid = 0;
+                    S.chk_valid = 0;
+                    push_frame(S.x_new, row_begin(P.g, S.x_new));
+                    S.phase = PH_REWIRE;
+                    continue;
+                }
+                case PH_REWIRE:
+                {
+                    if (!rewire_run(k, T)) return;   // REQ_BFS or REQ_CHECK posted
+                    if (Q->status != 0) continue;
                     if (!S.attach_mode) update_selection_probability(cta, k);
                     S.conn_x = S.x_new;
                     S.req = REQ_CONN;
@@ -2933,20 +2970,33 @@ IMOMD_HD inline void run_streaming_query(Cta& cta, const PlannerDev& P, int slot
 }
 
 // ====================================================== batched expansion ====
-// imomd_expand_batch: B expansions per tree per STEP.  The K trees of a query are expanded
-// CONCURRENTLY, one cooperating group (a warp on the device) per tree: everything an expansion
-// does to its own tree -- sample, nearest frontier vertex, jump-point hops, choose-parent,
-// frontier / min-heuristic maintenance, the rewire cascade -- is exactly the sequential code of
-// the exact mode and touches only that tree's records and its row of the heuristic matrix.  What
-// an expansion does to state the trees SHARE (updateConnectionTree_: contacts, union-find,
-// distance / connection-node matrices; updateSelectionProbability: probability rows, is_done) is
-// logged with the values of that moment and applied by the whole CTA after the step, in tree
-// order and program order.  So a step differs from B reference passes only in WHEN the other
-// trees' state is looked at (end of the step), and in how the injected stream is read: every
-// (pass, tree) owns a fixed slot of kBatchWords words, so that trees can draw independently.
-// Deterministic: the result depends on neither the number of groups nor their timing.
+// imomd_expand_batch: B expansions per tree per STEP (north_star (2), (4)).  A step has four parts:
+//
+//  1. ATTACH, the K trees of a query CONCURRENTLY, one cooperating group (a warp on the device)
+//     per tree taking trees from a counter: sample, nearest frontier vertex, jump-point hops,
+//     choose-parent, frontier / min-heuristic maintenance -- the sequential code of the exact
+//     mode on the tree's own records and its own row of the heuristic matrix.  The new vertex is
+//     only QUEUED for rewiring.  Samples come from fixed slots of kBatchWords words per (pass,
+//     tree) of the injected stream, so that trees draw independently.
+//  2. REWIRE, the whole CTA over all trees at once: a label-correcting relaxation from the queued
+//     vertices.  A vertex whose cost went down offers cost + w to its visited neighbours; a
+//     neighbour takes an offer when its label (cost, parent id) gets lexicographically smaller --
+//     one 128-bit compare-and-swap on the {parent, frontier slot, cost} head of its record.  The
+//     fixed point (every visited vertex at its cheapest cost through visited vertices, lowest
+//     parent id among equal offers) does not depend on the order in which offers arrive: the
+//     deterministic resolution of concurrent cost / parent updates.  This replaces the recursive
+//     cascade of rewireTree_ (:561-600), whose order is inherently sequential.
+//  3. CONNECT: the connection check (updateConnectionTree_ :645-706) of every vertex attached or
+//     changed in the step against the other trees, with the final costs of the step: per pair of
+//     trees the smallest cost sum (lowest vertex id on ties) replaces the distance when it beats
+//     it by more than 0.1 (:680).
+//  4. The selection-probability tests (:602-643) in tree order and program order, with the
+//     heuristic entry logged at the time of the expansion.
+//
+// Deterministic: the result depends on neither the number of groups nor their timing.  Child rows
+// are not maintained (the relaxation walks the road graph, not the tree), so a planner that has
+// run batched steps cannot continue in the exact mode before a reset.
 constexpr uint32_t kBatchWords = 8;
-constexpr uint32_t kEvChunk = 32;
 
 struct BatchShared
 {
@@ -2955,26 +3005,49 @@ struct BatchShared
     int32_t active[IMOMD_KMAX];
     int32_t n_active;
     int32_t stop;
-    // the other trees' (parent, cost) at the vertices of a chunk of logged connection checks
-    uint32_t gpar[kEvChunk][IMOMD_KMAX];
-    double gcost[kEvChunk][IMOMD_KMAX];
+    uint32_t next_tree;                  // trees are handed to the groups from this counter
+    uint32_t relax_items, relax_changes; // work counters of the step
+    uint32_t dirty_n[2][IMOMD_KMAX];     // relaxation queues (ping-pong) per tree
+    uint32_t chk_n[IMOMD_KMAX];          // vertices whose connection check is due
+    uint64_t tree_cycles[IMOMD_KMAX];    // cycles the tree's group spent on its batch in this step
+    // connection candidates of the step per unordered pair (a > b): index a(a-1)/2 + b
+    unsigned long long cand_d[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
+    uint32_t cand_x[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
 };
 
-// One group: up to B expansions of tree k (fewer when its frontier runs empty).
+// the scratch of tree k inside the slot's arena: [rewire queue A | rewire queue B | check list]
+IMOMD_HD inline uint32_t batch_share(const PlannerDev& P) { return P.arena_entries / (uint32_t)P.K; }
+IMOMD_HD inline uint32_t* batch_queue(const PlannerDev& P, int slot, int k, int which)
+{
+    const uint32_t share = batch_share(P);
+    return P.arena + (size_t)slot * P.arena_entries + (size_t)k * share + (size_t)which * (share / 4);
+}
+IMOMD_HD inline uint32_t* batch_checks(const PlannerDev& P, int slot, int k)
+{
+    const uint32_t share = batch_share(P);
+    return P.arena + (size_t)slot * P.arena_entries + (size_t)k * share + (size_t)(share / 2);
+}
+
+// One group: up to B attaches of tree k (fewer when its frontier runs empty).
 template <int KW, class Grp>
-IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, int k, Shared& S, uint32_t* lvl,
-                                       int B, uint64_t pass0)
+IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, int k, Shared& S, int B, uint64_t pass0)
 {
     const int K = P.K;
     if (grp.tid() == 0)
     {
-        const uint32_t share = P.arena_entries / (uint32_t)K;
-        S.arena = P.arena + (size_t)slot * P.arena_entries + (size_t)k * share;
-        S.arena_cap = share;
+        const uint32_t share = batch_share(P);
+        S.arena = P.arena + (size_t)slot * P.arena_entries;   // (no rewire frames in this mode)
+        S.arena_cap = 0;
         S.clist = P.clist_tree + ((size_t)slot * K + k) * 2 * (size_t)P.chunks;
         S.ev = P.events + ((size_t)slot * K + k) * (size_t)P.ev_cap;
         S.ev_n = 0;
         S.exp_n = 0;
+        S.dirty = batch_queue(P, slot, k, 0);
+        S.dirty_n = 0;
+        S.dirty_cap = share / 4;
+        S.chk = batch_checks(P, slot, k);
+        S.chk_n = 0;
+        S.chk_cap = share / 2;
         S.batch = 1;
         S.attach_mode = 0;
         S.k = k;
@@ -3002,21 +3075,18 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
         {
             const int req = S.req;
             if (req == REQ_EXIT) break;
+            const long long t0 = grp.clock();
             if (req == REQ_NN) svc_nearest(grp, P, slot, k, S, (double*)nullptr, S.clist, &S.near_ties, &S.unresolved_ties, true);
             else if (req == REQ_RESCAN) svc_rescan(grp, P, slot, k, S, (double*)nullptr);
             else if (req == REQ_MHINS) svc_mhins(grp, P, slot, k, S);
-            else if (req == REQ_BFS)
-            {
-                svc_bfs_w<KW>(grp, P, slot, k, S, lvl);
-                grp.sync();
-                if (S.bfs_hi != IMOMD_NONE) svc_check<KW>(grp, P, slot, k, S);
-            }
-            else if (req == REQ_CHECK) svc_check<KW>(grp, P, slot, k, S);
             grp.sync();
             if (grp.tid() == 0)
             {
+                const long long t1 = grp.clock();
+                S.gprof[req & 7] += (uint64_t)(t1 - t0);
                 Seq<KW> seq(P, slot, S);
                 seq.step(grp, 1);
+                S.gprof[7] += (uint64_t)(grp.clock() - t1);
             }
             grp.sync();
         }
@@ -3024,70 +3094,233 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
     grp.sync();
 }
 
-// The whole CTA: the logged cross-tree effects of one step, trees in id order, each tree's
-// events in the order its expansions produced them.
-template <int KW, class Blk>
-IMOMD_HD inline void batch_apply_events(Blk& blk, const PlannerDev& P, int slot, Shared& S0, BatchShared& BS)
+// One offer round of the relaxation for vertex u of tree T: u's cost + w to every visited
+// neighbour, accepted when (cost, parent) gets lexicographically smaller.  A neighbour whose COST
+// went down joins the next queue; every neighbour that changed joins the check list.
+template <int W, class Blk>
+IMOMD_HD inline void relax_vertex(Blk& blk, const PlannerDev& P, const TreeRef& T, uint32_t u, uint32_t* next_q,
+                                  uint32_t* next_n, uint32_t q_cap, uint32_t* chk, uint32_t* chk_n, uint32_t chk_cap,
+                                  QueryDev* Q, uint32_t* changes)
 {
-    QueryDev* Q = S0.Q;
-    const int K = P.K;
-    for (int k = 0; k < K; ++k)
+    const GraphDev& g = P.g;
+    const uint32_t e0 = row_begin(g, u), d = g.deg[u];
+    // (heads are read past the L1: other threads change them with compare-and-swap at the L2)
+    const double cu = head_from(blk.load_cg(reinterpret_cast<const U4*>(T.hp(u)))).cost;
+    uint32_t ys[W];
+    double ws[W];
+    U4 hs[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i)
     {
-        const uint32_t n = BS.ev_count[k];
-        const BEvent* ev = P.events + ((size_t)slot * K + k) * (size_t)P.ev_cap;
-        for (uint32_t e0 = 0; e0 < n; e0 += kEvChunk)
+        if ((uint32_t)i < d)
         {
-            const uint32_t cnt = n - e0 < kEvChunk ? n - e0 : kEvChunk;
-            for (uint32_t i = (uint32_t)blk.tid(); i < cnt * (uint32_t)K; i += (uint32_t)blk.nt())
-            {
-                const uint32_t e = i / (uint32_t)K, o = i % (uint32_t)K;
-                const BEvent E = ev[e0 + e];
-                if (E.kind == 0u && (int)o != k)
-                {
-                    const size_t qt = (size_t)slot * K + o;
-                    const U4 t = *reinterpret_cast<const U4*>(P.trec + (qt * (size_t)P.g.n + E.x) * (size_t)P.trec_stride);
-                    unsigned long long bits = ((unsigned long long)t.w << 32) | (unsigned long long)t.z;
-                    double c;
-                    memcpy(&c, &bits, 8);
-                    BS.gpar[e][o] = t.x;
-                    BS.gcost[e][o] = c;
-                }
-            }
-            blk.sync();
-            if (blk.tid() == 0)
-            {
-                Seq<KW> seq(P, slot, S0);
-                TreeRef T = tree_ref_of(P, slot, k, S0);
-                for (uint32_t e = 0; e < cnt; ++e)
-                {
-                    const BEvent E = ev[e0 + e];
-                    if (E.kind == 0u)
-                    {
-                        for (int o = 0; o < K; ++o)
-                        {
-                            S0.conn_par[o] = BS.gpar[e][o];
-                            S0.conn_cost[o] = BS.gcost[e][o];
-                        }
-                        seq.apply_connection(k, T, E.x, E.val);
-                    }
-                    else
-                    {
-                        seq.selection_probability_apply(blk, k, (int)E.aux, E.val, E.extra);
-                    }
-                }
-            }
-            blk.sync();
+            ys[i] = g.col[e0 + i];
+            ws[i] = g.w[e0 + i];
         }
-        if (blk.tid() == 0) Q->expansions += (int64_t)BS.exp_count[k];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if ((uint32_t)i < d) hs[i] = blk.load_cg(reinterpret_cast<const U4*>(T.hp(ys[i])));
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+    {
+        if ((uint32_t)i >= d) continue;
+        const uint32_t y = ys[i];
+        const double p = cu + ws[i];
+        U4 cur = hs[i];
+        for (;;)
+        {
+            if (cur.x == IMOMD_NONE) break;                  // not visited
+            unsigned long long bits = ((unsigned long long)cur.w << 32) | (unsigned long long)cur.z;
+            double cy;
+            memcpy(&cy, &bits, 8);
+            const bool lower = p < cy;
+            if (!(lower || (p == cy && u < cur.x))) break;
+            unsigned long long pb;
+            memcpy(&pb, &p, 8);
+            U4 want;
+            want.x = u;
+            want.y = cur.y;
+            want.z = (uint32_t)pb;
+            want.w = (uint32_t)(pb >> 32);
+            const U4 seen = blk.cas_head(reinterpret_cast<U4*>(T.hp(y)), cur, want);
+            if (seen.x == cur.x && seen.y == cur.y && seen.z == cur.z && seen.w == cur.w)
+            {
+                blk.counter_add(changes, 1u);
+                uint32_t at = blk.counter_add(chk_n, 1u);
+                if (at < chk_cap) chk[at] = y;
+                else Q->status = 3;
+                if (lower)
+                {
+                    at = blk.counter_add(next_n, 1u);
+                    if (at < q_cap) next_q[at] = y;
+                    else Q->status = 3;
+                }
+                break;
+            }
+            cur = seen;
+        }
     }
 }
 
-// `steps` steps of B expansions per tree for query hq in slot `slot`.  SG: one Shared per group;
-// lvl_all: one level buffer (2 * kLevelCap words) per group.
+// The whole CTA: the rewiring relaxation of one step over all trees, level by level.
+template <int KW, class Blk>
+IMOMD_HD inline void batch_relax(Blk& blk, const PlannerDev& P, int slot, Shared& S0, BatchShared& BS)
+{
+    QueryDev* Q = S0.Q;
+    const int K = P.K;
+    const uint32_t q_cap = batch_share(P) / 4, chk_cap = batch_share(P) / 2;
+    int cur = 0;
+    for (;;)
+    {
+        uint32_t total = 0;
+        for (int k = 0; k < K; ++k)
+        {
+            uint32_t n = BS.dirty_n[cur][k];
+            total += n < q_cap ? n : q_cap;
+        }
+        if (total == 0 || Q->status != 0) break;
+        for (uint32_t i = (uint32_t)blk.tid(); i < total; i += (uint32_t)blk.nt())
+        {
+            int k = 0;
+            uint32_t j = i;
+            for (;;)
+            {
+                uint32_t n = BS.dirty_n[cur][k];
+                n = n < q_cap ? n : q_cap;
+                if (j < n) break;
+                j -= n;
+                ++k;
+            }
+            const uint32_t u = batch_queue(P, slot, k, cur)[j];
+            relax_vertex<KW>(blk, P, tree_ref_of(P, slot, k, S0), u, batch_queue(P, slot, k, cur ^ 1),
+                             &BS.dirty_n[cur ^ 1][k], q_cap, batch_checks(P, slot, k), &BS.chk_n[k], chk_cap, Q,
+                             &BS.relax_changes);
+        }
+        blk.sync();
+        if (blk.tid() == 0)
+        {
+            BS.relax_items += total;
+            for (int k = 0; k < K; ++k) BS.dirty_n[cur][k] = 0;
+        }
+        cur ^= 1;
+        blk.sync();
+    }
+    blk.fence();     // the attach code of the next step reads the heads through the L1
+    blk.sync();
+}
+
+IMOMD_HD inline int pair_index(int a, int b) { return a > b ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; }
+
+// The whole CTA: connection checks of the step's attached / changed vertices with the final costs.
+template <int KW, class Blk>
+IMOMD_HD inline void batch_connect(Blk& blk, const PlannerDev& P, int slot, Shared& S0, BatchShared& BS)
+{
+    QueryDev* Q = S0.Q;
+    const int K = P.K;
+    const int pairs = K * (K - 1) / 2;
+    const uint32_t chk_cap = batch_share(P) / 2;
+    for (int i = blk.tid(); i < pairs; i += blk.nt())
+    {
+        BS.cand_d[i] = ~0ull;
+        BS.cand_x[i] = IMOMD_NONE;
+    }
+    blk.sync();
+    uint32_t total = 0;
+    for (int k = 0; k < K; ++k) total += BS.chk_n[k] < chk_cap ? BS.chk_n[k] : chk_cap;
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        // pass 0: the smallest sum per pair; pass 1: the lowest vertex that attains it
+        for (uint32_t i = (uint32_t)blk.tid(); i < total; i += (uint32_t)blk.nt())
+        {
+            int k = 0;
+            uint32_t j = i;
+            for (;;)
+            {
+                uint32_t n = BS.chk_n[k] < chk_cap ? BS.chk_n[k] : chk_cap;
+                if (j < n) break;
+                j -= n;
+                ++k;
+            }
+            const uint32_t x = batch_checks(P, slot, k)[j];
+            const double ck = head_from(blk.load_cg(reinterpret_cast<const U4*>(tree_ref_of(P, slot, k, S0).hp(x)))).cost;
+            for (int o = 0; o < K; ++o)
+            {
+                if (o == k) continue;
+                const THead ho = head_from(blk.load_cg(reinterpret_cast<const U4*>(tree_ref_of(P, slot, o, S0).hp(x))));
+                if (ho.parent == IMOMD_NONE) continue;
+                const double dsum = ck + ho.cost;
+                unsigned long long bits;
+                memcpy(&bits, &dsum, 8);
+                const int pi = pair_index(k, o);
+                if (pass == 0) blk.atomic_min_u64(&BS.cand_d[pi], bits);
+                else if (bits == BS.cand_d[pi]) blk.atomic_min_u32(&BS.cand_x[pi], x);
+            }
+        }
+        blk.sync();
+    }
+    if (blk.tid() == 0)
+    {
+        S0.stat[6] += total;
+        Seq<KW> seq(P, slot, S0);
+        for (int a = 0; a < K; ++a)
+        {
+            for (int b = 0; b < a; ++b)
+            {
+                const int pi = a * (a - 1) / 2 + b;
+                if (BS.cand_d[pi] == ~0ull) continue;
+                double best;
+                memcpy(&best, &BS.cand_d[pi], 8);
+                if (!Q->contact[pi])
+                {
+                    Q->contact[pi] = 1;
+                    seq.connect_two_trees(b, a);
+                }
+                if (best < sm_D(S0)[a * K + b] - 0.1)
+                {
+                    sm_D(S0)[a * K + b] = best;
+                    sm_D(S0)[b * K + a] = best;
+                    sm_CN(S0)[a * K + b] = BS.cand_x[pi];
+                    sm_CN(S0)[b * K + a] = BS.cand_x[pi];
+                    Q->dm_updated = 1;
+                }
+            }
+        }
+    }
+    blk.sync();
+}
+
+// One thread: the logged selection-probability tests of the step, trees in id order, each tree's
+// tests in the order its expansions produced them.
+template <int KW, class Blk>
+IMOMD_HD inline void batch_apply_tests(Blk& blk, const PlannerDev& P, int slot, Shared& S0, BatchShared& BS)
+{
+    QueryDev* Q = S0.Q;
+    const int K = P.K;
+    if (blk.tid() == 0)
+    {
+        Seq<KW> seq(P, slot, S0);
+        for (int k = 0; k < K; ++k)
+        {
+            const uint32_t n = BS.ev_count[k];
+            const BEvent* ev = P.events + ((size_t)slot * K + k) * (size_t)P.ev_cap;
+            for (uint32_t e = 0; e < n; ++e)
+            {
+                const BEvent E = ev[e];
+                seq.selection_probability_apply(blk, k, (int)E.aux, E.val, E.extra);
+            }
+            Q->expansions += (int64_t)BS.exp_count[k];
+        }
+    }
+    blk.sync();
+}
+
+// `steps` steps of B expansions per tree for query hq in slot `slot`.  SG: one Shared per group.
 template <int KW, class Blk, class Grp>
 IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, int slot, int hq, int steps, int B,
-                                       Shared* SG, BatchShared& BS, uint32_t* lvl_all, double* mat,
-                                       unsigned char* hot)
+                                       Shared* SG, BatchShared& BS, double* mat, unsigned char* hot)
 {
     assume_planner(P);
     QueryDev* Qg = P.query + hq;
@@ -3116,12 +3349,15 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
         S.stop = 0;
         S.it = 0;
         for (int i = 0; i < 8; ++i) S.stat[i] = 0;
+        for (int i = 0; i < 8; ++i) S.gprof[i] = 0;
         S.near_ties = S.unresolved_ties = S.certified_ties = 0;
         S.arena = P.arena + (size_t)slot * P.arena_entries;
         S.arena_cap = 0;
         S.clist = nullptr;
         S.ev = nullptr;
         S.ev_n = S.exp_n = 0;
+        S.dirty = S.chk = nullptr;
+        S.dirty_n = S.dirty_cap = S.chk_n = S.chk_cap = 0;
     }
     blk.sync();
     Shared& S0 = SG[0];
@@ -3152,9 +3388,13 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
                 BS.active[k] = (Q->frontier_count[k] != 0 && !Q->is_done[k]) ? 1 : 0;
                 BS.ev_count[k] = 0;
                 BS.exp_count[k] = 0;
+                BS.dirty_n[0][k] = BS.dirty_n[1][k] = 0;
+                BS.chk_n[k] = 0;
                 active += BS.active[k];
             }
             BS.n_active = active;
+            BS.next_tree = 0;
+            BS.relax_items = BS.relax_changes = 0;
             BS.stop = 0;
             if (Q->status != 0) BS.stop = 1;
             else if (active == 0)
@@ -3173,23 +3413,61 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
         if (BS.stop) break;
         const uint64_t pass0 = (uint64_t)Q->iterations;
         blk.sync();
+        const long long ts0 = blk.clock();
+        // 1. attach: the groups take trees from the counter
         Shared& S = SG[grp.group()];
-        for (int k = grp.group(); k < K; k += G)
+        for (;;)
         {
+            uint32_t k = 0;
+            if (grp.tid() == 0) k = blk.counter_add(&BS.next_tree, 1u);
+            k = grp.bcast(k);
+            if (k >= (uint32_t)K) break;
             if (!BS.active[k]) continue;
-            batch_expand_tree<KW>(grp, P, slot, k, S, lvl_all + (size_t)grp.group() * 2 * kLevelCap, B, pass0);
+            const long long tk0 = grp.clock();
+            batch_expand_tree<KW>(grp, P, slot, (int)k, S, B, pass0);
             if (grp.tid() == 0)
             {
                 BS.ev_count[k] = S.ev_n;
                 BS.exp_count[k] = S.exp_n;
+                BS.dirty_n[0][k] = S.dirty_n;
+                BS.chk_n[k] = S.chk_n;
+                BS.tree_cycles[k] = (uint64_t)(grp.clock() - tk0);
             }
         }
         blk.sync();
-        batch_apply_events<KW>(blk, P, slot, S0, BS);
+        const long long ts1 = blk.clock();
+        // 2. rewire, 3. connect, 4. selection-probability tests
+        batch_relax<KW>(blk, P, slot, S0, BS);
+        const long long ts2 = blk.clock();
+        batch_connect<KW>(blk, P, slot, S0, BS);
+        batch_apply_tests<KW>(blk, P, slot, S0, BS);
         if (blk.tid() == 0)
         {
             Q->iterations += B;
             Q->word_cursor = (uint64_t)Q->iterations * (uint64_t)K * kBatchWords;
+            S0.stat[2] += BS.relax_items;
+            S0.stat[3] += (uint64_t)BS.relax_items * (uint64_t)P.g.width;
+            S0.stat[4] += BS.relax_changes;
+            // where a step goes (imomd_get_profile): 1 = the trees' attach batches summed, 2 = the
+            // slowest tree's, 3 = the attach part as the block saw it, 4 = the relaxation,
+            // 5 = connection checks + selection-probability tests
+            uint64_t sum = 0, mx = 0;
+            for (int k = 0; k < K; ++k)
+            {
+                if (!BS.active[k]) continue;
+                sum += BS.tree_cycles[k];
+                if (BS.tree_cycles[k] > mx) mx = BS.tree_cycles[k];
+                Q->prof_count[1] += 1;
+            }
+            Q->prof_cycles[1] += sum;
+            Q->prof_cycles[2] += mx;
+            Q->prof_count[2] += 1;
+            Q->prof_cycles[3] += (uint64_t)(ts1 - ts0);
+            Q->prof_count[3] += 1;
+            Q->prof_cycles[4] += (uint64_t)(ts2 - ts1);
+            Q->prof_count[4] += BS.relax_items;
+            Q->prof_cycles[5] += (uint64_t)(blk.clock() - ts2);
+            Q->prof_count[5] += 1;
         }
         blk.sync();
     }
@@ -3209,6 +3487,7 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
             Q->near_ties += SG[g].near_ties;
             Q->unresolved_ties += SG[g].unresolved_ties;
             Q->certified_ties += SG[g].certified_ties;
+            for (int i = 0; i < 8; ++i) Q->phase_cycles[i] += SG[g].gprof[i];
         }
         Q->resume_k = 0;
         Q->busy_cycles = (uint64_t)(blk.clock() - busy0);
@@ -3250,8 +3529,7 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
 // a streaming planner's query in the batched mode (cf. run_streaming_query)
 template <int KW, class Blk, class Grp>
 IMOMD_HD inline void run_streaming_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, int slot, int hq, int steps,
-                                                 int B, Shared* SG, BatchShared& BS, uint32_t* lvl_all, double* mat,
-                                                 unsigned char* hot)
+                                                 int B, Shared* SG, BatchShared& BS, double* mat, unsigned char* hot)
 {
     const long long t0 = blk.clock();
     {
@@ -3269,7 +3547,7 @@ IMOMD_HD inline void run_streaming_query_batched(Blk& blk, Grp& grp, const Plann
         construct_trees(P, slot, hq);
     }
     blk.sync();
-    run_query_batched<KW>(blk, grp, P, slot, hq, steps, B, SG, BS, lvl_all, mat, hot);
+    run_query_batched<KW>(blk, grp, P, slot, hq, steps, B, SG, BS, mat, hot);
     blk.sync();
     uint64_t h = 0, sum = 0;
     tree_hash(blk, P, slot, SG[0], P.arena + (size_t)slot * P.arena_entries, P.arena_entries, &h, &sum);

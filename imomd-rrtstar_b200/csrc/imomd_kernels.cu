@@ -145,6 +145,41 @@ struct CtaDev
         r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
         return r;
     }
+    __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+    // batched mode: lexicographic-min update of a record head {parent, frontier slot, cost}: one
+    // 128-bit compare-and-swap at the L2 (returns what was there)
+    __device__ __forceinline__ U4 cas_head(U4* addr, const U4& expect, const U4& want) const
+    {
+        unsigned long long elo = ((unsigned long long)expect.y << 32) | expect.x;
+        unsigned long long ehi = ((unsigned long long)expect.w << 32) | expect.z;
+        unsigned long long wlo = ((unsigned long long)want.y << 32) | want.x;
+        unsigned long long whi = ((unsigned long long)want.w << 32) | want.z;
+        unsigned long long olo, ohi;
+        asm volatile(
+            "{\n\t"
+            ".reg .b128 e, w, o;\n\t"
+            "mov.b128 e, {%2, %3};\n\t"
+            "mov.b128 w, {%4, %5};\n\t"
+            "atom.relaxed.gpu.global.cas.b128 o, [%6], e, w;\n\t"
+            "mov.b128 {%0, %1}, o;\n\t"
+            "}"
+            : "=l"(olo), "=l"(ohi)
+            : "l"(elo), "l"(ehi), "l"(wlo), "l"(whi), "l"(addr)
+            : "memory");
+        U4 r;
+        r.x = (uint32_t)olo; r.y = (uint32_t)(olo >> 32); r.z = (uint32_t)ohi; r.w = (uint32_t)(ohi >> 32);
+        return r;
+    }
+    __device__ __forceinline__ U4 load_cg(const U4* p) const
+    {
+        uint4 t = __ldcg(reinterpret_cast<const uint4*>(p));
+        U4 r;
+        r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
+        return r;
+    }
+    __device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned long long v) const { atomicMin(p, v); }
+    __device__ __forceinline__ void atomic_min_u32(uint32_t* p, uint32_t v) const { atomicMin(p, v); }
+    __device__ __forceinline__ void fence() const { __threadfence(); }
     // Exact values from the host (ONE thread calls): the n coordinate pairs go to this CTA's
     // mailbox in mapped pinned host memory, the host thread waiting for the launch (wait_stream)
     // answers with the reference's haversine evaluated by glibc.  System-scope release / acquire.
@@ -317,6 +352,7 @@ struct WarpDev
     __device__ __forceinline__ int group() const { return (int)(threadIdx.x >> 5); }
     __device__ __forceinline__ int n_groups() const { return (int)(blockDim.x >> 5); }
     __device__ __forceinline__ bool warp_all(bool p) const { return __all_sync(0xFFFFFFFFu, p) != 0; }
+    __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(0xFFFFFFFFu, v, 0); }
     __device__ __forceinline__ uint32_t warp_scan_small(uint32_t v, int maxv, uint32_t* total) const
     {
         const unsigned full = 0xFFFFFFFFu;
@@ -520,8 +556,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand_batch(const __gr
     constexpr size_t kShared = ((sizeof(Shared) + 15) / 16) * 16;
     Shared* SG = reinterpret_cast<Shared*>(smem_raw);
     BatchShared& BS = *reinterpret_cast<BatchShared*>(smem_raw + NW * kShared);
-    uint32_t* lvl_all = reinterpret_cast<uint32_t*>(smem_raw + NW * kShared + ((sizeof(BatchShared) + 15) / 16) * 16);
-    double* mat = reinterpret_cast<double*>(lvl_all + (size_t)NW * 2 * kLevelCap);
+    double* mat = reinterpret_cast<double*>(smem_raw + NW * kShared + ((sizeof(BatchShared) + 15) / 16) * 16);
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev blk;
     WarpDev grp;
@@ -538,13 +573,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand_batch(const __gr
             const int hq = next_q;
             __syncthreads();
             if (hq >= P.Q) break;
-            run_streaming_query_batched<KW>(blk, grp, P, (int)blockIdx.x, hq, steps, B, SG, BS, lvl_all, mat, hot);
+            run_streaming_query_batched<KW>(blk, grp, P, (int)blockIdx.x, hq, steps, B, SG, BS, mat, hot);
         }
         return;
     }
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
-        run_query_batched<KW>(blk, grp, P, q, q, steps, B, SG, BS, lvl_all, mat, hot);
+        run_query_batched<KW>(blk, grp, P, q, q, steps, B, SG, BS, mat, hot);
         __syncthreads();
     }
 }
@@ -836,6 +871,8 @@ struct imomd_planner
     uint64_t certified_requests = 0;
     size_t smem_batch = 0;          // dynamic shared memory of k_expand_batch
     bool batch_ready = false;       // event logs / per-tree chunk lists allocated
+    bool batch_ran = false;         // resident planner: batched steps ran since the last reset (child rows
+                                    // are not maintained there, so the exact mode may not continue)
 };
 
 struct imomd_ctx
@@ -902,6 +939,7 @@ cudaError_t wait_stream(imomd_planner* p)
 int planner_fill_initial(imomd_planner* p)
 {
     PlannerDev& d = p->d;
+    p->batch_ran = false;
     const size_t QK = (size_t)d.Q * d.K;
     CU(cudaMemcpyAsync(p->dest_d, p->dest_h.data(), QK * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
     CU(cudaMemcpyAsync(p->prob_d, p->prob_h.data(), QK * d.K * sizeof(double), cudaMemcpyHostToDevice, p->stream));
@@ -1430,6 +1468,9 @@ int imomd_expand_async(imomd_planner* p, int iters)
 {
     if (!p) return fail(IMOMD_ERR_ARG, "null planner");
     if (iters < 0) return fail(IMOMD_ERR_ARG, "negative iteration count");
+    if (p->batch_ran && !p->d.streaming)
+        return fail(IMOMD_ERR_ARG, "batched steps ran on this planner: reset it before the exact mode (the batched "
+                                   "mode does not maintain the child rows the exact rewiring walks)");
     CU(cudaSetDevice(p->g->device));
     CU(cudaEventRecord(p->ev0, p->stream));
     {
@@ -1470,13 +1511,13 @@ int imomd_expand_batch_async(imomd_planner* p, int steps, int B)
     {
         CU(wait_stream(p));
         const size_t sk = (size_t)d.slots * d.K;
-        d.ev_cap = 2048;
+        d.ev_cap = 16384;
         CU(dmalloc(&d.events, sk * d.ev_cap));
         CU(dmalloc(&d.clist_tree, sk * 2 * (size_t)d.chunks));
         const size_t cells_unused = 0;
         (void)cells_unused;
         p->smem_batch = (kBatchThreads / 32) * (((sizeof(Shared) + 15) / 16) * 16) + ((sizeof(BatchShared) + 15) / 16) * 16 +
-                        (size_t)(kBatchThreads / 32) * 2 * kLevelCap * sizeof(uint32_t) + (size_t)d.K * d.K * 32 +
+                        (size_t)d.K * d.K * 32 +
                         ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)d.K * sizeof(TreeRef) + 64;
         cudaError_t e = cudaSuccess;
         auto set = [&](const void* f) {
@@ -1489,6 +1530,7 @@ int imomd_expand_batch_async(imomd_planner* p, int steps, int B)
         CU(e);
         p->batch_ready = true;
     }
+    p->batch_ran = true;
     CU(cudaEventRecord(p->ev0, p->stream));
     const int ctas = d.streaming ? d.slots : d.Q;
     if (d.streaming) CU(cudaMemsetAsync(p->queue, 0, 2 * sizeof(uint32_t), p->stream));
@@ -1667,6 +1709,18 @@ int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* c
             fprintf(stderr, "  phase %-10s steps %10llu  cycles/step %8.0f\n", names[i],
                     (unsigned long long)pc[8 + i], pc[8 + i] ? (double)pc[i] / (double)pc[8 + i] : 0.0);
     }
+    return IMOMD_OK;
+}
+
+int imomd_get_phase_cycles(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts)
+{
+    if (!p || query < 0 || query >= p->d.Q || !cycles || !counts)
+        return fail(IMOMD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(p->g->device));
+    CU(wait_stream(p));
+    QueryDev* qd = p->d.query + query;
+    CU(cudaMemcpy(cycles, qd->phase_cycles, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(counts, qd->phase_count, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return IMOMD_OK;
 }
 

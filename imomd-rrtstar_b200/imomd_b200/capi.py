@@ -94,6 +94,8 @@ def cuda_lib():
         L.imomd_get_visit_order.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.imomd_get_profile.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
                                         np.ctypeslib.ndpointer(np.uint64, flags="C")]
+        L.imomd_get_phase_cycles.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
+                                             np.ctypeslib.ndpointer(np.uint64, flags="C")]
         L.imomd_get_flags.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.imomd_get_tree.argtypes = [vp, C.c_int, C.c_int, u32p, f64p]
         L.imomd_get_frontier.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -290,6 +292,11 @@ class DevicePlanner:
         d = {names[i]: (int(cyc[i]), int(cnt[i])) for i in range(1, 8)}
         d["bfs_vertices_levels"] = (int(cyc[0]), int(cnt[0]))
         return d
+
+    def phase_cycles(self, q=0):
+        cyc = np.zeros(8, np.uint64); cnt = np.zeros(8, np.uint64)
+        _check(cuda_lib().imomd_get_phase_cycles(self.h, q, cyc, cnt))
+        return cyc, cnt
 
     def tree(self, k, q=0):
         par = np.empty(self.g.n, np.uint32); cost = np.empty(self.g.n)

@@ -149,16 +149,27 @@ int imomd_planner_clear_words(imomd_planner* p);
 int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports);
 int imomd_expand_async(imomd_planner* p, int iters);
 int imomd_sync(imomd_planner* p, imomd_query_report* reports);
-/* BATCHED expansion (north_star (2), (4)): `steps` steps, each of them B expansions of EVERY tree of
- * every query.  The K trees of a query are expanded concurrently -- one warp per tree runs the very
- * code of the exact mode on its own tree: sample, nearest frontier vertex, jump-point hops,
- * choose-parent, frontier / heuristic maintenance, rewire cascade -- while what an expansion does
- * to state the trees share (updateConnectionTree_ :645-706, updateSelectionProbability :602-643)
- * is logged with the values of that moment and applied after the step, in tree order and program
- * order.  Samples come from the injected stream in fixed slots of 8 words per (pass, tree).
- * Deterministic; differs from B reference passes only in when the other trees are looked at.
- * imomd_expand (one sample per tree per pass, sequential) remains the exact, batch-size-1 mode.
- * A report's `iterations` counts passes (steps * B).  Not available in pseudo mode. */
+/* BATCHED expansion (north_star (2) "batched random sampling", (4) "atomic cost/parent updates resolved
+ * deterministically"): `steps` steps, each of them B expansions of EVERY tree of every query.
+ *   1. attach: the K trees of a query concurrently, one warp per tree: sample, nearest frontier
+ *      vertex, jump-point hops, choose-parent, frontier / min-heuristic maintenance (the code of the
+ *      exact mode on the tree's own records).  Samples come from the injected stream in fixed
+ *      slots of 8 words per (pass, tree).
+ *   2. rewire: rewireTree_ (:561-600) for all new vertices of all trees at once, as a
+ *      label-correcting relaxation over the road graph by the whole CTA: a vertex whose cost went
+ *      down offers cost + w to its visited neighbours, a neighbour takes the offer when its
+ *      (cost, parent id) gets lexicographically smaller -- one 128-bit compare-and-swap on the
+ *      record head.  The fixed point (cheapest cost through visited vertices, lowest parent id
+ *      among equal offers) is independent of the order of the offers.
+ *   3. connect: updateConnectionTree_ (:645-706) of every vertex attached or changed in the step
+ *      with the step's final costs; per pair of trees the smallest sum (lowest vertex on ties)
+ *      replaces the distance when it beats it by more than 0.1 (:680).
+ *   4. the updateSelectionProbability tests (:602-643) in tree order and program order.
+ * Deterministic (independent of warp timing); NOT the reference's sequence: the exact,
+ * batch-size-1 parity mode is imomd_expand.  Costs are never worse than what the reference's
+ * cascade leaves for the same visited vertices.  A report's `iterations` counts passes
+ * (steps * B).  Not available in pseudo mode; a resident planner must be reset before it goes
+ * back to imomd_expand (child rows are not maintained by the relaxation). */
 int imomd_expand_batch(imomd_planner* p, int steps, int B, imomd_query_report* reports);
 int imomd_expand_batch_async(imomd_planner* p, int steps, int B);
 /* ImomdRRT::findShortestPath's max_time test runs after EVERY pass (:258-262): with a budget
@@ -169,6 +180,10 @@ int imomd_set_time_budget(imomd_planner* p, double seconds);
  * nearest search, heuristic rescan, heuristic insert, connection gather, cost propagation,
  * rewire batch check; index 7 = the serial steps in between (development / profiling aid) */
 int imomd_get_profile(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts);
+/* exact mode: cycles / counts of the serial steps by the phase they started in (next tree, after
+ * nearest, jump-point search, insert, finish, rewire, last connection check); batched mode: cycles
+ * the per-tree groups spent per kind of work (index as in imomd_get_profile), summed over groups */
+int imomd_get_phase_cycles(imomd_planner* p, int query, uint64_t* cycles, uint64_t* counts);
 /* the last comparison the device could not decide within 1e-12 relative (see
  * imomd_query_report.unresolved_ties): {kind 1 nearest / 2 heuristic rescan, tree, other tree,
  * best value, runner-up value, vertex taken, sample lat, sample lon} */

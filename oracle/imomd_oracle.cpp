@@ -249,9 +249,16 @@ struct orc_planner
     uint64_t cdf_overrun = 0;
 
     // ---- batched mode (restatement of imomd_expand_batch's semantics, DESIGN.md "Batched mode"):
-    // the trees of a step are expanded independently; updateConnectionTree_ / the selection-
-    // probability test are logged with the values of the moment and applied after the step in
-    // tree order.  Samples come from fixed 8-word slots of the mt19937{0} stream.
+    // a STEP = B expansions of every tree.  (1) Every tree, independently: sample (fixed 8-word
+    // slots of the mt19937{0} stream), nearest frontier vertex, jump-point hops, choose-parent,
+    // frontier / min-heuristic maintenance -- the new vertex is only queued for rewiring.  (2) Per
+    // tree, the rewiring as a label-correcting relaxation from the queued vertices: a vertex whose
+    // cost went down offers cost + w to its visited neighbours; a neighbour takes the offer when
+    // (cost, parent id) gets lexicographically smaller.  The fixed point does not depend on the
+    // order of the offers.  (3) Connection checks of every vertex added or changed in the step
+    // against the other trees with the FINAL costs: per pair the smallest sum (lowest vertex on
+    // ties) replaces the distance when it beats it by more than 0.1.  (4) The selection-probability
+    // tests in tree order and program order.  Children lists are not maintained in this mode.
     struct Event
     {
         int kind;          // 0 connection check, 1 selection-probability test
@@ -260,6 +267,7 @@ struct orc_planner
         double val;        // cost of x / min-heuristic value
     };
     bool defer = false;
+    bool no_children = false;           // batched mode: child rows are neither read nor written
     std::vector<Event> events;          // of the tree being expanded
     std::vector<uint32_t> word_cache;   // outputs 0, 1, 2, ... of mt19937{0}
     Mt19937 word_gen{0};
@@ -274,6 +282,7 @@ struct orc_planner
     // ---- children container order: SURVEY.md 8a-7 (unordered_set<size_t>, <= 13) ----
     void chl_insert(Tree& t, uint32_t p, uint32_t x)
     {
+        if (no_children) return;
         uint32_t base = g->row_ptr[p];
         uint32_t n = t.nchl[p];
         uint32_t* row = &t.chl[base];
@@ -301,6 +310,7 @@ struct orc_planner
     }
     void chl_erase(Tree& t, uint32_t p, uint32_t x)
     {
+        if (no_children) return;
         uint32_t base = g->row_ptr[p];
         uint32_t n = t.nchl[p];
         uint32_t* row = &t.chl[base];
@@ -316,6 +326,7 @@ struct orc_planner
     }
     void chl_assign_single(Tree& t, uint32_t p, uint32_t x)
     {
+        if (no_children) return;
         t.chl[g->row_ptr[p]] = x;
         t.nchl[p] = 1;
     }
@@ -785,11 +796,38 @@ struct orc_planner
         }
     }
 
-    // one step of the batched mode: B expansions per tree, cross-tree effects afterwards
+    // rewiring of the batched mode: label-correcting relaxation from `work` (appended to as costs
+    // go down); every vertex whose (cost, parent) changes is reported in `changed`
+    void relax(Tree& t, std::vector<uint32_t>& work, std::vector<uint32_t>& changed)
+    {
+        size_t head = 0;
+        while (head < work.size())
+        {
+            uint32_t u = work[head++];
+            double cu = t.cost[u];
+            for (uint32_t e = g->row_ptr[u]; e < g->row_ptr[u + 1]; ++e)
+            {
+                uint32_t y = g->col[e];
+                if (!t.visited(y)) continue;
+                double p = cu + g->w[e];
+                if (p < t.cost[y] || (p == t.cost[y] && u < t.parent[y]))
+                {
+                    bool lower = p < t.cost[y];
+                    t.cost[y] = p;
+                    t.parent[y] = u;
+                    changed.push_back(y);
+                    if (lower) work.push_back(y);
+                }
+            }
+        }
+    }
+
+    // one step of the batched mode: B expansions per tree (see the member comment above)
     uint64_t batched_step(int B)
     {
         uint64_t expansions = 0;
-        std::vector<std::vector<Event>> logs(K);
+        std::vector<std::vector<Event>> plog(K);
+        std::vector<std::vector<uint32_t>> check(K), dirty(K);
         std::vector<char> active(K);
         int n_active = 0;
         for (int k = 0; k < K; ++k)
@@ -803,6 +841,7 @@ struct orc_planner
             return 0;
         }
         defer = true;
+        no_children = true;
         for (int k = 0; k < K; ++k)
         {
             if (!active[k]) continue;
@@ -817,21 +856,66 @@ struct orc_planner
                 uint32_t x_new = steer(t, rlat, rlon, nullptr, nullptr);
                 connect_new_node(t, x_new);
                 update_expandables(t, x_new, true);
-                rewire(t, x_new);
                 update_selection_probability(t, rid);
-                update_connection(t, x_new);
+                if (t.visited(x_new))
+                {
+                    dirty[k].push_back(x_new);
+                    update_connection(t, x_new);
+                }
                 ++expansions;
             }
-            logs[k] = events;
+            for (const Event& e : events)
+            {
+                if (e.kind == 0) check[k].push_back(e.x);
+                else plog[k].push_back(e);
+            }
         }
         defer = false;
+        for (int k = 0; k < K; ++k) relax(trees[k], dirty[k], check[k]);
+        // connection checks with the final costs, per unordered pair of trees
+        for (int a = 0; a < K; ++a)
+        {
+            for (int b = 0; b < a; ++b)
+            {
+                double best = INFINITY;
+                uint32_t arg = NONE;
+                bool touch = false;
+                for (int side = 0; side < 2; ++side)
+                {
+                    const Tree& t = trees[side ? b : a];
+                    const Tree& o = trees[side ? a : b];
+                    for (uint32_t x : check[side ? b : a])
+                    {
+                        if (!o.visited(x)) continue;
+                        touch = true;
+                        double d = t.cost[x] + o.cost[x];
+                        if (d < best || (d == best && x < arg))
+                        {
+                            best = d;
+                            arg = x;
+                        }
+                    }
+                }
+                if (!touch) continue;
+                int set_idx = a * (a - 1) / 2 + b;
+                if (!contact[set_idx])
+                {
+                    contact[set_idx] = 1;
+                    connect_two_trees(b, a);
+                }
+                if (best < D[(size_t)a * K + b] - 0.1)
+                {
+                    D[(size_t)a * K + b] = best;
+                    D[(size_t)b * K + a] = best;
+                    CN[(size_t)a * K + b] = arg;
+                    CN[(size_t)b * K + a] = arg;
+                    dm_updated = true;
+                }
+            }
+        }
         for (int k = 0; k < K; ++k)
         {
-            for (const Event& e : logs[k])
-            {
-                if (e.kind == 0) apply_connection(trees[k], e.x, e.val);
-                else apply_selection_probability(trees[k], e.other, e.val);
-            }
+            for (const Event& e : plog[k]) apply_selection_probability(trees[k], e.other, e.val);
         }
         batch_passes += (uint64_t)B;
         return expansions;

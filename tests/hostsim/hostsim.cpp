@@ -59,6 +59,17 @@ struct CtaHost
     uint32_t reduce_min_u32(uint32_t v, uint32_t*) const { return v; }
     void counter_or(uint32_t* p, uint32_t v) const { *p |= v; }
     int group() const { return 0; }       // batched mode: one group walks the trees one by one
+    uint32_t bcast(uint32_t v) const { return v; }
+    U4 cas_head(U4* addr, const U4& expect, const U4& want) const
+    {
+        U4 seen = *addr;
+        if (seen.x == expect.x && seen.y == expect.y && seen.z == expect.z && seen.w == expect.w) *addr = want;
+        return seen;
+    }
+    U4 load_cg(const U4* p) const { return *p; }
+    void atomic_min_u64(unsigned long long* p, unsigned long long v) const { if (v < *p) *p = v; }
+    void atomic_min_u32(uint32_t* p, uint32_t v) const { if (v < *p) *p = v; }
+    void fence() const {}
     int n_groups() const { return 1; }
     mutable uint64_t fake_ns = 0;
     uint64_t now_ns() const { return fake_ns += 1000; }   // every reading is 1 us later
@@ -280,10 +291,9 @@ void hs_expand_batch(void* hp, int steps, int B, ReportDev* reports)
         const int slot = p->d.streaming ? hq % p->d.slots : hq;
 #define HS_BATCH(W)                                                                                              \
     if (p->d.streaming)                                                                                          \
-        run_streaming_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->lvl.data(),           \
-                                       p->mat.data(), hot);                                                      \
+        run_streaming_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->mat.data(), hot);    \
     else                                                                                                         \
-        run_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->lvl.data(), p->mat.data(), hot);
+        run_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->mat.data(), hot);
         if (p->d.g.width == 4) { HS_BATCH(4) }
         else if (p->d.g.width == 8) { HS_BATCH(8) }
         else { HS_BATCH(16) }

@@ -247,3 +247,24 @@ def test_widened_tie_band_is_certified_exactly():
     rep2 = hp2.expand(600)[0]
     assert rep2.certified_ties == 0 and rep2.unresolved_ties > 20 and hp2.certified() == 0
     op.close(); hp.close(); hp2.close()
+
+
+@pytest.mark.parametrize("kind,K,gb,B", [("grid60", 6, 1.0, 1), ("grid60", 6, 1.0, 4), ("grid90", 12, 1.0, 16),
+                                         ("road", 5, 1.0, 8), ("road", 7, 0.5, 3), ("grid60", 4, 0.3, 32)])
+def test_batched_mode_matches_its_restatement(kind, K, gb, B):
+    """imomd_expand_batch's device logic (attach per tree, rewiring as a label-correcting
+    relaxation, connection checks with the final costs, selection-probability tests) against the
+    oracle's restatement of the same semantics: trees bit for bit, K x K state."""
+    g = {"grid60": lambda: graphs.jittered_grid(60, seed=2), "grid90": lambda: graphs.jittered_grid(90, seed=3),
+         "road": lambda: graphs.road_like(6000, seed=5)}[kind]()
+    dest = graphs.pick_destinations(g, K, seed=11)
+    op = ol.OraclePlanner(g, dest, gb)
+    hp = hs.HostSimPlanner(g, [dest], [op.matrices()["P"]], gb)
+    hp.feed(_words(400000))
+    for steps in (1, 7, 60):
+        rep = hp.expand_batch(steps, B)[0]
+        e = op.iterate_batched(steps, B)
+        assert rep.status == 0 and rep.expansions == e and rep.iterations == steps * B
+        assert hp.treehash()[0] == op.treehash()
+        compare_with_oracle(hp, op, K, True)
+    op.close(); hp.close()
