@@ -77,6 +77,8 @@ def parse():
                     help="grid = BASELINE configs[2] (default); san_pablo = configs[4]: 1024 "
                          "source/target queries (K = 2) on the bundled san_pablo road graph")
     ap.add_argument("--no-ttfs", action="store_true", help="skip the time-to-first-solution side measurement")
+    ap.add_argument("--batch", type=int, default=16,
+                    help="B of the batched-mode leg (B expansions per tree per step); 0 skips the leg")
     ap.add_argument("--cpu-sample-iters", type=int, default=0,
                     help="iterations of the CPU sample (0 = same as --iters)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -477,6 +479,77 @@ def ga_islands_leg(device, rank, world, generations=5):
             "migration_allgather_us": mig_us}
 
 
+def batched_leg(dp, args, g, K, exact_states, peak, device):
+    """The BATCHED mode (imomd_expand_batch) on the very queries of the timed batch: B expansions per
+    tree per step, trees of a query attached concurrently, rewiring as a relaxation, connection
+    checks with the step's final costs.  Not the reference's sequence (the exact mode above is the
+    parity mode): reported beside it with its own roofline figure, a determinism check (two runs,
+    identical TREEHASHes) and the quality of what it builds -- the RTSP tour over the distance
+    matrix of the first queries against the exact mode's at the same number of passes."""
+    from imomd_b200 import capi
+    B = args.batch
+    steps = args.iters // B
+    streaming = dp.info()["streaming"]
+    if not streaming:
+        dp.reset()
+    dp.expand_batch(steps, B)                                   # warm-up
+    first = None
+    ms, exps = [], []
+    for _ in range(2):
+        if not streaming:
+            dp.reset()
+        reps = dp.expand_batch(steps, B)
+        bad = sorted({r.status for r in reps if r.status != 0})
+        if bad:
+            return {"error": f"device run status {bad}"}
+        ms.append(dp.last_kernel_ms()); exps.append(sum(r.expansions for r in reps))
+        hashes = [int(r.tree_hash) for r in reps] if streaming else [dp.treehash(q)[0] for q in range(min(len(reps), 16))]
+        if first is None:
+            first = hashes
+    counters = dp.counters()
+    bytes_step, parts = algorithmic_bytes(counters, g.arcs / g.n, K)
+    st = dp.states()
+    # quality: (1) the pairwise connection distances both modes found, entry by entry; (2) the RTSP
+    # tour over the whole matrix for (up to 32) queries that both modes fully connected
+    De, Db = exact_states["D"], st["D"]
+    off = ~np.eye(K, dtype=bool)[None, :, :]
+    fe, fb = np.isfinite(De) & off, np.isfinite(Db) & off
+    both_f = fe & fb
+    ratio_d = (Db[both_f] / De[both_f]) if both_f.any() else np.zeros(0)
+    full_e = np.isfinite(De).all(axis=(1, 2)); full_b = np.isfinite(Db).all(axis=(1, 2))
+    ratios = []
+    for q in np.nonzero(full_e & full_b)[0][:32]:
+        fs = capi.FacadeSolver(device); ce, _, _ = fs.solve(np.ascontiguousarray(De[q]), 0, K - 1); fs.close()
+        fs = capi.FacadeSolver(device); cb, _, _ = fs.solve(np.ascontiguousarray(Db[q]), 0, K - 1); fs.close()
+        ratios.append(cb / ce)
+    both = len(ratios)
+    conn_b, conn_e = int(full_b.sum()), int(full_e.sum())
+    launch_s = ms[-1] / 1e3
+    return {"B": B, "steps_per_query": steps, "passes_per_query": steps * B,
+            "value": sum(exps) / (sum(ms) / 1e3), "unit": UNIT, "kernel_ms": [round(x, 1) for x in ms],
+            "expansions_per_launch": int(exps[-1]),
+            "deterministic": first == hashes,
+            "roofline": {"bound": "hbm", "achieved": bytes_step / launch_s / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_step / launch_s / 1e9 / peak, "kernel": "k_expand_batch",
+                         "algorithmic_bytes_per_launch": bytes_step, **{k: float(v) for k, v in parts.items()}},
+            "fully_connected_queries": {"batched": conn_b, "exact": conn_e, "of": len(reps)},
+            "connected_pairs": {"batched": int(fb.sum() // 2), "exact": int(fe.sum() // 2), "both": int(both_f.sum() // 2),
+                                "distance_ratio_batched_over_exact": {
+                                    "mean": float(ratio_d.mean()) if ratio_d.size else None,
+                                    "median": float(np.median(ratio_d)) if ratio_d.size else None,
+                                    "p95": float(np.percentile(ratio_d, 95)) if ratio_d.size else None},
+                                "note": "tree pairs with a connection (finite distance-matrix entry) after the same number "
+                                        "of passes, all queries; ratio over the pairs both modes connected"},
+            "tour_cost_vs_exact": {"queries_compared": both, "mean_ratio": float(np.mean(ratios)) if ratios else None,
+                                   "max_ratio": float(np.max(ratios)) if ratios else None,
+                                   "min_ratio": float(np.min(ratios)) if ratios else None,
+                                   "note": "RTSP tour (EciGenSolver) over the distance matrix each mode built in the same "
+                                           "number of passes, up to 32 queries that both modes fully connected"},
+            "unresolved_ties": int(sum(r.unresolved_ties for r in reps)),
+            "note": "semantics: DESIGN.md 'Batched mode'; parity of this mode is against its CPU restatement "
+                    "(oracle/imomd_oracle.cpp batched_step), bit for bit, in tests/test_cuda_batched.py"}
+
+
 def b200_arm(args):
     import torch
     from imomd_b200 import capi
@@ -561,6 +634,16 @@ def b200_arm(args):
         t_dev, t_e2e = float(t[0]), float(t[1])
         exp_total = float(e[0])
     side = {}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if args.batch > 0 and rank == 0 and getattr(args, "workload", "grid") == "grid":
+        try:
+            side["batched"] = batched_leg(dp, args, g, K, states, peak, device)
+        except Exception as ex:
+            side["batched"] = {"error": repr(ex)}
     if not args.no_side_legs and getattr(args, "workload", "grid") == "grid":
         # side legs run on every rank (they shard); rank 0 reports them
         dp.close(); dp = None
@@ -578,11 +661,6 @@ def b200_arm(args):
             dist.destroy_process_group()
         return 0
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     avg_deg = g.arcs / g.n
     # counters are cumulative over the last set_queries (= one step); per launch:
     bytes_step, parts = algorithmic_bytes(counters, avg_deg, K)

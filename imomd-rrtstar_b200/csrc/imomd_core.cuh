@@ -2997,6 +2997,9 @@ IMOMD_HD inline void run_streaming_query(Cta& cta, const PlannerDev& P, int slot
 // are not maintained (the relaxation walks the road graph, not the tree), so a planner that has
 // run batched steps cannot continue in the exact mode before a reset.
 constexpr uint32_t kBatchWords = 8;
+constexpr uint32_t kGroupLbCap = 512;   // cell lower bounds a group keeps in shared memory between the two
+                                        // passes of a pruned search (frontiers with more occupied cells
+                                        // recompute them)
 
 struct BatchShared
 {
@@ -3006,7 +3009,7 @@ struct BatchShared
     int32_t n_active;
     int32_t stop;
     uint32_t next_tree;                  // trees are handed to the groups from this counter
-    uint32_t relax_items, relax_changes; // work counters of the step
+    uint32_t relax_items, relax_changes, relax_levels;   // work counters of the step
     uint32_t dirty_n[2][IMOMD_KMAX];     // relaxation queues (ping-pong) per tree
     uint32_t chk_n[IMOMD_KMAX];          // vertices whose connection check is due
     uint64_t tree_cycles[IMOMD_KMAX];    // cycles the tree's group spent on its batch in this step
@@ -3015,8 +3018,12 @@ struct BatchShared
     uint32_t cand_x[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
 };
 
-// the scratch of tree k inside the slot's arena: [rewire queue A | rewire queue B | check list]
+// the scratch of tree k inside the slot's arena: [rewire queue A | rewire queue B | check list].
+// (Measured: queue entries that carry the cost they were queued with save the dependent load of the
+// vertex's own record but make offers from costs that are already out of date -- 60 % more offer
+// rounds, the relaxation 10 % slower.  An offer round reads the vertex's CURRENT cost.)
 IMOMD_HD inline uint32_t batch_share(const PlannerDev& P) { return P.arena_entries / (uint32_t)P.K; }
+IMOMD_HD inline uint32_t batch_queue_cap(const PlannerDev& P) { return batch_share(P) / 4; }
 IMOMD_HD inline uint32_t* batch_queue(const PlannerDev& P, int slot, int k, int which)
 {
     const uint32_t share = batch_share(P);
@@ -3030,7 +3037,8 @@ IMOMD_HD inline uint32_t* batch_checks(const PlannerDev& P, int slot, int k)
 
 // One group: up to B attaches of tree k (fewer when its frontier runs empty).
 template <int KW, class Grp>
-IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, int k, Shared& S, int B, uint64_t pass0)
+IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, int k, Shared& S, double* lbg, int B,
+                                       uint64_t pass0)
 {
     const int K = P.K;
     if (grp.tid() == 0)
@@ -3044,7 +3052,7 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
         S.exp_n = 0;
         S.dirty = batch_queue(P, slot, k, 0);
         S.dirty_n = 0;
-        S.dirty_cap = share / 4;
+        S.dirty_cap = batch_queue_cap(P);
         S.chk = batch_checks(P, slot, k);
         S.chk_n = 0;
         S.chk_cap = share / 2;
@@ -3076,8 +3084,9 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
             const int req = S.req;
             if (req == REQ_EXIT) break;
             const long long t0 = grp.clock();
-            if (req == REQ_NN) svc_nearest(grp, P, slot, k, S, (double*)nullptr, S.clist, &S.near_ties, &S.unresolved_ties, true);
-            else if (req == REQ_RESCAN) svc_rescan(grp, P, slot, k, S, (double*)nullptr);
+            double* lb = (lbg != nullptr && S.Q->n_occ[k] <= kGroupLbCap) ? lbg : nullptr;
+            if (req == REQ_NN) svc_nearest(grp, P, slot, k, S, lb, S.clist, &S.near_ties, &S.unresolved_ties, true);
+            else if (req == REQ_RESCAN) svc_rescan(grp, P, slot, k, S, lb);
             else if (req == REQ_MHINS) svc_mhins(grp, P, slot, k, S);
             grp.sync();
             if (grp.tid() == 0)
@@ -3098,9 +3107,9 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
 // neighbour, accepted when (cost, parent) gets lexicographically smaller.  A neighbour whose COST
 // went down joins the next queue; every neighbour that changed joins the check list.
 template <int W, class Blk>
-IMOMD_HD inline void relax_vertex(Blk& blk, const PlannerDev& P, const TreeRef& T, uint32_t u, uint32_t* next_q,
-                                  uint32_t* next_n, uint32_t q_cap, uint32_t* chk, uint32_t* chk_n, uint32_t chk_cap,
-                                  QueryDev* Q, uint32_t* changes)
+IMOMD_HD inline void relax_vertex(Blk& blk, const PlannerDev& P, const TreeRef& T, uint32_t u,
+                                  uint32_t* next_q, uint32_t* next_n, uint32_t q_cap, uint32_t* chk, uint32_t* chk_n,
+                                  uint32_t chk_cap, QueryDev* Q, uint32_t* changes)
 {
     const GraphDev& g = P.g;
     const uint32_t e0 = row_begin(g, u), d = g.deg[u];
@@ -3171,7 +3180,7 @@ IMOMD_HD inline void batch_relax(Blk& blk, const PlannerDev& P, int slot, Shared
 {
     QueryDev* Q = S0.Q;
     const int K = P.K;
-    const uint32_t q_cap = batch_share(P) / 4, chk_cap = batch_share(P) / 2;
+    const uint32_t q_cap = batch_queue_cap(P), chk_cap = batch_share(P) / 2;
     int cur = 0;
     for (;;)
     {
@@ -3203,6 +3212,7 @@ IMOMD_HD inline void batch_relax(Blk& blk, const PlannerDev& P, int slot, Shared
         if (blk.tid() == 0)
         {
             BS.relax_items += total;
+            BS.relax_levels += 1;
             for (int k = 0; k < K; ++k) BS.dirty_n[cur][k] = 0;
         }
         cur ^= 1;
@@ -3320,7 +3330,7 @@ IMOMD_HD inline void batch_apply_tests(Blk& blk, const PlannerDev& P, int slot, 
 // `steps` steps of B expansions per tree for query hq in slot `slot`.  SG: one Shared per group.
 template <int KW, class Blk, class Grp>
 IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, int slot, int hq, int steps, int B,
-                                       Shared* SG, BatchShared& BS, double* mat, unsigned char* hot)
+                                       Shared* SG, BatchShared& BS, double* lb_all, double* mat, unsigned char* hot)
 {
     assume_planner(P);
     QueryDev* Qg = P.query + hq;
@@ -3394,7 +3404,7 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
             }
             BS.n_active = active;
             BS.next_tree = 0;
-            BS.relax_items = BS.relax_changes = 0;
+            BS.relax_items = BS.relax_changes = BS.relax_levels = 0;
             BS.stop = 0;
             if (Q->status != 0) BS.stop = 1;
             else if (active == 0)
@@ -3424,7 +3434,8 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
             if (k >= (uint32_t)K) break;
             if (!BS.active[k]) continue;
             const long long tk0 = grp.clock();
-            batch_expand_tree<KW>(grp, P, slot, (int)k, S, B, pass0);
+            batch_expand_tree<KW>(grp, P, slot, (int)k, S, lb_all ? lb_all + (size_t)grp.group() * kGroupLbCap : nullptr, B,
+                                  pass0);
             if (grp.tid() == 0)
             {
                 BS.ev_count[k] = S.ev_n;
@@ -3463,7 +3474,7 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
             Q->prof_cycles[2] += mx;
             Q->prof_count[2] += 1;
             Q->prof_cycles[3] += (uint64_t)(ts1 - ts0);
-            Q->prof_count[3] += 1;
+            Q->prof_count[3] += BS.relax_levels;
             Q->prof_cycles[4] += (uint64_t)(ts2 - ts1);
             Q->prof_count[4] += BS.relax_items;
             Q->prof_cycles[5] += (uint64_t)(blk.clock() - ts2);
@@ -3529,7 +3540,8 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
 // a streaming planner's query in the batched mode (cf. run_streaming_query)
 template <int KW, class Blk, class Grp>
 IMOMD_HD inline void run_streaming_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, int slot, int hq, int steps,
-                                                 int B, Shared* SG, BatchShared& BS, double* mat, unsigned char* hot)
+                                                 int B, Shared* SG, BatchShared& BS, double* lb_all, double* mat,
+                                                 unsigned char* hot)
 {
     const long long t0 = blk.clock();
     {
@@ -3547,7 +3559,7 @@ IMOMD_HD inline void run_streaming_query_batched(Blk& blk, Grp& grp, const Plann
         construct_trees(P, slot, hq);
     }
     blk.sync();
-    run_query_batched<KW>(blk, grp, P, slot, hq, steps, B, SG, BS, mat, hot);
+    run_query_batched<KW>(blk, grp, P, slot, hq, steps, B, SG, BS, lb_all, mat, hot);
     blk.sync();
     uint64_t h = 0, sum = 0;
     tree_hash(blk, P, slot, SG[0], P.arena + (size_t)slot * P.arena_entries, P.arena_entries, &h, &sum);

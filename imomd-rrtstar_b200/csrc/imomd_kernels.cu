@@ -556,7 +556,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand_batch(const __gr
     constexpr size_t kShared = ((sizeof(Shared) + 15) / 16) * 16;
     Shared* SG = reinterpret_cast<Shared*>(smem_raw);
     BatchShared& BS = *reinterpret_cast<BatchShared*>(smem_raw + NW * kShared);
-    double* mat = reinterpret_cast<double*>(smem_raw + NW * kShared + ((sizeof(BatchShared) + 15) / 16) * 16);
+    double* lb_all = reinterpret_cast<double*>(smem_raw + NW * kShared + ((sizeof(BatchShared) + 15) / 16) * 16);
+    double* mat = lb_all + (size_t)NW * kGroupLbCap;
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev blk;
     WarpDev grp;
@@ -573,13 +574,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand_batch(const __gr
             const int hq = next_q;
             __syncthreads();
             if (hq >= P.Q) break;
-            run_streaming_query_batched<KW>(blk, grp, P, (int)blockIdx.x, hq, steps, B, SG, BS, mat, hot);
+            run_streaming_query_batched<KW>(blk, grp, P, (int)blockIdx.x, hq, steps, B, SG, BS, lb_all, mat, hot);
         }
         return;
     }
     for (int q = blockIdx.x; q < P.Q; q += gridDim.x)
     {
-        run_query_batched<KW>(blk, grp, P, q, q, steps, B, SG, BS, mat, hot);
+        run_query_batched<KW>(blk, grp, P, q, q, steps, B, SG, BS, lb_all, mat, hot);
         __syncthreads();
     }
 }
@@ -1517,7 +1518,7 @@ int imomd_expand_batch_async(imomd_planner* p, int steps, int B)
         const size_t cells_unused = 0;
         (void)cells_unused;
         p->smem_batch = (kBatchThreads / 32) * (((sizeof(Shared) + 15) / 16) * 16) + ((sizeof(BatchShared) + 15) / 16) * 16 +
-                        (size_t)d.K * d.K * 32 +
+                        (size_t)(kBatchThreads / 32) * kGroupLbCap * sizeof(double) + (size_t)d.K * d.K * 32 +
                         ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)d.K * sizeof(TreeRef) + 64;
         cudaError_t e = cudaSuccess;
         auto set = [&](const void* f) {

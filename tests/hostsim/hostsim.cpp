@@ -291,9 +291,9 @@ void hs_expand_batch(void* hp, int steps, int B, ReportDev* reports)
         const int slot = p->d.streaming ? hq % p->d.slots : hq;
 #define HS_BATCH(W)                                                                                              \
     if (p->d.streaming)                                                                                          \
-        run_streaming_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->mat.data(), hot);    \
+        run_streaming_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->lb.data(), p->mat.data(), hot);    \
     else                                                                                                         \
-        run_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->mat.data(), hot);
+        run_query_batched<W>(cta, cta, p->d, slot, hq, steps, B, &p->S, p->BS, p->lb.data(), p->mat.data(), hot);
         if (p->d.g.width == 4) { HS_BATCH(4) }
         else if (p->d.g.width == 8) { HS_BATCH(8) }
         else { HS_BATCH(16) }

@@ -48,7 +48,7 @@ for B in Bs:
     cnt = dp.counters()[:nq].astype(np.float64).mean(axis=0)
     print(json.dumps(dict(B=B, per_query_ms=dict(sum_tree_attach=mc(pc[1]), slowest_tree_per_step=mc(pc[2]),
                                                  attach_part=mc(pc[3]), relaxation=mc(pc[4]), connect_and_tests=mc(pc[5])),
-                          steps=int(pn[2] / nq), relax_items_per_query=int(pn[4] / nq),
+                          steps=int(pn[2] / nq), relax_levels_per_query=int(pn[3] / nq), relax_items_per_query=int(pn[4] / nq),
                           relax_changes_per_query=int(cnt[4]), checked_vertices_per_query=int(cnt[6]),
                           group_ms_by_work=dict(nn=mc(gc[1]), rescan=mc(gc[2]), mhins=mc(gc[3]), serial=mc(gc[7])))), flush=True)
     print(json.dumps(dict(mode="batched", Q=Q, slots=slots, passes=passes, B=B, kernel_ms=round(ms, 1), wall_s=round(wall, 3),
