@@ -3106,6 +3106,12 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
 // One offer round of the relaxation for vertex u of tree T: u's cost + w to every visited
 // neighbour, accepted when (cost, parent) gets lexicographically smaller.  A neighbour whose COST
 // went down joins the next queue; every neighbour that changed joins the check list.
+// Measured alternatives (bench workload, B = 16, relaxation 187-194 ms per query as it stands: a
+// level costs about 5.9 k cycles + 1.2 k per vertex, 188 levels per step): all first swaps of a
+// vertex in flight together + rotating queues with one barrier per level -- no change (194 ms);
+// queue entries that carry their cost -- offers from costs already out of date, 60 % more rounds,
+// 210 ms; the thread following the chain itself instead of queueing (depth-first order) -- 75 %
+// more accepted offers, 231 ms.  Breadth-first levels are the cheap order for this relaxation.
 template <int W, class Blk>
 IMOMD_HD inline void relax_vertex(Blk& blk, const PlannerDev& P, const TreeRef& T, uint32_t u,
                                   uint32_t* next_q, uint32_t* next_n, uint32_t q_cap, uint32_t* chk, uint32_t* chk_n,
@@ -3190,7 +3196,7 @@ IMOMD_HD inline void batch_relax(Blk& blk, const PlannerDev& P, int slot, Shared
             uint32_t n = BS.dirty_n[cur][k];
             total += n < q_cap ? n : q_cap;
         }
-        if (total == 0 || Q->status != 0) break;
+        if (total == 0) break;      // (uniform across the CTA: the counts of the level being read are stable)
         for (uint32_t i = (uint32_t)blk.tid(); i < total; i += (uint32_t)blk.nt())
         {
             int k = 0;
