@@ -3169,6 +3169,9 @@ IMOMD_HD inline void relax_vertex(Blk& blk, const PlannerDev& P, const TreeRef& 
                 else Q->status = 3;
                 if (lower)
                 {
+                    // y's own offer round comes a level later: its adjacency row on the way to the L2
+                    blk.prefetch_l2(g.col + row_begin(g, y));
+                    blk.prefetch_l2(g.w + row_begin(g, y));
                     at = blk.counter_add(next_n, 1u);
                     if (at < q_cap) next_q[at] = y;
                     else Q->status = 3;

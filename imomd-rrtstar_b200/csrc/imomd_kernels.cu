@@ -180,6 +180,7 @@ struct CtaDev
     __device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned long long v) const { atomicMin(p, v); }
     __device__ __forceinline__ void atomic_min_u32(uint32_t* p, uint32_t v) const { atomicMin(p, v); }
     __device__ __forceinline__ void fence() const { __threadfence(); }
+    __device__ __forceinline__ void prefetch_l2(const void* p) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
     // Exact values from the host (ONE thread calls): the n coordinate pairs go to this CTA's
     // mailbox in mapped pinned host memory, the host thread waiting for the launch (wait_stream)
     // answers with the reference's haversine evaluated by glibc.  System-scope release / acquire.

@@ -70,6 +70,7 @@ struct CtaHost
     void atomic_min_u64(unsigned long long* p, unsigned long long v) const { if (v < *p) *p = v; }
     void atomic_min_u32(uint32_t* p, uint32_t v) const { if (v < *p) *p = v; }
     void fence() const {}
+    void prefetch_l2(const void*) const {}
     int n_groups() const { return 1; }
     mutable uint64_t fake_ns = 0;
     uint64_t now_ns() const { return fake_ns += 1000; }   // every reading is 1 us later
