@@ -24,10 +24,11 @@ expandTree_ calls per second, whole job (all queries, all GPUs).
   cpu_baseline   the unmodified reference (oracle/_ref/ref_probe) on the box's host cores,
                  one process per core, a bounded sample of the same workload
 
-A step processes `--queries` (1184) queries per GPU through `--slots` (296 = two CTAs per SM)
+A step processes `--queries` (2368) queries per GPU through `--slots` (296 = two CTAs per SM)
 sets of per-query device state: the planner STREAMS -- CTAs take the next query from a device
-work queue as their slot falls free, so a step is four "waves" deep and ends with the slowest
-tail of the last ones instead of the slowest query of a single wave.
+work queue as their slot falls free, so a step is eight "waves" deep and ends with the slowest
+tail of the last ones instead of the slowest query of a single wave (per-query busy time spreads
+from 0.55 x to 2.3 x its mean: `batch` in the line).
 
   parity   the unmodified reference runs queries 0 .. cores-1 of the same batch at the same depth
            (it is the cpu_baseline leg); its TREEHASH, expansion count and tree
@@ -67,7 +68,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries", type=int, default=1184, help="independent queries per GPU and step")
+    ap.add_argument("--queries", type=int, default=2368, help="independent queries per GPU and step")
     ap.add_argument("--slots", type=int, default=296,
                     help="sets of per-query device state (queries stream through them); 0 = one per query")
     ap.add_argument("--no-side-legs", action="store_true", help="skip the san_pablo_1024 / ga side measurements")
@@ -295,7 +296,7 @@ def reference_arm(args):
         for s in range(args.steps):
             rate, info = run_reference_sample(g, dests, iters, cores, gf)
             if rate is None:
-                print(json.dumps({"impl": "reference", "unavailable": info}))
+                emit({"impl": "reference", "unavailable": info})
                 return 0
             rates.append(rate)
             t_total += info["loop_seconds"]
@@ -318,7 +319,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -386,10 +387,13 @@ def ga_leg(device):
 
 def san_pablo_leg(device, rank, world, iters=3000, n_queries=1024):
     """BASELINE configs[4]: 1024 source/target queries (K = 2) on san_pablo.osm, STRONG scaling:
-    the same 1024 queries over however many GPUs there are, ranks pulling chunks of 32 queries
-    from a shared counter (sharding.run_sharded, no data-path collective), every rank's planner
-    streaming its chunk; per-query TREEHASHes gathered and folded into one fingerprint that must
-    not depend on the number of GPUs (the driver's per-N lines carry it)."""
+    the same 1024 queries over however many GPUs there are (sharding.run_sharded, query q on rank
+    q mod N, no data-path collective), every rank's planner streaming its share; per-query
+    TREEHASHes gathered and folded into one fingerprint that must not depend on the number of GPUs
+    (the driver's per-N lines carry it).  The job is bounded by its slowest query (one source /
+    target pair keeps rewiring most of the 6 809-vertex map: 0.67 s of the 0.8 s a single GPU needs
+    for all 1024), so more GPUs cannot shorten it much; dynamic chunks of 32 queries (measured on
+    2 GPUs: 5.2 s) leave most SMs without a CTA."""
     import hashlib
     import torch
     from imomd_b200 import graphs, sharding
@@ -407,8 +411,9 @@ def san_pablo_leg(device, rank, world, iters=3000, n_queries=1024):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = sharding.run_sharded(g, dests, iters, ex, world=world, rank=rank, dynamic_chunk=32 if world > 1 else 0,
-                               tag="san_pablo_1024")
+    # static shares (query q on rank q mod world): a K = 2 query is a few hundred microseconds of
+    # work per pass, chunks small enough to balance would leave most SMs of a GPU without a CTA
+    res = sharding.run_sharded(g, dests, iters, ex, world=world, rank=rank, dynamic_chunk=0, tag="san_pablo_1024")
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     kernel_s = ex.kernel_ms / 1e3
@@ -424,6 +429,8 @@ def san_pablo_leg(device, rank, world, iters=3000, n_queries=1024):
             "expansions": int(exps), "seconds": wall, "expansions_per_s": exps / wall,
             "max_rank_kernel_seconds": kernel_s, "tree_vertices": int(sum(r["tree_vertices"] for r in res)),
             "unresolved_ties": int(sum(r["unresolved_ties"] for r in res)),
+            "slowest_query_seconds": max(r.get("busy_cycles", 0) for r in res) / 1.965e9,
+            "mean_query_seconds": float(np.mean([r.get("busy_cycles", 0) for r in res])) / 1.965e9,
             "treehash_fingerprint": fp, "note": "fingerprint = sha256 over the 1024 per-query TREEHASHes in query "
             "order: identical for every GPU count"}
 
@@ -768,7 +775,7 @@ def b200_arm(args):
                 if diffs:
                     line["parity"]["mismatches"] = diffs[:8]
                     parity_failed = f"{len(diffs)} of {len(info['runs'])} checked queries differ from the reference"
-    print(json.dumps(line))
+    emit(line)
     dg.close()
     if world > 1:
         import torch.distributed as dist
@@ -779,8 +786,23 @@ def b200_arm(args):
     return 0
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's real stdout"""
+    (_JSON_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_JSON_OUT or sys.stdout).flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # stdout carries exactly one JSON line: whatever libraries print (NCCL's version banner, the
+    # facade's progress rows) goes to stderr
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
     return b200_arm(args)

@@ -103,7 +103,8 @@ class CudaExecutor:
         hashes = [int(r.tree_hash) for r in reps] if dp.info()["streaming"] else \
             [dp.treehash(q)[0] for q in range(len(reps))]
         out = [dict(expansions=int(r.expansions), tree_vertices=int(r.tree_vertices), status=int(r.status),
-                    treehash=hashes[q], unresolved_ties=int(r.unresolved_ties), D=st["D"][q].copy())
+                    treehash=hashes[q], unresolved_ties=int(r.unresolved_ties), busy_cycles=int(r.busy_cycles),
+                    D=st["D"][q].copy())
                for q, r in enumerate(reps)]
         dp.close()
         return out
