@@ -349,7 +349,7 @@ IMOMD_HD inline TreeRef tree_ref(const PlannerDev& P, int q, int k)
     t.base = P.trec + qt * (size_t)P.g.n * P.trec_stride;
     t.cell_head = P.cell_head + qt * cells;
     t.cell_cnt = P.cell_cnt + qt * cells;
-    t.occ = P.occ + qt * 2 * cells;
+    t.occ = P.occ + qt * (2 * cells + P.dirty_words);
     t.rec = P.rec + qt * (size_t)P.chunks * IMOMD_CHUNK;
     t.chunk_next = P.chunk_next + qt * P.chunks;
     t.free_stack = P.free_stack + qt * P.chunks;
@@ -587,6 +587,22 @@ IMOMD_HD inline int certify_argmin(Cta& cta, const GraphDev& g, Shared& S, uint3
 
 // --------------------------------------------------- frontier hash (serial) ---
 
+// Streaming planners keep one bit per vertex record of a tree, set when the record is first
+// written (the vertex enters the frontier or the tree): recycling a slot and hashing its trees
+// then walk n / 32 words per tree instead of n records (reset_slot, tree_hash).  The bitmap sits
+// behind the tree's occ lists.  Different trees never share a word; a tree's records are written by
+// one thread at a time in every mode, the atomic only keeps the update a single memory operation.
+IMOMD_HD inline void dirty_mark(const PlannerDev& P, const TreeRef& T, uint32_t v)
+{
+    if (P.dirty_words == 0) return;
+    uint32_t* w = T.occ + 2 * (size_t)P.g.G * P.g.G + (v >> 5);
+#ifdef __CUDA_ARCH__
+    atomicOr(w, 1u << (v & 31));
+#else
+    *w |= 1u << (v & 31);
+#endif
+}
+
 IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& T, int k,
                                uint32_t v)
 {
@@ -620,6 +636,7 @@ IMOMD_HD inline bool fr_insert(const PlannerDev& P, QueryDev* Q, const TreeRef& 
     uint32_t slot = head * IMOMD_CHUNK + off;
     T.rec[slot] = r;
     T.set_fslot(v, slot);
+    dirty_mark(P, T, v);
     T.cell_cnt[c] = cnt + 1;
     Q->frontier_count[k] += 1;
     return true;
@@ -1141,6 +1158,7 @@ struct Seq
         {
             Q->tree_size[k] += 1;
             log_visit(k, x_new);
+            dirty_mark(P, T, x_new);
         }
         T.set_parent(x_new, via);
         if (!S.batch) chl_assign_single_w<KW>(T.chl(via), x_new);
@@ -1198,6 +1216,7 @@ struct Seq
             {
                 Q->tree_size[k] += 1;
                 log_visit(k, x_new);
+                dirty_mark(P, T, x_new);
             }
             T.set_parent(x_new, x_parent);
             if (!S.batch) chl_insert_w<KW>(T.chl(x_parent), x_new);
@@ -2574,6 +2593,7 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q, int hq)
         Q->view_root[i] = root;
         T.set_parent(root, root);
         T.set_cost(root, 0.0);
+        dirty_mark(P, T, root);
         Q->tree_size[i] = 1;
         if (P.pseudo) P.visit_log[((size_t)q * K + i) * g.n] = root;
         Q->ds_parent[i] = i;
@@ -2606,20 +2626,66 @@ IMOMD_HD inline void construct_trees(const PlannerDev& P, int q, int hq)
 // takes the next query from a work queue, rebuilds its slot for it, runs the query to completion
 // and keeps only the header (K x K matrices, counters, tree hash).
 
+IMOMD_HD inline int lowest_bit(uint32_t w)
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)w) - 1;
+#else
+    return __builtin_ctz(w);
+#endif
+}
+IMOMD_HD inline uint32_t count_bits(uint32_t w)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(w);
+#else
+    return (uint32_t)__builtin_popcount(w);
+#endif
+}
+
 // All threads: the slot back to "nothing visited, empty frontier hashes, all chunks free".
+// The records start out all-ones (planner creation) and every record a query writes is marked in
+// its tree's dirty bitmap (dirty_mark), so only the marked records are rewritten: a query touches
+// a few percent of the K n records of a slot.
 template <class Cta>
 IMOMD_HD inline void reset_slot(Cta& cta, const PlannerDev& P, int slot)
 {
     const size_t K = (size_t)P.K;
     const size_t cells = (size_t)P.g.G * P.g.G;
-    // all-ones = not visited / not in the frontier / no children; streaming 128-bit stores: the
-    // 12 n records of a slot must not evict the resident queries' working sets from L2
-    unsigned char* base = P.trec + (size_t)slot * K * (size_t)P.g.n * P.trec_stride;
-    const size_t vecs = K * (size_t)P.g.n * P.trec_stride / 16;
+    // all-ones = not visited / not in the frontier / no children
     U4 ones;
     ones.x = ones.y = ones.z = ones.w = IMOMD_NONE;
-    U4* dst = reinterpret_cast<U4*>(base);
-    for (size_t i = (size_t)cta.tid(); i < vecs; i += (size_t)cta.nt()) cta.store_streaming(dst + i, ones);
+    const uint32_t vec_per_rec = P.trec_stride / 16;
+    if (P.dirty_words != 0)
+    {
+        const size_t dw = P.dirty_words;
+        for (size_t i = (size_t)cta.tid(); i < K * dw; i += (size_t)cta.nt())
+        {
+            const size_t qt = (size_t)slot * K + i / dw;
+            uint32_t* word = P.occ + qt * (2 * cells + dw) + 2 * cells + i % dw;
+            uint32_t bits = *word;
+            if (bits == 0) continue;
+            *word = 0u;
+            unsigned char* base = P.trec + qt * (size_t)P.g.n * P.trec_stride;
+            const size_t v0 = (i % dw) * 32;
+            while (bits != 0)
+            {
+                const int b = lowest_bit(bits);
+                bits &= bits - 1;
+                U4* r = reinterpret_cast<U4*>(base + (v0 + (size_t)b) * P.trec_stride);
+                for (uint32_t j = 0; j < vec_per_rec; ++j) r[j] = ones;
+            }
+        }
+    }
+    else
+    {
+        // no bitmap: all K n records, with streaming 128-bit stores (they must not evict the
+        // resident queries' working sets from L2)
+        unsigned char* base = P.trec + (size_t)slot * K * (size_t)P.g.n * P.trec_stride;
+        const size_t vecs = K * (size_t)P.g.n * P.trec_stride / 16;
+        U4* dst = reinterpret_cast<U4*>(base);
+        for (size_t i = (size_t)cta.tid(); i < vecs; i += (size_t)cta.nt()) cta.store_streaming(dst + i, ones);
+    }
     uint32_t* ch = P.cell_head + (size_t)slot * K * cells;
     uint32_t* cc = P.cell_cnt + (size_t)slot * K * cells;
     for (size_t i = (size_t)cta.tid(); i < K * cells; i += (size_t)cta.nt())
@@ -2681,11 +2747,71 @@ IMOMD_HD inline void tree_hash(Cta& cta, const PlannerDev& P, int slot, Shared& 
     const uint32_t n = P.g.n;
     uint64_t h = 1469598103934665603ull;
     uint64_t sum = 0;
-    const uint32_t tile = (uint32_t)cta.nt() * kHashPerThread;
     uint32_t filled = 0;          // entries waiting in buf (uniform across the CTA)
+    // thread 0 folds the waiting entries (the FNV chain is sequential)
+    auto fold = [&]() {
+        cta.sync();
+        if (cta.tid() == 0)
+        {
+            for (uint32_t i = 0; i < filled; ++i)
+            {
+                const uint32_t* e = buf + 4 * (size_t)i;
+                h = (h ^ (uint64_t)e[0]) * 1099511628211ull;
+                h = (h ^ (uint64_t)e[1]) * 1099511628211ull;
+                h = (h ^ (((uint64_t)e[3] << 32) | e[2])) * 1099511628211ull;
+            }
+        }
+        filled = 0;
+        cta.sync();
+    };
+    auto put = [&](int k, uint32_t at, uint32_t v, const U4& hd) {
+        uint32_t* e = buf + 4 * (size_t)at;
+        e[0] = v;
+        e[1] = hd.x;
+        e[2] = hd.z;
+        e[3] = hd.w;
+        sum += tree_sum_term(k, v, hd.x, ((uint64_t)hd.w << 32) | hd.z);
+    };
     for (int k = 0; k < P.K; ++k)
     {
-        const unsigned char* base = P.trec + ((size_t)slot * P.K + k) * (size_t)n * P.trec_stride;
+        const size_t qt = (size_t)slot * P.K + k;
+        const unsigned char* base = P.trec + qt * (size_t)n * P.trec_stride;
+        if (P.dirty_words != 0)
+        {
+            // streaming planner: only the records marked in the tree's dirty bitmap can be
+            // visited; one bitmap word (32 vertices) per thread and tile, in vertex order
+            const uint32_t dw = P.dirty_words;
+            const uint32_t* bm = P.occ + qt * (2 * (size_t)P.g.G * P.g.G + dw) + 2 * (size_t)P.g.G * P.g.G;
+            const uint32_t tile = (uint32_t)cta.nt();
+            for (uint32_t w0 = 0; w0 < dw; w0 += tile)
+            {
+                const uint32_t wi = w0 + (uint32_t)cta.tid();
+                uint32_t bits = wi < dw ? bm[wi] : 0u;
+                uint32_t vis = 0;
+                while (bits != 0)
+                {
+                    const int b = lowest_bit(bits);
+                    bits &= bits - 1;
+                    const uint32_t v = wi * 32u + (uint32_t)b;
+                    if (*reinterpret_cast<const uint32_t*>(base + (size_t)v * P.trec_stride) != IMOMD_NONE) vis |= 1u << b;
+                }
+                uint32_t total = 0;
+                uint32_t off = cta.scan_exclusive(count_bits(vis), &total, S.scan);
+                while (vis != 0)
+                {
+                    const int b = lowest_bit(vis);
+                    vis &= vis - 1;
+                    const uint32_t v = wi * 32u + (uint32_t)b;
+                    put(k, filled + off, v, *reinterpret_cast<const U4*>(base + (size_t)v * P.trec_stride));
+                    ++off;
+                }
+                filled += total;
+                // fold at the end of every tree and whenever the next tile might not fit
+                if (w0 + tile >= dw || 4 * ((size_t)filled + (size_t)tile * 32) > cap) fold();
+            }
+            continue;
+        }
+        const uint32_t tile = (uint32_t)cta.nt() * kHashPerThread;
         for (uint32_t v0 = 0; v0 < n; v0 += tile)
         {
             U4 hd[kHashPerThread];
@@ -2705,33 +2831,13 @@ IMOMD_HD inline void tree_hash(Cta& cta, const PlannerDev& P, int slot, Shared& 
             {
                 if (hd[j].x != IMOMD_NONE)
                 {
-                    uint32_t* e = buf + 4 * (size_t)(filled + off);
-                    e[0] = first + j;
-                    e[1] = hd[j].x;
-                    e[2] = hd[j].z;
-                    e[3] = hd[j].w;
+                    put(k, filled + off, first + j, hd[j]);
                     ++off;
-                    sum += tree_sum_term(k, first + j, hd[j].x, ((uint64_t)hd[j].w << 32) | hd[j].z);
                 }
             }
             filled += total;
             // fold at the end of every tree and whenever the next tile might not fit
-            if (v0 + tile >= n || 4 * (size_t)(filled + tile) > cap)
-            {
-                cta.sync();
-                if (cta.tid() == 0)
-                {
-                    for (uint32_t i = 0; i < filled; ++i)
-                    {
-                        const uint32_t* e = buf + 4 * (size_t)i;
-                        h = (h ^ (uint64_t)e[0]) * 1099511628211ull;
-                        h = (h ^ (uint64_t)e[1]) * 1099511628211ull;
-                        h = (h ^ (((uint64_t)e[3] << 32) | e[2])) * 1099511628211ull;
-                    }
-                }
-                filled = 0;
-                cta.sync();
-            }
+            if (v0 + tile >= n || 4 * (size_t)(filled + tile) > cap) fold();
         }
     }
     sum = cta.reduce_sum_u64(sum, S.red);

@@ -1123,7 +1123,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     const size_t chunks = (size_t)d.chunks;
     d.trec_stride = 16u + 4u * (uint32_t)g->d.width;
     // bytes of device state one resident query needs (trees, frontier hashes, scratch)
-    const size_t per_slot = (size_t)K * (n * d.trec_stride + cells * (4 + 4 + 8 + 8 + 8) +
+    const size_t per_slot = (size_t)K * (n * d.trec_stride + n / 8 + cells * (4 + 4 + 8 + 8 + 8) +
                                          chunks * (IMOMD_CHUNK * sizeof(VRec) + 8)) +
                             (size_t)d.arena_entries * 4 + chunks * 8 + (size_t)d.log_entries * 8 +
                             (d.pseudo ? (size_t)K * n * 4 : 0);
@@ -1154,7 +1154,15 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     PCU(dmalloc(&d.free_stack, sk * chunks));
     PCU(dmalloc(&d.lbd, sk * cells));
     PCU(dmalloc(&d.ubd, sk * cells));
-    PCU(dmalloc(&d.occ, sk * 2 * cells));
+    // streaming planners: a dirty bitmap of every tree's records behind its occ lists, and the
+    // records all-ones ONCE -- from here on a slot is recycled by rewriting the marked records
+    d.dirty_words = d.streaming ? (uint32_t)((n + 31) / 32) : 0u;
+    PCU(dmalloc(&d.occ, sk * (2 * cells + d.dirty_words)));
+    if (d.streaming)
+    {
+        PCU(cudaMemsetAsync(d.occ, 0, sk * (2 * cells + d.dirty_words) * sizeof(uint32_t), p->stream));
+        PCU(cudaMemsetAsync(d.trec, 0xFF, sk * n * d.trec_stride, p->stream));
+    }
     PCU(dmalloc(&d.arena, (size_t)slots * d.arena_entries));
     PCU(dmalloc(&d.clist, (size_t)slots * 2 * chunks));
     PCU(dmalloc(&d.log, (size_t)slots * 2 * d.log_entries));

@@ -198,10 +198,13 @@ struct PlannerDev
     unsigned char* trec;       // [Q*K][n] vertex records of trec_stride bytes:
                                //   {u32 parent, u32 frontier slot, f64 cost, u32 child[width]}
     uint32_t trec_stride;      // 16 + 4 * width
-    uint32_t pad1_;
+    uint32_t dirty_words;      // streaming planners: words of the per-tree "record touched" bitmap that
+                               // follows each tree's occ lists (slot recycling and the tree hash walk it
+                               // instead of all n records); 0 = no bitmap (resident planners)
     uint32_t* cell_head;       // [Q*K][G*G]
     uint32_t* cell_cnt;        // [Q*K][G*G]
-    uint32_t* occ;             // [Q*K][2*G*G] list of occupied cells, then cell -> list position
+    uint32_t* occ;             // [Q*K][2*G*G + dirty_words] list of occupied cells, cell -> list position,
+                               // then the dirty bitmap of the tree's records (bit v: record v was written)
     VRec* rec;                 // [Q*K][chunks*32]
     uint32_t* chunk_next;      // [Q*K][chunks]
     uint32_t* free_stack;      // [Q*K][chunks]

@@ -182,7 +182,8 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->free_stack.resize(qk * chunks);
     p->lbd.resize(qk * cells);
     p->ubd.resize(qk * cells);
-    p->occ.assign(qk * 2 * cells, 0);
+    d.dirty_words = d.streaming ? (uint32_t)((n + 31) / 32) : 0u;
+    p->occ.assign(qk * (2 * cells + d.dirty_words), 0);
     p->arena.resize((size_t)slots * d.arena_entries);
     p->clist.resize((size_t)slots * 2 * chunks);
     p->log.resize((size_t)slots * 2 * d.log_entries);

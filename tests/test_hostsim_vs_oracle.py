@@ -200,11 +200,13 @@ def test_device_treehash_matches_oracle():
     op.close(); hp.close()
 
 
-@pytest.mark.parametrize("slots", [1, 2, 3])
-def test_streaming_slots_reproduce_every_query(slots):
+@pytest.mark.parametrize("slots,kind", [(1, "grid"), (2, "grid"), (3, "grid"), (2, "road")])
+def test_streaming_slots_reproduce_every_query(slots, kind):
     """A streaming planner (fewer state slots than queries) rebuilds a slot for every query it
-    takes: per-query results equal the oracle's, whatever ran in the slot before."""
-    g = graphs.jittered_grid(48, seed=9)
+    takes -- only the records the previous query marked in the trees' dirty bitmaps -- and hashes
+    its trees through the same bitmaps: per-query results equal the oracle's, whatever ran in the
+    slot before ("road": jump-point hops visit vertices that were never in the frontier)."""
+    g = graphs.jittered_grid(48, seed=9) if kind == "grid" else graphs.road_like(4000, seed=6)
     dests = [graphs.pick_destinations(g, 4, seed=20 + q) for q in range(5)]
     ops = [ol.OraclePlanner(g, d) for d in dests]
     probs = [o.matrices()["P"] for o in ops]
