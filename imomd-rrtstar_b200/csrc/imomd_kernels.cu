@@ -1309,14 +1309,15 @@ int imomd_attach_list(imomd_planner* p, int query, int tree, const uint32_t* ver
         if (vertices[i] >= p->d.g.n) return fail(IMOMD_ERR_ARG, "attach list: vertex id out of range");
     CU(cudaSetDevice(p->g->device));
     CU(cudaMemcpyAsync(p->d.attach_list, vertices, (size_t)count * 4, cudaMemcpyHostToDevice, p->stream));
-    // One WARP per launch: an attach is a chain of small dependent steps (no frontier search), so
-    // the 256-thread CTA of the expansion kernel only added block barriers between them; with 32
-    // threads every barrier is a warp barrier and the idle lanes prefetch the list's next entries
-    // (warm_attach).  IMOMD_ATTACH_THREADS overrides (development aid).
+    // The whole CTA: a merge re-parents large subtrees, so its time goes to the cost propagation and
+    // the examination of the updated vertices' rewire calls, which use every thread (measured on the
+    // bug-trap merge, profiles/README.md: 136 ms with 256 threads, 148 / 155 / 178 ms with 128 / 64 /
+    // 32); the second warp prefetches what the list's next entries touch (warm_attach).
+    // IMOMD_ATTACH_THREADS overrides (development aid).
     static const int attach_threads = [] {
         const char* e = getenv("IMOMD_ATTACH_THREADS");
-        int v = e ? atoi(e) : 32;
-        return (v >= 32 && v <= kThreads && v % 32 == 0) ? v : 32;
+        int v = e ? atoi(e) : kThreads;
+        return (v >= 32 && v <= kThreads && v % 32 == 0) ? v : kThreads;
     }();
     const int w = p->d.g.width;
     if (w == 4) k_attach<4><<<1, attach_threads, p->smem_bytes, p->stream>>>(p->d, query, tree, count);

@@ -145,7 +145,12 @@ int imomd_planner_clear_words(imomd_planner* p);
 /* `iters` passes of expandTreeLayers_ (:329-356) for every query of the planner, in
  * one persistent kernel.  reports[n_queries] may be NULL.  Asynchronous variant:
  * imomd_expand_async enqueues on the planner's stream, imomd_sync waits and fills
- * the reports. */
+ * the reports.  A query whose word cursor reaches the end of the injected stream stops
+ * after its last complete expansion with status IMOMD_RUN_NEED_WORDS and
+ * `iterations` < iters: feed more words and call again with the REMAINING passes.
+ * That resume is per call, not per query -- a planner with several queries must be
+ * fed up front (an expansion draws at most 8 words: iters * K * 8 + a margin covers
+ * every query), because a second call runs its `iters` for all of them. */
 int imomd_expand(imomd_planner* p, int iters, imomd_query_report* reports);
 int imomd_expand_async(imomd_planner* p, int iters);
 int imomd_sync(imomd_planner* p, imomd_query_report* reports);
