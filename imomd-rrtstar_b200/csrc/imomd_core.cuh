@@ -3119,6 +3119,7 @@ struct BatchShared
     uint32_t dirty_n[2][IMOMD_KMAX];     // relaxation queues (ping-pong) per tree
     uint32_t chk_n[IMOMD_KMAX];          // vertices whose connection check is due
     uint64_t tree_cycles[IMOMD_KMAX];    // cycles the tree's group spent on its batch in this step
+    uint64_t relax_cycles[IMOMD_KMAX];   // ... and on the tree's relaxation
     // connection candidates of the step per unordered pair (a > b): index a(a-1)/2 + b
     unsigned long long cand_d[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
     uint32_t cand_x[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
@@ -3289,52 +3290,41 @@ IMOMD_HD inline void relax_vertex(Blk& blk, const PlannerDev& P, const TreeRef& 
     }
 }
 
-// The whole CTA: the rewiring relaxation of one step over all trees, level by level.
-template <int KW, class Blk>
-IMOMD_HD inline void batch_relax(Blk& blk, const PlannerDev& P, int slot, Shared& S0, BatchShared& BS)
+// One group: the rewiring relaxation of tree k to its fixed point, level by level, right after the
+// tree's attaches.  A tree's records are touched by nobody else during the step, so the trees relax
+// independently of each other: no block barrier per level, and a deep chain in one tree does not
+// hold the other trees' levels back (the fixed point does not depend on the order of the offers).
+// Returns the cycles spent.
+template <int KW, class Grp>
+IMOMD_HD inline void batch_relax_tree(Grp& grp, const PlannerDev& P, int slot, int k, Shared& S, BatchShared& BS)
 {
-    QueryDev* Q = S0.Q;
-    const int K = P.K;
+    QueryDev* Q = S.Q;
     const uint32_t q_cap = batch_queue_cap(P), chk_cap = batch_share(P) / 2;
+    const TreeRef T = tree_ref_of(P, slot, k, S);
+    uint32_t* chk = batch_checks(P, slot, k);
+    uint32_t items = 0, levels = 0;
     int cur = 0;
     for (;;)
     {
-        uint32_t total = 0;
-        for (int k = 0; k < K; ++k)
-        {
-            uint32_t n = BS.dirty_n[cur][k];
-            total += n < q_cap ? n : q_cap;
-        }
-        if (total == 0) break;      // (uniform across the CTA: the counts of the level being read are stable)
-        for (uint32_t i = (uint32_t)blk.tid(); i < total; i += (uint32_t)blk.nt())
-        {
-            int k = 0;
-            uint32_t j = i;
-            for (;;)
-            {
-                uint32_t n = BS.dirty_n[cur][k];
-                n = n < q_cap ? n : q_cap;
-                if (j < n) break;
-                j -= n;
-                ++k;
-            }
-            const uint32_t u = batch_queue(P, slot, k, cur)[j];
-            relax_vertex<KW>(blk, P, tree_ref_of(P, slot, k, S0), u, batch_queue(P, slot, k, cur ^ 1),
-                             &BS.dirty_n[cur ^ 1][k], q_cap, batch_checks(P, slot, k), &BS.chk_n[k], chk_cap, Q,
-                             &BS.relax_changes);
-        }
-        blk.sync();
-        if (blk.tid() == 0)
-        {
-            BS.relax_items += total;
-            BS.relax_levels += 1;
-            for (int k = 0; k < K; ++k) BS.dirty_n[cur][k] = 0;
-        }
+        uint32_t n = BS.dirty_n[cur][k];   // (uniform across the group: the level being read is complete)
+        n = n < q_cap ? n : q_cap;
+        if (n == 0) break;
+        const uint32_t* queue = batch_queue(P, slot, k, cur);
+        for (uint32_t i = (uint32_t)grp.tid(); i < n; i += (uint32_t)grp.nt())
+            relax_vertex<KW>(grp, P, T, queue[i], batch_queue(P, slot, k, cur ^ 1), &BS.dirty_n[cur ^ 1][k], q_cap, chk,
+                             &BS.chk_n[k], chk_cap, Q, &BS.relax_changes);
+        grp.sync();
+        if (grp.tid() == 0) BS.dirty_n[cur][k] = 0;
+        items += n;
+        levels += 1;
         cur ^= 1;
-        blk.sync();
+        grp.sync();
     }
-    blk.fence();     // the attach code of the next step reads the heads through the L1
-    blk.sync();
+    if (grp.tid() == 0 && levels != 0)
+    {
+        grp.counter_add(&BS.relax_items, items);
+        grp.counter_add(&BS.relax_levels, levels);
+    }
 }
 
 IMOMD_HD inline int pair_index(int a, int b) { return a > b ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; }
@@ -3551,20 +3541,25 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
             const long long tk0 = grp.clock();
             batch_expand_tree<KW>(grp, P, slot, (int)k, S, lb_all ? lb_all + (size_t)grp.group() * kGroupLbCap : nullptr, B,
                                   pass0);
+            const long long tk1 = grp.clock();
             if (grp.tid() == 0)
             {
                 BS.ev_count[k] = S.ev_n;
                 BS.exp_count[k] = S.exp_n;
                 BS.dirty_n[0][k] = S.dirty_n;
                 BS.chk_n[k] = S.chk_n;
-                BS.tree_cycles[k] = (uint64_t)(grp.clock() - tk0);
+                BS.tree_cycles[k] = (uint64_t)(tk1 - tk0);
             }
+            grp.sync();
+            // 2. rewire: the tree's relaxation, by the same group
+            batch_relax_tree<KW>(grp, P, slot, (int)k, S, BS);
+            if (grp.tid() == 0) BS.relax_cycles[k] = (uint64_t)(grp.clock() - tk1);
         }
         blk.sync();
-        const long long ts1 = blk.clock();
-        // 2. rewire, 3. connect, 4. selection-probability tests
-        batch_relax<KW>(blk, P, slot, S0, BS);
+        blk.fence();     // heads changed by compare-and-swap at the L2; the next reads go through the L1
+        blk.sync();
         const long long ts2 = blk.clock();
+        // 3. connect, 4. selection-probability tests
         batch_connect<KW>(blk, P, slot, S0, BS);
         batch_apply_tests<KW>(blk, P, slot, S0, BS);
         if (blk.tid() == 0)
@@ -3574,23 +3569,25 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
             S0.stat[2] += BS.relax_items;
             S0.stat[3] += (uint64_t)BS.relax_items * (uint64_t)P.g.width;
             S0.stat[4] += BS.relax_changes;
-            // where a step goes (imomd_get_profile): 1 = the trees' attach batches summed, 2 = the
-            // slowest tree's, 3 = the attach part as the block saw it, 4 = the relaxation,
+            // where a step goes (imomd_get_profile): 1 = the trees' attach batches summed (group
+            // cycles), 2 = the slowest tree's attach + relaxation, 3 = attach + relaxation as the
+            // block saw them, 4 = the trees' relaxations summed (group cycles),
             // 5 = connection checks + selection-probability tests
-            uint64_t sum = 0, mx = 0;
+            uint64_t sum = 0, mx = 0, rsum = 0;
             for (int k = 0; k < K; ++k)
             {
                 if (!BS.active[k]) continue;
                 sum += BS.tree_cycles[k];
-                if (BS.tree_cycles[k] > mx) mx = BS.tree_cycles[k];
+                rsum += BS.relax_cycles[k];
+                if (BS.tree_cycles[k] + BS.relax_cycles[k] > mx) mx = BS.tree_cycles[k] + BS.relax_cycles[k];
                 Q->prof_count[1] += 1;
             }
             Q->prof_cycles[1] += sum;
             Q->prof_cycles[2] += mx;
             Q->prof_count[2] += 1;
-            Q->prof_cycles[3] += (uint64_t)(ts1 - ts0);
+            Q->prof_cycles[3] += (uint64_t)(ts2 - ts0);
             Q->prof_count[3] += BS.relax_levels;
-            Q->prof_cycles[4] += (uint64_t)(ts2 - ts1);
+            Q->prof_cycles[4] += rsum;
             Q->prof_count[4] += BS.relax_items;
             Q->prof_cycles[5] += (uint64_t)(blk.clock() - ts2);
             Q->prof_count[5] += 1;

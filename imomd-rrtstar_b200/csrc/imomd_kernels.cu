@@ -370,6 +370,19 @@ struct WarpDev
     }
     __device__ __forceinline__ uint32_t counter_add(uint32_t* p, uint32_t v) const { return atomicAdd(p, v); }
     __device__ __forceinline__ void counter_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
+    // the relaxation of one tree runs on the tree's group (batch_relax_tree): same record-head
+    // primitives as the block's
+    __device__ __forceinline__ U4 cas_head(U4* addr, const U4& expect, const U4& want) const
+    {
+        CtaDev c;
+        return c.cas_head(addr, expect, want);
+    }
+    __device__ __forceinline__ U4 load_cg(const U4* p) const
+    {
+        CtaDev c;
+        return c.load_cg(p);
+    }
+    __device__ __forceinline__ void prefetch_l2(const void* p) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
     __device__ __forceinline__ uint64_t now_ns() const
     {
         uint64_t t;

@@ -32,9 +32,9 @@ for B in Bs:
     busy = np.array([r.busy_cycles for r in reps], np.float64)
     st = dp.states()
     conn = sum(1 for q in range(Q) if np.isfinite(st["D"][q]).all())
-    # where the steps went (query-averaged): attach batches of the trees summed / slowest tree /
-    # attach part as the block saw it / relaxation / connection checks + tests, and the groups'
-    # attach cycles by kind of work
+    # where the steps went (query-averaged): attach batches and relaxations of the trees summed
+    # (group cycles) / slowest tree (attach + relaxation) / that part as the block saw it /
+    # connection checks + tests, and the groups' attach cycles by kind of work
     pc = np.zeros(8); pn = np.zeros(8); gc = np.zeros(8)
     nq = min(Q, 64)
     for q in range(nq):
@@ -46,8 +46,9 @@ for B in Bs:
         gc += c.astype(np.float64)
     mc = lambda x: round(float(x) / nq / 1.965e6, 1)
     cnt = dp.counters()[:nq].astype(np.float64).mean(axis=0)
-    print(json.dumps(dict(B=B, per_query_ms=dict(sum_tree_attach=mc(pc[1]), slowest_tree_per_step=mc(pc[2]),
-                                                 attach_part=mc(pc[3]), relaxation=mc(pc[4]), connect_and_tests=mc(pc[5])),
+    print(json.dumps(dict(B=B, per_query_ms=dict(sum_tree_attach=mc(pc[1]), sum_tree_relaxation=mc(pc[4]),
+                                                 slowest_tree_per_step=mc(pc[2]), attach_and_relax_part=mc(pc[3]),
+                                                 connect_and_tests=mc(pc[5])),
                           steps=int(pn[2] / nq), relax_levels_per_query=int(pn[3] / nq), relax_items_per_query=int(pn[4] / nq),
                           relax_changes_per_query=int(cnt[4]), checked_vertices_per_query=int(cnt[6]),
                           group_ms_by_work=dict(nn=mc(gc[1]), rescan=mc(gc[2]), mhins=mc(gc[3]), serial=mc(gc[7])))), flush=True)
