@@ -3,11 +3,12 @@ Joins `ncu -i X.ncu-rep --page source --csv` (per SASS instruction, absolute add
 line table of the same kernel from `nvdisasm -g -fun <symbol index> <cubin>` (offsets + //## File lines).
    cuobjdump -xelf all lib/libimomd_b200.so; cuobjdump -elf X.cubin | grep '.text.*<kernel>'   # info column = index
    nvdisasm -g -fun 0x<index> X.cubin > k.sass
-   python tools/ncu_line_summary.py source.csv k.sass "title" [top] > profiles/rNN_<kernel>_lines.txt"""
+   python tools/ncu_line_summary.py source.csv k.sass "title" [top] [source root] > profiles/rNN_<kernel>_lines.txt"""
 import csv, re, sys, collections
 
 src, sass, title = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+src_root = sys.argv[5] if len(sys.argv) > 5 else "/root/repo"   # the sources of the build that was profiled
 line_of = {}
 cur = None
 started = False
@@ -50,7 +51,7 @@ def source_line(f, l):
     if f not in text:
         try:
             import glob
-            p = glob.glob(f"/root/repo/**/{f}", recursive=True)
+            p = glob.glob(f"{src_root}/**/{f}", recursive=True)
             text[f] = open(p[0], errors="replace").read().splitlines() if p else []
         except OSError:
             text[f] = []
