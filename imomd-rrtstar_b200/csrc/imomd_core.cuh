@@ -2923,9 +2923,10 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
     uint32_t attach_seen = IMOMD_NONE;
     int warm_k = -1;              // tree whose nearest search has just finished (helpers prefetch)
     uint32_t warm_x = IMOMD_NONE;
+    const bool prof = P.profile != 0;   // per-request cycle counters (imomd_set_profiling): development aid
     for (;;)
     {
-        long long t0 = cta.clock();
+        long long t0 = prof ? cta.clock() : 0;
         if (warm_k >= 0) warm_x = S.result.id1;
         // attach mode: warm the upcoming list entries once per entry (when the position moved)
         uint32_t attach_at = IMOMD_NONE;
@@ -2939,8 +2940,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
             int ph0 = S.phase & 7;
             Seq<KW> seq(P, q, S);
             seq.step(cta, iters);
-            Q->phase_cycles[ph0] += (uint64_t)(cta.clock() - t0);
-            Q->phase_count[ph0] += 1;
+            if (prof)
+            {
+                Q->phase_cycles[ph0] += (uint64_t)(cta.clock() - t0);
+                Q->phase_count[ph0] += 1;
+            }
         }
         else if (warm_k >= 0)
         {
@@ -2955,8 +2959,8 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
         int req = S.req;
         int k = S.k;
         warm_k = -1;
-        long long t1 = cta.clock();
-        if (cta.tid() == 0)
+        long long t1 = prof ? cta.clock() : 0;
+        if (prof && cta.tid() == 0)
         {
             Q->prof_cycles[7] += (uint64_t)(t1 - t0);
             Q->prof_count[7] += 1;
@@ -2980,7 +2984,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
         }
         else if (req == REQ_CHECK) svc_check<KW>(cta, P, q, k, S);
         cta.sync();
-        if (cta.tid() == 0)
+        if (prof && cta.tid() == 0)
         {
             Q->prof_cycles[req & 7] += (uint64_t)(cta.clock() - t1);
             Q->prof_count[req & 7] += 1;
@@ -3190,7 +3194,8 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
         {
             const int req = S.req;
             if (req == REQ_EXIT) break;
-            const long long t0 = grp.clock();
+            const bool prof = P.profile != 0;
+            const long long t0 = prof ? grp.clock() : 0;
             double* lb = (lbg != nullptr && S.Q->n_occ[k] <= kGroupLbCap) ? lbg : nullptr;
             if (req == REQ_NN) svc_nearest(grp, P, slot, k, S, lb, S.clist, &S.near_ties, &S.unresolved_ties, true);
             else if (req == REQ_RESCAN) svc_rescan(grp, P, slot, k, S, lb);
@@ -3198,11 +3203,11 @@ IMOMD_HD inline void batch_expand_tree(Grp& grp, const PlannerDev& P, int slot, 
             grp.sync();
             if (grp.tid() == 0)
             {
-                const long long t1 = grp.clock();
-                S.gprof[req & 7] += (uint64_t)(t1 - t0);
+                const long long t1 = prof ? grp.clock() : 0;
+                if (prof) S.gprof[req & 7] += (uint64_t)(t1 - t0);
                 Seq<KW> seq(P, slot, S);
                 seq.step(grp, 1);
-                S.gprof[7] += (uint64_t)(grp.clock() - t1);
+                if (prof) S.gprof[7] += (uint64_t)(grp.clock() - t1);
             }
             grp.sync();
         }

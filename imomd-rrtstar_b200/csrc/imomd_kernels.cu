@@ -1130,6 +1130,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     d.goal_bias = params->goal_bias;
     d.tie_rel = params->tie_band > 0.0 ? params->tie_band : kTieRel;
     d.pseudo = params->pseudo_mode ? 1 : 0;
+    d.profile = getenv("IMOMD_PROFILE") ? 1u : 0u;
     const size_t n = g->d.n;
     const size_t cells = (size_t)g->d.G * g->d.G;
     default_sizes(d, params->frontier_chunks, params->arena_entries, params->log_entries);
@@ -1712,6 +1713,13 @@ int imomd_get_flags(imomd_planner* p, int query, int32_t* connected, int32_t* dm
     CU(cudaMemcpy(v, &qd->connected, sizeof(v), cudaMemcpyDeviceToHost));   // connected, dm_updated
     if (connected) *connected = v[0];
     if (dm_updated) *dm_updated = v[1];
+    return IMOMD_OK;
+}
+
+int imomd_set_profiling(imomd_planner* p, int on)
+{
+    if (!p) return fail(IMOMD_ERR_ARG, "bad argument");
+    p->d.profile = on ? 1u : 0u;
     return IMOMD_OK;
 }
 

@@ -221,7 +221,8 @@ struct PlannerDev
     // batched mode (imomd_expand_batch): per (slot, tree) event logs and chunk work lists
     BEvent* events;            // [slots*K][ev_cap]
     uint32_t ev_cap;
-    uint32_t pad2_;
+    uint32_t profile;          // 1: the kernels keep the per-request cycle counters of imomd_get_profile /
+                               // imomd_get_phase_cycles (three clock reads per state-machine step; off by default)
     uint32_t* clist_tree;      // [slots*K][2*chunks]
     // injected random words
     const uint32_t* words;

@@ -92,6 +92,7 @@ def cuda_lib():
                                          C.POINTER(C.c_uint64)]
         L.imomd_clear_dm_updated.argtypes = [vp, C.c_int]
         L.imomd_get_visit_order.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.imomd_set_profiling.argtypes = [vp, C.c_int]
         L.imomd_get_profile.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
                                         np.ctypeslib.ndpointer(np.uint64, flags="C")]
         L.imomd_get_phase_cycles.argtypes = [vp, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C"),
@@ -284,6 +285,10 @@ class DevicePlanner:
         ms = C.c_float()
         _check(cuda_lib().imomd_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def set_profiling(self, on=True):
+        """Per-request cycle counters of profile() / phase_cycles(): off unless switched on."""
+        _check(cuda_lib().imomd_set_profiling(self.h, 1 if on else 0))
 
     def profile(self, q=0):
         cyc = np.zeros(8, np.uint64); cnt = np.zeros(8, np.uint64)

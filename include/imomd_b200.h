@@ -181,6 +181,10 @@ int imomd_expand_batch_async(imomd_planner* p, int steps, int B);
  * set, an imomd_expand launch stops after the first pass that ends more than `seconds` after
  * the launch began (imomd_query_report.iterations tells how many ran).  0 = none. */
 int imomd_set_time_budget(imomd_planner* p, double seconds);
+/* The per-request cycle counters below cost three clock reads per state-machine step, so the
+ * kernels keep them only after imomd_set_profiling(p, 1) (default: off, or on when the planner is
+ * created with IMOMD_PROFILE=1 in the environment).  Takes effect with the next launch. */
+int imomd_set_profiling(imomd_planner* p, int on);
 /* cumulative SM-clock cycles and call counts per kind of work of one query: index 1..6 =
  * nearest search, heuristic rescan, heuristic insert, connection gather, cost propagation,
  * rewire batch check; index 7 = the serial steps in between (development / profiling aid) */

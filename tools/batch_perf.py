@@ -19,6 +19,7 @@ for q in range(Q):
 dg = capi.DeviceGraph(g)
 probs = np.stack([capi.selection_probabilities(g, d) for d in dests])
 dp = capi.DevicePlanner(dg, dests, probs, max_resident=slots if slots < Q else 0)
+dp.set_profiling(True)
 print(dp.info(), flush=True)
 dp.feed(capi.mt19937_words(0, passes * K * 8 + 4096))
 for B in Bs:

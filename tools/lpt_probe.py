@@ -29,7 +29,7 @@ chunks = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 iters = 3000
 g, dests = bench.make_workload(A, 0)
 K = len(dests[0])
-dg = capi.DeviceGraph(g); dp = capi.DevicePlanner(dg, dests)
+dg = capi.DeviceGraph(g); dp = capi.DevicePlanner(dg, dests); dp.set_profiling(True)
 dp.feed(capi.mt19937_words(0, iters * K * 8 + 4096))
 per = []; prev = np.zeros(A.queries); wall = 0.0
 for c in range(chunks):

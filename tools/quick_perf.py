@@ -9,6 +9,7 @@ def run(name, g, dests, iters_list, **kw):
     dg = capi.DeviceGraph(g)
     t0 = time.time()
     dp = capi.DevicePlanner(dg, dests, **kw)
+    dp.set_profiling(True)
     t_create = time.time() - t0
     dp.feed(capi.mt19937_words(0, 3_000_000))
     out = []

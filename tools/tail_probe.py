@@ -9,7 +9,7 @@ class A: grid = 1000; queries = 296; workload = "grid"
 g = None
 for rank in [int(a) for a in sys.argv[1:]] or [0]:
     g, dests = bench.make_workload(A, rank)
-    dg = capi.DeviceGraph(g); dp = capi.DevicePlanner(dg, dests)
+    dg = capi.DeviceGraph(g); dp = capi.DevicePlanner(dg, dests); dp.set_profiling(True)
     dp.feed(capi.mt19937_words(0, 3000 * 12 * 8 + 4096))
     reps = dp.expand(3000)
     ms = dp.last_kernel_ms()
