@@ -1221,6 +1221,20 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
 #define IMOMD_SET_ALL(W) set((const void*)k_expand<256, 1, W>); set((const void*)k_expand<256, 2, W>); set((const void*)k_attach<W>);
         IMOMD_SET_ALL(4) IMOMD_SET_ALL(8) IMOMD_SET_ALL(16)
 #undef IMOMD_SET_ALL
+        // Single-CTA kernels (the merge's k_attach, the one-query-per-SM latency build of k_expand)
+        // want the rest of the SM's unified L1 / shared memory as L1: their chains of dependent
+        // record loads hit it or wait for the L2.  Carveout = what one CTA needs, in percent.
+        {
+            int smem_sm = 0;
+            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g->device);
+            const int pct = smem_sm > 0 ? (int)std::min<size_t>(100, (100 * (p->smem_bytes + 2048) + smem_sm - 1) / smem_sm) : 50;
+            auto carve = [&](const void* f) {
+                cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                if (r != cudaSuccess) e = r;
+            };
+            carve((const void*)k_attach<4>); carve((const void*)k_attach<8>); carve((const void*)k_attach<16>);
+            carve((const void*)k_expand<256, 1, 4>); carve((const void*)k_expand<256, 1, 8>); carve((const void*)k_expand<256, 1, 16>);
+        }
         PCU(e);
     }
     PCU(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize,
