@@ -1224,6 +1224,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
         // Single-CTA kernels (the merge's k_attach, the one-query-per-SM latency build of k_expand)
         // want the rest of the SM's unified L1 / shared memory as L1: their chains of dependent
         // record loads hit it or wait for the L2.  Carveout = what one CTA needs, in percent.
+        if (!getenv("IMOMD_NO_CARVEOUT"))
         {
             int smem_sm = 0;
             cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g->device);

@@ -120,6 +120,26 @@ def test_reset_reproduces():
     dp.close(); dg.close(); op.close()
 
 
+def test_profiling_counters_are_opt_in():
+    """imomd_get_profile / imomd_get_phase_cycles: the kernels keep the per-request cycle counters
+    only after imomd_set_profiling(p, 1); results do not depend on the switch."""
+    g = graphs.jittered_grid(50, seed=8)
+    dest = graphs.pick_destinations(g, 4, seed=4)
+    op, dg, dp = _pair(g, dest)
+    dp.feed(capi.mt19937_words(0, 100000))
+    dp.expand(150)
+    prof = dp.profile(0); prof.pop("bfs_vertices_levels")
+    assert all(c == 0 and n == 0 for c, n in prof.values())
+    dp.set_profiling(True)
+    dp.expand(150)
+    prof = dp.profile(0); prof.pop("bfs_vertices_levels")
+    assert prof["nn"][1] > 0 and prof["nn"][0] > 0 and prof["serial"][0] > 0
+    assert dp.phase_cycles(0)[0].sum() > 0
+    op.iterate(300)
+    compare_with_oracle(dp, op, 4, False)
+    dp.close(); dg.close(); op.close()
+
+
 def test_walk_to_root_and_word_starvation():
     g = graphs.jittered_grid(50, seed=5)
     dest = graphs.pick_destinations(g, 5, seed=2)
