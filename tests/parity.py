@@ -30,13 +30,14 @@ def compare_with_oracle(impl, op, K, exact_heuristics, q=0, check_frontier=True)
     pa, pb = si["P"], mo["P"]
     assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64)), "probability matrix differs"
     assert np.array_equal(conv_ids(si["mh_id"]), mo["mh_id"]), "min-heuristic holders differ"
-    if exact_heuristics:
-        assert np.array_equal(si["mh_val"].view(np.uint64), mo["mh_val"].view(np.uint64))
-    else:
-        a, b = si["mh_val"], mo["mh_val"]
-        fin = np.isfinite(b)
-        assert np.array_equal(np.isfinite(a), fin)
-        assert np.allclose(a[fin], b[fin], rtol=1e-12, atol=0.0)
+    # min-heuristic VALUES: the device logic evaluates the heuristics' haversine with its own
+    # small-argument polynomials (imomd_core.cuh haversine_pc), the oracle with glibc like the
+    # reference.  exact_heuristics (host simulation: same libm otherwise): within a few ulp;
+    # else (CUDA libm): within the 1e-12 band inside which comparisons are decided on glibc's values.
+    a, b = si["mh_val"], mo["mh_val"]
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    assert np.allclose(a[fin], b[fin], rtol=2e-15 if exact_heuristics else 1e-12, atol=0.0)
     assert np.array_equal(si["is_done"], fo["is_done"])
     assert np.array_equal(si["ds_parent"], fo["ds_parent"])
     assert si["connected"] == fo["connected"] and si["dm_updated"] == fo["dm_updated"]
