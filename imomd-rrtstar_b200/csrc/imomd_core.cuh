@@ -1885,8 +1885,8 @@ IMOMD_HD inline void warm_expansion(Cta& cta, const PlannerDev& P, const TreeRef
 }
 
 // The same idea for imomd_attach_list (pseudo-tree merge): the vertices to attach are known in
-// advance, so while thread 0 works on entry i the other lanes of the (single-warp) CTA fetch what
-// entries i+1 .. i+8 will touch: the vertex's adjacency row, the tree records and child rows of its
+// advance, so while thread 0 works on entry i the second warp of the CTA (the other lanes of the
+// warp when the kernel is launched with 32 threads) fetches what entries i+1 .. i+8 will touch: the vertex's adjacency row, the tree records and child rows of its
 // neighbours, their hash cells.  Nothing is written; stale reads are harmless.
 template <class Cta>
 IMOMD_HD inline void warm_attach(Cta& cta, const PlannerDev& P, const TreeRef& T, uint32_t at, uint32_t n, Shared& S)

@@ -519,9 +519,9 @@ __global__ void k_init_trees(const __grid_constant__ PlannerDev P)
 }
 
 // The expansion kernel in two register budgets: a latency build (one query per SM, all
-// 255 registers, no spills) for planners with few queries, and a throughput build (four
-// CTAs per SM) whose point is to hide each query's dependent-load latency behind the
-// other resident queries.
+// 255 registers, no spills) for planners with few queries, and a throughput build (two
+// CTAs per SM, 128 registers) whose point is to hide each query's dependent-load latency behind
+// the other resident query.
 // The planner descriptor is a __grid_constant__ parameter: the device logic takes it by reference
 // (noinline services), and without the qualifier every field read would go through a per-thread
 // LOCAL copy of the 200-byte struct (measured: 6.5 % of the batch time, 300 bytes of stack).
