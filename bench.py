@@ -78,6 +78,7 @@ def parse():
                     help="grid = BASELINE configs[2] (default); san_pablo = configs[4]: 1024 "
                          "source/target queries (K = 2) on the bundled san_pablo road graph")
     ap.add_argument("--no-ttfs", action="store_true", help="skip the time-to-first-solution side measurement")
+    ap.add_argument("--ttfs-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--batch", type=int, default=16,
                     help="B of the batched-mode leg (B expansions per tree per step); 0 skips the leg")
     ap.add_argument("--cpu-sample-iters", type=int, default=0,
@@ -725,14 +726,15 @@ def b200_arm(args):
     # time to first solution of ONE query through the drop-in C++ facade (planner construction ->
     # first accepted RTSP tour, same 100-pass cadence) next to the unmodified reference
     if not args.no_ttfs and not args.no_cpu_baseline and world == 1:
+        # in a process of their own: what a user of the drop-in facade runs is a fresh process, and
+        # this one has just cycled 143 GB of device memory through the allocator (measured: the same
+        # bug-trap run takes 0.28 s in a fresh process and 0.32-0.35 s here)
         try:
-            line["ttfs"] = measure_ttfs(g, dests[0], device)
+            out = subprocess.check_output([sys.executable, os.path.abspath(__file__), "--ttfs-only", "--grid",
+                                           str(args.grid), "--gpus", "1"], text=True, timeout=900)
+            line.update(json.loads(out.strip().splitlines()[-1]))
         except Exception as ex:
-            line["ttfs"] = {"error": str(ex)}
-        try:
-            line["ttfs_bugtrap"] = measure_ttfs_bugtrap(device)
-        except Exception as ex:
-            line["ttfs_bugtrap"] = {"error": str(ex)}
+            line["ttfs"] = {"error": repr(ex)}
     if not args.no_side_legs and world == 1:
         try:
             line["ga"] = ga_leg(device)
@@ -805,6 +807,22 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.ttfs_only:
+        # child of the main arm: time to first solution through the drop-in facade (same device)
+        device = dist_env()[2]
+        g, dests = make_workload(argparse.Namespace(grid=args.grid, queries=1, workload="grid"), 0)
+        res = {}
+        try:
+            res["ttfs"] = measure_ttfs(g, dests[0], device)
+        except Exception as ex:
+            res["ttfs"] = {"error": str(ex)}
+        try:
+            res["ttfs_bugtrap"] = measure_ttfs_bugtrap(device)
+        except Exception as ex:
+            res["ttfs_bugtrap"] = {"error": str(ex)}
+        res["ttfs"]["process"] = res["ttfs_bugtrap"]["process"] = "a fresh process per measurement leg (bench.py --ttfs-only)"
+        emit(res)
+        return 0
     return b200_arm(args)
 
 
