@@ -3127,7 +3127,7 @@ IMOMD_HD inline void run_streaming_query(Cta& cta, const PlannerDev& P, int slot
 // are not maintained (the relaxation walks the road graph, not the tree), so a planner that has
 // run batched steps cannot continue in the exact mode before a reset.
 constexpr uint32_t kBatchWords = 8;
-constexpr uint32_t kGroupLbCap = 512;   // cell lower bounds a group keeps in shared memory between the two
+constexpr uint32_t kGroupLbCap = 256;   // cell lower bounds a group keeps in shared memory between the two
                                         // passes of a pruned search (frontiers with more occupied cells
                                         // recompute them)
 
