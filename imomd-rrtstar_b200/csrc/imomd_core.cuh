@@ -84,6 +84,10 @@ enum Phase
     PH_LAST_CONN = 6
 };
 constexpr uint32_t kCheckBatch = 64;   // rewire calls examined per speculative check
+// Cell lower bounds a CTA keeps in shared memory between the two passes of a pruned search: one per
+// OCCUPIED cell, at most kCtaLbCap (a frontier that occupies more cells recomputes its bounds in the
+// second pass).  What the G x G table of round 1 took beyond that is L1 now.
+constexpr uint32_t kCtaLbCap = 1024;
 
 // include/osm_converter/compute_haversine.hpp:41-58, same expression order.
 IMOMD_HD IMOMD_NOINLINE double haversine(double lat1, double lon1, double lat2, double lon2)
@@ -320,6 +324,11 @@ IMOMD_HD inline THead head_from(const U4& t)
 }
 
 // padded adjacency rows (see GraphDev)
+IMOMD_HD inline uint32_t lb_entries(const PlannerDev& P)
+{
+    const uint32_t cells = (uint32_t)P.g.G * (uint32_t)P.g.G;
+    return cells < kCtaLbCap ? cells : kCtaLbCap;
+}
 IMOMD_HD inline uint32_t row_begin(const GraphDev& g, uint32_t v) { return v * (uint32_t)g.width; }
 IMOMD_HD inline uint32_t row_end(const GraphDev& g, uint32_t v) { return v * (uint32_t)g.width + g.deg[v]; }
 
@@ -2988,10 +2997,11 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
         if (req == REQ_EXIT) break;
         if (req == REQ_NN)
         {
-            svc_nearest(cta, P, q, k, S, lb, S.clist, &S.near_ties, &S.unresolved_ties, true);
+            svc_nearest(cta, P, q, k, S, Q->n_occ[k] <= lb_entries(P) ? lb : nullptr, S.clist, &S.near_ties,
+                        &S.unresolved_ties, true);
             warm_k = k;
         }
-        else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, lb);
+        else if (req == REQ_RESCAN) svc_rescan(cta, P, q, k, S, Q->n_occ[k] <= lb_entries(P) ? lb : nullptr);
         else if (req == REQ_MHINS) svc_mhins(cta, P, q, k, S);
         else if (req == REQ_CONN) svc_conn_gather(cta, P, q, S.conn_x, S);
         else if (req == REQ_BFS)
@@ -3127,6 +3137,7 @@ IMOMD_HD inline void run_streaming_query(Cta& cta, const PlannerDev& P, int slot
 // are not maintained (the relaxation walks the road graph, not the tree), so a planner that has
 // run batched steps cannot continue in the exact mode before a reset.
 constexpr uint32_t kBatchWords = 8;
+// (the exact mode's CTA keeps up to kCtaLbCap of them: lb_entries)
 constexpr uint32_t kGroupLbCap = 256;   // cell lower bounds a group keeps in shared memory between the two
                                         // passes of a pruned search (frontiers with more occupied cells
                                         // recompute them)

@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_expand(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
-    uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + (size_t)P.g.G * P.g.G);
+    uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + lb_entries(P));
     double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev cta;
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(kThreads) k_attach(const __grid_constant__ Pla
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     double* lb = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
-    uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + (size_t)P.g.G * P.g.G);
+    uint32_t* lvl = reinterpret_cast<uint32_t*>(lb + lb_entries(P));
     double* mat = reinterpret_cast<double*>(lvl + 2 * kLevelCap);
     unsigned char* hot = reinterpret_cast<unsigned char*>(mat + (size_t)P.K * P.K * 4);
     CtaDev cta;
@@ -684,7 +684,8 @@ k_nearest(const __grid_constant__ PlannerDev P, int n, const imomd_nn_query* __r
             S.qlon = nq.lon;
         }
         __syncthreads();
-        svc_nearest(cta, P, nq.query, nq.tree, S, lb, clist, &near_ties, &unresolved, false);
+        svc_nearest(cta, P, nq.query, nq.tree, S, P.query[nq.query].n_occ[nq.tree] <= lb_entries(P) ? lb : nullptr, clist,
+                    &near_ties, &unresolved, false);
         __syncthreads();
         if (threadIdx.x == 0)
         {
@@ -1208,7 +1209,7 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     p->prob_h.assign(prob, prob + (size_t)n_queries * K * K);
     PCU(dmalloc(&p->dest_d, (size_t)n_queries * K));
     PCU(dmalloc(&p->prob_d, (size_t)n_queries * K * K));
-    p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + cells * sizeof(double) +
+    p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + std::min<size_t>(cells, kCtaLbCap) * sizeof(double) +
                     2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32 +
                     ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)K * sizeof(TreeRef);
     {
