@@ -493,7 +493,7 @@ struct Shared
     int32_t rescan_o[IMOMD_KMAX];
     int32_t n_ys;
     uint32_t ys[IMOMD_MAXDEG];
-    double h[IMOMD_MAXDEG * IMOMD_KMAX];
+    double* h;             // [width * K] haversine of the inserted vertices to the K roots (behind the tree views)
     // work list of the pruned search
     uint32_t n_list;
     uint32_t n_cells, n_recs;   // statistics of the current search
@@ -2167,12 +2167,14 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
     QueryDev* Q = S.Q;
     int K = Q->K;
     int m = S.n_ys;
+    double* hv = S.h;       // [m][K], m <= the graph's adjacency width
+    IMOMD_ASSUME_SHARED(hv);
     for (int i = cta.tid(); i < m * K; i += cta.nt())
     {
         int yi = i / K, o = i % K;
         uint32_t y = S.ys[yi];
         uint32_t r = Q->view_root[o];
-        S.h[yi * IMOMD_KMAX + o] = haversine_pc(g.lat[y], g.lon[y], g.coslat[y], g.lat[r], g.lon[r], g.coslat[r]);
+        hv[i] = haversine_pc(g.lat[y], g.lon[y], g.coslat[y], g.lat[r], g.lon[r], g.coslat[r]);
     }
     if (cta.tid() == 0) S.mh_tie_mask = 0u;
     cta.sync();
@@ -2184,7 +2186,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
         bool close = false;
         for (int yi = 0; yi < m; ++yi)
         {
-            double h = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
+            double h = hv[yi * K + k] + hv[yi * K + o];
             // (an inserted vertex that already IS the holder compares equal in any arithmetic)
             if (arg != IMOMD_NONE && S.ys[yi] != arg && fabs(h - best) <= P.tie_rel * best) close = true;
             if (h < best)
@@ -2226,7 +2228,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_mhins(Cta& cta, const PlannerDev& P, int q, int
             for (int yi = 0; yi < m; ++yi)
             {
                 ids[n] = S.ys[yi];
-                dev[n] = S.h[yi * IMOMD_KMAX + k] + S.h[yi * IMOMD_KMAX + o];
+                dev[n] = hv[yi * K + k] + hv[yi * K + o];
                 ++n;
             }
             // (rounds of IMOMD_TIE_PAIRS / 2 candidates per mailbox request)
@@ -2907,6 +2909,7 @@ IMOMD_HD inline void run_query(Cta& cta, const PlannerDev& P, int q, int hq, int
         for (int i = 0; i < 8; ++i) S.stat[i] = 0;
         S.near_ties = S.unresolved_ties = S.certified_ties = 0;
         S.tref = tref;
+        S.h = reinterpret_cast<double*>(tref + P.K);
         S.mP = mat;
         S.mD = mat + KK;
         S.mMHv = mat + 2 * KK;
@@ -3490,6 +3493,7 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
         Shared& S = SG[g];
         S.Q = Q;
         S.tref = tref;
+        S.h = reinterpret_cast<double*>(tref + K) + (size_t)g * P.g.width * K;
         S.mP = mat;
         S.mD = mat + KK;
         S.mMHv = mat + 2 * KK;

@@ -1211,7 +1211,8 @@ int imomd_planner_create(imomd_graph* g, int n_queries, int K, const uint32_t* d
     PCU(dmalloc(&p->prob_d, (size_t)n_queries * K * K));
     p->smem_bytes = ((sizeof(Shared) + 15) / 16) * 16 + std::min<size_t>(cells, kCtaLbCap) * sizeof(double) +
                     2 * kLevelCap * sizeof(uint32_t) + (size_t)K * K * 32 +
-                    ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)K * sizeof(TreeRef);
+                    ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)K * sizeof(TreeRef) +
+                    (size_t)g->d.width * K * sizeof(double);
     {
         cudaError_t e = cudaSuccess;
         auto set = [&](const void* f) {
@@ -1559,7 +1560,8 @@ int imomd_expand_batch_async(imomd_planner* p, int steps, int B)
         (void)cells_unused;
         p->smem_batch = (kBatchThreads / 32) * (((sizeof(Shared) + 15) / 16) * 16) + ((sizeof(BatchShared) + 15) / 16) * 16 +
                         (size_t)(kBatchThreads / 32) * kGroupLbCap * sizeof(double) + (size_t)d.K * d.K * 32 +
-                        ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)d.K * sizeof(TreeRef) + 64;
+                        ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16 + (size_t)d.K * sizeof(TreeRef) +
+                        (size_t)(kBatchThreads / 32) * d.g.width * d.K * sizeof(double) + 64;
         cudaError_t e = cudaSuccess;
         auto set = [&](const void* f) {
             cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_batch);

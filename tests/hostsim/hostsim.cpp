@@ -191,7 +191,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->lb.resize(cells);
     p->lvl.resize(2 * kLevelCap);
     p->mat.resize((size_t)K * K * 4);
-    p->hot.resize(IMOMD_QUERY_HOT_BYTES + 64 + (size_t)K * sizeof(TreeRef));
+    p->hot.resize(IMOMD_QUERY_HOT_BYTES + 64 + (size_t)K * sizeof(TreeRef) + (size_t)d.g.width * K * sizeof(double));
     d.query = p->query.data();
     d.trec = reinterpret_cast<unsigned char*>(((uintptr_t)p->trec.data() + 15) & ~(uintptr_t)15);
     d.cell_head = p->cell_head.data();
