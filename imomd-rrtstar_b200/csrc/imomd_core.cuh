@@ -87,7 +87,7 @@ constexpr uint32_t kCheckBatch = 64;   // rewire calls examined per speculative 
 // Cell lower bounds a CTA keeps in shared memory between the two passes of a pruned search: one per
 // OCCUPIED cell, at most kCtaLbCap (a frontier that occupies more cells recomputes its bounds in the
 // second pass).  What the G x G table of round 1 took beyond that is L1 now.
-constexpr uint32_t kCtaLbCap = 1024;
+constexpr uint32_t kCtaLbCap = 256;
 
 // include/osm_converter/compute_haversine.hpp:41-58, same expression order.
 IMOMD_HD IMOMD_NOINLINE double haversine(double lat1, double lon1, double lat2, double lon2)
@@ -2310,7 +2310,7 @@ IMOMD_HD IMOMD_NOINLINE void svc_conn_gather(Cta& cta, const PlannerDev& P, int 
 // memory, a child row is one 128-bit load, the read-modify-write of the children's costs
 // is deferred by one round so that only the child-row load is on the critical path, and
 // levels of at most 32 vertices are walked by warp 0 alone with shuffles (no block barrier).
-constexpr uint32_t kLevelCap = 512;
+constexpr uint32_t kLevelCap = 256;
 
 template <int W>
 struct BfsPending
