@@ -3159,8 +3159,10 @@ struct BatchShared
     uint64_t tree_cycles[IMOMD_KMAX];    // cycles the tree's group spent on its batch in this step
     uint64_t relax_cycles[IMOMD_KMAX];   // ... and on the tree's relaxation
     // connection candidates of the step per unordered pair (a > b): index a(a-1)/2 + b
-    unsigned long long cand_d[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
-    uint32_t cand_x[IMOMD_KMAX * (IMOMD_KMAX - 1) / 2];
+    // (K (K - 1) / 2 entries each; they live in the groups' cell-bound caches, which are idle
+    // while the block runs the connection checks)
+    unsigned long long* cand_d;
+    uint32_t* cand_x;
 };
 
 // the scratch of tree k inside the slot's arena: [rewire queue A | rewire queue B | check list].
@@ -3488,6 +3490,13 @@ IMOMD_HD inline void run_query_batched(Blk& blk, Grp& grp, const PlannerDev& P, 
     }
     TreeRef* tref = reinterpret_cast<TreeRef*>(hot + ((IMOMD_QUERY_HOT_BYTES + 15) / 16) * 16);
     for (int k = blk.tid(); k < K; k += blk.nt()) tref[k] = tree_ref(P, slot, k);
+    if (blk.tid() == 0)
+    {
+        // (kGroupLbCap doubles per group: 2 KB at least, K (K - 1) / 2 <= 496 pairs of 12 bytes need 6 KB
+        // of the G >= 4 groups' 8 KB; the host simulation sizes its one buffer accordingly)
+        BS.cand_d = reinterpret_cast<unsigned long long*>(lb_all);
+        BS.cand_x = reinterpret_cast<uint32_t*>(BS.cand_d + K * (K - 1) / 2);
+    }
     for (int g = blk.tid(); g < G; g += blk.nt())
     {
         Shared& S = SG[g];

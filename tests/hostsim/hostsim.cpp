@@ -188,7 +188,7 @@ void* hs_create(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const 
     p->clist.resize((size_t)slots * 2 * chunks);
     p->log.resize((size_t)slots * 2 * d.log_entries);
     p->reports.resize(Q);
-    p->lb.resize(cells);
+    p->lb.resize(std::max<size_t>(cells, 1024));   // (also holds the batched mode's connection candidates)
     p->lvl.resize(2 * kLevelCap);
     p->mat.resize((size_t)K * K * 4);
     p->hot.resize(IMOMD_QUERY_HOT_BYTES + 64 + (size_t)K * sizeof(TreeRef) + (size_t)d.g.width * K * sizeof(double));
