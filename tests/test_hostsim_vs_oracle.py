@@ -182,6 +182,24 @@ def test_attach_list_matches_reference_merge_step(kind, K, warm):
     hp.close()
 
 
+def test_frontier_with_more_occupied_cells_than_the_bound_table():
+    """The CTA keeps the cell bounds of a search for at most 256 occupied cells (kCtaLbCap); a
+    frontier that occupies more (64 x 64 hash over a small map, uniform samples: long thin trees)
+    recomputes its bounds in the second pass of the search.  Same trees as the oracle either way."""
+    g = graphs.jittered_grid(120, seed=13)
+    dest = graphs.pick_destinations(g, 3, seed=2)
+    op, hp = _pair(g, dest, 0.0, grid_dim=64)
+    hp.feed(_words(400000))
+    e = hp.expand(2500)[0].expansions
+    assert e == op.iterate(2500)
+    # the premise: some tree's frontier is spread over more than 256 cells of the 64 x 64 hash
+    cell = lambda v: (np.minimum(((g.lat[v] - g.lat.min()) / (np.ptp(g.lat) / 64)).astype(int), 63) * 64 +
+                      np.minimum(((g.lon[v] - g.lon.min()) / (np.ptp(g.lon) / 64)).astype(int), 63))
+    assert max(len(set(cell(np.asarray(hp.frontier(k), np.int64)).tolist())) for k in range(3)) > 256
+    compare_with_oracle(hp, op, 3, True)
+    op.close(); hp.close()
+
+
 def test_device_treehash_matches_oracle():
     """tree_hash (the routine behind imomd_get_treehash and the streaming planners' reports) ==
     the SURVEY Appendix A TREEHASH of the oracle's trees."""
